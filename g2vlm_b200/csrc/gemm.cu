@@ -1,0 +1,436 @@
+// g2vlm_b200 — grouped (token-type-routed) bf16 GEMM on tcgen05 tensor cores.
+//
+// One persistent, warp-specialised kernel per epilogue:
+//   warp 0      TMA producer   (cp.async.bulk.tensor, 128-byte swizzle, 4-stage mbarrier ring)
+//   warp 1      MMA issuer     (tcgen05.mma 128x256x16, fp32 accumulators in TMEM, 2 accumulator
+//                               stages so the epilogue of tile i overlaps the main loop of i+1)
+//   warps 2..5  epilogue       (tcgen05.ld -> registers -> fused bias / GELU / SwiGLU /
+//                               LayerScale+residual -> global)
+// Routing: tokens are permuted once per forward so each expert's rows are contiguous ("gather by
+// expert"); an M tile therefore belongs to exactly one expert and selects that expert's weight rows
+// by a row offset into the stacked weight matrix — each expert runs as one dense GEMM and both run
+// in the same launch. See include/g2vlm_b200.h for the reference call sites this replaces.
+#include "common.cuh"
+
+namespace g2 {
+
+constexpr int BM = 128;
+constexpr int BN = 256;
+constexpr int BK = 64;
+constexpr int STAGES = 4;
+constexpr int A_BYTES = BM * BK * 2;
+constexpr int B_BYTES = BN * BK * 2;
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int GEMM_THREADS = 192;
+constexpr int PANEL_M = 16;  // rasterisation: 16 M tiles x all N tiles per panel (L2 reuse)
+constexpr int GEMM_SMEM = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+
+struct GemmKParams {
+  CUtensorMap tmA;
+  CUtensorMap tmB;
+  int n_groups;
+  int grp_row0[2];
+  int grp_rows[2];
+  int grp_mtile0[3];
+  int N, K;
+  int n_tiles_n;
+  int num_tiles;
+  int num_kb;
+  uint32_t flags;
+  uint32_t scale_groups;
+  void* out;
+  long long ldo;
+  const float* bias;
+  const float* scale;
+  const float* residual;
+  long long ldr;
+};
+
+struct TileCoord {
+  int g, row0, rows_valid, n_tile;
+};
+
+__device__ __forceinline__ TileCoord decode_tile(const GemmKParams& p, int tile) {
+  const int mt_total = p.grp_mtile0[p.n_groups];
+  const int per_panel = PANEL_M * p.n_tiles_n;
+  const int panel = tile / per_panel;
+  const int r = tile - panel * per_panel;
+  const int panel_h = min(PANEL_M, mt_total - panel * PANEL_M);
+  const int n_tile = r / panel_h;
+  const int m = panel * PANEL_M + (r - n_tile * panel_h);
+  TileCoord t;
+  t.g = (p.n_groups > 1 && m >= p.grp_mtile0[1]) ? 1 : 0;
+  const int m_local = m - p.grp_mtile0[t.g];
+  t.row0 = p.grp_row0[t.g] + m_local * BM;
+  t.rows_valid = min(BM, p.grp_rows[t.g] - m_local * BM);
+  t.n_tile = n_tile;
+  return t;
+}
+
+__device__ __forceinline__ float gelu_erf(float x) {
+  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+}
+
+// ---- epilogues: each thread owns one accumulator row; `v` holds 32 consecutive columns ----------
+template <int EPI>
+__device__ __forceinline__ void epilogue_tile(const GemmKParams& p, const TileCoord& t,
+                                              uint32_t taddr, int r_in_tile) {
+  const bool row_ok = r_in_tile < t.rows_valid;
+  const long long row = t.row0 + r_in_tile;
+  const int n0 = t.n_tile * BN;
+
+  if constexpr (EPI == G2VLM_EPI_SWIGLU_BF16) {
+    // columns [0,128) of the tile = gate, [128,256) = up, for output columns n_tile*128 + [0,128)
+    __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out) + row * p.ldo + t.n_tile * 128;
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+      uint32_t vg[32], vu[32];
+      tmem_ld32(taddr + c * 32, vg);
+      tmem_ld32(taddr + 128 + c * 32, vu);
+      tmem_wait_ld();
+      if (row_ok) {
+        uint32_t packed[16];
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+          float o[2];
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            // reference rounding points: gate_proj -> bf16, silu -> bf16, up_proj -> bf16, mul -> bf16
+            const float g = bf16_round(__uint_as_float(vg[j + e]));
+            const float u = bf16_round(__uint_as_float(vu[j + e]));
+            const float s = bf16_round(g / (1.0f + __expf(-g)));
+            o[e] = s * u;
+          }
+          packed[j >> 1] = pack_bf16x2(o[0], o[1]);
+        }
+        uint4* dst = reinterpret_cast<uint4*>(out + c * 32);
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          dst[q] = make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
+      }
+    }
+    return;
+  } else {
+    const float* bias = p.bias ? p.bias + (long long)t.g * p.N : nullptr;
+    const bool use_scale = p.scale != nullptr && ((p.scale_groups >> t.g) & 1u);
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      const int col0 = n0 + c * 32;
+      if (col0 >= p.N) break;  // warp-uniform
+      uint32_t v[32];
+      tmem_ld32(taddr + c * 32, v);
+      tmem_wait_ld();
+      if (!row_ok) continue;
+      const bool full = (col0 + 32 <= p.N);
+      float f[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+      if (bias) {
+        if (full) {
+          const float4* b4 = reinterpret_cast<const float4*>(bias + col0);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float4 b = __ldg(b4 + q);
+            f[4 * q] += b.x; f[4 * q + 1] += b.y; f[4 * q + 2] += b.z; f[4 * q + 3] += b.w;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (col0 + j < p.N) f[j] += __ldg(bias + col0 + j);
+        }
+      }
+
+      if constexpr (EPI == G2VLM_EPI_STORE_BF16) {
+        if (p.flags & G2VLM_GEMM_GELU) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = gelu_erf(bf16_round(f[j]));
+        }
+        __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out) + row * p.ldo + col0;
+        if (full) {
+          uint4* dst = reinterpret_cast<uint4*>(out);
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            dst[q] = make_uint4(pack_bf16x2(f[8 * q], f[8 * q + 1]), pack_bf16x2(f[8 * q + 2], f[8 * q + 3]),
+                                pack_bf16x2(f[8 * q + 4], f[8 * q + 5]), pack_bf16x2(f[8 * q + 6], f[8 * q + 7]));
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (col0 + j < p.N) out[j] = __float2bfloat16_rn(f[j]);
+        }
+      } else if constexpr (EPI == G2VLM_EPI_RESID_F32) {
+        // x += [bf16]( gamma * bf16(acc + bias) )   (reference: g2vlm/qwen2vl.py:885-887, 907-909)
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = bf16_round(f[j]);
+        if (use_scale) {
+          if (full) {
+            const float4* s4 = reinterpret_cast<const float4*>(p.scale + col0);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const float4 s = __ldg(s4 + q);
+              f[4 * q] *= s.x; f[4 * q + 1] *= s.y; f[4 * q + 2] *= s.z; f[4 * q + 3] *= s.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.N) f[j] *= __ldg(p.scale + col0 + j);
+          }
+          if (p.flags & G2VLM_GEMM_ROUND_AFTER_SCALE) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = bf16_round(f[j]);
+          }
+        }
+        float* out = reinterpret_cast<float*>(p.out) + row * p.ldo + col0;
+        if (full) {
+          float4* o4 = reinterpret_cast<float4*>(out);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            float4 x = o4[q];
+            x.x += f[4 * q]; x.y += f[4 * q + 1]; x.z += f[4 * q + 2]; x.w += f[4 * q + 3];
+            o4[q] = x;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (col0 + j < p.N) out[j] += f[j];
+        }
+      } else {  // G2VLM_EPI_STORE_F32
+        if (p.flags & G2VLM_GEMM_ROUND_BF16) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = bf16_round(f[j]);
+        }
+        float* out = reinterpret_cast<float*>(p.out) + row * p.ldo + col0;
+        const float* res = p.residual ? p.residual + row * p.ldr + col0 : nullptr;
+        const bool accum = (p.flags & G2VLM_GEMM_ACCUMULATE) != 0;
+        const bool relu = (p.flags & G2VLM_GEMM_RELU) != 0;
+        if (full) {
+          float4* o4 = reinterpret_cast<float4*>(out);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            float4 x = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
+            if (accum) {
+              const float4 o = o4[q];
+              x.x += o.x; x.y += o.y; x.z += o.z; x.w += o.w;
+            }
+            if (relu) {
+              x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f);
+            }
+            if (res) {
+              const float4 rr = *reinterpret_cast<const float4*>(res + 4 * q);
+              x.x += rr.x; x.y += rr.y; x.z += rr.z; x.w += rr.w;
+            }
+            o4[q] = x;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            if (col0 + j < p.N) {
+              float x = f[j];
+              if (accum) x += out[j];
+              if (relu) x = fmaxf(x, 0.f);
+              if (res) x += res[j];
+              out[j] = x;
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
+template <int EPI>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_tcgen05_kernel(const __grid_constant__ GemmKParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  // 128-byte swizzle atoms are 1024 B: align the operand ring on the SHARED address
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&p.tmA);
+    tma_prefetch_desc(&p.tmB);
+  }
+  if (warp == 1) {
+    if (elect_one()) {
+      for (int s = 0; s < STAGES; ++s) {
+        mbar_init(&full_bar[s], 1);
+        mbar_init(&empty_bar[s], 1);
+      }
+      for (int s = 0; s < 2; ++s) {
+        mbar_init(&tmem_full_bar[s], 1);
+        mbar_init(&tmem_empty_bar[s], 128);
+      }
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc<512>(tmem_slot);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------- TMA producer ---------------------------------------------
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const TileCoord t = decode_tile(p, tile);
+        const int b_row = t.g * p.N + t.n_tile * BN;
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
+          uint8_t* sa = smem + stage * STAGE_BYTES;
+          tma_load_2d(sa, &p.tmA, &full_bar[stage], kb * BK, t.row0);
+          tma_load_2d(sa + A_BYTES, &p.tmB, &full_bar[stage], kb * BK, b_row);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------- MMA issuer -----------------------------------------------
+    if (elect_one()) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + stage * STAGE_BYTES);
+          const uint32_t b_addr = a_addr + A_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            umma_ss(d_tmem, umma_desc_kmajor(a_addr + k * 32), umma_desc_kmajor(b_addr + k * 32),
+                    idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tmem_full_bar[acc]);  // accumulator complete -> epilogue
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else {
+    // ------------------------------- epilogue warps -------------------------------------------
+    const int sub = warp & 3;  // TMEM sub-partition this warp may access: lanes [32*sub, 32*sub+32)
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const TileCoord t = decode_tile(p, tile);
+      mbar_wait(&tmem_full_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(sub * 32) << 16) + acc * BN;
+      epilogue_tile<EPI>(p, t, taddr, sub * 32 + lane);
+      tc_fence_before();
+      mbar_arrive(&tmem_empty_bar[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+template <int EPI>
+static int launch_gemm(const GemmKParams& kp, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    G2_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<EPI>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
+    attr_set = true;
+  }
+  const int grid = kp.num_tiles < num_sms() ? kp.num_tiles : num_sms();
+  gemm_bf16_tcgen05_kernel<EPI><<<grid, GEMM_THREADS, GEMM_SMEM, stream>>>(kp);
+  G2_CUDA_OK(cudaGetLastError());
+  return G2VLM_OK;
+}
+
+}  // namespace g2
+
+extern "C" int g2vlm_gemm_bf16(const g2vlm_gemm_args* a, void* stream_) {
+  using namespace g2;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  G2_REQUIRE(a != nullptr, "gemm: null args");
+  G2_REQUIRE(a->A && a->B && a->out, "gemm: null tensor");
+  G2_REQUIRE(a->n_groups == 1 || a->n_groups == 2, "gemm: n_groups must be 1 or 2");
+  G2_REQUIRE(a->N > 0 && a->K > 0, "gemm: N and K must be positive");
+  G2_REQUIRE(a->K % 8 == 0 && a->lda % 8 == 0 && a->ldb % 8 == 0, "gemm: K, lda, ldb must be multiples of 8");
+  G2_REQUIRE(a->epilogue >= 0 && a->epilogue <= 3, "gemm: unknown epilogue");
+  if (a->epilogue == G2VLM_EPI_SWIGLU_BF16) {
+    G2_REQUIRE(a->N % 256 == 0, "gemm: SwiGLU epilogue needs N (= 2*intermediate) % 256 == 0");
+    G2_REQUIRE(a->ldo % 8 == 0, "gemm: ldo must be a multiple of 8");
+  } else if (a->epilogue == G2VLM_EPI_STORE_BF16) {
+    G2_REQUIRE(a->ldo % 8 == 0, "gemm: ldo must be a multiple of 8");
+  } else {
+    G2_REQUIRE(a->ldo % 4 == 0, "gemm: ldo must be a multiple of 4");
+    G2_REQUIRE(a->residual == nullptr || a->ldr % 4 == 0, "gemm: ldr must be a multiple of 4");
+  }
+  G2_REQUIRE((reinterpret_cast<uintptr_t>(a->out) & 15) == 0, "gemm: out must be 16-byte aligned");
+  G2_REQUIRE(a->bias == nullptr || (reinterpret_cast<uintptr_t>(a->bias) & 15) == 0, "gemm: bias alignment");
+  G2_REQUIRE(a->bias == nullptr || a->n_groups == 1 || a->N % 4 == 0, "gemm: stacked bias needs N % 4 == 0");
+  G2_REQUIRE(a->scale == nullptr || (reinterpret_cast<uintptr_t>(a->scale) & 15) == 0, "gemm: scale alignment");
+
+  GemmKParams kp;
+  memset(&kp, 0, sizeof(kp));
+  int mt = 0;
+  long long max_row = 0;
+  for (int g = 0; g < a->n_groups; ++g) {
+    G2_REQUIRE(a->group_rows[g] >= 0 && a->group_row0[g] >= 0, "gemm: negative group extent");
+    kp.grp_row0[g] = a->group_row0[g];
+    kp.grp_rows[g] = a->group_rows[g];
+    kp.grp_mtile0[g] = mt;
+    mt += cdiv(a->group_rows[g], BM);
+    const long long end = (long long)a->group_row0[g] + a->group_rows[g];
+    if (end > max_row) max_row = end;
+  }
+  kp.grp_mtile0[a->n_groups] = mt;
+  if (a->n_groups == 1) kp.grp_mtile0[2] = mt;
+  G2_REQUIRE(max_row <= a->a_rows, "gemm: group rows exceed a_rows");
+  if (mt == 0) return G2VLM_OK;  // empty input: nothing to do
+  kp.n_groups = a->n_groups;
+  kp.N = a->N;
+  kp.K = a->K;
+  kp.n_tiles_n = cdiv(a->N, BN);
+  kp.num_tiles = mt * kp.n_tiles_n;
+  kp.num_kb = cdiv(a->K, BK);
+  kp.flags = a->flags;
+  kp.scale_groups = a->scale_groups;
+  kp.out = a->out;
+  kp.ldo = a->ldo;
+  kp.bias = a->bias;
+  kp.scale = a->scale;
+  kp.residual = a->residual;
+  kp.ldr = a->ldr;
+
+  int rc = make_tmap_2d_bf16(&kp.tmA, a->A, (uint64_t)a->a_rows, (uint64_t)a->K, (uint64_t)a->lda * 2, BM, BK);
+  if (rc) return rc;
+  rc = make_tmap_2d_bf16(&kp.tmB, a->B, (uint64_t)a->n_groups * a->N, (uint64_t)a->K, (uint64_t)a->ldb * 2, BN, BK);
+  if (rc) return rc;
+
+  switch (a->epilogue) {
+    case G2VLM_EPI_STORE_BF16: return launch_gemm<G2VLM_EPI_STORE_BF16>(kp, stream);
+    case G2VLM_EPI_SWIGLU_BF16: return launch_gemm<G2VLM_EPI_SWIGLU_BF16>(kp, stream);
+    case G2VLM_EPI_RESID_F32: return launch_gemm<G2VLM_EPI_RESID_F32>(kp, stream);
+    default: return launch_gemm<G2VLM_EPI_STORE_F32>(kp, stream);
+  }
+}

@@ -1,0 +1,150 @@
+"""Parity of the tcgen05 grouped GEMM (through the C ABI) against an fp32 torch reference of the
+same op with the reference's rounding points (nn.Linear under bf16 autocast returns bf16)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _mk(rows, K, N, ng, seed=0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    a = (torch.randn(rows, K, generator=g) * 0.5).to(torch.bfloat16).cuda()
+    w = (torch.randn(ng * N, K, generator=g) * 0.05).to(torch.bfloat16).cuda()
+    bias = (torch.randn(ng * N, generator=g) * 0.1).float().cuda()
+    return a, w, bias
+
+
+def _ref_linear(a, w, bias, groups, N):
+    out = torch.zeros(a.shape[0], N, device=a.device, dtype=torch.float32)
+    for g, (r0, rows) in enumerate(groups):
+        wg = w[g * N:(g + 1) * N].float()
+        y = a[r0:r0 + rows].float() @ wg.T
+        if bias is not None:
+            y = y + bias[g * N:(g + 1) * N]
+        out[r0:r0 + rows] = y
+    return out
+
+
+def _relerr(x, ref):
+    return ((x.float() - ref.float()).abs().max() / ref.float().abs().max().clamp_min(1e-30)).item()
+
+
+@pytest.mark.parametrize("rows,K,N,groups", [
+    (300, 256, 512, None),                       # single group, ragged M
+    (1000, 1536, 2048, [(0, 937), (937, 63)]),   # two experts, second tiny (MoT und rows)
+    (128, 64, 256, None),                        # one k-block
+    (77, 320, 588, None),                        # N tail (pixel-shuffle head), K tail
+    (2 * 148 * 128 + 5, 512, 768, None),         # > 2 waves of tiles, persistent loop
+])
+def test_store_bf16(rows, K, N, groups):
+    from g2vlm_b200 import ops
+    ng = 1 if groups is None else len(groups)
+    a, w, bias = _mk(rows, K, N, ng)
+    groups_ = groups or [(0, rows)]
+    out = torch.full((rows, N), float("nan"), device="cuda", dtype=torch.bfloat16)
+    ops.gemm(a, w, out, epilogue=ops.EPI_STORE_BF16, groups=groups, bias=bias)
+    torch.cuda.synchronize()
+    ref = _ref_linear(a, w, bias, groups_, N)
+    covered = torch.zeros(rows, dtype=torch.bool, device="cuda")
+    for r0, n in groups_:
+        covered[r0:r0 + n] = True
+    assert torch.isfinite(out[covered].float()).all()
+    assert _relerr(out[covered], ref[covered]) < 1e-2  # bf16 output rounding (2^-8)
+    # exact after rounding the fp32 reference to bf16, up to accumulation-order noise
+    diff = (out[covered].float() - ref[covered].to(torch.bfloat16).float()).abs()
+    assert (diff > 0).float().mean() < 0.05
+
+
+def test_empty_group_is_noop():
+    from g2vlm_b200 import ops
+    a, w, bias = _mk(16, 64, 256, 1)
+    out = torch.zeros(16, 256, device="cuda", dtype=torch.bfloat16)
+    ops.gemm(a, w, out, epilogue=ops.EPI_STORE_BF16, groups=[(0, 0)], bias=bias)
+    torch.cuda.synchronize()
+    assert (out == 0).all()
+
+
+def test_gelu():
+    from g2vlm_b200 import ops
+    a, w, bias = _mk(500, 256, 1024, 1, seed=1)
+    out = torch.empty(500, 1024, device="cuda", dtype=torch.bfloat16)
+    ops.gemm(a, w, out, epilogue=ops.EPI_STORE_BF16, bias=bias, flags=ops.GEMM_GELU)
+    ref = torch.nn.functional.gelu(_ref_linear(a, w, bias, [(0, 500)], 1024).to(torch.bfloat16).float())
+    assert _relerr(out, ref) < 1e-2
+
+
+def test_swiglu():
+    from g2vlm_b200 import ops
+    rows, K, I = 700, 256, 512
+    g = torch.Generator().manual_seed(2)
+    a = (torch.randn(rows, K, generator=g) * 0.5).to(torch.bfloat16).cuda()
+    wg = (torch.randn(2, I, K, generator=g) * 0.08).to(torch.bfloat16).cuda()   # per expert
+    wu = (torch.randn(2, I, K, generator=g) * 0.08).to(torch.bfloat16).cuda()
+    # interleave gate/up in blocks of 128 rows per expert (layout the SwiGLU epilogue expects)
+    w = torch.stack([wg.view(2, I // 128, 128, K), wu.view(2, I // 128, 128, K)], dim=2).reshape(2 * 2 * I, K).contiguous()
+    groups = [(0, 600), (600, 100)]
+    out = torch.empty(rows, I, device="cuda", dtype=torch.bfloat16)
+    ops.gemm(a, w, out, epilogue=ops.EPI_SWIGLU_BF16, groups=groups)
+    ref = torch.empty(rows, I, device="cuda")
+    for e, (r0, n) in enumerate(groups):
+        x = a[r0:r0 + n].float()
+        gt = (x @ wg[e].float().T).to(torch.bfloat16)
+        up = (x @ wu[e].float().T).to(torch.bfloat16)
+        ref[r0:r0 + n] = (torch.nn.functional.silu(gt.float()).to(torch.bfloat16).float() * up.float())
+    assert _relerr(out, ref) < 1.5e-2
+
+
+def test_resid_f32_layerscale():
+    from g2vlm_b200 import ops
+    rows, K, N = 900, 512, 512
+    a, w, _ = _mk(rows, K, N, 2, seed=3)
+    groups = [(0, 850), (850, 50)]
+    gamma = (torch.rand(N) + 0.5).cuda()
+    x0 = torch.randn(rows, N, device="cuda")
+    x = x0.clone()
+    ops.gemm(a, w, x, epilogue=ops.EPI_RESID_F32, groups=groups, scale=gamma, scale_groups=1,
+             flags=ops.GEMM_ROUND_AFTER_SCALE)
+    y = _ref_linear(a, w, None, groups, N).to(torch.bfloat16).float()
+    y[:850] = (y[:850] * gamma).to(torch.bfloat16).float()
+    ref = x0 + y
+    assert _relerr(x, ref) < 5e-3
+
+
+def test_store_f32_flags():
+    from g2vlm_b200 import ops
+    rows, K, N = 333, 256, 512
+    a, w, bias = _mk(rows, K, N, 1, seed=4)
+    res = torch.randn(rows, N, device="cuda")
+    out = torch.empty(rows, N, device="cuda")
+    ops.gemm(a, w, out, epilogue=ops.EPI_STORE_F32, bias=bias, flags=ops.GEMM_RELU, residual=res)
+    ref = torch.relu(_ref_linear(a, w, bias, [(0, rows)], N)) + res
+    assert _relerr(out, ref) < 1e-4
+    # accumulate pass (split-bf16 second term)
+    out2 = out.clone()
+    ops.gemm(a, w, out2, epilogue=ops.EPI_STORE_F32, flags=ops.GEMM_ACCUMULATE)
+    ref2 = ref + _ref_linear(a, w, None, [(0, rows)], N)
+    assert _relerr(out2, ref2) < 1e-4
+
+
+def test_full_size_mot_qkv_timing():
+    """Config-2 sized routed QKV projection: M = 16*1369 geo + 32 und rows, K = 1536, N = 2048."""
+    from g2vlm_b200 import ops
+    n_geo, n_und, K, N = 16 * 1369, 32, 1536, 2048
+    rows = n_geo + n_und
+    a, w, bias = _mk(rows, K, N, 2, seed=5)
+    groups = [(0, n_geo), (n_geo, n_und)]
+    out = torch.empty(rows, N, device="cuda", dtype=torch.bfloat16)
+    for _ in range(3):
+        ops.gemm(a, w, out, epilogue=ops.EPI_STORE_BF16, groups=groups, bias=bias)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    ev[0].record()
+    for _ in range(10):
+        ops.gemm(a, w, out, epilogue=ops.EPI_STORE_BF16, groups=groups, bias=bias)
+    ev[1].record()
+    torch.cuda.synchronize()
+    ms = ev[0].elapsed_time(ev[1]) / 10
+    tflops = 2 * rows * K * N / ms / 1e9
+    print(f"\nqkv gemm {ms:.3f} ms  {tflops:.1f} TFLOP/s")
+    idx = torch.randint(0, rows, (512,), device="cuda")
+    ref = _ref_linear(a, w, bias, groups, N)
+    assert _relerr(out[idx], ref[idx]) < 1e-2
