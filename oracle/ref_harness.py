@@ -1,0 +1,186 @@
+"""TEST INFRASTRUCTURE — harness that runs the UNMODIFIED reference (`/root/reference`) on CPU.
+
+Only `tests/`, `oracle/make_golden.py`, `__graft_entry__.smoke()` and `bench.py`'s cpu_baseline /
+`--impl reference` legs may import this module; the product package `g2vlm_b200` never does.
+`/root/reference` exists only in the build container, so everything here is used to (a) pin the
+restatement in `oracle/restate.py` against the real reference classes and (b) generate the golden
+fixtures under `tests/golden/` (script: `oracle/make_golden.py`).  On the GPU box this module is
+unusable and `available()` returns False.
+
+The reference cannot run unmodified on CPU (hard bf16 casts + flash-attn + `.cuda()` + HF-hub
+downloads + transformers-4.49 symbols); the shims below are in-process only and
+edit nothing under /root/reference:
+  1. stub `easydict`; inject three transformers-4.49 symbols removed in 5.x; register
+     ROPE_INIT_FUNCTIONS['default'];
+  2. redirect `torch.amp.autocast('cuda')` to 'cpu' so the nested enable/disable regions
+     (g2vlm.py:1190-1226, camera_head.py:59) behave as on a GPU;
+  3. replace `flash_attn_varlen_func` (g2vlm/qwen2vl.py:643, dinov2_model.py:49) by a per-segment
+     SDPA with GQA, bottom-right causal mask and ZEROS for rows outside every segment (flash-attn
+     leaves them uninitialised — quirk Q1);
+  4. build configs in code (the HF JSON files are not in the repo) and a stub tokenizer.
+"""
+from __future__ import annotations
+
+import importlib
+import os
+import sys
+import types
+
+import torch
+
+REFERENCE_ROOT = os.environ.get("G2VLM_REFERENCE_ROOT", "/root/reference")
+
+
+def available() -> bool:
+    return os.path.isdir(os.path.join(REFERENCE_ROOT, "modeling", "g2vlm"))
+
+
+# ---- shim 3: flash_attn_varlen_func stand-in ----------------------------------------------------
+def varlen_sdpa(q, k, v, cu_seqlens_q, cu_seqlens_k, max_seqlen_q=None, max_seqlen_k=None,
+                causal=False, **kw):
+    """q (Tq,Hq,D), k/v (Tk,Hk,D) -> (Tq,Hq,D); rows outside every segment are zero."""
+    out = torch.zeros_like(q)
+    hq, hk = q.shape[1], k.shape[1]
+    cq = [int(x) for x in cu_seqlens_q]
+    ck = [int(x) for x in cu_seqlens_k]
+    for i in range(len(cq) - 1):
+        qs = q[cq[i]:cq[i + 1]].transpose(0, 1)  # (Hq, Lq, D)
+        ks = k[ck[i]:ck[i + 1]].transpose(0, 1)
+        vs = v[ck[i]:ck[i + 1]].transpose(0, 1)
+        if hq != hk:
+            ks = ks.repeat_interleave(hq // hk, dim=0)
+            vs = vs.repeat_interleave(hq // hk, dim=0)
+        lq, lk = qs.shape[1], ks.shape[1]
+        mask = None
+        if causal:
+            mask = torch.ones(lq, lk, dtype=torch.bool).tril(diagonal=lk - lq)
+        o = torch.nn.functional.scaled_dot_product_attention(qs[None], ks[None], vs[None], attn_mask=mask)[0]
+        out[cq[i]:cq[i + 1]] = o.transpose(0, 1)
+    return out
+
+
+_installed = False
+
+
+def install_shims() -> None:
+    global _installed
+    if _installed:
+        return
+    if not available():
+        raise RuntimeError(f"reference tree not found under {REFERENCE_ROOT}")
+    sys.dont_write_bytecode = True  # the tree is read-only
+    for p in (REFERENCE_ROOT, os.path.join(REFERENCE_ROOT, "modeling")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+
+    # 1. missing third-party modules / symbols
+    if "easydict" not in sys.modules:
+        m = types.ModuleType("easydict")
+        m.EasyDict = dict
+        sys.modules["easydict"] = m
+    if "flash_attn" not in sys.modules or not torch.cuda.is_available():
+        fa = types.ModuleType("flash_attn")
+        fa.flash_attn_varlen_func = varlen_sdpa
+        fa.flash_attn_func = None
+        sys.modules["flash_attn"] = fa
+
+    class _Dummy:  # placeholder classes only referenced in isinstance / annotations
+        pass
+
+    def _none2(*a, **k):
+        return None, None
+
+    for mod, name, val in [
+        ("transformers.cache_utils", "SlidingWindowCache", _Dummy),
+        ("transformers.pytorch_utils", "find_pruneable_heads_and_indices", _none2),
+        ("transformers.utils.backbone_utils", "get_aligned_output_features_output_indices", _none2),
+    ]:
+        mm = importlib.import_module(mod)
+        if not hasattr(mm, name):
+            setattr(mm, name, val)
+    from transformers.modeling_rope_utils import ROPE_INIT_FUNCTIONS
+
+    def _default_rope(cfg, device=None, **kw):
+        d = cfg.hidden_size // cfg.num_attention_heads
+        inv = 1.0 / (cfg.rope_theta ** (torch.arange(0, d, 2, dtype=torch.int64).float() / d))
+        return inv, 1.0
+
+    ROPE_INIT_FUNCTIONS.setdefault("default", _default_rope)
+    ROPE_INIT_FUNCTIONS.setdefault("mrope", _default_rope)
+
+    # 2. autocast('cuda') -> 'cpu'
+    _orig_autocast = torch.amp.autocast_mode.autocast
+
+    class _ac(_orig_autocast):
+        def __init__(self, device_type="cuda", *a, **k):
+            super().__init__("cpu" if device_type == "cuda" else device_type, *a, **k)
+
+    torch.amp.autocast = _ac
+    torch.amp.autocast_mode.autocast = _ac
+    torch.autocast = _ac
+    torch.cuda.amp.autocast = lambda *a, **k: _ac("cpu", *a, **k)
+    _installed = True
+
+
+class StubTokenizer:
+    """`tokenizer.encode(prompt)` -> fixed 6 ids, so K0 = 1 (bos) + 6 = 7."""
+
+    def encode(self, prompt):
+        return [11, 12, 13, 14, 15, 16]
+
+
+NEW_TOKEN_IDS = dict(bos_token_id=1, eos_token_id=2, start_of_image=3, end_of_image=4)
+
+TINY = dict(
+    llm=dict(hidden_size=256, num_hidden_layers=2, num_attention_heads=2, num_key_value_heads=1,
+             intermediate_size=512, vocab_size=512, rms_norm_eps=1e-6, rope_theta=1000000.0,
+             max_position_embeddings=32768),
+    dino=dict(hidden_size=64, num_hidden_layers=2, num_attention_heads=2, mlp_ratio=4,
+              image_size=518, patch_size=14, num_register_tokens=4, layer_norm_eps=1e-6),
+    vit=dict(depth=1, embed_dim=64, hidden_size=256, num_heads=2, mlp_ratio=2, patch_size=14),
+)
+
+FULL = dict(
+    llm=dict(hidden_size=1536, num_hidden_layers=28, num_attention_heads=12, num_key_value_heads=2,
+             intermediate_size=8960, vocab_size=151936, rms_norm_eps=1e-6, rope_theta=1000000.0,
+             max_position_embeddings=32768),
+    dino=dict(hidden_size=1024, num_hidden_layers=24, num_attention_heads=16, mlp_ratio=4,
+              image_size=518, patch_size=14, num_register_tokens=4, layer_norm_eps=1e-6),
+    vit=dict(depth=1, embed_dim=64, hidden_size=1536, num_heads=2, mlp_ratio=2, patch_size=14),
+)
+
+
+def build_reference_model(dims=TINY, visual_und=True):
+    """Constructs the reference G2VLM from its own classes (mirrors g2vlm_utils.py:31-55)."""
+    install_shims()
+    from modeling.dinov2_with_registers.configuration_dinov2_with_registers import Dinov2WithRegistersConfig
+    from modeling.g2vlm.dinov2_model import Dinov2WithRegistersModel
+    from modeling.g2vlm.g2vlm import G2VLM, G2VLMConfig
+    from modeling.g2vlm.qwen2vl import Qwen2VLConfig, Qwen2VLForCausalLM
+    from modeling.qwen2vl.configuration_qwen2_vl import Qwen2VLVisionConfig
+    from modeling.qwen2vl.modeling_qwen2_vl import Qwen2VisionTransformerPretrainedModel
+    import modeling.g2vlm.dinov2_model as _dm
+    import modeling.g2vlm.qwen2vl as _qm
+
+    _qm.flash_attn_varlen_func = varlen_sdpa
+    _dm.flash_attn_varlen_func = varlen_sdpa
+
+    llm = Qwen2VLConfig(pad_token_id=None, rope_scaling={"type": "mrope", "mrope_section": [16, 24, 24]},
+                        qk_norm=True, layer_module="Qwen2VLMoTDecoderLayer", tie_word_embeddings=False,
+                        **dims["llm"])
+    dino = Dinov2WithRegistersConfig(**dims["dino"])
+    vit = Qwen2VLVisionConfig(**dims["vit"])
+    cfg = G2VLMConfig(visual_und=visual_und, visual_recon=True, llm_config=llm, vit_config=vit,
+                      dino_config=dino, vit_max_num_patch_per_side=36)
+    lm = Qwen2VLForCausalLM(llm)
+    vm = Qwen2VisionTransformerPretrainedModel(vit) if visual_und else None
+    dm = Dinov2WithRegistersModel(dino)
+    model = G2VLM(lm, vm, dm, cfg).eval()
+    return model
+
+
+def run_reference_recon(model, images):
+    """images: list of PIL images (or paths). Returns the reference's prediction dict (CPU)."""
+    install_shims()
+    with torch.no_grad():
+        return model.recon(StubTokenizer(), dict(NEW_TOKEN_IDS), None, images)

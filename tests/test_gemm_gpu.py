@@ -33,7 +33,7 @@ def _relerr(x, ref):
     (300, 256, 512, None),                       # single group, ragged M
     (1000, 1536, 2048, [(0, 937), (937, 63)]),   # two experts, second tiny (MoT und rows)
     (128, 64, 256, None),                        # one k-block
-    (77, 320, 588, None),                        # N tail (pixel-shuffle head), K tail
+    (77, 328, 600, None),                        # N tail, K tail (not multiples of the 256 / 64 tile)
     (2 * 148 * 128 + 5, 512, 768, None),         # > 2 waves of tiles, persistent loop
 ])
 def test_store_bf16(rows, K, N, groups):
@@ -124,6 +124,16 @@ def test_store_f32_flags():
     ops.gemm(a, w, out2, epilogue=ops.EPI_STORE_F32, flags=ops.GEMM_ACCUMULATE)
     ref2 = ref + _ref_linear(a, w, None, [(0, rows)], N)
     assert _relerr(out2, ref2) < 1e-4
+
+
+def test_store_f32_pixel_shuffle_head_shape():
+    """N = 588 = 3*14*14 (Pi3LinearPts3d.proj): N tail inside a 32-column chunk."""
+    from g2vlm_b200 import ops
+    rows, K, N = 200, 1024, 588
+    a, w, bias = _mk(rows, K, N, 1, seed=6)
+    out = torch.full((rows, N), float("nan"), device="cuda")
+    ops.gemm(a, w, out, epilogue=ops.EPI_STORE_F32, bias=bias)
+    assert _relerr(out, _ref_linear(a, w, bias, [(0, rows)], N)) < 1e-4
 
 
 def test_full_size_mot_qkv_timing():
