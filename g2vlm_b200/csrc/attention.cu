@@ -1,0 +1,384 @@
+// g2vlm_b200 — varlen / GQA attention on tcgen05 tensor cores (QK^T and PV), accumulators in TMEM.
+//
+// Replaces flash_attn_varlen_func (modeling/g2vlm/qwen2vl.py:643-652, dinov2_model.py:49-58) and the
+// per-view SDPA calls of the Pi3 decoders (modeling/pi3/models/layers/attention.py:255-259,370-372).
+//
+// One CTA = one work item (<= 256 query rows of one segment) x one query head, two 128-row query
+// tiles in flight ("ping-pong"): while the softmax warps of tile 0 turn S0 into P0, the tensor core
+// runs tile 1's MMAs and vice versa.
+//   warp 0        TMA producer: Q tiles once, K/V blocks of 128 keys through an mbarrier ring
+//   warp 1        MMA issuer:   S_t = Q_t K^T (SS, K-major operands) ; O_t += P_t V (TS: P read from
+//                               TMEM, V is an MN-major B operand straight from the [key][d] layout)
+//   warps 4-7     softmax of tile 0 (one thread per query row), warps 8-11 softmax of tile 1:
+//                 tcgen05.ld S -> running max / exp2 / row sum -> bf16 P written back to TMEM over S
+//                 (tcgen05.st); lazy rescale of O in TMEM only when the running max grows by > 2^8
+//                 (exact: the stale max cancels in the final 1/l normalisation); final O/l -> global.
+// TMEM columns: S0/P0 [0,128)  S1/P1 [128,256)  O0 [256,256+D)  O1 [384,384+D).
+#include "common.cuh"
+
+namespace g2 {
+
+constexpr int ATT_BM = 128;       // query rows per tile
+constexpr int ATT_BN = 128;       // keys per block
+constexpr int ATT_THREADS = 384;  // 12 warps
+constexpr float ATT_RESCALE_TAU = 8.0f;
+
+struct AttnKParams {
+  CUtensorMap tmQ, tmK, tmV;
+  const int* work;  // [n_items][8]: q_tile_begin, q_seg_begin, q_seg_end, k_begin, k_end, -, -, -
+  __nv_bfloat16* out;
+  long long ldo;
+  int q_heads_per_kv;
+  int causal;
+  float scale_log2;
+};
+
+template <int D>
+struct AttnCfg {
+  static constexpr int kBoxes = D / 64;                  // 64-column TMA boxes per row tile
+  static constexpr int kTileBytes = ATT_BM * D * 2;      // one 128 x D bf16 tile
+  static constexpr int kStages = (D == 128) ? 2 : 4;     // K/V ring depth
+  static constexpr int kSmem = 2 * kTileBytes + kStages * 2 * kTileBytes + 1024 + 512;
+};
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+template <int D>
+__global__ void __launch_bounds__(ATT_THREADS, 1)
+attention_tcgen05_kernel(const __grid_constant__ AttnKParams p) {
+  using Cfg = AttnCfg<D>;
+  constexpr int KSTEPS_QK = D / 16;       // MMAs per S tile (K = head dim)
+  constexpr int KSTEPS_PV = ATT_BN / 16;  // MMAs per PV block (K = keys)
+  constexpr int BOX_BYTES = ATT_BM * 128; // one 64-col box of 128 rows
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint8_t* sQ = smem;                              // 2 tiles
+  uint8_t* sKV = smem + 2 * Cfg::kTileBytes;       // kStages x (K tile, V tile)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sKV + Cfg::kStages * 2 * Cfg::kTileBytes);
+  uint64_t* q_full = bars;                         // [1]
+  uint64_t* k_full = bars + 1;                     // [kStages]
+  uint64_t* v_full = k_full + Cfg::kStages;
+  uint64_t* k_empty = v_full + Cfg::kStages;
+  uint64_t* v_empty = k_empty + Cfg::kStages;
+  uint64_t* s_full = v_empty + Cfg::kStages;       // [2]
+  uint64_t* p_full = s_full + 2;                   // [2]
+  uint64_t* o_done = p_full + 2;                   // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int* w = p.work + blockIdx.x * 8;
+  const int q_tile_begin = w[0], q_seg_begin = w[1], q_seg_end = w[2], k_begin = w[3], k_end = w[4];
+  const int head = blockIdx.y;
+  const int kv_head = head / p.q_heads_per_kv;
+  const int len_q = q_seg_end - q_seg_begin;
+  const int len_k = k_end - k_begin;
+  const int rows_here = min(2 * ATT_BM, q_seg_end - q_tile_begin);
+  // keys needed by this CTA (causal: bottom-right aligned, as flash-attn)
+  int k_needed = len_k;
+  if (p.causal) {
+    const int last_row = q_tile_begin + rows_here - 1 - q_seg_begin;
+    k_needed = max(0, min(len_k, last_row + (len_k - len_q) + 1));
+  }
+  const int nblk = (k_needed + ATT_BN - 1) / ATT_BN;
+
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&p.tmQ);
+    tma_prefetch_desc(&p.tmK);
+    tma_prefetch_desc(&p.tmV);
+  }
+  if (warp == 1) {
+    if (elect_one()) {
+      mbar_init(q_full, 1);
+      for (int s = 0; s < Cfg::kStages; ++s) {
+        mbar_init(&k_full[s], 1);
+        mbar_init(&v_full[s], 1);
+        mbar_init(&k_empty[s], 1);
+        mbar_init(&v_empty[s], 1);
+      }
+      for (int t = 0; t < 2; ++t) {
+        mbar_init(&s_full[t], 1);
+        mbar_init(&p_full[t], 128);
+        mbar_init(&o_done[t], 1);
+      }
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc<512>(tmem_slot);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tS[2] = {tmem_base, tmem_base + 128};
+  const uint32_t tO[2] = {tmem_base + 256, tmem_base + 384};
+
+  if (warp == 0) {
+    // ------------------------------------ TMA producer ----------------------------------------
+    if (elect_one() && nblk > 0) {
+      mbar_arrive_expect_tx(q_full, 2 * Cfg::kTileBytes);
+#pragma unroll
+      for (int t = 0; t < 2; ++t)
+#pragma unroll
+        for (int b = 0; b < Cfg::kBoxes; ++b)
+          tma_load_2d(sQ + t * Cfg::kTileBytes + b * BOX_BYTES, &p.tmQ, q_full, head * D + b * 64,
+                      q_tile_begin + t * ATT_BM);
+      for (int j = 0; j < nblk; ++j) {
+        const int s = j % Cfg::kStages;
+        const uint32_t par = ((j / Cfg::kStages) & 1) ^ 1;
+        uint8_t* sk = sKV + s * 2 * Cfg::kTileBytes;
+        uint8_t* sv = sk + Cfg::kTileBytes;
+        mbar_wait(&k_empty[s], par);
+        mbar_arrive_expect_tx(&k_full[s], Cfg::kTileBytes);
+#pragma unroll
+        for (int b = 0; b < Cfg::kBoxes; ++b)
+          tma_load_2d(sk + b * BOX_BYTES, &p.tmK, &k_full[s], kv_head * D + b * 64, k_begin + j * ATT_BN);
+        mbar_wait(&v_empty[s], par);
+        mbar_arrive_expect_tx(&v_full[s], Cfg::kTileBytes);
+#pragma unroll
+        for (int b = 0; b < Cfg::kBoxes; ++b)
+          tma_load_2d(sv + b * BOX_BYTES, &p.tmV, &v_full[s], kv_head * D + b * 64, k_begin + j * ATT_BN);
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------ MMA issuer ------------------------------------------
+    if (elect_one() && nblk > 0) {
+      constexpr uint32_t idesc_qk = umma_idesc_bf16(ATT_BM, ATT_BN, 0, 0);
+      constexpr uint32_t idesc_pv = umma_idesc_bf16(ATT_BM, D, 0, 1);  // B (= V) is MN-major
+      const uint32_t q_addr = smem_u32(sQ);
+      const uint32_t kv_addr = smem_u32(sKV);
+
+      auto issue_qk = [&](int t, int s) {
+        const uint32_t qa = q_addr + t * Cfg::kTileBytes;
+        const uint32_t ka = kv_addr + s * 2 * Cfg::kTileBytes;
+#pragma unroll
+        for (int k = 0; k < KSTEPS_QK; ++k) {
+          const uint32_t off = (k >> 2) * BOX_BYTES + (k & 3) * 32;
+          umma_ss(tS[t], umma_desc_kmajor(qa + off), umma_desc_kmajor(ka + off), idesc_qk, k != 0);
+        }
+        umma_commit(&s_full[t]);
+      };
+      auto issue_pv = [&](int t, int s, int j) {
+        const uint32_t va = kv_addr + s * 2 * Cfg::kTileBytes + Cfg::kTileBytes;
+#pragma unroll
+        for (int k = 0; k < KSTEPS_PV; ++k) {
+          // 16 keys = 16 rows of 128 B inside each 64-column box; boxes are BOX_BYTES apart (LBO)
+          umma_ts(tO[t], tS[t] + k * 8, umma_desc_mnmajor(va + k * 2048, BOX_BYTES), idesc_pv,
+                  (j | k) != 0);
+        }
+        umma_commit(&o_done[t]);
+      };
+
+      mbar_wait(q_full, 0);
+      mbar_wait(&k_full[0], 0);
+      tc_fence_after();
+      issue_qk(0, 0);
+      issue_qk(1, 0);
+      umma_commit(&k_empty[0]);
+      for (int j = 0; j < nblk; ++j) {
+        const int s = j % Cfg::kStages;
+        const uint32_t par = (j / Cfg::kStages) & 1;
+        const int s1 = (j + 1) % Cfg::kStages;
+        const uint32_t par1 = ((j + 1) / Cfg::kStages) & 1;
+        mbar_wait(&v_full[s], par);
+        mbar_wait(&p_full[0], j & 1);
+        tc_fence_after();
+        issue_pv(0, s, j);
+        if (j + 1 < nblk) {
+          mbar_wait(&k_full[s1], par1);
+          tc_fence_after();
+          issue_qk(0, s1);
+        }
+        mbar_wait(&p_full[1], j & 1);
+        tc_fence_after();
+        issue_pv(1, s, j);
+        umma_commit(&v_empty[s]);
+        if (j + 1 < nblk) {
+          issue_qk(1, s1);
+          umma_commit(&k_empty[s1]);
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------ softmax / correction / epilogue ---------------------
+    const int t = (warp - 4) >> 2;              // query tile 0 or 1
+    const int sub = warp & 3;                   // TMEM sub-partition
+    const int r_in_tile = sub * 32 + lane;
+    const int row = q_tile_begin + t * ATT_BM + r_in_tile;  // global query row
+    const bool row_ok = row < q_seg_end;
+    const uint32_t lane_off = static_cast<uint32_t>(sub * 32) << 16;
+    const uint32_t tS_w = tS[t] + lane_off;
+    const uint32_t tO_w = tO[t] + lane_off;
+    // number of keys this row may see
+    int limit = len_k;
+    if (p.causal) limit = max(0, min(len_k, (row - q_seg_begin) + (len_k - len_q) + 1));
+
+    float m_used = 0.f;  // running max in the scaled log2 domain (possibly stale by <= TAU)
+    float l_run = 0.f;
+
+    for (int j = 0; j < nblk; ++j) {
+      mbar_wait(&s_full[t], j & 1);
+      tc_fence_after();
+      uint32_t sv[128];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) tmem_ld32(tS_w + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&sv[c * 32]));
+      tmem_wait_ld();
+
+      const int col_base = j * ATT_BN;
+      if (col_base + ATT_BN > limit) {
+#pragma unroll
+        for (int i = 0; i < 128; ++i)
+          if (col_base + i >= limit) sv[i] = 0xff800000u;  // -inf
+      }
+      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < 128; i += 4) {
+        mx0 = fmaxf(mx0, __uint_as_float(sv[i]));
+        mx1 = fmaxf(mx1, __uint_as_float(sv[i + 1]));
+        mx2 = fmaxf(mx2, __uint_as_float(sv[i + 2]));
+        mx3 = fmaxf(mx3, __uint_as_float(sv[i + 3]));
+      }
+      const float m_blk = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * p.scale_log2;  // may be -inf
+
+      if (j == 0) {
+        m_used = (m_blk == -INFINITY) ? 0.f : m_blk;
+      } else {
+        const bool need = m_blk > m_used + ATT_RESCALE_TAU;
+        if (__any_sync(0xffffffffu, need)) {
+          // rare path: O_t must be multiplied by 2^(m_used - m_new) before the next PV accumulates
+          mbar_wait(&o_done[t], (j - 1) & 1);
+          tc_fence_after();
+          const float m_new = need ? m_blk : m_used;
+          const float alpha = ex2_approx(m_used - m_new);
+#pragma unroll 1
+          for (int c = 0; c < D / 32; ++c) {
+            uint32_t ov[32];
+            tmem_ld32(tO_w + c * 32, ov);
+            tmem_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * alpha);
+            tmem_st32(tO_w + c * 32, ov);
+          }
+          tmem_wait_st();
+          l_run *= alpha;
+          m_used = m_new;
+        }
+      }
+
+      // P = 2^(s*scale - m), packed to bf16 pairs, written over S (columns [0,64) of the S region)
+      float sum0 = 0.f, sum1 = 0.f;
+      const float neg_m = -m_used;
+#pragma unroll
+      for (int i = 0; i < 128; i += 2) {
+        const float p0 = ex2_approx(fmaf(__uint_as_float(sv[i]), p.scale_log2, neg_m));
+        const float p1 = ex2_approx(fmaf(__uint_as_float(sv[i + 1]), p.scale_log2, neg_m));
+        sum0 += p0;
+        sum1 += p1;
+        sv[i >> 1] = pack_bf16x2(p0, p1);  // in place: slot i/2 <= i is already consumed
+      }
+      l_run += sum0 + sum1;
+      tmem_st32(tS_w, *reinterpret_cast<uint32_t(*)[32]>(&sv[0]));
+      tmem_st32(tS_w + 32, *reinterpret_cast<uint32_t(*)[32]>(&sv[32]));
+      tmem_wait_st();
+      tc_fence_before();
+      mbar_arrive(&p_full[t]);
+    }
+
+    // epilogue: O / l -> bf16 -> global (each thread owns one output row of D contiguous values)
+    if (nblk > 0) {
+      mbar_wait(&o_done[t], (nblk - 1) & 1);
+      tc_fence_after();
+      const float inv_l = l_run > 0.f ? 1.0f / l_run : 0.f;
+      __nv_bfloat16* orow = p.out + (long long)row * p.ldo + head * D;
+#pragma unroll 1
+      for (int c = 0; c < D / 32; ++c) {
+        uint32_t ov[32];
+        tmem_ld32(tO_w + c * 32, ov);
+        tmem_wait_ld();
+        if (row_ok) {
+          uint4* dst = reinterpret_cast<uint4*>(orow + c * 32);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            dst[q] = make_uint4(
+                pack_bf16x2(__uint_as_float(ov[8 * q]) * inv_l, __uint_as_float(ov[8 * q + 1]) * inv_l),
+                pack_bf16x2(__uint_as_float(ov[8 * q + 2]) * inv_l, __uint_as_float(ov[8 * q + 3]) * inv_l),
+                pack_bf16x2(__uint_as_float(ov[8 * q + 4]) * inv_l, __uint_as_float(ov[8 * q + 5]) * inv_l),
+                pack_bf16x2(__uint_as_float(ov[8 * q + 6]) * inv_l, __uint_as_float(ov[8 * q + 7]) * inv_l));
+          }
+        }
+      }
+    } else if (row_ok) {
+      // no visible keys at all: flash-attn writes zeros
+      uint4* dst = reinterpret_cast<uint4*>(p.out + (long long)row * p.ldo + head * D);
+#pragma unroll
+      for (int q = 0; q < D / 8; ++q) dst[q] = make_uint4(0, 0, 0, 0);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+template <int D>
+static int launch_attention(const AttnKParams& kp, int n_items, int n_heads, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    G2_CUDA_OK(cudaFuncSetAttribute(attention_tcgen05_kernel<D>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg<D>::kSmem));
+    attr_set = true;
+  }
+  attention_tcgen05_kernel<D><<<dim3(n_items, n_heads), ATT_THREADS, AttnCfg<D>::kSmem, stream>>>(kp);
+  G2_CUDA_OK(cudaGetLastError());
+  return G2VLM_OK;
+}
+
+}  // namespace g2
+
+extern "C" int g2vlm_attention(const g2vlm_attn_args* a, void* stream_) {
+  using namespace g2;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  G2_REQUIRE(a != nullptr, "attention: null args");
+  G2_REQUIRE(a->q && a->k && a->v && a->out, "attention: null tensor");
+  G2_REQUIRE(a->head_dim == 64 || a->head_dim == 128, "attention: head_dim must be 64 or 128 (pad 96 to 128)");
+  G2_REQUIRE(a->num_q_heads > 0 && a->num_kv_heads > 0 && a->num_q_heads % a->num_kv_heads == 0,
+             "attention: num_q_heads must be a multiple of num_kv_heads");
+  G2_REQUIRE(a->ldq % 8 == 0 && a->ldk % 8 == 0 && a->ldv % 8 == 0 && a->ldo % 8 == 0,
+             "attention: leading dimensions must be multiples of 8");
+  G2_REQUIRE((reinterpret_cast<uintptr_t>(a->out) & 15) == 0, "attention: out must be 16-byte aligned");
+  G2_REQUIRE(a->n_items >= 0, "attention: negative n_items");
+  if (a->n_items == 0) return G2VLM_OK;
+  G2_REQUIRE(a->work_items != nullptr, "attention: null work table");
+  G2_REQUIRE(a->q_rows > 0 && a->kv_rows > 0, "attention: empty q/kv");
+
+  AttnKParams kp;
+  memset(&kp, 0, sizeof(kp));
+  const int D = a->head_dim;
+  int rc = make_tmap_2d_bf16(&kp.tmQ, a->q, (uint64_t)a->q_rows, (uint64_t)a->num_q_heads * D,
+                             (uint64_t)a->ldq * 2, ATT_BM, 64);
+  if (rc) return rc;
+  rc = make_tmap_2d_bf16(&kp.tmK, a->k, (uint64_t)a->kv_rows, (uint64_t)a->num_kv_heads * D,
+                         (uint64_t)a->ldk * 2, ATT_BN, 64);
+  if (rc) return rc;
+  rc = make_tmap_2d_bf16(&kp.tmV, a->v, (uint64_t)a->kv_rows, (uint64_t)a->num_kv_heads * D,
+                         (uint64_t)a->ldv * 2, ATT_BN, 64);
+  if (rc) return rc;
+  kp.work = a->work_items;
+  kp.out = reinterpret_cast<__nv_bfloat16*>(a->out);
+  kp.ldo = a->ldo;
+  kp.q_heads_per_kv = a->num_q_heads / a->num_kv_heads;
+  kp.causal = a->causal;
+  kp.scale_log2 = a->softmax_scale * 1.4426950408889634f;
+  if (D == 128) return launch_attention<128>(kp, a->n_items, a->num_q_heads, stream);
+  return launch_attention<64>(kp, a->n_items, a->num_q_heads, stream);
+}

@@ -105,3 +105,57 @@ def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, epilogue: int,
         args.residual, args.ldr = residual.data_ptr(), residual.stride(0)
     _check(_lib.load().g2vlm_gemm_bf16(ctypes.byref(args), _stream()))
     return out
+
+
+class AttnArgs(ctypes.Structure):
+    _fields_ = [
+        ("q", ctypes.c_void_p), ("ldq", ctypes.c_int64), ("q_rows", ctypes.c_int64),
+        ("k", ctypes.c_void_p), ("ldk", ctypes.c_int64),
+        ("v", ctypes.c_void_p), ("ldv", ctypes.c_int64), ("kv_rows", ctypes.c_int64),
+        ("out", ctypes.c_void_p), ("ldo", ctypes.c_int64),
+        ("num_q_heads", ctypes.c_int32), ("num_kv_heads", ctypes.c_int32),
+        ("head_dim", ctypes.c_int32), ("causal", ctypes.c_int32),
+        ("softmax_scale", ctypes.c_float), ("n_items", ctypes.c_int32),
+        ("work_items", ctypes.c_void_p),
+    ]
+
+
+ATTN_ROWS_PER_ITEM = 256
+
+
+def attention_work_table(cu_seqlens_q: Sequence[int], cu_seqlens_k: Sequence[int]) -> torch.Tensor:
+    """Host-side: segment table (flash-attn cu_seqlens) -> int32 [n_items, 8] work items (CPU).
+
+    One item per <= 256 query rows of a segment; see g2vlm_attention in include/g2vlm_b200.h.
+    """
+    items = []
+    for i in range(len(cu_seqlens_q) - 1):
+        qb, qe = int(cu_seqlens_q[i]), int(cu_seqlens_q[i + 1])
+        kb, ke = int(cu_seqlens_k[i]), int(cu_seqlens_k[i + 1])
+        for t0 in range(qb, qe, ATTN_ROWS_PER_ITEM):
+            items.append([t0, qb, qe, kb, ke, 0, 0, 0])
+    return torch.tensor(items, dtype=torch.int32).reshape(-1, 8)
+
+
+def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tensor, work: torch.Tensor,
+              *, num_q_heads: int, num_kv_heads: int, head_dim: int, scale: float,
+              causal: bool = False) -> torch.Tensor:
+    """out[rows covered by `work`] = softmax(scale * q k^T) v, per segment; q/k/v/out are 2-D bf16
+    views [rows, heads*head_dim] (they may be column slices of one fused QKV buffer)."""
+    for t, n in ((q, "q"), (k, "k"), (v, "v"), (out, "out")):
+        _req(t, torch.bfloat16, n)
+    _req(work, torch.int32, "work")
+    if work.dim() != 2 or work.shape[1] != 8 or not work.is_contiguous():
+        raise G2Error("attention: work table must be a contiguous int32 [n, 8] tensor")
+    if k.shape[0] != v.shape[0]:
+        raise G2Error("attention: k and v must have the same number of rows")
+    args = AttnArgs()
+    args.q, args.ldq, args.q_rows = q.data_ptr(), q.stride(0), q.shape[0]
+    args.k, args.ldk = k.data_ptr(), k.stride(0)
+    args.v, args.ldv, args.kv_rows = v.data_ptr(), v.stride(0), k.shape[0]
+    args.out, args.ldo = out.data_ptr(), out.stride(0)
+    args.num_q_heads, args.num_kv_heads, args.head_dim = num_q_heads, num_kv_heads, head_dim
+    args.causal, args.softmax_scale = int(causal), float(scale)
+    args.n_items, args.work_items = work.shape[0], work.data_ptr()
+    _check(_lib.load().g2vlm_attention(ctypes.byref(args), _stream()))
+    return out

@@ -88,6 +88,49 @@ typedef struct g2vlm_gemm_args {
 
 int g2vlm_gemm_bf16(const g2vlm_gemm_args* args, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Varlen / GQA attention on tcgen05 tensor cores:  out = softmax(scale * Q K^T [+ causal mask]) V
+ *
+ * Replaces
+ *   flash_attn_varlen_func (MoT shared attention)   modeling/g2vlm/qwen2vl.py:643-652
+ *   flash_attn_varlen_func (DINO, segments of P)    modeling/g2vlm/dinov2_model.py:49-58
+ *   SDPA self-attention per view (Pi3 decoders)     modeling/pi3/models/layers/attention.py:370-372
+ *   SDPA cross-attention to view 0                  modeling/pi3/models/layers/attention.py:255-259
+ *
+ * q is [q_rows, num_q_heads*head_dim] bf16 (leading dim ldq), k / v are [kv_rows,
+ * num_kv_heads*head_dim] (ldk / ldv), out is [q_rows, num_q_heads*head_dim] (ldo). The segment
+ * structure (cu_seqlens_q / cu_seqlens_k of flash-attn; per-view batches of SDPA) is given as a
+ * DEVICE table of work items, 8 int32 each:
+ *   {q_tile_begin, q_seg_begin, q_seg_end, k_begin, k_end, 0, 0, 0}
+ * one item per <= 256 consecutive query rows [q_tile_begin, min(q_tile_begin+256, q_seg_end)) of a
+ * segment whose queries are rows [q_seg_begin, q_seg_end) and whose keys are rows [k_begin, k_end).
+ * Query rows covered by no item are NOT written (flash-attn leaves them uninitialised, SURVEY.md
+ * quirk Q1; the caller defines them, the host mirror zero-fills). causal = bottom-right aligned
+ * mask as in flash-attn. K/V rows in [k_end, round_up(k_end,128)) that lie inside kv_rows must hold
+ * finite values. head_dim in {64, 128} (the 96-wide Pi3 heads are zero-padded to 128 by the caller).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct g2vlm_attn_args {
+  const void* q;
+  int64_t ldq;
+  int64_t q_rows;
+  const void* k;
+  int64_t ldk;
+  const void* v;
+  int64_t ldv;
+  int64_t kv_rows;
+  void* out;
+  int64_t ldo;
+  int32_t num_q_heads;
+  int32_t num_kv_heads;
+  int32_t head_dim;
+  int32_t causal;
+  float softmax_scale;
+  int32_t n_items;
+  const int32_t* work_items; /* DEVICE int32 [n_items][8] */
+} g2vlm_attn_args;
+
+int g2vlm_attention(const g2vlm_attn_args* args, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

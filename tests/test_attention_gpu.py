@@ -1,0 +1,133 @@
+"""Parity of the tcgen05 attention kernel (through the C ABI) against an fp32 torch reference:
+softmax(scale * q k^T) v per segment with GQA, bottom-right causal mask, ragged segments."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _ref_attention(q, k, v, cu_q, cu_k, hq, hk, d, scale, causal):
+    out = torch.zeros(q.shape[0], hq * d, device=q.device, dtype=torch.float32)
+    qf, kf, vf = q.float(), k.float(), v.float()
+    for i in range(len(cu_q) - 1):
+        qs = qf[cu_q[i]:cu_q[i + 1]].view(-1, hq, d).transpose(0, 1)
+        ks = kf[cu_k[i]:cu_k[i + 1]].view(-1, hk, d).transpose(0, 1).repeat_interleave(hq // hk, 0)
+        vs = vf[cu_k[i]:cu_k[i + 1]].view(-1, hk, d).transpose(0, 1).repeat_interleave(hq // hk, 0)
+        s = (qs @ ks.transpose(1, 2)) * scale
+        if causal:
+            lq, lk = s.shape[1], s.shape[2]
+            mask = torch.ones(lq, lk, dtype=torch.bool, device=q.device).tril(diagonal=lk - lq)
+            s = s.masked_fill(~mask, float("-inf"))
+        p = torch.softmax(s, dim=-1)
+        o = p @ vs
+        out[cu_q[i]:cu_q[i + 1]] = o.transpose(0, 1).reshape(-1, hq * d)
+    return out
+
+
+def _run(cu_q, cu_k, hq, hk, d, causal=False, seed=0, q_rows=None, kv_rows=None, scale=None, std=1.0):
+    from g2vlm_b200 import ops
+    g = torch.Generator().manual_seed(seed)
+    q_rows = q_rows or cu_q[-1]
+    kv_rows = kv_rows or cu_k[-1]
+    q = (torch.randn(q_rows, hq * d, generator=g) * std).to(torch.bfloat16).cuda()
+    k = (torch.randn(kv_rows, hk * d, generator=g) * std).to(torch.bfloat16).cuda()
+    v = torch.randn(kv_rows, hk * d, generator=g).to(torch.bfloat16).cuda()
+    out = torch.full((q_rows, hq * d), 7.0, device="cuda", dtype=torch.bfloat16)
+    work = ops.attention_work_table(cu_q, cu_k).cuda()
+    scale = scale or 1.0 / math.sqrt(d)
+    ops.attention(q, k, v, out, work, num_q_heads=hq, num_kv_heads=hk, head_dim=d, scale=scale, causal=causal)
+    torch.cuda.synchronize()
+    ref = _ref_attention(q, k, v, cu_q, cu_k, hq, hk, d, scale, causal)
+    covered = torch.zeros(q_rows, dtype=torch.bool, device="cuda")
+    for i in range(len(cu_q) - 1):
+        covered[cu_q[i]:cu_q[i + 1]] = True
+    err = (out[covered].float() - ref[covered]).abs().max().item()
+    assert torch.isfinite(out.float()).all()
+    assert (out[~covered] == 7.0).all(), "rows outside every segment must not be written"
+    return err, ref[covered].abs().max().item()
+
+
+@pytest.mark.parametrize("lq,lk,hq,hk,d", [
+    (128, 128, 1, 1, 128),     # one block, one tile
+    (256, 256, 2, 1, 128),     # both tiles, GQA
+    (300, 1000, 12, 2, 128),   # ragged q and k tails, MoT head layout
+    (1371 * 2 + 7, 1371 * 2 + 7, 12, 2, 128),
+    (700, 700, 4, 4, 64),      # DINO head dim
+])
+def test_single_segment(lq, lk, hq, hk, d):
+    err, mag = _run([0, lq], [0, lk], hq, hk, d)
+    assert err < 2e-2 * max(mag, 1.0), (err, mag)
+
+
+def test_sharp_softmax_triggers_rescale():
+    # large logits: running max jumps by more than 2^8 between blocks -> lazy rescale path
+    err, mag = _run([0, 256], [0, 1024], 2, 1, 128, std=4.0, seed=3)
+    assert err < 3e-2 * max(mag, 1.0), (err, mag)
+
+
+def test_multi_segment_dino_quirk_layout():
+    # N=3 "images": segments of P=777 over a sequence of 3*(777+5) rows; last 15 rows uncovered
+    P, N = 777, 3
+    cu = [i * P for i in range(N + 1)]
+    err, mag = _run(cu, cu, 4, 4, 64, q_rows=N * (P + 5), kv_rows=N * (P + 5))
+    assert err < 2e-2 * max(mag, 1.0)
+
+
+def test_cross_attention_to_view0():
+    # every view's queries attend to view 0's keys (Pi3 CrossBlockRope context)
+    P, N = 500, 3
+    cu_q = [i * P for i in range(N + 1)]
+    from g2vlm_b200 import ops
+    g = torch.Generator().manual_seed(5)
+    hq = hk = 2
+    d = 128
+    q = torch.randn(N * P, hq * d, generator=g).to(torch.bfloat16).cuda()
+    k = torch.randn(P, hk * d, generator=g).to(torch.bfloat16).cuda()
+    v = torch.randn(P, hk * d, generator=g).to(torch.bfloat16).cuda()
+    out = torch.empty(N * P, hq * d, device="cuda", dtype=torch.bfloat16)
+    items = []
+    for i in range(N):
+        for t0 in range(cu_q[i], cu_q[i + 1], 256):
+            items.append([t0, cu_q[i], cu_q[i + 1], 0, P, 0, 0, 0])
+    work = torch.tensor(items, dtype=torch.int32).cuda()
+    scale = 96 ** -0.5
+    ops.attention(q, k, v, out, work, num_q_heads=hq, num_kv_heads=hk, head_dim=d, scale=scale)
+    ref = torch.cat([_ref_attention(q[cu_q[i]:cu_q[i + 1]], k, v, [0, P], [0, P], hq, hk, d, scale, False) for i in range(N)])
+    assert (out.float() - ref).abs().max().item() < 2e-2
+
+
+@pytest.mark.parametrize("lq,lk", [(7, 7), (300, 300), (100, 356)])
+def test_causal(lq, lk):
+    err, mag = _run([0, lq], [0, lk], 2, 1, 128, causal=True, seed=2)
+    assert err < 2e-2 * max(mag, 1.0)
+
+
+def test_strided_fused_qkv_buffer_and_timing():
+    """Config-2 MoT shape: q/k/v are column slices of one [T+K0, 2048] buffer; 12:2 GQA, d=128."""
+    from g2vlm_b200 import ops
+    T, K0 = 16 * 1371, 7
+    g = torch.Generator().manual_seed(1)
+    qkv = torch.randn(T + K0, 2048, generator=g).to(torch.bfloat16).cuda()
+    q, k, v = qkv[:, :1536], qkv[:, 1536:1792], qkv[:, 1792:]
+    out = torch.empty(T, 1536, device="cuda", dtype=torch.bfloat16)
+    work = ops.attention_work_table([0, T], [0, T + K0]).cuda()
+    scale = 1 / math.sqrt(128)
+    kw = dict(num_q_heads=12, num_kv_heads=2, head_dim=128, scale=scale)
+    for _ in range(2):
+        ops.attention(q[:T], k, v, out, work, **kw)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    ev[0].record()
+    for _ in range(5):
+        ops.attention(q[:T], k, v, out, work, **kw)
+    ev[1].record()
+    torch.cuda.synchronize()
+    ms = ev[0].elapsed_time(ev[1]) / 5
+    print(f"\nattention T={T}: {ms:.3f} ms  {4 * T * (T + K0) * 12 * 128 / ms / 1e9:.1f} TFLOP/s")
+    rows = torch.arange(0, T, 997, device="cuda")[:16]
+    qs = q[rows].float().view(-1, 12, 128).transpose(0, 1)
+    ks = k.float().view(-1, 2, 128).transpose(0, 1).repeat_interleave(6, 0)
+    vs = v.float().view(-1, 2, 128).transpose(0, 1).repeat_interleave(6, 0)
+    ref = (torch.softmax(qs @ ks.transpose(1, 2) * scale, -1) @ vs).transpose(0, 1).reshape(-1, 1536)
+    assert (out[rows].float() - ref).abs().max().item() < 2e-2
