@@ -1,0 +1,193 @@
+"""Model dimensions and the reference ``state_dict`` key schema of the recon path.
+
+The product loads the reference's checkpoint keys unchanged (names confirmed by
+dumping ``G2VLM(...).state_dict()`` of the reference classes — see tests/golden/state_dict_keys.json).
+The JSON configs of the released checkpoint are not in the reference repo, so dimensions are inputs
+(``G2Config``), with the two configurations used by tests and the benchmark predefined below.
+"""
+from __future__ import annotations
+
+from collections import OrderedDict
+from dataclasses import dataclass, field
+from typing import Dict, Tuple
+
+import torch
+
+
+@dataclass(frozen=True)
+class G2Config:
+    # Qwen2-VL MoT language model (modeling/g2vlm/qwen2vl.py:50-234)
+    hidden_size: int = 1536
+    num_layers: int = 28
+    num_heads: int = 12
+    num_kv_heads: int = 2
+    intermediate_size: int = 8960
+    vocab_size: int = 151936
+    rms_norm_eps: float = 1e-6
+    rope_theta: float = 1000000.0
+    mrope_section: Tuple[int, int, int] = (16, 24, 24)  # hard-coded, modeling_qwen2_vl.py:562-566
+    # DINOv2-with-registers encoder
+    dino_hidden: int = 1024
+    dino_layers: int = 24
+    dino_heads: int = 16
+    dino_mlp_ratio: int = 4
+    dino_image_size: int = 518
+    dino_patch: int = 14
+    dino_registers: int = 4
+    dino_ln_eps: float = 1e-6
+    # Pi3 heads (modeling/g2vlm/g2vlm.py:162-203, transformer_head.py:9-56)
+    dec_depth: int = 5
+    dec_heads: int = 16
+    dec_mlp_ratio: int = 4
+    point_dim: int = 1024
+    camera_dim: int = 512
+    rope2d_base: float = 100.0  # 'rope100', g2vlm.py:152
+    train_conf_pi3: bool = False
+
+    @property
+    def head_dim(self) -> int:
+        return self.hidden_size // self.num_heads
+
+    @property
+    def dino_head_dim(self) -> int:
+        return self.dino_hidden // self.dino_heads
+
+    @property
+    def dec_head_dim(self) -> int:
+        return self.hidden_size // self.dec_heads
+
+    @property
+    def dino_grid(self) -> int:
+        return self.dino_image_size // self.dino_patch
+
+
+FULL = G2Config()
+TINY = G2Config(hidden_size=256, num_layers=2, num_heads=2, num_kv_heads=1, intermediate_size=512,
+                vocab_size=512, dino_hidden=64, dino_layers=2, dino_heads=2)
+
+
+def state_dict_schema(cfg: G2Config) -> "OrderedDict[str, Tuple[int, ...]]":
+    """name -> shape of every parameter the recon path reads, in the reference's registration order."""
+    H, I, hd = cfg.hidden_size, cfg.intermediate_size, cfg.head_dim
+    nq, nkv = cfg.num_heads * hd, cfg.num_kv_heads * hd
+    s: "OrderedDict[str, Tuple[int, ...]]" = OrderedDict()
+    lm = "language_model.model."
+    s[lm + "embed_tokens.weight"] = (cfg.vocab_size, H)
+    for i in range(cfg.num_layers):
+        p = f"{lm}layers.{i}."
+        s[p + "ls1.gamma"] = (H,)
+        s[p + "ls2.gamma"] = (H,)
+        for sfx in ("", "_moe_geo"):
+            if sfx == "":
+                s[p + "self_attn.q_proj.weight"] = (nq, H); s[p + "self_attn.q_proj.bias"] = (nq,)
+                s[p + "self_attn.k_proj.weight"] = (nkv, H); s[p + "self_attn.k_proj.bias"] = (nkv,)
+                s[p + "self_attn.v_proj.weight"] = (nkv, H); s[p + "self_attn.v_proj.bias"] = (nkv,)
+                s[p + "self_attn.o_proj.weight"] = (H, nq)
+                s[p + "self_attn.q_norm.weight"] = (hd,); s[p + "self_attn.k_norm.weight"] = (hd,)
+                s[p + "self_attn.q_norm_moe_geo.weight"] = (hd,); s[p + "self_attn.k_norm_moe_geo.weight"] = (hd,)
+            else:
+                s[p + "self_attn.q_proj_moe_geo.weight"] = (nq, H); s[p + "self_attn.q_proj_moe_geo.bias"] = (nq,)
+                s[p + "self_attn.k_proj_moe_geo.weight"] = (nkv, H); s[p + "self_attn.k_proj_moe_geo.bias"] = (nkv,)
+                s[p + "self_attn.v_proj_moe_geo.weight"] = (nkv, H); s[p + "self_attn.v_proj_moe_geo.bias"] = (nkv,)
+                s[p + "self_attn.o_proj_moe_geo.weight"] = (H, nq)
+        for m in ("mlp", "mlp_moe_geo"):
+            s[p + f"{m}.gate_proj.weight"] = (I, H)
+            s[p + f"{m}.up_proj.weight"] = (I, H)
+            s[p + f"{m}.down_proj.weight"] = (H, I)
+        for n in ("input_layernorm", "input_layernorm_moe_geo", "post_attention_layernorm",
+                  "post_attention_layernorm_moe_geo"):
+            s[p + n + ".weight"] = (H,)
+    s[lm + "norm.weight"] = (H,)
+    s[lm + "norm_moe_geo.weight"] = (H,)
+
+    D, g = cfg.dino_hidden, cfg.dino_grid
+    d = "dino_model."
+    s[d + "embeddings.cls_token"] = (1, 1, D)
+    s[d + "embeddings.register_tokens"] = (1, cfg.dino_registers, D)
+    s[d + "embeddings.position_embeddings"] = (1, g * g + 1, D)
+    s[d + "embeddings.patch_embeddings.projection.weight"] = (D, 3, cfg.dino_patch, cfg.dino_patch)
+    s[d + "embeddings.patch_embeddings.projection.bias"] = (D,)
+    for i in range(cfg.dino_layers):
+        p = f"{d}encoder.layer.{i}."
+        s[p + "norm1.weight"] = (D,); s[p + "norm1.bias"] = (D,)
+        for n in ("query", "key", "value"):
+            s[p + f"attention.attention.{n}.weight"] = (D, D); s[p + f"attention.attention.{n}.bias"] = (D,)
+        s[p + "attention.output.dense.weight"] = (D, D); s[p + "attention.output.dense.bias"] = (D,)
+        s[p + "layer_scale1.lambda1"] = (D,)
+        s[p + "norm2.weight"] = (D,); s[p + "norm2.bias"] = (D,)
+        s[p + "mlp.fc1.weight"] = (D * cfg.dino_mlp_ratio, D); s[p + "mlp.fc1.bias"] = (D * cfg.dino_mlp_ratio,)
+        s[p + "mlp.fc2.weight"] = (D, D * cfg.dino_mlp_ratio); s[p + "mlp.fc2.bias"] = (D,)
+        s[p + "layer_scale2.lambda1"] = (D,)
+    s[d + "layernorm.weight"] = (D,); s[d + "layernorm.bias"] = (D,)
+    s["dino2llm.weight"] = (H, D); s["dino2llm.bias"] = (H,)
+
+    F = H * cfg.dec_mlp_ratio
+
+    def block(p, cross):
+        s[p + "norm1.weight"] = (H,); s[p + "norm1.bias"] = (H,)
+        s[p + "attn.qkv.weight"] = (3 * H, H); s[p + "attn.qkv.bias"] = (3 * H,)
+        s[p + "attn.proj.weight"] = (H, H); s[p + "attn.proj.bias"] = (H,)
+        s[p + "norm2.weight"] = (H,); s[p + "norm2.bias"] = (H,)
+        if cross:
+            s[p + "norm_y.weight"] = (H,); s[p + "norm_y.bias"] = (H,)
+            for n in ("q_proj", "k_proj", "v_proj", "proj"):
+                s[p + f"cross_attn.{n}.weight"] = (H, H); s[p + f"cross_attn.{n}.bias"] = (H,)
+            s[p + "norm3.weight"] = (H,); s[p + "norm3.bias"] = (H,)
+        s[p + "mlp.fc1.weight"] = (F, H); s[p + "mlp.fc1.bias"] = (F,)
+        s[p + "mlp.fc2.weight"] = (H, F); s[p + "mlp.fc2.bias"] = (H,)
+
+    def decoder(name, out_dim, cross=False):
+        for i in range(cfg.dec_depth):
+            block(f"{name}.blocks.{i}.", cross)
+        s[f"{name}.linear_out.weight"] = (out_dim, H); s[f"{name}.linear_out.bias"] = (out_dim,)
+
+    ps2 = cfg.dino_patch ** 2
+    decoder("point_decoder", cfg.point_dim)
+    s["point_head.proj.weight"] = (3 * ps2, cfg.point_dim); s["point_head.proj.bias"] = (3 * ps2,)
+    decoder("camera_decoder", cfg.camera_dim)
+    C = cfg.camera_dim
+    for i in range(2):
+        for j in (1, 2, 3):
+            s[f"camera_head.res_conv.{i}.res_conv{j}.weight"] = (C, C)
+            s[f"camera_head.res_conv.{i}.res_conv{j}.bias"] = (C,)
+    for j in (0, 2):
+        s[f"camera_head.more_mlps.{j}.weight"] = (C, C); s[f"camera_head.more_mlps.{j}.bias"] = (C,)
+    s["camera_head.fc_t.weight"] = (3, C); s["camera_head.fc_t.bias"] = (3,)
+    s["camera_head.fc_rot.weight"] = (9, C); s["camera_head.fc_rot.bias"] = (9,)
+    decoder("global_points_decoder", cfg.point_dim, cross=True)
+    s["global_point_head.proj.weight"] = (3 * ps2, cfg.point_dim); s["global_point_head.proj.bias"] = (3 * ps2,)
+    if cfg.train_conf_pi3:
+        decoder("conf_decoder", cfg.point_dim)
+        s["conf_head.proj.weight"] = (ps2, cfg.point_dim); s["conf_head.proj.bias"] = (ps2,)
+    return s
+
+
+def init_synthetic(cfg: G2Config, seed: int = 0, embed_rows: int | None = None) -> Dict[str, torch.Tensor]:
+    """Seeded synthetic weights: Linear/Conv/Embedding/bias/token tensors ~ N(0, 0.02^2),
+    norm weights and LayerScale/lambda ~ U(0.5, 1.5); geo and und experts independent.  Each tensor has
+    its own generator keyed by (seed, index) so the result does not depend on generation order.
+    ``embed_rows`` truncates the embedding table (the benchmark only needs the few ids recon uses)."""
+    sd: Dict[str, torch.Tensor] = {}
+    for idx, (name, shape) in enumerate(state_dict_schema(cfg).items()):
+        if name.endswith("embed_tokens.weight") and embed_rows is not None:
+            shape = (embed_rows, shape[1])
+        g = torch.Generator().manual_seed(seed * 1000003 + idx)
+        leaf = name.rsplit(".", 2)
+        is_norm_w = name.endswith(".weight") and ("norm" in leaf[-2] or leaf[-2] == "layernorm")
+        if is_norm_w or name.endswith(".gamma") or name.endswith(".lambda1"):
+            t = torch.rand(shape, generator=g) + 0.5
+        elif name.endswith(".bias") and ("norm" in leaf[-2] or leaf[-2] == "layernorm"):
+            t = torch.randn(shape, generator=g) * 0.02
+        else:
+            t = torch.randn(shape, generator=g) * 0.02
+        sd[name] = t
+    return sd
+
+
+def synthetic_views(n_views: int, height: int, width: int, seed: int = 1) -> torch.Tensor:
+    """(N,3,H,W) in [0,1]: uniform noise smoothed by a 7x7 box blur."""
+    g = torch.Generator().manual_seed(seed)
+    x = torch.rand(n_views, 3, height, width, generator=g)
+    k = torch.ones(3, 1, 7, 7) / 49.0
+    x = torch.nn.functional.conv2d(torch.nn.functional.pad(x, (3, 3, 3, 3), mode="replicate"), k, groups=3)
+    return x.clamp_(0, 1)

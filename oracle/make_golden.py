@@ -1,0 +1,102 @@
+"""TEST INFRASTRUCTURE — generates tests/golden/* by running the UNMODIFIED reference under the CPU
+harness (oracle/ref_harness.py).  Run in the build container only (needs /root/reference):
+
+    python -m oracle.make_golden
+
+Fixtures (all produced by the reference's own classes, tiny random-init model, seeded inputs):
+  state_dict_keys.json      name -> shape of G2VLM(...).state_dict() for the tiny and the full dims
+  recon_tiny_{a,b}.pt       routing/permutation/position index tensors from the reference's
+                            prepare_prompts_addbos / prepare_dino_images_pi3 (exact-match targets),
+                            camera poses, strided samples of the point maps and of last_hidden.
+Case a: 3 views 70x518 (non-square -> bicubic pos-embed resample; quirk-Q1 uncovered rows);
+case b: 2 views 518x518 (native 37x37 grid).
+"""
+from __future__ import annotations
+
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+from PIL import Image
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from g2vlm_b200 import schema  # noqa: E402
+from oracle import ref_harness as rh  # noqa: E402
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+CASES = {"a": dict(n=3, h=70, w=518, seed=1), "b": dict(n=2, h=518, w=518, seed=2)}
+STRIDE_H, STRIDE_W, STRIDE_T = 5, 7, 13
+
+
+def views_u8(n, h, w, seed):
+    v = schema.synthetic_views(n, h, w, seed=seed)
+    return (v * 255).round().to(torch.uint8)
+
+
+def to_pil(u8):
+    return [Image.fromarray(u8[i].permute(1, 2, 0).numpy()) for i in range(u8.shape[0])]
+
+
+def run_case(model, case):
+    u8 = views_u8(case["n"], case["h"], case["w"], case["seed"])
+    pil = to_pil(u8)
+    tok = rh.StubTokenizer()
+    ids = dict(rh.NEW_TOKEN_IDS)
+    gi_text, newlens, new_rope = model.prepare_prompts_addbos([0], [0], ["Reconstruct the 3D scene."], tok, ids)
+    gi_dino, _, _ = model.prepare_dino_images_pi3(newlens, new_rope, pil, None, ids)
+    captured = {}
+    orig = model.reconstruct
+
+    def spy(*a, **k):
+        captured["last_hidden"] = k["selected_hidden_states"].detach().clone()
+        return orig(*a, **k)
+
+    model.reconstruct = spy
+    try:
+        pred = rh.run_reference_recon(model, pil)
+    finally:
+        model.reconstruct = orig
+    out = dict(case=case, stride=(STRIDE_H, STRIDE_W, STRIDE_T))
+    for k in ("packed_text_ids", "packed_text_position_ids", "packed_text_indexes", "text_token_lens"):
+        out["text." + k] = gi_text[k].clone()
+    for k in ("packed_text_ids", "packed_text_indexes", "dino_token_seqlens", "packed_dino_token_indexes",
+              "packed_position_ids", "packed_seqlens", "packed_indexes", "packed_key_value_indexes",
+              "key_values_lens"):
+        out["dino." + k] = gi_dino[k].clone()
+    out["camera_poses"] = pred["camera_poses"].float().clone()
+    for k in ("points", "local_points", "global_points"):
+        out[k] = pred[k].float()[:, :, ::STRIDE_H, ::STRIDE_W].clone()
+        out[k + ".absmax"] = pred[k].float().abs().max()
+    out["last_hidden"] = captured["last_hidden"].float()[::STRIDE_T].clone()
+    out["last_hidden.absmax"] = captured["last_hidden"].float().abs().max()
+    out["images_u8_checksum"] = int(u8.to(torch.int64).sum())
+    return out
+
+
+def main():
+    os.makedirs(GOLDEN, exist_ok=True)
+    torch.manual_seed(0)
+    model = rh.build_reference_model(rh.TINY, visual_und=False)
+    keys = {"tiny": {k: list(v.shape) for k, v in model.state_dict().items()}}
+    sd = schema.init_synthetic(schema.TINY, seed=0)
+    msg = model.load_state_dict(sd, strict=False)
+    assert not msg.unexpected_keys, msg.unexpected_keys
+    for name, case in CASES.items():
+        out = run_case(model, case)
+        torch.save(out, os.path.join(GOLDEN, f"recon_tiny_{name}.pt"))
+        print("wrote", name, {k: tuple(v.shape) for k, v in out.items() if torch.is_tensor(v) and v.dim() > 0})
+    # full-size key schema: build on the meta device (no 18 GB allocation)
+    with torch.device("meta"):
+        full = rh.build_reference_model(rh.FULL, visual_und=False)
+    keys["full"] = {k: list(v.shape) for k, v in full.state_dict().items()}
+    with open(os.path.join(GOLDEN, "state_dict_keys.json"), "w") as f:
+        json.dump(keys, f, indent=0, sort_keys=True)
+    print("wrote state_dict_keys.json", len(keys["tiny"]), len(keys["full"]))
+
+
+if __name__ == "__main__":
+    main()

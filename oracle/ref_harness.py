@@ -78,8 +78,12 @@ def install_shims() -> None:
         m = types.ModuleType("easydict")
         m.EasyDict = dict
         sys.modules["easydict"] = m
-    if "flash_attn" not in sys.modules or not torch.cuda.is_available():
+    try:  # the real wheel imports fine without a GPU; its functions are replaced after import
+        import flash_attn  # noqa: F401
+    except Exception:
+        from importlib.machinery import ModuleSpec
         fa = types.ModuleType("flash_attn")
+        fa.__spec__ = ModuleSpec("flash_attn", None)
         fa.flash_attn_varlen_func = varlen_sdpa
         fa.flash_attn_func = None
         sys.modules["flash_attn"] = fa

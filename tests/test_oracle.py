@@ -1,0 +1,88 @@
+"""CPU tests of the oracle: the restatement (oracle/restate.py) against (1) golden fixtures produced
+by the unmodified reference (oracle/make_golden.py -> tests/golden) and (2) the live reference when
+/root/reference is present (build container).  Also pins the state_dict key schema."""
+import json
+import os
+
+import pytest
+import torch
+
+from g2vlm_b200 import schema
+from oracle import ref_harness, restate
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+TOL_BF16 = 2e-2  # BASELINE.json: max rel err <= 2e-2 in bf16 mode
+
+
+def _views(case):
+    v = schema.synthetic_views(case["n"], case["h"], case["w"], seed=case["seed"])
+    return (v * 255).round() / 255.0  # the reference reads 8-bit images (PIL -> ToTensor)
+
+
+def _maxrel(a, b, scale=None):
+    scale = b.abs().max() if scale is None else scale
+    return ((a - b).abs().max() / scale).item()
+
+
+@pytest.fixture(scope="module")
+def tiny_sd():
+    return schema.init_synthetic(schema.TINY, seed=0)
+
+
+@pytest.mark.parametrize("name", ["a", "b"])
+def test_indices_match_reference_exactly(name):
+    g = torch.load(os.path.join(GOLDEN, f"recon_tiny_{name}.pt"))
+    gi, newlens, new_rope = restate.prepare_prompts_addbos([11, 12, 13, 14, 15, 16], 1)
+    for k in ("packed_text_ids", "packed_text_position_ids", "packed_text_indexes", "text_token_lens"):
+        assert torch.equal(gi[k], g["text." + k]), k
+    gd, _, _ = restate.prepare_dino_images(_views(g["case"]), newlens[0], new_rope[0], 3, 4)
+    for k in ("packed_text_ids", "packed_text_indexes", "dino_token_seqlens", "packed_dino_token_indexes",
+              "packed_position_ids", "packed_seqlens", "packed_indexes", "packed_key_value_indexes",
+              "key_values_lens"):
+        assert gd[k].dtype == g["dino." + k].dtype, k
+        assert torch.equal(gd[k], g["dino." + k]), k
+
+
+@pytest.mark.parametrize("name", ["a", "b"])
+def test_restatement_matches_reference_golden(name, tiny_sd):
+    g = torch.load(os.path.join(GOLDEN, f"recon_tiny_{name}.pt"))
+    sh, sw, st = g["stride"]
+    collect = {}
+    out = restate.recon(tiny_sd, schema.TINY, _views(g["case"]), mode="bf16", collect=collect)
+    assert _maxrel(collect["last_hidden"][::st], g["last_hidden"], g["last_hidden.absmax"]) < TOL_BF16
+    for k in ("points", "local_points", "global_points"):
+        assert _maxrel(out[k][:, :, ::sh, ::sw], g[k], g[k + ".absmax"]) < TOL_BF16, k
+    assert _maxrel(out["camera_poses"], g["camera_poses"]) < TOL_BF16
+    assert out["conf"] is None
+
+
+def test_schema_matches_reference_state_dict_keys():
+    keys = json.load(open(os.path.join(GOLDEN, "state_dict_keys.json")))
+    for cfg, name in ((schema.TINY, "tiny"), (schema.FULL, "full")):
+        ours = {k: list(v) for k, v in schema.state_dict_schema(cfg).items()}
+        ref = {k: v for k, v in keys[name].items()
+               if not k.startswith("vit_model.") and k not in ("language_model.lm_head.weight",
+                                                               "dino_model.embeddings.mask_token")}
+        assert ours == ref
+
+
+@pytest.mark.skipif(not ref_harness.available(), reason="/root/reference not present (GPU box)")
+def test_restatement_matches_live_reference(tiny_sd):
+    """Fresh inputs (not the golden ones) through the unmodified reference classes."""
+    from oracle.make_golden import to_pil, views_u8
+    model = ref_harness.build_reference_model(ref_harness.TINY, visual_und=False)
+    model.load_state_dict(tiny_sd, strict=False)
+    u8 = views_u8(2, 98, 518, seed=11)
+    ref = ref_harness.run_reference_recon(model, to_pil(u8))
+    out = restate.recon(tiny_sd, schema.TINY, u8.float() / 255.0, mode="bf16")
+    for k in ("points", "local_points", "global_points", "camera_poses"):
+        assert _maxrel(out[k], ref[k].float()) < TOL_BF16, k
+    assert torch.equal(ref["images"][0], u8.float() / 255.0)
+
+
+def test_fp32_mode_close_to_bf16_mode(tiny_sd):
+    v = _views(dict(n=2, h=42, w=518, seed=5))
+    a = restate.recon(tiny_sd, schema.TINY, v, mode="fp32")
+    b = restate.recon(tiny_sd, schema.TINY, v, mode="bf16")
+    for k in ("points", "global_points", "camera_poses"):
+        assert _maxrel(b[k], a[k]) < 3e-2, k
