@@ -1,0 +1,674 @@
+"""Host-side mirror of the reference model interface for the recon path, driving the CUDA kernels.
+
+`G2VLMFast` keeps the reference's call shapes:
+    recon(tokenizer, new_token_ids, dino_image_transform, images, prompt=...) -> dict
+    forward_cache_update_text(...) -> NaiveCache
+    forward_cache_update_dino(...) -> (NaiveCache, last_hidden_state)
+    reconstruct(...) -> dict
+(reference: modeling/g2vlm/g2vlm.py:1240-1303, 701-733, 968-1039, 1143-1238) and consumes the
+reference `state_dict` key names unchanged (`from_state_dict`).  All arithmetic runs in the kernel
+library through `g2vlm_b200.ops`; torch is used for device buffers, streams and host<->device copies
+only.  There is no CPU / PyTorch fallback: constructing the model without the built library raises.
+
+Internal row order of the MoT stack ("gather by expert"): the T packed tokens are permuted ONCE per
+forward to [geo rows (packed_dino_token_indexes order) | und rows (packed_text_indexes order)] so each
+expert's rows are contiguous and every routed Linear is one grouped GEMM; non-causal attention is
+permutation invariant, and the result is scattered back to the packed order at the end.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Sequence
+
+import torch
+
+from . import _lib, host_prep, ops
+from .schema import G2Config, state_dict_schema
+
+
+class NaiveCache:
+    """Same contract as the reference's NaiveCache (modeling/g2vlm/qwen2vl.py:237-251)."""
+
+    def __init__(self, num_layers: int):
+        self.key_cache = {k: None for k in range(num_layers)}
+        self.value_cache = {k: None for k in range(num_layers)}
+
+    @property
+    def num_layers(self):
+        return len(self.key_cache)
+
+    @property
+    def seq_lens(self):
+        return self.key_cache[0].shape[0] if self.key_cache[0] is not None else 0
+
+
+def _pad_dim(hd: int) -> int:
+    if hd <= 64:
+        return 64
+    if hd <= 128:
+        return 128
+    raise ValueError(f"head_dim {hd} > 128 is not supported by the attention kernel")
+
+
+def _bf16(t: torch.Tensor, device) -> torch.Tensor:
+    return t.to(torch.bfloat16).contiguous().to(device)
+
+
+def _f32(t: torch.Tensor, device) -> torch.Tensor:
+    return t.float().contiguous().to(device)
+
+
+def _bias_bf16(t: torch.Tensor, device) -> torch.Tensor:
+    """autocast casts the bias of a Linear to bf16: keep its bf16-rounded value, stored as fp32."""
+    return t.to(torch.bfloat16).float().contiguous().to(device)
+
+
+def _pad_head_rows(w: torch.Tensor, n_heads: int, hd: int, hp: int) -> torch.Tensor:
+    """[n_heads*hd, ...] -> [n_heads*hp, ...] (zero rows appended to every head)."""
+    if hd == hp:
+        return w
+    shape = (n_heads, hd) + tuple(w.shape[1:])
+    out = torch.zeros((n_heads, hp) + tuple(w.shape[1:]), dtype=w.dtype)
+    out[:, :hd] = w.reshape(shape)
+    return out.reshape((n_heads * hp,) + tuple(w.shape[1:]))
+
+
+def _pad_head_cols(w: torch.Tensor, n_heads: int, hd: int, hp: int) -> torch.Tensor:
+    """[out, n_heads*hd] -> [out, n_heads*hp]."""
+    if hd == hp:
+        return w
+    out = torch.zeros(w.shape[0], n_heads, hp, dtype=w.dtype)
+    out[:, :, :hd] = w.reshape(w.shape[0], n_heads, hd)
+    return out.reshape(w.shape[0], n_heads * hp)
+
+
+def _interleave_gate_up(gate: torch.Tensor, up: torch.Tensor) -> torch.Tensor:
+    """[I, H] x 2 -> [2I, H] with blocks of 128 gate rows followed by the matching 128 up rows."""
+    I, H = gate.shape
+    assert I % 128 == 0, "intermediate_size must be a multiple of 128"
+    return torch.stack([gate.view(I // 128, 128, H), up.view(I // 128, 128, H)], dim=1).reshape(2 * I, H)
+
+
+def _split_hi_lo_hi(w: torch.Tensor) -> torch.Tensor:
+    """fp32 weight [N, K] -> bf16 [N, 3K] = [hi | lo | hi] (pairs with activations [hi | hi | lo])."""
+    hi = w.to(torch.bfloat16)
+    lo = (w - hi.float()).to(torch.bfloat16)
+    return torch.cat([hi, lo, hi], dim=1)
+
+
+class _Buffers:
+    """Shape-keyed cache of device workspaces (allocated once, reused across calls)."""
+
+    def __init__(self, device):
+        self.device = device
+        self._b: Dict[tuple, torch.Tensor] = {}
+
+    def get(self, name: str, shape, dtype, zero: bool = False) -> torch.Tensor:
+        key = (name, tuple(shape), dtype)
+        t = self._b.get(key)
+        if t is None:
+            t = (torch.zeros if zero else torch.empty)(shape, dtype=dtype, device=self.device)
+            self._b[key] = t
+        return t
+
+
+class G2VLMFast:
+    def __init__(self, cfg: G2Config, state_dict: Dict[str, torch.Tensor], device="cuda"):
+        if not torch.cuda.is_available():
+            raise RuntimeError("G2VLMFast needs a CUDA device (sm_100a); there is no CPU fallback")
+        _lib.load()  # fail loudly if the kernel library is missing
+        if cfg.head_dim != 128:
+            raise ValueError("LLM head_dim must be 128 (mrope_section is hard-coded to [16,24,24])")
+        if cfg.train_conf_pi3:
+            raise NotImplementedError("conf branch (train_conf_pi3) is not built yet")
+        self.cfg = cfg
+        self.device = torch.device(device)
+        self.buf = _Buffers(self.device)
+        missing = [k for k in state_dict_schema(cfg) if k not in state_dict]
+        if missing:
+            raise KeyError(f"state_dict is missing {len(missing)} keys, e.g. {missing[:4]}")
+        self._pack(state_dict)
+        self._rope2d_cache: Dict[tuple, tuple] = {}
+        self._pos_cache: Dict[tuple, torch.Tensor] = {}
+        self._work_cache: Dict[tuple, torch.Tensor] = {}
+
+    @classmethod
+    def from_state_dict(cls, cfg: G2Config, state_dict, device="cuda") -> "G2VLMFast":
+        return cls(cfg, state_dict, device)
+
+    # ------------------------------------------------------------------------------------------
+    # weight packing (one-time; reference key names in, kernel-friendly layouts out)
+    # ------------------------------------------------------------------------------------------
+    def _pack(self, sd):
+        cfg, dev = self.cfg, self.device
+        g = lambda k: sd[k].detach().float().cpu()
+        lm = "language_model.model."
+        self.embed = _f32(g(lm + "embed_tokens.weight"), dev)
+        self.layers = []
+        for i in range(cfg.num_layers):
+            p = f"{lm}layers.{i}."
+            a = p + "self_attn."
+            L = {}
+            qkv, bias = [], []
+            for sfx in ("_moe_geo", ""):  # expert order: geo (group 0), und (group 1)
+                qkv += [g(a + f"q_proj{sfx}.weight"), g(a + f"k_proj{sfx}.weight"), g(a + f"v_proj{sfx}.weight")]
+                bias += [g(a + f"q_proj{sfx}.bias"), g(a + f"k_proj{sfx}.bias"), g(a + f"v_proj{sfx}.bias")]
+            L["wqkv"] = _bf16(torch.cat(qkv, 0), dev)
+            L["bqkv"] = _bias_bf16(torch.cat(bias, 0), dev)
+            L["wo"] = _bf16(torch.cat([g(a + "o_proj_moe_geo.weight"), g(a + "o_proj.weight")], 0), dev)
+            L["wgu"] = _bf16(torch.cat([
+                _interleave_gate_up(g(p + "mlp_moe_geo.gate_proj.weight"), g(p + "mlp_moe_geo.up_proj.weight")),
+                _interleave_gate_up(g(p + "mlp.gate_proj.weight"), g(p + "mlp.up_proj.weight"))], 0), dev)
+            L["wdown"] = _bf16(torch.cat([g(p + "mlp_moe_geo.down_proj.weight"), g(p + "mlp.down_proj.weight")], 0), dev)
+            for n in ("input_layernorm", "post_attention_layernorm"):
+                L[n + "_geo"] = _f32(g(p + n + "_moe_geo.weight"), dev)
+                L[n + "_und"] = _f32(g(p + n + ".weight"), dev)
+            for n in ("q_norm", "k_norm"):
+                L[n + "_geo"] = _f32(g(a + n + "_moe_geo.weight"), dev)
+                L[n + "_und"] = _f32(g(a + n + ".weight"), dev)
+            L["ls1"] = _f32(g(p + "ls1.gamma"), dev)
+            L["ls2"] = _f32(g(p + "ls2.gamma"), dev)
+            self.layers.append(L)
+        self.norm_geo = _f32(g(lm + "norm_moe_geo.weight"), dev)
+        self.norm_und = _f32(g(lm + "norm.weight"), dev)
+        hd = cfg.head_dim
+        inv = 1.0 / (cfg.rope_theta ** (torch.arange(0, hd, 2, dtype=torch.int64).float() / hd))
+        self.inv_freq = inv.contiguous().to(dev)
+
+        # ---- DINO ----
+        D, nh, dhd = cfg.dino_hidden, cfg.dino_heads, cfg.dino_head_dim
+        self.dino_hp = _pad_dim(dhd)
+        d = "dino_model."
+        kp = 3 * cfg.dino_patch ** 2
+        self.dino_kpad = (kp + 63) // 64 * 64
+        wp = torch.zeros(D, self.dino_kpad)
+        wp[:, :kp] = g(d + "embeddings.patch_embeddings.projection.weight").reshape(D, kp)
+        self.dino_wpatch = _bf16(wp, dev)
+        self.dino_bpatch = _bias_bf16(g(d + "embeddings.patch_embeddings.projection.bias"), dev)
+        self.dino_cls = _f32(g(d + "embeddings.cls_token").reshape(D), dev)
+        self.dino_reg = _f32(g(d + "embeddings.register_tokens").reshape(cfg.dino_registers, D), dev)
+        self.dino_pos_table = g(d + "embeddings.position_embeddings")  # CPU master, resampled per grid
+        self.dino_layers = []
+        for i in range(cfg.dino_layers):
+            p = f"{d}encoder.layer.{i}."
+            at = p + "attention.attention."
+            L = {}
+            L["wqkv"] = _bf16(torch.cat([_pad_head_rows(g(at + f"{n}.weight"), nh, dhd, self.dino_hp)
+                                         for n in ("query", "key", "value")], 0), dev)
+            L["bqkv"] = _bias_bf16(torch.cat([_pad_head_rows(g(at + f"{n}.bias"), nh, dhd, self.dino_hp)
+                                              for n in ("query", "key", "value")], 0), dev)
+            L["wdense"] = _bf16(_pad_head_cols(g(p + "attention.output.dense.weight"), nh, dhd, self.dino_hp), dev)
+            L["bdense"] = _bias_bf16(g(p + "attention.output.dense.bias"), dev)
+            L["wfc1"] = _bf16(g(p + "mlp.fc1.weight"), dev); L["bfc1"] = _bias_bf16(g(p + "mlp.fc1.bias"), dev)
+            L["wfc2"] = _bf16(g(p + "mlp.fc2.weight"), dev); L["bfc2"] = _bias_bf16(g(p + "mlp.fc2.bias"), dev)
+            for n in ("norm1", "norm2"):
+                L[n + "w"] = _f32(g(p + n + ".weight"), dev); L[n + "b"] = _f32(g(p + n + ".bias"), dev)
+            L["ls1"] = _f32(g(p + "layer_scale1.lambda1"), dev)
+            L["ls2"] = _f32(g(p + "layer_scale2.lambda1"), dev)
+            self.dino_layers.append(L)
+        self.dino_lnw = _f32(g(d + "layernorm.weight"), dev)
+        self.dino_lnb = _f32(g(d + "layernorm.bias"), dev)
+        self.w_dino2llm = _bf16(g("dino2llm.weight"), dev)
+        self.b_dino2llm = _bias_bf16(g("dino2llm.bias"), dev)
+
+        # ---- Pi3 decoders ----
+        H, dh, ehd = cfg.hidden_size, cfg.dec_heads, cfg.dec_head_dim
+        self.dec_hp = _pad_dim(ehd)
+
+        def pack_block(p, cross):
+            B = {}
+            qkv_w = g(p + "attn.qkv.weight").reshape(3, dh * ehd, H)
+            qkv_b = g(p + "attn.qkv.bias").reshape(3, dh * ehd)
+            B["wqkv"] = _bf16(torch.cat([_pad_head_rows(qkv_w[j], dh, ehd, self.dec_hp) for j in range(3)], 0), dev)
+            B["bqkv"] = _bias_bf16(torch.cat([_pad_head_rows(qkv_b[j], dh, ehd, self.dec_hp) for j in range(3)], 0), dev)
+            B["wproj"] = _bf16(_pad_head_cols(g(p + "attn.proj.weight"), dh, ehd, self.dec_hp), dev)
+            B["bproj"] = _bias_bf16(g(p + "attn.proj.bias"), dev)
+            names = ["norm1", "norm2"] + (["norm3", "norm_y"] if cross else [])
+            for n in names:
+                B[n + "w"] = _f32(g(p + n + ".weight"), dev); B[n + "b"] = _f32(g(p + n + ".bias"), dev)
+            if cross:
+                c = p + "cross_attn."
+                B["wcq"] = _bf16(_pad_head_rows(g(c + "q_proj.weight"), dh, ehd, self.dec_hp), dev)
+                B["bcq"] = _bias_bf16(_pad_head_rows(g(c + "q_proj.bias"), dh, ehd, self.dec_hp), dev)
+                B["wckv"] = _bf16(torch.cat([_pad_head_rows(g(c + "k_proj.weight"), dh, ehd, self.dec_hp),
+                                             _pad_head_rows(g(c + "v_proj.weight"), dh, ehd, self.dec_hp)], 0), dev)
+                B["bckv"] = _bias_bf16(torch.cat([_pad_head_rows(g(c + "k_proj.bias"), dh, ehd, self.dec_hp),
+                                                  _pad_head_rows(g(c + "v_proj.bias"), dh, ehd, self.dec_hp)], 0), dev)
+                B["wcproj"] = _bf16(_pad_head_cols(g(c + "proj.weight"), dh, ehd, self.dec_hp), dev)
+                B["bcproj"] = _bias_bf16(g(c + "proj.bias"), dev)
+            B["wfc1"] = _bf16(g(p + "mlp.fc1.weight"), dev); B["bfc1"] = _bias_bf16(g(p + "mlp.fc1.bias"), dev)
+            B["wfc2"] = _bf16(g(p + "mlp.fc2.weight"), dev); B["bfc2"] = _bias_bf16(g(p + "mlp.fc2.bias"), dev)
+            return B
+
+        self.decoders = {}
+        for name, cross in (("point_decoder", False), ("camera_decoder", False), ("global_points_decoder", True)):
+            blocks = [pack_block(f"{name}.blocks.{i}.", cross) for i in range(cfg.dec_depth)]
+            self.decoders[name] = dict(blocks=blocks, cross=cross,
+                                       wout=_bf16(g(f"{name}.linear_out.weight"), dev),
+                                       bout=_bias_bf16(g(f"{name}.linear_out.bias"), dev))
+        # fp32 heads (autocast disabled in the reference): split-bf16 weights, exact fp32 biases
+        for hname in ("point_head", "global_point_head"):
+            w = g(hname + ".proj.weight")
+            hi = w.to(torch.bfloat16)
+            setattr(self, hname + "_whi", _bf16(hi, dev))
+            setattr(self, hname + "_wlo", _bf16(w - hi.float(), dev))
+            setattr(self, hname + "_b", _f32(g(hname + ".proj.bias"), dev))
+        self.cam = {}
+        for i in range(2):
+            for j in (1, 2, 3):
+                k = f"camera_head.res_conv.{i}.res_conv{j}"
+                self.cam[f"r{i}{j}w"] = _bf16(_split_hi_lo_hi(g(k + ".weight")), dev)
+                self.cam[f"r{i}{j}b"] = _f32(g(k + ".bias"), dev)
+        for j in (0, 2):
+            self.cam[f"m{j}w"] = _bf16(_split_hi_lo_hi(g(f"camera_head.more_mlps.{j}.weight")), dev)
+            self.cam[f"m{j}b"] = _f32(g(f"camera_head.more_mlps.{j}.bias"), dev)
+        for n in ("fc_t", "fc_rot"):
+            self.cam[n + "w"] = _f32(g(f"camera_head.{n}.weight"), dev)
+            self.cam[n + "b"] = _f32(g(f"camera_head.{n}.bias"), dev)
+
+    # ------------------------------------------------------------------------------------------
+    # small cached host-built tables
+    # ------------------------------------------------------------------------------------------
+    def _work(self, cu_q: Sequence[int], cu_k: Sequence[int], tag: str) -> torch.Tensor:
+        key = (tag, tuple(cu_q), tuple(cu_k))
+        t = self._work_cache.get(key)
+        if t is None:
+            t = ops.attention_work_table(cu_q, cu_k).to(self.device)
+            self._work_cache[key] = t
+        return t
+
+    def _cross_work(self, n_views: int, P: int) -> torch.Tensor:
+        key = ("cross", n_views, P)
+        t = self._work_cache.get(key)
+        if t is None:
+            items = [[t0, v * P, (v + 1) * P, 0, P, 0, 0, 0]
+                     for v in range(n_views) for t0 in range(v * P, (v + 1) * P, ops.ATTN_ROWS_PER_ITEM)]
+            t = torch.tensor(items, dtype=torch.int32).to(self.device)
+            self._work_cache[key] = t
+        return t
+
+    def _dino_pos(self, gh: int, gw: int, square: bool) -> torch.Tensor:
+        """position_embeddings for a gh x gw grid; bicubic-antialias resample of the learned table when
+        the grid differs (interpolate_pos_encoding, modeling_dinov2_with_registers.py:93-145).  This
+        depends on the weights and the grid only, so it is computed once per grid and cached."""
+        key = (gh, gw, square)
+        t = self._pos_cache.get(key)
+        if t is None:
+            cfg = self.cfg
+            pos = self.dino_pos_table
+            g0 = cfg.dino_grid
+            if not (gh * gw == g0 * g0 and square):
+                pp = pos[:, 1:].reshape(1, g0, g0, -1).permute(0, 3, 1, 2)
+                pp = torch.nn.functional.interpolate(pp, size=(gh, gw), mode="bicubic", align_corners=False,
+                                                     antialias=True)
+                pos = torch.cat((pos[:, :1], pp.permute(0, 2, 3, 1).reshape(1, gh * gw, -1)), dim=1)
+            t = pos[0].contiguous().to(self.device)
+            self._pos_cache[key] = t
+        return t
+
+    def _rope2d_tables(self, gh: int, gw: int):
+        """cos/sin tables of RoPE2D built exactly like the reference's cache (pos_embed.py:118-128):
+        angles cast to bf16 BEFORE cos/sin (quirk Q2), cos/sin stored in bf16.  Unique columns only."""
+        key = (gh, gw)
+        t = self._rope2d_cache.get(key)
+        if t is None:
+            D = self.cfg.dec_head_dim // 2
+            inv_freq = 1.0 / (self.cfg.rope2d_base ** (torch.arange(0, D, 2).float() / D))
+            tt = torch.arange(max(gh, gw), dtype=inv_freq.dtype)
+            freqs = torch.einsum("i,j->ij", tt, inv_freq).to(torch.bfloat16)
+            t = (freqs.cos().float().contiguous().to(self.device), freqs.sin().float().contiguous().to(self.device))
+            self._rope2d_cache[key] = t
+        return t
+
+    # ------------------------------------------------------------------------------------------
+    # MoT language model
+    # ------------------------------------------------------------------------------------------
+    def _mot_layer(self, L, x, T, n_geo, qkv, attn, act, hbuf, cos, sin, work, kv_rows, causal, round_normed):
+        cfg = self.cfg
+        H, I = cfg.hidden_size, cfg.intermediate_size
+        nq, nkv, hd = cfg.num_heads, cfg.num_kv_heads, cfg.head_dim
+        groups = [(0, n_geo), (n_geo, T - n_geo)]
+        ops.rmsnorm_routed(x, hbuf, L["input_layernorm_geo"], L["input_layernorm_und"], n_geo, cfg.rms_norm_eps, rows=T)
+        ops.gemm(hbuf[:T], L["wqkv"], qkv, epilogue=ops.EPI_STORE_BF16, groups=groups, bias=L["bqkv"])
+        ops.qknorm_mrope(qkv, T, n_geo, nq, nkv, hd, L["q_norm_geo"], L["k_norm_geo"], L["q_norm_und"],
+                         L["k_norm_und"], cos, sin, cfg.rms_norm_eps, round_normed=round_normed)
+        ops.attention(qkv[:T, : nq * hd], qkv[:kv_rows, nq * hd:(nq + nkv) * hd], qkv[:kv_rows, (nq + nkv) * hd:],
+                      attn, work, num_q_heads=nq, num_kv_heads=nkv, head_dim=hd, scale=1.0 / math.sqrt(hd),
+                      causal=causal)
+        ops.gemm(attn[:T], L["wo"], x, epilogue=ops.EPI_RESID_F32, groups=groups, scale=L["ls1"], scale_groups=1,
+                 flags=ops.GEMM_ROUND_AFTER_SCALE)
+        ops.rmsnorm_routed(x, hbuf, L["post_attention_layernorm_geo"], L["post_attention_layernorm_und"], n_geo,
+                           cfg.rms_norm_eps, rows=T)
+        ops.gemm(hbuf[:T], L["wgu"], act, epilogue=ops.EPI_SWIGLU_BF16, groups=groups)
+        ops.gemm(act[:T], L["wdown"], x, epilogue=ops.EPI_RESID_F32, groups=groups, scale=L["ls2"], scale_groups=1,
+                 flags=ops.GEMM_ROUND_AFTER_SCALE)
+
+    def _mot_buffers(self, rows_q: int, rows_kv: int):
+        cfg = self.cfg
+        nq, nkv, hd = cfg.num_heads, cfg.num_kv_heads, cfg.head_dim
+        qkv = self.buf.get("mot.qkv", (rows_kv, (nq + 2 * nkv) * hd), torch.bfloat16)
+        attn = self.buf.get("mot.attn", (rows_q, nq * hd), torch.bfloat16)
+        act = self.buf.get("mot.act", (rows_q, cfg.intermediate_size), torch.bfloat16)
+        hbuf = self.buf.get("mot.h", (rows_q, cfg.hidden_size), torch.bfloat16)
+        return qkv, attn, act, hbuf
+
+    @torch.no_grad()
+    def forward_cache_update_text(self, past_key_values: NaiveCache, packed_text_ids, packed_text_position_ids,
+                                  text_token_lens, packed_text_indexes, packed_key_value_indexes, key_values_lens):
+        """Text prefill, mode='und', causal, empty cache (reference g2vlm.py:701-733)."""
+        cfg, dev = self.cfg, self.device
+        if int(key_values_lens.sum()) != 0 or len(text_token_lens) != 1:
+            raise NotImplementedError("prefill supports a single prompt on an empty cache (the recon path)")
+        K0 = int(packed_text_ids.numel())
+        nq, nkv, hd = cfg.num_heads, cfg.num_kv_heads, cfg.head_dim
+        ids = packed_text_ids.to(dev, torch.long)
+        x = torch.empty(K0, cfg.hidden_size, dtype=torch.float32, device=dev)
+        ops.gather_rows(self.embed, x, ids, K0)
+        pos = packed_text_position_ids.to(dev, torch.long).contiguous()
+        cos = torch.empty(K0, hd // 2, dtype=torch.float32, device=dev)
+        sin = torch.empty_like(cos)
+        ops.mrope_table(pos, self.inv_freq, cos, sin, cfg.mrope_section)
+        qkv, attn, act, hbuf = self._mot_buffers(K0, K0)
+        work = self._work([0, K0], [0, K0], "text")
+        for i, L in enumerate(self.layers):
+            # all rows belong to the und expert: group 0 (geo) is empty
+            self._mot_layer(L, x, K0, 0, qkv, attn, act, hbuf, cos, sin, work, K0, True, True)
+            kv = qkv[:K0, nq * hd:].clone()
+            past_key_values.key_cache[i] = kv[:, : nkv * hd].view(K0, nkv, hd)
+            past_key_values.value_cache[i] = kv[:, nkv * hd:].view(K0, nkv, hd)
+        return past_key_values
+
+    @torch.no_grad()
+    def language_model_forward_geo(self, packed_sequence, packed_position_ids, packed_geo_token_indexes,
+                                   packed_text_indexes, past_key_values: NaiveCache,
+                                   update_past_key_values: bool = True, collect: Optional[list] = None):
+        """Qwen2VLModel.forward_inference(mode='geo', is_causal=False) incl. the routed final norm
+        (reference g2vlm/qwen2vl.py:1267-1337).  packed_sequence: fp32 [T, H] in packed order."""
+        cfg, dev = self.cfg, self.device
+        nq, nkv, hd, H = cfg.num_heads, cfg.num_kv_heads, cfg.head_dim, cfg.hidden_size
+        T = packed_sequence.shape[0]
+        geo = packed_geo_token_indexes.to(dev, torch.long)
+        und = packed_text_indexes.to(dev, torch.long)
+        n_geo = int(geo.numel())
+        perm = torch.cat([geo, und]).contiguous()  # internal row i <- packed row perm[i]
+        if int(perm.numel()) != T:
+            raise ValueError("geo + text indexes must cover every packed row exactly once")
+        K0 = past_key_values.seq_lens
+        x = self.buf.get("mot.x", (T, H), torch.float32)
+        ops.gather_rows(packed_sequence, x, perm, T)
+        cos_p = self.buf.get("mot.cos_p", (T, hd // 2), torch.float32)
+        sin_p = self.buf.get("mot.sin_p", (T, hd // 2), torch.float32)
+        ops.mrope_table(packed_position_ids.to(dev, torch.long).contiguous(), self.inv_freq, cos_p, sin_p,
+                        cfg.mrope_section)
+        cos = self.buf.get("mot.cos", (T, hd // 2), torch.float32)
+        sin = self.buf.get("mot.sin", (T, hd // 2), torch.float32)
+        ops.gather_rows(cos_p, cos, perm, T)
+        ops.gather_rows(sin_p, sin, perm, T)
+        qkv, attn, act, hbuf = self._mot_buffers(T, T + K0)
+        work = self._work([0, T], [0, T + K0], "geo")
+        kvw = 2 * nkv * hd
+        for i, L in enumerate(self.layers):
+            if K0:
+                # prefix K/V of the und prefill become key rows [T, T+K0) (KV merge, qwen2vl.py:621-638)
+                pk = past_key_values.key_cache[i].reshape(K0, nkv * hd)
+                pv = past_key_values.value_cache[i].reshape(K0, nkv * hd)
+                ops.gather_rows(pk, qkv[T:, nq * hd:(nq + nkv) * hd], None, K0)
+                ops.gather_rows(pv, qkv[T:, (nq + nkv) * hd:], None, K0)
+            self._mot_layer(L, x, T, n_geo, qkv, attn, act, hbuf, cos, sin, work, T + K0, False, False)
+            if update_past_key_values:
+                # reference order of the merged cache: prefix rows, then the packed query rows
+                merged = torch.empty(T + K0, kvw, dtype=torch.bfloat16, device=dev)
+                if K0:
+                    ops.gather_rows(qkv[T:, nq * hd:], merged, None, K0)
+                ops.gather_rows(qkv[:T, nq * hd:], merged[K0:], perm, T, scatter=True)
+                past_key_values.key_cache[i] = merged[:, : nkv * hd].view(T + K0, nkv, hd)
+                past_key_values.value_cache[i] = merged[:, nkv * hd:].view(T + K0, nkv, hd)
+            if collect is not None:
+                y = torch.empty(T, H, dtype=torch.float32, device=dev)
+                ops.gather_rows(x, y, perm, T, scatter=True)
+                collect.append(y)
+        y_int = self.buf.get("mot.y", (T, H), torch.float32)
+        ops.rmsnorm_routed(x, y_int, self.norm_geo, self.norm_und, n_geo, cfg.rms_norm_eps, rows=T)
+        last = torch.empty(T, H, dtype=torch.float32, device=dev)
+        ops.gather_rows(y_int, last, perm, T, scatter=True)
+        return last, past_key_values
+
+    # ------------------------------------------------------------------------------------------
+    # DINO encoder
+    # ------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def dino_forward(self, packed_pixel_values, dino_token_seqlens, collect: Optional[list] = None):
+        """Dinov2WithRegistersModel.forward with the caller's cu_seqlens (reference
+        g2vlm/dinov2_model.py:301-356, g2vlm.py:988-992) -> bf16 tokens [N*P, D] (post final LN,
+        cls/registers dropped)."""
+        cfg, dev = self.cfg, self.device
+        img = packed_pixel_values.to(dev, torch.float32).contiguous()
+        N, _, Hh, Ww = img.shape
+        p = cfg.dino_patch
+        gh, gw = Hh // p, Ww // p
+        P, S, D = gh * gw, gh * gw + 1 + cfg.dino_registers, cfg.dino_hidden
+        nh, hp = cfg.dino_heads, self.dino_hp
+        rows = N * S
+        patches = self.buf.get("dino.patches", (N * P, self.dino_kpad), torch.bfloat16)
+        ops.im2col_patches(img, patches, p)
+        emb = self.buf.get("dino.emb", (N * P, D), torch.bfloat16)
+        ops.gemm(patches, self.dino_wpatch, emb, epilogue=ops.EPI_STORE_BF16, bias=self.dino_bpatch)
+        x = self.buf.get("dino.x", (rows, D), torch.float32)
+        ops.dino_embed(emb, self.dino_cls, self.dino_reg, self._dino_pos(gh, gw, Hh == Ww), x, N, P, cfg.dino_registers)
+        cu = [0]
+        for n in dino_token_seqlens.tolist():
+            cu.append(cu[-1] + int(n))
+        if cu[-1] > rows:
+            raise ValueError("dino_token_seqlens exceed the number of DINO rows")
+        work = self._work(cu, cu, "dino")
+        h = self.buf.get("dino.h", (rows, D), torch.bfloat16)
+        qkv = self.buf.get("dino.qkv", (rows, 3 * nh * hp), torch.bfloat16)
+        # rows covered by no segment are never written by the attention kernel: they stay ZERO
+        # (definition of the uninitialised flash-attn rows, quirk Q1)
+        attn = self.buf.get("dino.attn", (rows, nh * hp), torch.bfloat16, zero=True)
+        mid = self.buf.get("dino.mid", (rows, D * cfg.dino_mlp_ratio), torch.bfloat16)
+        scale = 1.0 / math.sqrt(cfg.dino_head_dim)
+        for L in self.dino_layers:
+            ops.layernorm(x, h, L["norm1w"], L["norm1b"], cfg.dino_ln_eps)
+            ops.gemm(h, L["wqkv"], qkv, epilogue=ops.EPI_STORE_BF16, bias=L["bqkv"])
+            ops.attention(qkv[:, : nh * hp], qkv[:, nh * hp: 2 * nh * hp], qkv[:, 2 * nh * hp:], attn, work,
+                          num_q_heads=nh, num_kv_heads=nh, head_dim=hp, scale=scale)
+            ops.gemm(attn, L["wdense"], x, epilogue=ops.EPI_RESID_F32, bias=L["bdense"], scale=L["ls1"], scale_groups=1)
+            ops.layernorm(x, h, L["norm2w"], L["norm2b"], cfg.dino_ln_eps)
+            ops.gemm(h, L["wfc1"], mid, epilogue=ops.EPI_STORE_BF16, bias=L["bfc1"], flags=ops.GEMM_GELU)
+            ops.gemm(mid, L["wfc2"], x, epilogue=ops.EPI_RESID_F32, bias=L["bfc2"], scale=L["ls2"], scale_groups=1)
+            if collect is not None:
+                collect.append(x.clone())
+        tokens = self.buf.get("dino.tokens", (N * P, D), torch.bfloat16)
+        ops.layernorm(x, tokens, self.dino_lnw, self.dino_lnb, cfg.dino_ln_eps, seg_in=S, seg_skip=1 + cfg.dino_registers)
+        return tokens
+
+    @torch.no_grad()
+    def forward_cache_update_dino(self, past_key_values: NaiveCache, packed_text_ids, packed_text_indexes,
+                                  packed_dino_token_indexes, dino_token_seqlens, packed_position_ids, packed_seqlens,
+                                  packed_indexes, packed_key_value_indexes, key_values_lens, packed_dino_images,
+                                  original_images, update_past_key_values: bool = True, collect: Optional[dict] = None):
+        """Reference: g2vlm.py:968-1039.  Returns (past_key_values, last_hidden_state [T, H] fp32)."""
+        cfg, dev = self.cfg, self.device
+        T, H = int(sum(packed_seqlens.tolist())), cfg.hidden_size
+        if packed_dino_images.shape[0] < 1:
+            raise ValueError("at least one view is required")
+        tokens = self.dino_forward(packed_dino_images, dino_token_seqlens,
+                                   collect=None if collect is None else collect.setdefault("dino_layers", []))
+        n_geo = tokens.shape[0]
+        geo_emb = self.buf.get("mot.geo_emb", (n_geo, H), torch.float32)
+        ops.gemm(tokens, self.w_dino2llm, geo_emb, epilogue=ops.EPI_STORE_F32, bias=self.b_dino2llm,
+                 flags=ops.GEMM_ROUND_BF16)
+        packed = self.buf.get("mot.packed", (T, H), torch.float32)
+        n_und = int(packed_text_ids.numel())
+        txt = self.buf.get("mot.txt", (n_und, H), torch.float32)
+        ops.gather_rows(self.embed, txt, packed_text_ids.to(dev, torch.long), n_und)
+        ops.gather_rows(txt, packed, packed_text_indexes.to(dev, torch.long), n_und, scatter=True)
+        ops.gather_rows(geo_emb, packed, packed_dino_token_indexes.to(dev, torch.long), n_geo, scatter=True)
+        if collect is not None:
+            collect["dino_tokens"] = tokens.float().clone()
+            collect["packed_sequence"] = packed.clone()
+        last, past_key_values = self.language_model_forward_geo(
+            packed, packed_position_ids, packed_dino_token_indexes, packed_text_indexes, past_key_values,
+            update_past_key_values=update_past_key_values,
+            collect=None if collect is None else collect.setdefault("mot_layers", []))
+        return past_key_values, last
+
+    # ------------------------------------------------------------------------------------------
+    # Pi3 decoders + heads
+    # ------------------------------------------------------------------------------------------
+    def _decoder(self, name, hidden, N, P, gh, gw, out, out_fp32_round=False, context=None):
+        """Pi3TransformerDecoder / Pi3ContextTransformerDecoder (transformer_head.py:48-56, 122-131)."""
+        cfg, dec = self.cfg, self.decoders[name]
+        H, dh, hp, ehd = cfg.hidden_size, cfg.dec_heads, self.dec_hp, cfg.dec_head_dim
+        rows = N * P
+        x = self.buf.get("dec.x", (rows, H), torch.float32)
+        ops.gather_rows(hidden, x, None, rows)
+        h = self.buf.get("dec.h", (rows, H), torch.bfloat16)
+        qkv = self.buf.get("dec.qkv", (rows, 3 * dh * hp), torch.bfloat16)
+        attn = self.buf.get("dec.attn", (rows, dh * hp), torch.bfloat16)
+        mid = self.buf.get("dec.mid", (rows, H * cfg.dec_mlp_ratio), torch.bfloat16)
+        cos, sin = self._rope2d_tables(gh, gw)
+        cu = [v * P for v in range(N + 1)]
+        work = self._work(cu, cu, "dec")
+        scale = 1.0 / math.sqrt(ehd)
+        if dec["cross"]:
+            yh = self.buf.get("dec.yh", (P, H), torch.bfloat16)
+            kvc = self.buf.get("dec.kvc", (P, 2 * dh * hp), torch.bfloat16)
+            qc = self.buf.get("dec.qc", (rows, dh * hp), torch.bfloat16)
+            cwork = self._cross_work(N, P)
+        for B in dec["blocks"]:
+            ops.layernorm(x, h, B["norm1w"], B["norm1b"], 1e-6)
+            ops.gemm(h, B["wqkv"], qkv, epilogue=ops.EPI_STORE_BF16, bias=B["bqkv"])
+            ops.rope2d(qkv, rows, 2 * dh, hp, ehd, P, gw, cos, sin)
+            ops.attention(qkv[:, : dh * hp], qkv[:, dh * hp: 2 * dh * hp], qkv[:, 2 * dh * hp:], attn, work,
+                          num_q_heads=dh, num_kv_heads=dh, head_dim=hp, scale=scale)
+            ops.gemm(attn, B["wproj"], x, epilogue=ops.EPI_RESID_F32, bias=B["bproj"])
+            if dec["cross"]:
+                # context = view 0's tokens for every view (g2vlm.py:1196): K/V projected ONCE per block
+                ops.layernorm(context, yh, B["norm_yw"], B["norm_yb"], 1e-6, rows=P)
+                ops.gemm(yh, B["wckv"], kvc, epilogue=ops.EPI_STORE_BF16, bias=B["bckv"])
+                ops.rope2d(kvc, P, dh, hp, ehd, P, gw, cos, sin)
+                ops.layernorm(x, h, B["norm2w"], B["norm2b"], 1e-6)
+                ops.gemm(h, B["wcq"], qc, epilogue=ops.EPI_STORE_BF16, bias=B["bcq"])
+                ops.rope2d(qc, rows, dh, hp, ehd, P, gw, cos, sin)
+                ops.attention(qc, kvc[:, : dh * hp], kvc[:, dh * hp:], attn, cwork, num_q_heads=dh, num_kv_heads=dh,
+                              head_dim=hp, scale=scale)
+                ops.gemm(attn, B["wcproj"], x, epilogue=ops.EPI_RESID_F32, bias=B["bcproj"])
+                ops.layernorm(x, h, B["norm3w"], B["norm3b"], 1e-6)
+            else:
+                ops.layernorm(x, h, B["norm2w"], B["norm2b"], 1e-6)
+            ops.gemm(h, B["wfc1"], mid, epilogue=ops.EPI_STORE_BF16, bias=B["bfc1"], flags=ops.GEMM_GELU)
+            ops.gemm(mid, B["wfc2"], x, epilogue=ops.EPI_RESID_F32, bias=B["bfc2"])
+        ops.cast_bf16(x, h)
+        if out.dtype == torch.bfloat16:
+            ops.gemm(h, dec["wout"], out, epilogue=ops.EPI_STORE_BF16, bias=dec["bout"])
+        else:  # `.float()` of the bf16 linear_out result
+            ops.gemm(h, dec["wout"], out, epilogue=ops.EPI_STORE_F32, bias=dec["bout"], flags=ops.GEMM_ROUND_BF16)
+        return out
+
+    def _linear_fp32(self, x, w3, b, out, relu=False, residual=None):
+        """True-fp32 nn.Linear (autocast disabled in the reference) on the bf16 tensor cores:
+        x = hi + lo, w = hi + lo, x.w ~ hi.hi + hi.lo + lo.hi as ONE GEMM over the concatenated K."""
+        rows, k = x.shape
+        xs = self.buf.get(f"fp32lin.{rows}x{k}", (rows, 3 * k), torch.bfloat16)
+        ops.split3(x, xs)
+        ops.gemm(xs, w3, out, epilogue=ops.EPI_STORE_F32, bias=b, flags=ops.GEMM_RELU if relu else 0, residual=residual)
+        return out
+
+    @torch.no_grad()
+    def reconstruct(self, past_key_values=None, packed_key_value_indexes=None, key_values_lens=None,
+                    selected_hidden_states=None, packed_dino_token_indexes=None, packed_dino_images=None,
+                    original_images=None, collect: Optional[dict] = None, **kwargs):
+        """Reference: g2vlm.py:1143-1238."""
+        cfg, dev = self.cfg, self.device
+        N, _, Hh, Ww = packed_dino_images.shape
+        p = cfg.dino_patch
+        gh, gw = Hh // p, Ww // p
+        P, H = gh * gw, cfg.hidden_size
+        rows = N * P
+        geo = packed_dino_token_indexes.to(dev, torch.long)
+        hidden = self.buf.get("rec.hidden", (rows, H), torch.float32)
+        ops.gather_rows(selected_hidden_states, hidden, geo, rows)
+
+        point_hidden = self.buf.get("rec.point_hidden", (rows, cfg.point_dim), torch.bfloat16)
+        self._decoder("point_decoder", hidden, N, P, gh, gw, point_hidden)
+        camera_hidden = self.buf.get("rec.camera_hidden", (rows, cfg.camera_dim), torch.float32)
+        self._decoder("camera_decoder", hidden, N, P, gh, gw, camera_hidden)
+        global_hidden = self.buf.get("rec.global_hidden", (rows, cfg.point_dim), torch.bfloat16)
+        self._decoder("global_points_decoder", hidden, N, P, gh, gw, global_hidden, context=hidden[:P])
+        if collect is not None:
+            collect.update(point_hidden=point_hidden.float().view(N, P, -1).clone(),
+                           camera_hidden=camera_hidden.view(N, P, -1).clone(),
+                           global_hidden=global_hidden.float().view(N, P, -1).clone())
+
+        # camera head: fp32 (camera_head.py:48-72)
+        C = cfg.camera_dim
+        feat = camera_hidden
+        t1 = self.buf.get("cam.t1", (rows, C), torch.float32)
+        t2 = self.buf.get("cam.t2", (rows, C), torch.float32)
+        f2 = self.buf.get("cam.f2", (rows, C), torch.float32)
+        f3 = self.buf.get("cam.f3", (rows, C), torch.float32)
+        for i, dst in ((0, f2), (1, f3)):
+            self._linear_fp32(feat, self.cam[f"r{i}1w"], self.cam[f"r{i}1b"], t1, relu=True)
+            self._linear_fp32(t1, self.cam[f"r{i}2w"], self.cam[f"r{i}2b"], t2, relu=True)
+            self._linear_fp32(t2, self.cam[f"r{i}3w"], self.cam[f"r{i}3b"], dst, relu=True, residual=feat)
+            feat = dst
+        pooled = self.buf.get("cam.pooled", (N, C), torch.float32)
+        ops.mean_pool(feat, pooled, N, P)
+        m1 = self.buf.get("cam.m1", (N, C), torch.float32)
+        m2 = self.buf.get("cam.m2", (N, C), torch.float32)
+        self._linear_fp32(pooled, self.cam["m0w"], self.cam["m0b"], m1, relu=True)
+        self._linear_fp32(m1, self.cam["m2w"], self.cam["m2b"], m2, relu=True)
+        poses = torch.empty(N, 4, 4, dtype=torch.float32, device=dev)
+        ops.camera_pose(m2, self.cam["fc_tw"], self.cam["fc_tb"], self.cam["fc_rotw"], self.cam["fc_rotb"], poses)
+
+        # point heads: fp32 Linear on bf16-exact activations = two bf16 GEMMs (W = hi + lo)
+        nf = 3 * p * p
+        feat_pts = self.buf.get("rec.feat_pts", (rows, nf), torch.float32)
+        local_points = torch.empty(N, Hh, Ww, 3, dtype=torch.float32, device=dev)
+        points = torch.empty(N, Hh, Ww, 3, dtype=torch.float32, device=dev)
+        global_points = torch.empty(N, Hh, Ww, 3, dtype=torch.float32, device=dev)
+        ops.gemm(point_hidden, self.point_head_whi, feat_pts, epilogue=ops.EPI_STORE_F32, bias=self.point_head_b)
+        ops.gemm(point_hidden, self.point_head_wlo, feat_pts, epilogue=ops.EPI_STORE_F32, flags=ops.GEMM_ACCUMULATE)
+        ops.points_epilogue(feat_pts, poses, local_points, points, N, Hh, Ww, p, 1)
+        ops.gemm(global_hidden, self.global_point_head_whi, feat_pts, epilogue=ops.EPI_STORE_F32,
+                 bias=self.global_point_head_b)
+        ops.gemm(global_hidden, self.global_point_head_wlo, feat_pts, epilogue=ops.EPI_STORE_F32,
+                 flags=ops.GEMM_ACCUMULATE)
+        ops.points_epilogue(feat_pts, None, global_points, None, N, Hh, Ww, p, 0)
+
+        if original_images is not None and original_images.dim() == 4:
+            original_images = original_images.unsqueeze(0)
+        return dict(points=points[None], local_points=local_points[None], conf=None, camera_poses=poses[None],
+                    global_points=global_points[None], images=original_images)
+
+    # ------------------------------------------------------------------------------------------
+    # the public entry point
+    # ------------------------------------------------------------------------------------------
+    prepare_prompts_addbos = staticmethod(host_prep.prepare_prompts_addbos)
+
+    def prepare_dino_images_pi3(self, curr_kvlens, curr_rope, images, transforms, new_token_ids):
+        return host_prep.prepare_dino_images_pi3(curr_kvlens, curr_rope, images, new_token_ids, self.cfg.dino_patch)
+
+    @torch.no_grad()
+    def recon(self, tokenizer, new_token_ids, dino_image_transform, images, prompt="Reconstruct the 3D scene.",
+              collect: Optional[dict] = None):
+        """Same call shape and result dict as the reference's G2VLM.recon (g2vlm.py:1240-1303).  Like the
+        reference, `dino_image_transform` and `prompt` are ignored (the prompt is hard-coded, :1264).
+        `images`: list of paths / PIL images, or an (N,3,H,W) tensor in [0,1] (H, W multiples of 14)."""
+        dev = self.device
+        past = NaiveCache(self.cfg.num_layers)
+        gi, newlens, new_rope = self.prepare_prompts_addbos([0], [0], ["Reconstruct the 3D scene."], tokenizer,
+                                                            new_token_ids)
+        gi = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in gi.items()}
+        past = self.forward_cache_update_text(past, **gi)
+        gi, newlens, new_rope = self.prepare_dino_images_pi3(newlens, new_rope, images, dino_image_transform,
+                                                             new_token_ids)
+        if collect is not None:
+            collect["generation_input"] = {k: v.clone() for k, v in gi.items() if torch.is_tensor(v)}
+        gi = {k: (v.to(dev, non_blocking=True) if torch.is_tensor(v) else v) for k, v in gi.items()}
+        past, last = self.forward_cache_update_dino(past, update_past_key_values=False, collect=collect, **gi)
+        if collect is not None:
+            collect["last_hidden"] = last.clone()
+        return self.reconstruct(past_key_values=past, selected_hidden_states=last, collect=collect, **gi)

@@ -159,3 +159,128 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tens
     args.n_items, args.work_items = work.shape[0], work.data_ptr()
     _check(_lib.load().g2vlm_attention(ctypes.byref(args), _stream()))
     return out
+
+
+# ---------------------------------------------------------------------------------------------------
+# memory-bound kernels
+# ---------------------------------------------------------------------------------------------------
+_i64, _i32, _f32, _vp = ctypes.c_int64, ctypes.c_int32, ctypes.c_float, ctypes.c_void_p
+
+
+def _call(name: str, *args) -> None:
+    _check(getattr(_lib.load(), name)(*args, _stream()))
+
+
+def gather_rows(src: torch.Tensor, dst: torch.Tensor, idx: Optional[torch.Tensor], n_rows: int,
+                scatter: bool = False, row_elems: Optional[int] = None) -> torch.Tensor:
+    """dst[i] = src[idx[i]] (or dst[idx[i]] = src[i] if scatter); idx None = plain row copy."""
+    if src.dtype != dst.dtype or not src.is_cuda or src.stride(-1) != 1 or dst.stride(-1) != 1:
+        raise G2Error("gather_rows: src/dst must be CUDA tensors of the same dtype, contiguous rows")
+    if idx is not None:
+        _req(idx, torch.int64, "idx")
+    width = (row_elems if row_elems is not None else min(src.shape[1], dst.shape[1])) * src.element_size()
+    _call("g2vlm_gather_rows", _vp(src.data_ptr()), _i64(src.stride(0) * src.element_size()),
+          _vp(dst.data_ptr()), _i64(dst.stride(0) * dst.element_size()), _ptr(idx), _i64(n_rows),
+          _i64(width), _i32(int(scatter)))
+    return dst
+
+
+def rmsnorm_routed(x, out, w_a, w_b, n_first: int, eps: float, rows: Optional[int] = None):
+    _req(x, torch.float32, "x")
+    rows = x.shape[0] if rows is None else rows
+    _call("g2vlm_rmsnorm_routed", _vp(x.data_ptr()), _i64(x.stride(0)), _vp(out.data_ptr()),
+          _i64(out.stride(0)), _i32(int(out.dtype == torch.bfloat16)), _vp(w_a.data_ptr()),
+          _vp(w_b.data_ptr()), _i64(rows), _i64(n_first), _i32(x.shape[1]), _f32(eps))
+    return out
+
+
+def layernorm(x, out, w, b, eps: float, rows: Optional[int] = None, seg_in: int = 0, seg_skip: int = 0):
+    _req(x, torch.float32, "x")
+    rows = x.shape[0] if rows is None else rows
+    _call("g2vlm_layernorm", _vp(x.data_ptr()), _i64(x.stride(0)), _vp(out.data_ptr()), _i64(out.stride(0)),
+          _i32(int(out.dtype == torch.bfloat16)), _vp(w.data_ptr()), _vp(b.data_ptr()), _i64(rows),
+          _i32(x.shape[1]), _f32(eps), _i32(seg_in), _i32(seg_skip))
+    return out
+
+
+def mrope_table(position_ids, inv_freq, cos, sin, sections):
+    _req(position_ids, torch.int64, "position_ids")
+    rows, half = position_ids.shape[1], inv_freq.numel()
+    _call("g2vlm_mrope_table", _vp(position_ids.data_ptr()), _i64(position_ids.stride(0)),
+          _vp(inv_freq.data_ptr()), _vp(cos.data_ptr()), _vp(sin.data_ptr()), _i64(rows), _i32(half),
+          _i32(sections[0]), _i32(sections[1]))
+
+
+def qknorm_mrope(qkv, rows, n_first, n_q, n_kv, head_dim, qw_a, kw_a, qw_b, kw_b, cos, sin, eps,
+                 round_normed=False):
+    _req(qkv, torch.bfloat16, "qkv")
+    _call("g2vlm_qknorm_mrope", _vp(qkv.data_ptr()), _i64(qkv.stride(0)), _i64(rows), _i64(n_first),
+          _i32(n_q), _i32(n_kv), _i32(head_dim), _vp(qw_a.data_ptr()), _vp(kw_a.data_ptr()),
+          _vp(qw_b.data_ptr()), _vp(kw_b.data_ptr()), _vp(cos.data_ptr()), _vp(sin.data_ptr()), _f32(eps),
+          _i32(int(round_normed)))
+
+
+def im2col_patches(images, out, patch: int):
+    _req(images, torch.float32, "images")
+    _req(out, torch.bfloat16, "out")
+    n, _, H, W = images.shape
+    if not images.is_contiguous() or not out.is_contiguous():
+        raise G2Error("im2col: contiguous tensors required")
+    _call("g2vlm_im2col_patches", _vp(images.data_ptr()), _vp(out.data_ptr()), _i32(n), _i32(H), _i32(W),
+          _i32(patch), _i32(out.shape[1]))
+    return out
+
+
+def dino_embed(patch_emb, cls, reg, pos, out, n: int, P: int, n_reg: int):
+    _req(patch_emb, torch.bfloat16, "patch_emb")
+    _req(out, torch.float32, "out")
+    _call("g2vlm_dino_embed", _vp(patch_emb.data_ptr()), _i64(patch_emb.stride(0)), _vp(cls.data_ptr()),
+          _vp(reg.data_ptr()), _vp(pos.data_ptr()), _vp(out.data_ptr()), _i32(n), _i32(P), _i32(n_reg),
+          _i32(out.shape[1]))
+    return out
+
+
+def rope2d(buf, rows, n_heads_total, head_stride, head_dim, tokens_per_view, grid_w, cos, sin, bf16_ops=True):
+    _req(buf, torch.bfloat16, "buf")
+    _call("g2vlm_rope2d", _vp(buf.data_ptr()), _i64(buf.stride(0)), _i64(rows), _i32(n_heads_total),
+          _i32(head_stride), _i32(head_dim), _i32(tokens_per_view), _i32(grid_w), _vp(cos.data_ptr()),
+          _vp(sin.data_ptr()), _i32(int(bf16_ops)))
+
+
+def points_epilogue(feat, poses, out0, out1, n, H, W, patch, mode):
+    _req(feat, torch.float32, "feat")
+    _call("g2vlm_points_epilogue", _vp(feat.data_ptr()), _i64(feat.stride(0)), _ptr(poses), _vp(out0.data_ptr()),
+          _ptr(out1), _i32(n), _i32(H), _i32(W), _i32(patch), _i32(mode))
+
+
+def mean_pool(x, out, n_views, tokens):
+    _req(x, torch.float32, "x")
+    _call("g2vlm_mean_pool", _vp(x.data_ptr()), _i64(x.stride(0)), _vp(out.data_ptr()), _i32(n_views),
+          _i32(tokens), _i32(x.shape[1]))
+    return out
+
+
+def split3(x, out, rows: Optional[int] = None):
+    _req(x, torch.float32, "x")
+    _req(out, torch.bfloat16, "out")
+    rows = x.shape[0] if rows is None else rows
+    _call("g2vlm_split3_f32", _vp(x.data_ptr()), _i64(x.stride(0)), _vp(out.data_ptr()), _i64(out.stride(0)),
+          _i64(rows), _i32(x.shape[1]))
+    return out
+
+
+def cast_bf16(x, out, rows: Optional[int] = None):
+    _req(x, torch.float32, "x")
+    _req(out, torch.bfloat16, "out")
+    rows = x.shape[0] if rows is None else rows
+    _call("g2vlm_cast_f32_to_bf16", _vp(x.data_ptr()), _i64(x.stride(0)), _vp(out.data_ptr()),
+          _i64(out.stride(0)), _i64(rows), _i32(x.shape[1]))
+    return out
+
+
+def camera_pose(feat, w_t, b_t, w_r, b_r, poses):
+    _req(feat, torch.float32, "feat")
+    _call("g2vlm_camera_pose", _vp(feat.data_ptr()), _i64(feat.stride(0)), _vp(w_t.data_ptr()),
+          _vp(b_t.data_ptr()), _vp(w_r.data_ptr()), _vp(b_r.data_ptr()), _vp(poses.data_ptr()),
+          _i32(feat.shape[0]), _i32(feat.shape[1]))
+    return poses

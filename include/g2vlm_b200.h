@@ -131,6 +131,104 @@ typedef struct g2vlm_attn_args {
 
 int g2vlm_attention(const g2vlm_attn_args* args, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Memory-bound kernels (vectorised, coalesced, warp-shuffle reductions). "Routed" kernels take the
+ * expert-permuted row order: rows [0, n_first) use the *_a weights, rows [n_first, rows) the *_b
+ * weights (geo expert first, und expert second).
+ * ---------------------------------------------------------------------------------------------- */
+
+/* dst[i, :] = src[idx[i], :] (gather) or dst[idx[i], :] = src[i, :] (scatter); idx == NULL is the
+ * identity. Rows are `row_bytes` long (multiple of 16; pointers / pitches 16-byte aligned).
+ * Replaces the index_select / index_put_ routing copies of modeling/g2vlm/qwen2vl.py:584-606,
+ * 657-658, 863-864, 1326-1328, the embedding lookup g2vlm.py:984 and the KV merge :621-638. */
+int g2vlm_gather_rows(const void* src, int64_t src_pitch_bytes, void* dst, int64_t dst_pitch_bytes,
+                      const int64_t* idx, int64_t n_rows, int64_t row_bytes, int32_t scatter,
+                      void* stream);
+
+/* Qwen2RMSNorm (modeling/qwen2vl/modeling_qwen2_vl.py:496-501), routed (g2vlm/qwen2vl.py:862-865,
+ * 897-898, 1326-1328): out = w * (x * rsqrt(mean(x^2) + eps)), x fp32 [rows, dim].
+ * out_bf16 != 0: out is bf16 (the `.to(torch.bfloat16)` that follows the norm), else fp32. */
+int g2vlm_rmsnorm_routed(const float* x, int64_t ldx, void* out, int64_t ldo, int32_t out_bf16,
+                         const float* w_a, const float* w_b, int64_t rows, int64_t n_first,
+                         int32_t dim, float eps, void* stream);
+
+/* nn.LayerNorm(eps, affine) fp32 -> bf16 or fp32 (DINO norm1/norm2/layernorm
+ * g2vlm/dinov2_model.py:203-210,285; Pi3 norm1/2/3/norm_y pi3/models/layers/block.py:281-382).
+ * If seg_in > 0 rows are grouped in segments of seg_in rows of which the first seg_skip are
+ * dropped from the output (final DINO norm + `[:, 1+num_register_tokens:]`, dinov2_model.py:351-354);
+ * output rows are then compacted. */
+int g2vlm_layernorm(const float* x, int64_t ldx, void* out, int64_t ldo, int32_t out_bf16,
+                    const float* w, const float* b, int64_t rows, int32_t dim, float eps,
+                    int32_t seg_in, int32_t seg_skip, void* stream);
+
+/* M-RoPE angle table (Qwen2VLRotaryEmbedding.forward modeling_qwen2_vl.py:141-166 + section gather
+ * of apply_multimodal_rotary_pos_emb :223-227): position_ids int64 [3, rows] (row stride ld_pos),
+ * inv_freq fp32 [half], sections s0+s1+s2 = half -> cos, sin fp32 [rows, half]. */
+int g2vlm_mrope_table(const int64_t* position_ids, int64_t ld_pos, const float* inv_freq,
+                      float* cos_out, float* sin_out, int64_t rows, int32_t half, int32_t s0,
+                      int32_t s1, void* stream);
+
+/* Per-head RMSNorm + M-RoPE, in place on a fused bf16 QKV buffer [rows, ld] whose columns are
+ * [q heads | k heads | v heads] x head_dim (=128): routed q_norm/k_norm weights, fp32 math, bf16
+ * result (g2vlm/qwen2vl.py:600-619; rotate_half modeling_qwen2_vl.py:170-174, 229-231).
+ * round_normed != 0 reproduces the `und` branch where the norm runs on a bf16 tensor (:575-576). */
+int g2vlm_qknorm_mrope(void* qkv, int64_t ld, int64_t rows, int64_t n_first, int32_t n_q_heads,
+                       int32_t n_kv_heads, int32_t head_dim, const float* qw_a, const float* kw_a,
+                       const float* qw_b, const float* kw_b, const float* cos_tab,
+                       const float* sin_tab, float eps, int32_t round_normed, void* stream);
+
+/* DINO patch embedding input: images fp32 [n, 3, H, W] -> bf16 patches [n*gh*gw, k_pad] in
+ * (channel, py, px) order = nn.Conv2d(3, D, 14, 14) as a GEMM
+ * (dinov2_with_registers/modeling_dinov2_with_registers.py:62,71); columns >= 3*p*p are zero. */
+int g2vlm_im2col_patches(const float* images, void* out, int32_t n, int32_t H, int32_t W,
+                         int32_t patch, int32_t k_pad, void* stream);
+
+/* Dinov2WithRegistersEmbeddings.forward (:147-171): rows per image = [cls+pos0, registers,
+ * patch_i + pos_{1+i}]; patch_emb bf16 [n*P, dim], pos fp32 [1+P, dim] (already resampled if the
+ * grid differs from the table), out fp32 [n*(1+n_reg+P), dim]. */
+int g2vlm_dino_embed(const void* patch_emb, int64_t ld_patch, const float* cls, const float* reg,
+                     const float* pos, float* out, int32_t n, int32_t P, int32_t n_reg, int32_t dim,
+                     void* stream);
+
+/* RoPE2D (pi3/models/layers/pos_embed.py:112-159) in place on the q and k parts of a fused bf16
+ * buffer [rows, ld]: n_heads_total heads of `head_stride` columns starting at column 0, of which the
+ * first head_dim columns are real (96 padded to 128). Token position: n = row % tokens_per_view,
+ * (y, x) = (n / grid_w, n % grid_w). cos/sin tables fp32 [n_pos, head_dim/4] are built by the host
+ * exactly as the reference's cache (:118-128; bf16-rounded angles in bf16 mode, quirk Q2).
+ * bf16_ops != 0: every elementwise product / sum is rounded to bf16 as in the reference. */
+int g2vlm_rope2d(void* buf, int64_t ld, int64_t rows, int32_t n_heads_total, int32_t head_stride,
+                 int32_t head_dim, int32_t tokens_per_view, int32_t grid_w, const float* cos_tab,
+                 const float* sin_tab, int32_t bf16_ops, void* stream);
+
+/* Pi3LinearPts3d pixel-shuffle (transformer_head.py:77-81) fused with the recon epilogue
+ * (g2vlm.py:1203-1205, 1226; homogenize_points pi3/utils/geometry.py:108-113).
+ * feat fp32 [n*gh*gw, 3*p*p]. mode 0: out0 = pixel-shuffled (n,H,W,3) (global_points);
+ * mode 1: out0 = local_points = (x*e^z, y*e^z, e^z), out1 = points = R*local + t with poses fp32
+ * [n,4,4]. */
+int g2vlm_points_epilogue(const float* feat, int64_t ld_feat, const float* poses, float* out0,
+                          float* out1, int32_t n, int32_t H, int32_t W, int32_t patch, int32_t mode,
+                          void* stream);
+
+/* out[v, :] = mean over the tokens of view v (AdaptiveAvgPool2d(1), camera_head.py:55). */
+int g2vlm_mean_pool(const float* x, int64_t ldx, float* out, int32_t n_views, int32_t tokens,
+                    int32_t dim, void* stream);
+
+/* fp32 [rows, k] -> bf16 [rows, 3k] = [hi | hi | lo] (split-bf16 operand for fp32-accurate GEMMs on
+ * the bf16 tensor cores; weights are stored as [hi | lo | hi]). */
+int g2vlm_split3_f32(const float* x, int64_t ldx, void* out, int64_t ldo, int64_t rows, int32_t k,
+                     void* stream);
+
+/* Elementwise dtype cast fp32 [rows, cols] -> bf16 (the implicit autocast cast in front of a Linear
+ * whose input is the fp32 residual stream, e.g. Pi3 linear_out, transformer_head.py:55). */
+int g2vlm_cast_f32_to_bf16(const float* x, int64_t ldx, void* out, int64_t ldo, int64_t rows,
+                           int32_t cols, void* stream);
+
+/* fc_t / fc_rot + svd_orthogonalize + 4x4 assembly (camera_head.py:59-93), fp32:
+ * feat fp32 [n, dim]; w_t [3, dim], b_t [3], w_r [9, dim], b_r [9] -> poses fp32 [n, 4, 4]. */
+int g2vlm_camera_pose(const float* feat, int64_t ldf, const float* w_t, const float* b_t,
+                      const float* w_r, const float* b_r, float* poses, int32_t n, int32_t dim,
+                      void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,112 @@
+"""End-to-end parity of the CUDA recon path (G2VLMFast, through the C ABI) against the CPU oracle
+(oracle/restate.py, bf16 mode) and against the golden fixtures produced by the unmodified reference.
+Tolerance: BASELINE.json — max rel err <= 2e-2 in bf16 mode (max|a-b| / max|ref|)."""
+import os
+
+import pytest
+import torch
+
+from g2vlm_b200 import schema
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+TOL = 2e-2
+
+
+class StubTokenizer:
+    def encode(self, prompt):
+        return [11, 12, 13, 14, 15, 16]
+
+
+TOKENS = dict(bos_token_id=1, eos_token_id=2, start_of_image=3, end_of_image=4)
+
+
+def _maxrel(a, b, scale=None):
+    a, b = a.float().cpu(), b.float().cpu()
+    scale = b.abs().max() if scale is None else scale
+    return ((a - b).abs().max() / scale).item()
+
+
+@pytest.fixture(scope="module")
+def tiny():
+    from g2vlm_b200.model import G2VLMFast
+    sd = schema.init_synthetic(schema.TINY, seed=0)
+    return sd, G2VLMFast(schema.TINY, sd)
+
+
+def _views(case):
+    v = schema.synthetic_views(case["n"], case["h"], case["w"], seed=case["seed"])
+    return (v * 255).round() / 255.0
+
+
+@pytest.mark.parametrize("case", [dict(n=3, h=70, w=518, seed=1), dict(n=2, h=140, w=518, seed=7)])
+def test_recon_matches_oracle_stagewise(tiny, case):
+    from oracle import restate
+    sd, model = tiny
+    v = _views(case)
+    c_ref, c_out = {}, {}
+    ref = restate.recon(sd, schema.TINY, v, mode="bf16", collect=c_ref)
+    out = model.recon(StubTokenizer(), dict(TOKENS), None, v, collect=c_out)
+    torch.cuda.synchronize()
+    # exact routing / permutation / position indices
+    gi_ref, _, _ = restate.prepare_dino_images(v, 7, 7, 3, 4)
+    for k in ("packed_text_indexes", "packed_dino_token_indexes", "packed_position_ids", "packed_indexes",
+              "packed_key_value_indexes", "dino_token_seqlens", "packed_seqlens", "packed_text_ids"):
+        assert torch.equal(c_out["generation_input"][k].cpu(), gi_ref[k]), k
+    errs = {}
+    for i, (a, b) in enumerate(zip(c_out["dino_layers"], c_ref["dino_layers"])):
+        errs[f"dino{i}"] = _maxrel(a, b)
+    errs["dino_tokens"] = _maxrel(c_out["dino_tokens"].view_as(c_ref["dino_tokens"]), c_ref["dino_tokens"])
+    errs["packed_sequence"] = _maxrel(c_out["packed_sequence"], c_ref["packed_sequence"])
+    for i, (a, b) in enumerate(zip(c_out["mot_layers"], c_ref["mot_layers"])):
+        errs[f"mot{i}"] = _maxrel(a, b)
+    errs["last_hidden"] = _maxrel(c_out["last_hidden"], c_ref["last_hidden"])
+    for k in ("point_hidden", "camera_hidden", "global_hidden"):
+        errs[k] = _maxrel(c_out[k], c_ref[k])
+    for k in ("local_points", "points", "global_points", "camera_poses"):
+        errs[k] = _maxrel(out[k], ref[k])
+    print("\n" + "\n".join(f"  {k:18s} {e:.3e}" for k, e in errs.items()))
+    bad = {k: e for k, e in errs.items() if not e < TOL}
+    assert not bad, bad
+    assert out["conf"] is None
+    assert torch.equal(out["images"][0].cpu(), v)
+
+
+@pytest.mark.parametrize("name", ["a", "b"])
+def test_recon_matches_reference_golden(tiny, name):
+    g = torch.load(os.path.join(GOLDEN, f"recon_tiny_{name}.pt"))
+    sh, sw, st = g["stride"]
+    _, model = tiny
+    c = {}
+    out = model.recon(StubTokenizer(), dict(TOKENS), None, _views(g["case"]), collect=c)
+    for k in ("packed_text_indexes", "packed_dino_token_indexes", "packed_position_ids", "packed_indexes",
+              "packed_key_value_indexes", "dino_token_seqlens"):
+        assert torch.equal(c["generation_input"][k].cpu(), g["dino." + k]), k
+    assert _maxrel(c["last_hidden"][::st], g["last_hidden"], g["last_hidden.absmax"]) < TOL
+    for k in ("points", "local_points", "global_points"):
+        assert _maxrel(out[k][:, :, ::sh, ::sw], g[k], g[k + ".absmax"]) < TOL, k
+    assert _maxrel(out["camera_poses"], g["camera_poses"]) < TOL
+
+
+def test_sub_boundaries_keep_reference_contract(tiny):
+    """forward_cache_update_text / _dino return a NaiveCache with the reference's layout."""
+    from g2vlm_b200.model import NaiveCache
+    from oracle import restate
+    sd, model = tiny
+    cfg = schema.TINY
+    v = _views(dict(n=2, h=42, w=518, seed=3))
+    gi, newlens, new_rope = model.prepare_prompts_addbos([0], [0], ["x"], StubTokenizer(), TOKENS)
+    past = model.forward_cache_update_text(NaiveCache(cfg.num_layers), **gi)
+    assert past.seq_lens == 7 and past.key_cache[0].shape == (7, cfg.num_kv_heads, cfg.head_dim)
+    ref_cache = restate.lm_prefill_und(sd, cfg, gi["packed_text_ids"], gi["packed_text_position_ids"], "bf16")
+    for i in range(cfg.num_layers):
+        assert _maxrel(past.key_cache[i], ref_cache[i][0]) < TOL
+        assert _maxrel(past.value_cache[i], ref_cache[i][1]) < TOL
+    gi2, _, _ = model.prepare_dino_images_pi3(newlens, new_rope, v, None, TOKENS)
+    past, last = model.forward_cache_update_dino(past, **gi2)
+    T = int(gi2["packed_seqlens"][0])
+    assert last.shape == (T, cfg.hidden_size) and last.dtype == torch.float32
+    assert past.key_cache[1].shape == (T + 7, cfg.num_kv_heads, cfg.head_dim)
+    assert past.key_cache[1].dtype == torch.bfloat16
+    # the prefix rows of the merged cache are the prefill K/V (packed_key_value_indexes = arange(K0))
+    assert _maxrel(past.key_cache[1][:7], ref_cache[1][0]) < TOL
