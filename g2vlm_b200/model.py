@@ -68,7 +68,7 @@ def _pad_head_rows(w: torch.Tensor, n_heads: int, hd: int, hp: int) -> torch.Ten
     if hd == hp:
         return w
     shape = (n_heads, hd) + tuple(w.shape[1:])
-    out = torch.zeros((n_heads, hp) + tuple(w.shape[1:]), dtype=w.dtype)
+    out = torch.zeros((n_heads, hp) + tuple(w.shape[1:]), dtype=w.dtype, device=w.device)
     out[:, :hd] = w.reshape(shape)
     return out.reshape((n_heads * hp,) + tuple(w.shape[1:]))
 
@@ -77,7 +77,7 @@ def _pad_head_cols(w: torch.Tensor, n_heads: int, hd: int, hp: int) -> torch.Ten
     """[out, n_heads*hd] -> [out, n_heads*hp]."""
     if hd == hp:
         return w
-    out = torch.zeros(w.shape[0], n_heads, hp, dtype=w.dtype)
+    out = torch.zeros(w.shape[0], n_heads, hp, dtype=w.dtype, device=w.device)
     out[:, :, :hd] = w.reshape(w.shape[0], n_heads, hd)
     return out.reshape(w.shape[0], n_heads * hp)
 
@@ -131,6 +131,13 @@ class G2VLMFast:
         self._rope2d_cache: Dict[tuple, tuple] = {}
         self._pos_cache: Dict[tuple, torch.Tensor] = {}
         self._work_cache: Dict[tuple, torch.Tensor] = {}
+        self.stage_events: Optional[list] = None  # bench.py: [(name, cuda event)] at stage boundaries
+
+    def _mark(self, name: str) -> None:
+        if self.stage_events is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            self.stage_events.append((name, ev))
 
     @classmethod
     def from_state_dict(cls, cfg: G2Config, state_dict, device="cuda") -> "G2VLMFast":
@@ -141,7 +148,7 @@ class G2VLMFast:
     # ------------------------------------------------------------------------------------------
     def _pack(self, sd):
         cfg, dev = self.cfg, self.device
-        g = lambda k: sd[k].detach().float().cpu()
+        g = lambda k: sd[k].detach().float()  # packed on whatever device the checkpoint lives on
         lm = "language_model.model."
         self.embed = _f32(g(lm + "embed_tokens.weight"), dev)
         self.layers = []
@@ -181,13 +188,14 @@ class G2VLMFast:
         d = "dino_model."
         kp = 3 * cfg.dino_patch ** 2
         self.dino_kpad = (kp + 63) // 64 * 64
-        wp = torch.zeros(D, self.dino_kpad)
-        wp[:, :kp] = g(d + "embeddings.patch_embeddings.projection.weight").reshape(D, kp)
+        wpatch = g(d + "embeddings.patch_embeddings.projection.weight").reshape(D, kp)
+        wp = torch.zeros(D, self.dino_kpad, device=wpatch.device)
+        wp[:, :kp] = wpatch
         self.dino_wpatch = _bf16(wp, dev)
         self.dino_bpatch = _bias_bf16(g(d + "embeddings.patch_embeddings.projection.bias"), dev)
         self.dino_cls = _f32(g(d + "embeddings.cls_token").reshape(D), dev)
         self.dino_reg = _f32(g(d + "embeddings.register_tokens").reshape(cfg.dino_registers, D), dev)
-        self.dino_pos_table = g(d + "embeddings.position_embeddings")  # CPU master, resampled per grid
+        self.dino_pos_table = g(d + "embeddings.position_embeddings")  # master table, resampled per grid
         self.dino_layers = []
         for i in range(cfg.dino_layers):
             p = f"{d}encoder.layer.{i}."
@@ -493,8 +501,10 @@ class G2VLMFast:
         T, H = int(sum(packed_seqlens.tolist())), cfg.hidden_size
         if packed_dino_images.shape[0] < 1:
             raise ValueError("at least one view is required")
+        self._mark("dino_begin")
         tokens = self.dino_forward(packed_dino_images, dino_token_seqlens,
                                    collect=None if collect is None else collect.setdefault("dino_layers", []))
+        self._mark("dino_end")
         n_geo = tokens.shape[0]
         geo_emb = self.buf.get("mot.geo_emb", (n_geo, H), torch.float32)
         ops.gemm(tokens, self.w_dino2llm, geo_emb, epilogue=ops.EPI_STORE_F32, bias=self.b_dino2llm,
@@ -512,6 +522,7 @@ class G2VLMFast:
             packed, packed_position_ids, packed_dino_token_indexes, packed_text_indexes, past_key_values,
             update_past_key_values=update_past_key_values,
             collect=None if collect is None else collect.setdefault("mot_layers", []))
+        self._mark("mot_end")
         return past_key_values, last
 
     # ------------------------------------------------------------------------------------------
@@ -638,6 +649,7 @@ class G2VLMFast:
                  flags=ops.GEMM_ACCUMULATE)
         ops.points_epilogue(feat_pts, None, global_points, None, N, Hh, Ww, p, 0)
 
+        self._mark("heads_end")
         if original_images is not None and original_images.dim() == 4:
             original_images = original_images.unsqueeze(0)
         return dict(points=points[None], local_points=local_points[None], conf=None, camera_poses=poses[None],
@@ -659,6 +671,7 @@ class G2VLMFast:
         `images`: list of paths / PIL images, or an (N,3,H,W) tensor in [0,1] (H, W multiples of 14)."""
         dev = self.device
         past = NaiveCache(self.cfg.num_layers)
+        self._mark("start")
         gi, newlens, new_rope = self.prepare_prompts_addbos([0], [0], ["Reconstruct the 3D scene."], tokenizer,
                                                             new_token_ids)
         gi = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in gi.items()}

@@ -21,7 +21,12 @@ class G2Error(RuntimeError):
     pass
 
 
+LAUNCHES = 0  # number of C-ABI kernel launches issued by this process (bench.py reads it)
+
+
 def _check(rc: int) -> None:
+    global LAUNCHES
+    LAUNCHES += 1
     if rc != 0:
         msg = _lib.load().g2vlm_last_error().decode()
         raise G2Error(f"g2vlm_b200 C ABI call failed (code {rc}): {msg}")

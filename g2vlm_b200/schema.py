@@ -162,24 +162,26 @@ def state_dict_schema(cfg: G2Config) -> "OrderedDict[str, Tuple[int, ...]]":
     return s
 
 
-def init_synthetic(cfg: G2Config, seed: int = 0, embed_rows: int | None = None) -> Dict[str, torch.Tensor]:
+def init_synthetic(cfg: G2Config, seed: int = 0, embed_rows: int | None = None,
+                   device: str = "cpu") -> Dict[str, torch.Tensor]:
     """Seeded synthetic weights: Linear/Conv/Embedding/bias/token tensors ~ N(0, 0.02^2),
     norm weights and LayerScale/lambda ~ U(0.5, 1.5); geo and und experts independent.  Each tensor has
     its own generator keyed by (seed, index) so the result does not depend on generation order.
-    ``embed_rows`` truncates the embedding table (the benchmark only needs the few ids recon uses)."""
+    ``embed_rows`` truncates the embedding table (the benchmark only needs the few ids recon uses).
+    ``device="cuda"`` generates on the GPU (fast for the 3.4 B-parameter full model; a different but
+    equally seeded stream than the CPU generator — copy the result to the host when the oracle needs
+    the same weights)."""
     sd: Dict[str, torch.Tensor] = {}
     for idx, (name, shape) in enumerate(state_dict_schema(cfg).items()):
         if name.endswith("embed_tokens.weight") and embed_rows is not None:
             shape = (embed_rows, shape[1])
-        g = torch.Generator().manual_seed(seed * 1000003 + idx)
+        g = torch.Generator(device=device).manual_seed(seed * 1000003 + idx)
         leaf = name.rsplit(".", 2)
         is_norm_w = name.endswith(".weight") and ("norm" in leaf[-2] or leaf[-2] == "layernorm")
         if is_norm_w or name.endswith(".gamma") or name.endswith(".lambda1"):
-            t = torch.rand(shape, generator=g) + 0.5
-        elif name.endswith(".bias") and ("norm" in leaf[-2] or leaf[-2] == "layernorm"):
-            t = torch.randn(shape, generator=g) * 0.02
+            t = torch.rand(shape, generator=g, device=device) + 0.5
         else:
-            t = torch.randn(shape, generator=g) * 0.02
+            t = torch.randn(shape, generator=g, device=device) * 0.02
         sd[name] = t
     return sd
 
