@@ -186,6 +186,8 @@ def main():
     ap.add_argument("--cpu-views", type=int, default=1)
     ap.add_argument("--cpu-layer-frac", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile", action="store_true",
+                    help="profiling run under ncu: skip the e2e arm and the CPU baseline, allow warmup < 3 (not a bench value)")
     ap.add_argument("--tiny", action="store_true", help="tiny model dims (smoke / debugging only; INVALID as a benchmark)")
     args = ap.parse_args()
 
@@ -204,7 +206,7 @@ def main():
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    if args.warmup < 3:
+    if args.warmup < 3 and not args.profile:
         args.warmup = 3  # timing rule: at least 3 warm-up steps
 
     cfg = schema.TINY if args.tiny else schema.FULL
@@ -298,9 +300,13 @@ def main():
             stage.setdefault("heads_ms", []).append(ev["mot_end"].elapsed_time(ev["heads_end"]))
     stage = {k: sum(v) / len(v) for k, v in stage.items()}
 
-    for _ in range(2):
-        step_e2e()
-    ms_e2e, _ = timed(step_e2e, args.steps)
+    if args.profile:
+        ms_e2e = float("nan")
+        args.no_cpu_baseline = True
+    else:
+        for _ in range(2):
+            step_e2e()
+        ms_e2e, _ = timed(step_e2e, args.steps)
 
     if rank != 0:
         if dist is not None:

@@ -117,10 +117,14 @@ attention_tcgen05_kernel(const __grid_constant__ AttnKParams p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tS[2] = {tmem_base, tmem_base + 128};
-  const uint32_t tO[2] = {tmem_base + 256, tmem_base + 384};
+  // TMEM columns of tile t: S/P at t*128, O at 256 + t*128 (plain arithmetic: no local arrays)
+  auto tS = [&](int t) { return tmem_base + static_cast<uint32_t>(t) * 128u; };
+  auto tO = [&](int t) { return tmem_base + 256u + static_cast<uint32_t>(t) * 128u; };
 
+  // Register budget (setmaxnreg must sit INSIDE each role branch so ptxas knows which budget governs
+  // which code): 4 control warps x 32 x 80 + 8 softmax warps x 32 x 208 = 63488 <= 65536.
   if (warp == 0) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
     // ------------------------------------ TMA producer ----------------------------------------
     if (elect_one() && nblk > 0) {
       mbar_arrive_expect_tx(q_full, 2 * Cfg::kTileBytes);
@@ -148,6 +152,7 @@ attention_tcgen05_kernel(const __grid_constant__ AttnKParams p) {
       }
     }
   } else if (warp == 1) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
     // ------------------------------------ MMA issuer ------------------------------------------
     if (elect_one() && nblk > 0) {
       constexpr uint32_t idesc_qk = umma_idesc_bf16(ATT_BM, ATT_BN, 0, 0);
@@ -161,7 +166,7 @@ attention_tcgen05_kernel(const __grid_constant__ AttnKParams p) {
 #pragma unroll
         for (int k = 0; k < KSTEPS_QK; ++k) {
           const uint32_t off = (k >> 2) * BOX_BYTES + (k & 3) * 32;
-          umma_ss(tS[t], umma_desc_kmajor(qa + off), umma_desc_kmajor(ka + off), idesc_qk, k != 0);
+          umma_ss(tS(t), umma_desc_kmajor(qa + off), umma_desc_kmajor(ka + off), idesc_qk, k != 0);
         }
         umma_commit(&s_full[t]);
       };
@@ -170,7 +175,7 @@ attention_tcgen05_kernel(const __grid_constant__ AttnKParams p) {
 #pragma unroll
         for (int k = 0; k < KSTEPS_PV; ++k) {
           // 16 keys = 16 rows of 128 B inside each 64-column box; boxes are BOX_BYTES apart (LBO)
-          umma_ts(tO[t], tS[t] + k * 8, umma_desc_mnmajor(va + k * 2048, BOX_BYTES), idesc_pv,
+          umma_ts(tO(t), tS(t) + k * 8, umma_desc_mnmajor(va + k * 2048, BOX_BYTES), idesc_pv,
                   (j | k) != 0);
         }
         umma_commit(&o_done[t]);
@@ -206,7 +211,10 @@ attention_tcgen05_kernel(const __grid_constant__ AttnKParams p) {
         }
       }
     }
-  } else if (warp >= 4) {
+  } else if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
     // ------------------------------------ softmax / correction / epilogue ---------------------
     const int t = (warp - 4) >> 2;              // query tile 0 or 1
     const int sub = warp & 3;                   // TMEM sub-partition
@@ -214,8 +222,8 @@ attention_tcgen05_kernel(const __grid_constant__ AttnKParams p) {
     const int row = q_tile_begin + t * ATT_BM + r_in_tile;  // global query row
     const bool row_ok = row < q_seg_end;
     const uint32_t lane_off = static_cast<uint32_t>(sub * 32) << 16;
-    const uint32_t tS_w = tS[t] + lane_off;
-    const uint32_t tO_w = tO[t] + lane_off;
+    const uint32_t tS_w = tS(t) + lane_off;
+    const uint32_t tO_w = tO(t) + lane_off;
     // number of keys this row may see
     int limit = len_k;
     if (p.causal) limit = max(0, min(len_k, (row - q_seg_begin) + (len_k - len_q) + 1));
