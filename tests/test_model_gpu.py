@@ -110,3 +110,30 @@ def test_sub_boundaries_keep_reference_contract(tiny):
     assert past.key_cache[1].dtype == torch.bfloat16
     # the prefix rows of the merged cache are the prefill K/V (packed_key_value_indexes = arange(K0))
     assert _maxrel(past.key_cache[1][:7], ref_cache[1][0]) < TOL
+
+
+def test_full_width_reduced_depth():
+    """Every kernel at its FULL-SIZE shapes (H 1536, I 8960, 12:2 GQA, DINO 1024, decoder 16x96 padded to
+    128, 518x518 views, P 1369) on a depth-1 model so that the CPU oracle finishes in seconds."""
+    from dataclasses import replace
+
+    from g2vlm_b200.model import G2VLMFast
+    from oracle import restate
+    cfg = replace(schema.FULL, num_layers=1, dino_layers=1, dec_depth=1)
+    sd = schema.init_synthetic(cfg, seed=3, embed_rows=32)
+    model = G2VLMFast(cfg, sd)
+    v = _views(dict(n=2, h=518, w=518, seed=4))
+    c_ref, c_out = {}, {}
+    ref = restate.recon(sd, cfg, v, mode="bf16", collect=c_ref)
+    out = model.recon(StubTokenizer(), dict(TOKENS), None, v, collect=c_out)
+    errs = {"dino_tokens": _maxrel(c_out["dino_tokens"].view_as(c_ref["dino_tokens"]), c_ref["dino_tokens"]),
+            "mot0": _maxrel(c_out["mot_layers"][0], c_ref["mot_layers"][0]),
+            "last_hidden": _maxrel(c_out["last_hidden"], c_ref["last_hidden"])}
+    for k in ("point_hidden", "camera_hidden", "global_hidden"):
+        errs[k] = _maxrel(c_out[k], c_ref[k])
+    for k in ("local_points", "points", "global_points", "camera_poses"):
+        errs[k] = _maxrel(out[k], ref[k])
+    print("\n" + "\n".join(f"  {k:18s} {e:.3e}" for k, e in errs.items()))
+    assert all(e < TOL for e in errs.values()), errs
+    del model
+    torch.cuda.empty_cache()
