@@ -331,7 +331,8 @@ class G2VLMFast:
     # ------------------------------------------------------------------------------------------
     # MoT language model
     # ------------------------------------------------------------------------------------------
-    def _mot_layer(self, L, x, T, n_geo, qkv, attn, act, hbuf, cos, sin, work, kv_rows, causal, round_normed):
+    def _mot_layer(self, L, x, T, n_geo, qkv, attn, act, hbuf, cos, sin, work, kv_rows, causal, round_normed,
+                   kv_exchange=None):
         cfg = self.cfg
         H, I = cfg.hidden_size, cfg.intermediate_size
         nq, nkv, hd = cfg.num_heads, cfg.num_kv_heads, cfg.head_dim
@@ -340,9 +341,12 @@ class G2VLMFast:
         ops.gemm(hbuf[:T], L["wqkv"], qkv, epilogue=ops.EPI_STORE_BF16, groups=groups, bias=L["bqkv"])
         ops.qknorm_mrope(qkv, T, n_geo, nq, nkv, hd, L["q_norm_geo"], L["k_norm_geo"], L["q_norm_und"],
                          L["k_norm_und"], cos, sin, cfg.rms_norm_eps, round_normed=round_normed)
-        ops.attention(qkv[:T, : nq * hd], qkv[:kv_rows, nq * hd:(nq + nkv) * hd], qkv[:kv_rows, (nq + nkv) * hd:],
-                      attn, work, num_q_heads=nq, num_kv_heads=nkv, head_dim=hd, scale=1.0 / math.sqrt(hd),
-                      causal=causal)
+        if kv_exchange is None:
+            k_all, v_all = qkv[:kv_rows, nq * hd:(nq + nkv) * hd], qkv[:kv_rows, (nq + nkv) * hd:]
+        else:  # view-sharded: all ranks' K/V rows (+ prefix) gathered over NVLink
+            k_all, v_all = kv_exchange(qkv)
+        ops.attention(qkv[:T, : nq * hd], k_all, v_all, attn, work, num_q_heads=nq, num_kv_heads=nkv, head_dim=hd,
+                      scale=1.0 / math.sqrt(hd), causal=causal)
         ops.gemm(attn[:T], L["wo"], x, epilogue=ops.EPI_RESID_F32, groups=groups, scale=L["ls1"], scale_groups=1,
                  flags=ops.GEMM_ROUND_AFTER_SCALE)
         ops.rmsnorm_routed(x, hbuf, L["post_attention_layernorm_geo"], L["post_attention_layernorm_und"], n_geo,
@@ -389,7 +393,8 @@ class G2VLMFast:
     @torch.no_grad()
     def language_model_forward_geo(self, packed_sequence, packed_position_ids, packed_geo_token_indexes,
                                    packed_text_indexes, past_key_values: NaiveCache,
-                                   update_past_key_values: bool = True, collect: Optional[list] = None):
+                                   update_past_key_values: bool = True, collect: Optional[list] = None,
+                                   group=None):
         """Qwen2VLModel.forward_inference(mode='geo', is_causal=False) incl. the routed final norm
         (reference g2vlm/qwen2vl.py:1267-1337).  packed_sequence: fp32 [T, H] in packed order."""
         cfg, dev = self.cfg, self.device
@@ -413,16 +418,39 @@ class G2VLMFast:
         ops.gather_rows(cos_p, cos, perm, T)
         ops.gather_rows(sin_p, sin, perm, T)
         qkv, attn, act, hbuf = self._mot_buffers(T, T + K0)
-        work = self._work([0, T], [0, T + K0], "geo")
         kvw = 2 * nkv * hd
+        kv_exchange = None
+        if group is not None:
+            # view-sharded sequence parallelism: this rank holds T of world*T rows (equal shards); per layer
+            # one all-gather of its K|V rows; keys = [rank 0 rows | ... | rank R-1 rows | K0 prefix rows]
+            import torch.distributed as dist
+            world = dist.get_world_size(group)
+            T_all = world * T
+            if update_past_key_values:
+                raise NotImplementedError("the merged NaiveCache is not materialised in view-sharded mode")
+            kv_send = self.buf.get("mot.kv_send", (T, kvw), torch.bfloat16)
+            kv_all = self.buf.get("mot.kv_all", (T_all + K0, kvw), torch.bfloat16)
+            work = self._work([0, T], [0, T_all + K0], "geo_sp")
+
+            def kv_exchange(qkv_):
+                ops.gather_rows(qkv_[:T, nq * hd:], kv_send, None, T)
+                dist.all_gather_into_tensor(kv_all[:T_all], kv_send, group=group)
+                return kv_all[:, : nkv * hd], kv_all[:, nkv * hd:]
+        else:
+            work = self._work([0, T], [0, T + K0], "geo")
         for i, L in enumerate(self.layers):
             if K0:
                 # prefix K/V of the und prefill become key rows [T, T+K0) (KV merge, qwen2vl.py:621-638)
                 pk = past_key_values.key_cache[i].reshape(K0, nkv * hd)
                 pv = past_key_values.value_cache[i].reshape(K0, nkv * hd)
-                ops.gather_rows(pk, qkv[T:, nq * hd:(nq + nkv) * hd], None, K0)
-                ops.gather_rows(pv, qkv[T:, (nq + nkv) * hd:], None, K0)
-            self._mot_layer(L, x, T, n_geo, qkv, attn, act, hbuf, cos, sin, work, T + K0, False, False)
+                if group is None:
+                    ops.gather_rows(pk, qkv[T:, nq * hd:(nq + nkv) * hd], None, K0)
+                    ops.gather_rows(pv, qkv[T:, (nq + nkv) * hd:], None, K0)
+                else:
+                    ops.gather_rows(pk, kv_all[T_all:, : nkv * hd], None, K0)
+                    ops.gather_rows(pv, kv_all[T_all:, nkv * hd:], None, K0)
+            self._mot_layer(L, x, T, n_geo, qkv, attn, act, hbuf, cos, sin, work, T + K0, False, False,
+                            kv_exchange=kv_exchange)
             if update_past_key_values:
                 # reference order of the merged cache: prefix rows, then the packed query rows
                 merged = torch.empty(T + K0, kvw, dtype=torch.bfloat16, device=dev)
@@ -444,30 +472,26 @@ class G2VLMFast:
     # ------------------------------------------------------------------------------------------
     # DINO encoder
     # ------------------------------------------------------------------------------------------
-    @torch.no_grad()
-    def dino_forward(self, packed_pixel_values, dino_token_seqlens, collect: Optional[list] = None):
-        """Dinov2WithRegistersModel.forward with the caller's cu_seqlens (reference
-        g2vlm/dinov2_model.py:301-356, g2vlm.py:988-992) -> bf16 tokens [N*P, D] (post final LN,
-        cls/registers dropped)."""
-        cfg, dev = self.cfg, self.device
-        img = packed_pixel_values.to(dev, torch.float32).contiguous()
-        N, _, Hh, Ww = img.shape
+    def _dino_embeddings(self, img, tag="dino"):
+        """Dinov2WithRegistersEmbeddings.forward: images (n,3,H,W) fp32 on device -> x fp32 [n*S, D]."""
+        cfg = self.cfg
+        n, _, Hh, Ww = img.shape
         p = cfg.dino_patch
         gh, gw = Hh // p, Ww // p
-        P, S, D = gh * gw, gh * gw + 1 + cfg.dino_registers, cfg.dino_hidden
-        nh, hp = cfg.dino_heads, self.dino_hp
-        rows = N * S
-        patches = self.buf.get("dino.patches", (N * P, self.dino_kpad), torch.bfloat16)
+        P, D = gh * gw, cfg.dino_hidden
+        S = P + 1 + cfg.dino_registers
+        patches = self.buf.get(tag + ".patches", (n * P, self.dino_kpad), torch.bfloat16)
         ops.im2col_patches(img, patches, p)
-        emb = self.buf.get("dino.emb", (N * P, D), torch.bfloat16)
+        emb = self.buf.get(tag + ".emb", (n * P, D), torch.bfloat16)
         ops.gemm(patches, self.dino_wpatch, emb, epilogue=ops.EPI_STORE_BF16, bias=self.dino_bpatch)
-        x = self.buf.get("dino.x", (rows, D), torch.float32)
-        ops.dino_embed(emb, self.dino_cls, self.dino_reg, self._dino_pos(gh, gw, Hh == Ww), x, N, P, cfg.dino_registers)
-        cu = [0]
-        for n in dino_token_seqlens.tolist():
-            cu.append(cu[-1] + int(n))
-        if cu[-1] > rows:
-            raise ValueError("dino_token_seqlens exceed the number of DINO rows")
+        x = self.buf.get(tag + ".x", (n * S, D), torch.float32)
+        ops.dino_embed(emb, self.dino_cls, self.dino_reg, self._dino_pos(gh, gw, Hh == Ww), x, n, P, cfg.dino_registers)
+        return x
+
+    def _dino_layers(self, x, rows, cu, collect=None):
+        """The 24 encoder layers in place on x[:rows] (fp32); attention segments `cu` (row offsets)."""
+        cfg = self.cfg
+        D, nh, hp = cfg.dino_hidden, cfg.dino_heads, self.dino_hp
         work = self._work(cu, cu, "dino")
         h = self.buf.get("dino.h", (rows, D), torch.bfloat16)
         qkv = self.buf.get("dino.qkv", (rows, 3 * nh * hp), torch.bfloat16)
@@ -476,6 +500,7 @@ class G2VLMFast:
         attn = self.buf.get("dino.attn", (rows, nh * hp), torch.bfloat16, zero=True)
         mid = self.buf.get("dino.mid", (rows, D * cfg.dino_mlp_ratio), torch.bfloat16)
         scale = 1.0 / math.sqrt(cfg.dino_head_dim)
+        x = x[:rows]
         for L in self.dino_layers:
             ops.layernorm(x, h, L["norm1w"], L["norm1b"], cfg.dino_ln_eps)
             ops.gemm(h, L["wqkv"], qkv, epilogue=ops.EPI_STORE_BF16, bias=L["bqkv"])
@@ -487,23 +512,96 @@ class G2VLMFast:
             ops.gemm(mid, L["wfc2"], x, epilogue=ops.EPI_RESID_F32, bias=L["bfc2"], scale=L["ls2"], scale_groups=1)
             if collect is not None:
                 collect.append(x.clone())
+
+    @torch.no_grad()
+    def dino_forward(self, packed_pixel_values, dino_token_seqlens, collect: Optional[list] = None):
+        """Dinov2WithRegistersModel.forward with the caller's cu_seqlens (reference
+        g2vlm/dinov2_model.py:301-356, g2vlm.py:988-992) -> bf16 tokens [N*P, D] (post final LN,
+        cls/registers dropped)."""
+        cfg, dev = self.cfg, self.device
+        img = packed_pixel_values.to(dev, torch.float32).contiguous()
+        N, _, Hh, Ww = img.shape
+        P = (Hh // cfg.dino_patch) * (Ww // cfg.dino_patch)
+        S, D = P + 1 + cfg.dino_registers, cfg.dino_hidden
+        rows = N * S
+        x = self._dino_embeddings(img)
+        cu = [0]
+        for n in dino_token_seqlens.tolist():
+            cu.append(cu[-1] + int(n))
+        if cu[-1] > rows:
+            raise ValueError("dino_token_seqlens exceed the number of DINO rows")
+        self._dino_layers(x, rows, cu, collect)
         tokens = self.buf.get("dino.tokens", (N * P, D), torch.bfloat16)
         ops.layernorm(x, tokens, self.dino_lnw, self.dino_lnb, cfg.dino_ln_eps, seg_in=S, seg_skip=1 + cfg.dino_registers)
+        return tokens
+
+    @torch.no_grad()
+    def dino_forward_sharded(self, packed_pixel_values_all, shard, group):
+        """View-sharded DINO (sharding.ViewShard): this rank runs the encoder on the flattened rows of ITS
+        attention segments (quirk Q1 makes segments straddle images, so the shard is by segment, every
+        other op being row-local), then one neighbour exchange re-associates rows with images.
+        packed_pixel_values_all: normalised images of the WHOLE scene (host or device); only the images
+        intersecting this rank's rows are embedded. Returns bf16 tokens [n_local*P, D] of the owned views."""
+        import torch.distributed as dist
+        cfg, dev = self.cfg, self.device
+        D, S, P = cfg.dino_hidden, shard.S, shard.P
+        ia, ib = shard.dino_images
+        img = packed_pixel_values_all[ia:ib].to(dev, torch.float32).contiguous()
+        x_img = self._dino_embeddings(img, tag="dino_sp")
+        g0, g1 = shard.dino_rows
+        rows = g1 - g0
+        x = self.buf.get("dino_sp.xrows", (rows, D), torch.float32)
+        ops.gather_rows(x_img[g0 - ia * S:], x, None, rows)
+        c0, c1 = shard.dino_covered_rows
+        cu = [i * P for i in range((c1 - c0) // P + 1)]  # local segment offsets (c0 == g0)
+        self._dino_layers(x, rows, cu)
+        r0, r1 = shard.recv_from_next
+        s0, s1 = shard.send_to_prev
+        normed = self.buf.get("dino_sp.normed", (rows + (r1 - r0), D), torch.bfloat16)
+        ops.layernorm(x, normed, self.dino_lnw, self.dino_lnb, cfg.dino_ln_eps, rows=rows)
+        reqs = []
+        if s1 > s0:
+            send = normed[s0 - g0:s1 - g0]
+            reqs.append(dist.P2POp(dist.isend, send, dist.get_global_rank(group, shard.rank - 1), group))
+        if r1 > r0:
+            recv = normed[rows:rows + (r1 - r0)]
+            reqs.append(dist.P2POp(dist.irecv, recv, dist.get_global_rank(group, shard.rank + 1), group))
+        if reqs:
+            for w in dist.batch_isend_irecv(reqs):
+                w.wait()
+        idx = torch.tensor(shard.token_row_index(), dtype=torch.long) - g0
+        tokens = self.buf.get("dino_sp.tokens", (shard.n_local * P, D), torch.bfloat16)
+        ops.gather_rows(normed, tokens, idx.to(dev), shard.n_local * P)
         return tokens
 
     @torch.no_grad()
     def forward_cache_update_dino(self, past_key_values: NaiveCache, packed_text_ids, packed_text_indexes,
                                   packed_dino_token_indexes, dino_token_seqlens, packed_position_ids, packed_seqlens,
                                   packed_indexes, packed_key_value_indexes, key_values_lens, packed_dino_images,
-                                  original_images, update_past_key_values: bool = True, collect: Optional[dict] = None):
-        """Reference: g2vlm.py:968-1039.  Returns (past_key_values, last_hidden_state [T, H] fp32)."""
+                                  original_images, update_past_key_values: bool = True, collect: Optional[dict] = None,
+                                  shard=None, group=None):
+        """Reference: g2vlm.py:968-1039.  Returns (past_key_values, last_hidden_state [T, H] fp32).
+        With `shard` (sharding.ViewShard) the index tensors describe the WHOLE scene and this rank processes
+        the packed rows of its views only (last_hidden_state then has the local rows)."""
         cfg, dev = self.cfg, self.device
         T, H = int(sum(packed_seqlens.tolist())), cfg.hidden_size
         if packed_dino_images.shape[0] < 1:
             raise ValueError("at least one view is required")
         self._mark("dino_begin")
-        tokens = self.dino_forward(packed_dino_images, dino_token_seqlens,
-                                   collect=None if collect is None else collect.setdefault("dino_layers", []))
+        if shard is None:
+            tokens = self.dino_forward(packed_dino_images, dino_token_seqlens,
+                                       collect=None if collect is None else collect.setdefault("dino_layers", []))
+        else:
+            tokens = self.dino_forward_sharded(packed_dino_images, shard, group)
+            # restrict the scene-wide index tensors to the packed rows [p0, p1) of the owned views
+            p0, p1 = shard.packed_rows
+            T = p1 - p0
+            tsel = (packed_text_indexes >= p0) & (packed_text_indexes < p1)
+            gsel = (packed_dino_token_indexes >= p0) & (packed_dino_token_indexes < p1)
+            packed_text_ids = packed_text_ids[tsel]
+            packed_text_indexes = packed_text_indexes[tsel] - p0
+            packed_dino_token_indexes = packed_dino_token_indexes[gsel] - p0
+            packed_position_ids = packed_position_ids[:, p0:p1]
         self._mark("dino_end")
         n_geo = tokens.shape[0]
         geo_emb = self.buf.get("mot.geo_emb", (n_geo, H), torch.float32)
@@ -521,7 +619,7 @@ class G2VLMFast:
         last, past_key_values = self.language_model_forward_geo(
             packed, packed_position_ids, packed_dino_token_indexes, packed_text_indexes, past_key_values,
             update_past_key_values=update_past_key_values,
-            collect=None if collect is None else collect.setdefault("mot_layers", []))
+            collect=None if collect is None else collect.setdefault("mot_layers", []), group=group)
         self._mark("mot_end")
         return past_key_values, last
 
@@ -590,24 +688,39 @@ class G2VLMFast:
     @torch.no_grad()
     def reconstruct(self, past_key_values=None, packed_key_value_indexes=None, key_values_lens=None,
                     selected_hidden_states=None, packed_dino_token_indexes=None, packed_dino_images=None,
-                    original_images=None, collect: Optional[dict] = None, **kwargs):
-        """Reference: g2vlm.py:1143-1238."""
+                    original_images=None, collect: Optional[dict] = None, shard=None, group=None, **kwargs):
+        """Reference: g2vlm.py:1143-1238.  With `shard`: selected_hidden_states holds this rank's packed rows
+        and the outputs cover the owned views; the context of the global-points decoder (view 0's hidden,
+        g2vlm.py:1196) is broadcast from rank 0."""
         cfg, dev = self.cfg, self.device
         N, _, Hh, Ww = packed_dino_images.shape
         p = cfg.dino_patch
         gh, gw = Hh // p, Ww // p
         P, H = gh * gw, cfg.hidden_size
-        rows = N * P
         geo = packed_dino_token_indexes.to(dev, torch.long)
+        if shard is not None:
+            p0, p1 = shard.packed_rows
+            geo = geo[(geo >= p0) & (geo < p1)] - p0
+            N = shard.n_local
+            if original_images is not None:
+                original_images = original_images[shard.v0:shard.v1]
+        rows = N * P
         hidden = self.buf.get("rec.hidden", (rows, H), torch.float32)
         ops.gather_rows(selected_hidden_states, hidden, geo, rows)
+        context = hidden[:P]
+        if shard is not None:
+            import torch.distributed as dist
+            context = self.buf.get("rec.context", (P, H), torch.float32)
+            if shard.rank == 0:
+                ops.gather_rows(hidden, context, None, P)
+            dist.broadcast(context, src=dist.get_global_rank(group, 0), group=group)
 
         point_hidden = self.buf.get("rec.point_hidden", (rows, cfg.point_dim), torch.bfloat16)
         self._decoder("point_decoder", hidden, N, P, gh, gw, point_hidden)
         camera_hidden = self.buf.get("rec.camera_hidden", (rows, cfg.camera_dim), torch.float32)
         self._decoder("camera_decoder", hidden, N, P, gh, gw, camera_hidden)
         global_hidden = self.buf.get("rec.global_hidden", (rows, cfg.point_dim), torch.bfloat16)
-        self._decoder("global_points_decoder", hidden, N, P, gh, gw, global_hidden, context=hidden[:P])
+        self._decoder("global_points_decoder", hidden, N, P, gh, gw, global_hidden, context=context)
         if collect is not None:
             collect.update(point_hidden=point_hidden.float().view(N, P, -1).clone(),
                            camera_hidden=camera_hidden.view(N, P, -1).clone(),
@@ -654,6 +767,34 @@ class G2VLMFast:
             original_images = original_images.unsqueeze(0)
         return dict(points=points[None], local_points=local_points[None], conf=None, camera_poses=poses[None],
                     global_points=global_points[None], images=original_images)
+
+    @torch.no_grad()
+    def recon_view_sharded(self, tokenizer, new_token_ids, images, group=None):
+        """ONE long scene split by view over the ranks of `group` (sequence parallelism; no reference
+        counterpart).  Every rank passes the same `images` ((N,3,H,W) tensor or list of
+        paths); returns the reference's result dict restricted to the views this rank owns
+        (`view_range` gives them) with `camera_poses` of ALL views all-gathered."""
+        import torch.distributed as dist
+
+        from .sharding import shard_views
+        group = group if group is not None else dist.group.WORLD
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        dev = self.device
+        past = NaiveCache(self.cfg.num_layers)
+        gi, newlens, new_rope = self.prepare_prompts_addbos([0], [0], ["Reconstruct the 3D scene."], tokenizer,
+                                                            new_token_ids)
+        past = self.forward_cache_update_text(past, **{k: v.to(dev) for k, v in gi.items()})  # replicated prefix
+        gi, _, _ = self.prepare_dino_images_pi3(newlens, new_rope, images, None, new_token_ids)
+        N, _, Hh, Ww = gi["packed_dino_images"].shape
+        P = (Hh // self.cfg.dino_patch) * (Ww // self.cfg.dino_patch)
+        shard = shard_views(N, P, rank, world, 1 + self.cfg.dino_registers)
+        past, last = self.forward_cache_update_dino(past, update_past_key_values=False, shard=shard, group=group, **gi)
+        pred = self.reconstruct(selected_hidden_states=last, shard=shard, group=group, **gi)
+        poses_all = torch.empty(world, shard.n_local, 4, 4, dtype=torch.float32, device=dev)
+        dist.all_gather_into_tensor(poses_all, pred["camera_poses"][0].contiguous(), group=group)
+        pred["camera_poses_all"] = poses_all.view(1, N, 4, 4)
+        pred["view_range"] = (shard.v0, shard.v1)
+        return pred
 
     # ------------------------------------------------------------------------------------------
     # the public entry point
