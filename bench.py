@@ -319,7 +319,10 @@ def main():
     value = world * n_views / (ms_per_step / 1e3)
     e2e_value = world * n_views / (ms_e2e / args.steps / 1e3)
     achieved = fl["mot_attention_launch"] / (att_mean_ms / 1e3) / 1e12 if att_mean_ms > 0 else 0.0
-    h2d = sum(v.numel() * v.element_size() for v in gi.values()) + sum(v.numel() * v.element_size() for v in gi_text.values())
+    # e2e: the raw views cross PCIe once (normalised on the device) + the index / position tensors
+    h2d = views_host.numel() * views_host.element_size() \
+        + sum(v.numel() * v.element_size() for k, v in gi.items() if k not in ("packed_dino_images", "original_images")) \
+        + sum(v.numel() * v.element_size() for v in gi_text.values())
     d2h = sum(v.numel() * v.element_size() for v in out_host.values())
     line = dict(
         metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,

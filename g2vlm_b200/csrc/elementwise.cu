@@ -175,8 +175,14 @@ __global__ void qknorm_mrope_kernel(__nv_bfloat16* __restrict__ qkv, long long l
 // ------------------------------------------------------------------------------------------------
 // DINO input side
 // ------------------------------------------------------------------------------------------------
+struct Norm3 {
+  float mean[3];
+  float std[3];
+  int enabled;
+};
+
 __global__ void im2col_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ out, int n, int H,
-                              int W, int patch, int k_pad) {
+                              int W, int patch, int k_pad, Norm3 nrm) {
   const int gh = H / patch, gw = W / patch;
   const long long total = (long long)n * gh * gw * k_pad;
   const int pp = patch * patch;
@@ -192,6 +198,8 @@ __global__ void im2col_kernel(const float* __restrict__ img, __nv_bfloat16* __re
       const int t = static_cast<int>(row - (long long)im * gh * gw);
       const int gy = t / gw, gx = t - gy * gw;
       v = img[(((long long)im * 3 + c) * H + gy * patch + py) * W + gx * patch + px];
+      // torchvision Normalize (g2vlm.py:950): sub then div in fp32 (IEEE-exact, same as the host op)
+      if (nrm.enabled) v = __fdiv_rn(__fsub_rn(v, nrm.mean[c]), nrm.std[c]);
     }
     out[i] = __float2bfloat16_rn(v);
   }
@@ -264,6 +272,61 @@ __global__ void rope2d_kernel(__nv_bfloat16* __restrict__ buf, long long ld, lon
     }
     p[0] = __float2bfloat16_rn(oa);
     p[quarter] = __float2bfloat16_rn(ob);
+  }
+}
+
+// vectorised variant (head_dim/4 a multiple of 8, e.g. 96 -> 24): each thread rotates 8 pairs with
+// 16-byte loads/stores
+__global__ void rope2d_vec8_kernel(__nv_bfloat16* __restrict__ buf, long long ld, long long rows, int n_heads,
+                                   int head_stride, int head_dim, int tokens_per_view, int grid_w,
+                                   const float* __restrict__ cos_tab, const float* __restrict__ sin_tab,
+                                   int bf16_ops) {
+  const int quarter = head_dim >> 2;
+  const int chunks = quarter >> 3;              // 8-pair chunks per axis
+  const long long total = rows * n_heads * 2 * chunks;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = static_cast<int>(i % chunks);
+    long long r = i / chunks;
+    const int axis = static_cast<int>(r & 1);
+    r >>= 1;
+    const int head = static_cast<int>(r % n_heads);
+    const long long row = r / n_heads;
+    const int tok = static_cast<int>(row % tokens_per_view);
+    const int position = axis == 0 ? tok / grid_w : tok % grid_w;
+    const float4* ct = reinterpret_cast<const float4*>(cos_tab + position * quarter + c * 8);
+    const float4* st = reinterpret_cast<const float4*>(sin_tab + position * quarter + c * 8);
+    const float4 c0 = __ldg(ct), c1 = __ldg(ct + 1), s0 = __ldg(st), s1 = __ldg(st + 1);
+    const float cs[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+    const float sn[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+    __nv_bfloat16* p = buf + row * ld + (long long)head * head_stride + axis * (head_dim >> 1) + c * 8;
+    uint4 ra = *reinterpret_cast<const uint4*>(p);
+    uint4 rb = *reinterpret_cast<const uint4*>(p + quarter);
+    uint32_t* ua = reinterpret_cast<uint32_t*>(&ra);
+    uint32_t* ub = reinterpret_cast<uint32_t*>(&rb);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const __nv_bfloat162 a2 = *reinterpret_cast<const __nv_bfloat162*>(&ua[e]);
+      const __nv_bfloat162 b2 = *reinterpret_cast<const __nv_bfloat162*>(&ub[e]);
+      const float a[2] = {__low2float(a2), __high2float(a2)};
+      const float b[2] = {__low2float(b2), __high2float(b2)};
+      float oa[2], ob[2];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const float cc = cs[2 * e + h], ss = sn[2 * e + h];
+        if (bf16_ops) {
+          oa[h] = bf16_round(a[h] * cc) + bf16_round(-b[h] * ss);
+          ob[h] = bf16_round(b[h] * cc) + bf16_round(a[h] * ss);
+        } else {
+          oa[h] = a[h] * cc - b[h] * ss;
+          ob[h] = b[h] * cc + a[h] * ss;
+        }
+      }
+      ua[e] = pack_bf16x2(oa[0], oa[1]);
+      ub[e] = pack_bf16x2(ob[0], ob[1]);
+    }
+    *reinterpret_cast<uint4*>(p) = ra;
+    *reinterpret_cast<uint4*>(p + quarter) = rb;
   }
 }
 
@@ -520,13 +583,20 @@ extern "C" int g2vlm_qknorm_mrope(void* qkv, int64_t ld, int64_t rows, int64_t n
 }
 
 extern "C" int g2vlm_im2col_patches(const float* images, void* out, int32_t n, int32_t H, int32_t W, int32_t patch,
-                                    int32_t k_pad, void* stream) {
+                                    int32_t k_pad, const float* mean3, const float* std3, void* stream) {
   G2_REQUIRE(images && out, "im2col: null tensor");
   G2_REQUIRE(patch > 0 && H % patch == 0 && W % patch == 0 && k_pad >= 3 * patch * patch, "im2col: bad geometry");
   if (n <= 0) return G2VLM_OK;
+  G2_REQUIRE((mean3 == nullptr) == (std3 == nullptr), "im2col: mean3 and std3 must be given together");
+  Norm3 nrm;
+  nrm.enabled = mean3 != nullptr;
+  for (int c = 0; c < 3; ++c) {
+    nrm.mean[c] = mean3 ? mean3[c] : 0.f;
+    nrm.std[c] = std3 ? std3[c] : 1.f;
+  }
   const long long total = (long long)n * (H / patch) * (W / patch) * k_pad;
   im2col_kernel<<<blocks_for(total, EW_THREADS * 4), EW_THREADS, 0, (cudaStream_t)stream>>>(
-      images, (__nv_bfloat16*)out, n, H, W, patch, k_pad);
+      images, (__nv_bfloat16*)out, n, H, W, patch, k_pad, nrm);
   G2_LAUNCH_CHECK();
   return G2VLM_OK;
 }
@@ -553,10 +623,19 @@ extern "C" int g2vlm_rope2d(void* buf, int64_t ld, int64_t rows, int32_t n_heads
   G2_REQUIRE(head_dim > 0 && head_dim % 4 == 0 && head_dim <= head_stride, "rope2d: head_dim % 4, <= head_stride");
   G2_REQUIRE(tokens_per_view > 0 && grid_w > 0, "rope2d: bad grid");
   if (rows <= 0) return G2VLM_OK;
-  const long long total = rows * n_heads_total * (head_dim / 2);
-  rope2d_kernel<<<blocks_for(total, EW_THREADS * 4), EW_THREADS, 0, (cudaStream_t)stream>>>(
-      (__nv_bfloat16*)buf, ld, rows, n_heads_total, head_stride, head_dim, tokens_per_view, grid_w, cos_tab, sin_tab,
-      bf16_ops);
+  const int quarter = head_dim / 4;
+  if (quarter % 8 == 0 && ld % 8 == 0 && head_stride % 8 == 0 && G2_ALIGNED16(buf) && G2_ALIGNED16(cos_tab) &&
+      G2_ALIGNED16(sin_tab)) {
+    const long long total = rows * n_heads_total * 2 * (quarter / 8);
+    rope2d_vec8_kernel<<<blocks_for(total, EW_THREADS * 2), EW_THREADS, 0, (cudaStream_t)stream>>>(
+        (__nv_bfloat16*)buf, ld, rows, n_heads_total, head_stride, head_dim, tokens_per_view, grid_w, cos_tab,
+        sin_tab, bf16_ops);
+  } else {
+    const long long total = rows * n_heads_total * (head_dim / 2);
+    rope2d_kernel<<<blocks_for(total, EW_THREADS * 4), EW_THREADS, 0, (cudaStream_t)stream>>>(
+        (__nv_bfloat16*)buf, ld, rows, n_heads_total, head_stride, head_dim, tokens_per_view, grid_w, cos_tab,
+        sin_tab, bf16_ops);
+  }
   G2_LAUNCH_CHECK();
   return G2VLM_OK;
 }

@@ -68,9 +68,13 @@ def prepare_prompts_addbos(curr_kvlens: List[int], curr_rope: List[int], prompts
 
 def prepare_dino_images_pi3(curr_kvlens: List[int], curr_rope: List[int],
                             images: Union[Sequence, torch.Tensor], new_token_ids: Dict[str, int],
-                            patch: int = 14) -> Tuple[Dict[str, torch.Tensor], List[int], List[int]]:
+                            patch: int = 14, normalize_on_host: bool = True
+                            ) -> Tuple[Dict[str, torch.Tensor], List[int], List[int]]:
     """Reference: g2vlm.py:868-966.  `images` may be paths / PIL images (loaded like the reference)
-    or an already loaded (N,3,H,W) tensor in [0,1] with H, W multiples of 14 (benchmark / tests)."""
+    or an already loaded (N,3,H,W) tensor in [0,1] with H, W multiples of 14 (benchmark / tests).
+    normalize_on_host=False defers the ImageNet normalisation (:950) to the device (fused into the
+    im2col kernel, bit-identical): `packed_dino_images` is then the SAME tensor as `original_images`, so
+    only one copy of the raw views crosses PCIe."""
     if not torch.is_tensor(images):
         images = load_and_resize14(images, 518)
     assert images.dim() == 4 and images.shape[1] == 3
@@ -100,8 +104,8 @@ def prepare_dino_images_pi3(curr_kvlens: List[int], curr_rope: List[int],
     mean = torch.tensor(RESNET_MEAN).view(1, 3, 1, 1)
     std = torch.tensor(RESNET_STD).view(1, 3, 1, 1)
     gi = {
-        "packed_dino_images": (images - mean) / std,
-        "original_images": images.clone(),
+        "packed_dino_images": (images - mean) / std if normalize_on_host else images,
+        "original_images": images.clone() if normalize_on_host else images,
         "packed_text_ids": torch.tensor([soi, eoi] * N, dtype=torch.long),
         "packed_text_indexes": text_idx,
         "dino_token_seqlens": torch.full((N,), P, dtype=torch.int),

@@ -132,6 +132,7 @@ class G2VLMFast:
         self._pos_cache: Dict[tuple, torch.Tensor] = {}
         self._work_cache: Dict[tuple, torch.Tensor] = {}
         self.stage_events: Optional[list] = None  # bench.py: [(name, cuda event)] at stage boundaries
+        self._raw_images = False  # True while recon() feeds un-normalised views (normalised on device)
 
     def _mark(self, name: str) -> None:
         if self.stage_events is not None:
@@ -473,7 +474,9 @@ class G2VLMFast:
     # DINO encoder
     # ------------------------------------------------------------------------------------------
     def _dino_embeddings(self, img, tag="dino"):
-        """Dinov2WithRegistersEmbeddings.forward: images (n,3,H,W) fp32 on device -> x fp32 [n*S, D]."""
+        """Dinov2WithRegistersEmbeddings.forward: images (n,3,H,W) fp32 on device -> x fp32 [n*S, D].
+        If self._raw_images is set the images are raw [0,1] views and the ImageNet normalisation is fused
+        into the im2col kernel."""
         cfg = self.cfg
         n, _, Hh, Ww = img.shape
         p = cfg.dino_patch
@@ -481,7 +484,10 @@ class G2VLMFast:
         P, D = gh * gw, cfg.dino_hidden
         S = P + 1 + cfg.dino_registers
         patches = self.buf.get(tag + ".patches", (n * P, self.dino_kpad), torch.bfloat16)
-        ops.im2col_patches(img, patches, p)
+        if self._raw_images:
+            ops.im2col_patches(img, patches, p, host_prep.RESNET_MEAN, host_prep.RESNET_STD)
+        else:
+            ops.im2col_patches(img, patches, p)
         emb = self.buf.get(tag + ".emb", (n * P, D), torch.bfloat16)
         ops.gemm(patches, self.dino_wpatch, emb, epilogue=ops.EPI_STORE_BF16, bias=self.dino_bpatch)
         x = self.buf.get(tag + ".x", (n * S, D), torch.float32)
@@ -801,8 +807,10 @@ class G2VLMFast:
     # ------------------------------------------------------------------------------------------
     prepare_prompts_addbos = staticmethod(host_prep.prepare_prompts_addbos)
 
-    def prepare_dino_images_pi3(self, curr_kvlens, curr_rope, images, transforms, new_token_ids):
-        return host_prep.prepare_dino_images_pi3(curr_kvlens, curr_rope, images, new_token_ids, self.cfg.dino_patch)
+    def prepare_dino_images_pi3(self, curr_kvlens, curr_rope, images, transforms, new_token_ids,
+                                normalize_on_host: bool = True):
+        return host_prep.prepare_dino_images_pi3(curr_kvlens, curr_rope, images, new_token_ids, self.cfg.dino_patch,
+                                                 normalize_on_host=normalize_on_host)
 
     @torch.no_grad()
     def recon(self, tokenizer, new_token_ids, dino_image_transform, images, prompt="Reconstruct the 3D scene.",
@@ -817,12 +825,20 @@ class G2VLMFast:
                                                             new_token_ids)
         gi = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in gi.items()}
         past = self.forward_cache_update_text(past, **gi)
+        # the raw views cross PCIe once; normalisation happens on the device (bit-identical to the host op)
         gi, newlens, new_rope = self.prepare_dino_images_pi3(newlens, new_rope, images, dino_image_transform,
-                                                             new_token_ids)
+                                                             new_token_ids, normalize_on_host=False)
         if collect is not None:
             collect["generation_input"] = {k: v.clone() for k, v in gi.items() if torch.is_tensor(v)}
-        gi = {k: (v.to(dev, non_blocking=True) if torch.is_tensor(v) else v) for k, v in gi.items()}
-        past, last = self.forward_cache_update_dino(past, update_past_key_values=False, collect=collect, **gi)
+        raw = gi["original_images"].to(dev, non_blocking=True)
+        gi = {k: (v.to(dev, non_blocking=True) if torch.is_tensor(v) and k not in ("packed_dino_images", "original_images")
+                  else v) for k, v in gi.items()}
+        gi["packed_dino_images"] = gi["original_images"] = raw
+        self._raw_images = True
+        try:
+            past, last = self.forward_cache_update_dino(past, update_past_key_values=False, collect=collect, **gi)
+        finally:
+            self._raw_images = False
         if collect is not None:
             collect["last_hidden"] = last.clone()
         return self.reconstruct(past_key_values=past, selected_hidden_states=last, collect=collect, **gi)

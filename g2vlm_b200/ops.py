@@ -225,14 +225,17 @@ def qknorm_mrope(qkv, rows, n_first, n_q, n_kv, head_dim, qw_a, kw_a, qw_b, kw_b
           _i32(int(round_normed)))
 
 
-def im2col_patches(images, out, patch: int):
+def im2col_patches(images, out, patch: int, mean=None, std=None):
+    """mean / std: 3-tuples -> normalise (x - mean[c]) / std[c] on the fly (raw [0,1] images in)."""
     _req(images, torch.float32, "images")
     _req(out, torch.bfloat16, "out")
     n, _, H, W = images.shape
     if not images.is_contiguous() or not out.is_contiguous():
         raise G2Error("im2col: contiguous tensors required")
+    m3 = (ctypes.c_float * 3)(*mean) if mean is not None else None
+    s3 = (ctypes.c_float * 3)(*std) if std is not None else None
     _call("g2vlm_im2col_patches", _vp(images.data_ptr()), _vp(out.data_ptr()), _i32(n), _i32(H), _i32(W),
-          _i32(patch), _i32(out.shape[1]))
+          _i32(patch), _i32(out.shape[1]), m3, s3)
     return out
 
 

@@ -179,9 +179,13 @@ int g2vlm_qknorm_mrope(void* qkv, int64_t ld, int64_t rows, int64_t n_first, int
 
 /* DINO patch embedding input: images fp32 [n, 3, H, W] -> bf16 patches [n*gh*gw, k_pad] in
  * (channel, py, px) order = nn.Conv2d(3, D, 14, 14) as a GEMM
- * (dinov2_with_registers/modeling_dinov2_with_registers.py:62,71); columns >= 3*p*p are zero. */
+ * (dinov2_with_registers/modeling_dinov2_with_registers.py:62,71); columns >= 3*p*p are zero.
+ * mean3 / std3: HOST pointers to 3 floats each, or both NULL. When given, the ImageNet normalisation
+ * (x - mean[c]) / std[c] of g2vlm.py:950 is applied on the fly (IEEE fp32 sub + div, bit-identical to
+ * the host-side torchvision op), so only the raw [0,1] images have to cross PCIe. */
 int g2vlm_im2col_patches(const float* images, void* out, int32_t n, int32_t H, int32_t W,
-                         int32_t patch, int32_t k_pad, void* stream);
+                         int32_t patch, int32_t k_pad, const float* mean3, const float* std3,
+                         void* stream);
 
 /* Dinov2WithRegistersEmbeddings.forward (:147-171): rows per image = [cls+pos0, registers,
  * patch_i + pos_{1+i}]; patch_emb bf16 [n*P, dim], pos fp32 [1+P, dim] (already resampled if the
