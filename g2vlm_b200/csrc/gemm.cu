@@ -4,8 +4,8 @@
 //   warp 0      TMA producer   (cp.async.bulk.tensor, 128-byte swizzle, 4-stage mbarrier ring)
 //   warp 1      MMA issuer     (tcgen05.mma 128x256x16, fp32 accumulators in TMEM, 2 accumulator
 //                               stages so the epilogue of tile i overlaps the main loop of i+1)
-//   warps 2..5  epilogue       (tcgen05.ld -> registers -> fused bias / GELU / SwiGLU /
-//                               LayerScale+residual -> global)
+//   warps 2..9  epilogue       (tcgen05.ld -> registers -> fused bias / GELU / SwiGLU / LayerScale+residual
+//                               -> swizzled smem transpose -> coalesced 16-byte global stores / RMW)
 // Routing: tokens are permuted once per forward so each expert's rows are contiguous ("gather by
 // expert"); an M tile therefore belongs to exactly one expert and selects that expert's weight rows
 // by a row offset into the stacked weight matrix — each expert runs as one dense GEMM and both run
@@ -21,9 +21,11 @@ constexpr int STAGES = 4;
 constexpr int A_BYTES = BM * BK * 2;
 constexpr int B_BYTES = BN * BK * 2;
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-constexpr int GEMM_THREADS = 192;
+constexpr int EPI_WARPS = 8;
+constexpr int GEMM_THREADS = 64 + EPI_WARPS * 32;
+constexpr int STAGING_BYTES = EPI_WARPS * 4096;  // per-warp 32x32 fp32 transpose buffer
 constexpr int PANEL_M = 16;  // rasterisation: 16 M tiles x all N tiles per panel (L2 reuse)
-constexpr int GEMM_SMEM = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int GEMM_SMEM = STAGES * STAGE_BYTES + STAGING_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 
 struct GemmKParams {
   CUtensorMap tmA;
@@ -71,62 +73,119 @@ __device__ __forceinline__ float gelu_erf(float x) {
   return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
 }
 
-// ---- epilogues: each thread owns one accumulator row; `v` holds 32 consecutive columns ----------
+// ---- epilogues -------------------------------------------------------------------------------------
+// 8 epilogue warps: warp w reads TMEM sub-partition w%4 (32 accumulator rows) and half of the tile's
+// columns. tcgen05.ld hands each THREAD one row x 32 columns; writing that straight to global memory
+// makes every warp instruction touch 32 different rows (32 L1 wavefronts). Each 32x32 chunk is therefore
+// transposed through a per-warp, XOR-swizzled shared-memory staging buffer so that a warp instruction
+// covers whole 128-byte row segments of 4 (fp32) / 8 (bf16) rows: coalesced stores and RMW.
+__device__ __forceinline__ void stage_store_bf16(uint8_t* stg, int lane, const uint32_t (&pk)[16],
+                                                 __nv_bfloat16* out_tile, long long ldo, int rows_ok,
+                                                 int cols_ok) {
+  // write: row = lane, four 16-byte segments; segment q lives at q ^ ((row >> 1) & 3)  (64-byte rows)
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int qs = q ^ ((lane >> 1) & 3);
+    *reinterpret_cast<uint4*>(stg + lane * 64 + qs * 16) =
+        make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+  }
+  __syncwarp();
+  const int seg = lane & 3;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int row = i * 8 + (lane >> 2);
+    const int qs = seg ^ ((row >> 1) & 3);
+    const uint4 v = *reinterpret_cast<const uint4*>(stg + row * 64 + qs * 16);
+    if (row < rows_ok) {
+      __nv_bfloat16* dst = out_tile + row * ldo + seg * 8;
+      if (seg * 8 + 8 <= cols_ok) {
+        *reinterpret_cast<uint4*>(dst) = v;
+      } else {
+        const __nv_bfloat16* e = reinterpret_cast<const __nv_bfloat16*>(&v);
+        for (int j = 0; j < 8; ++j)
+          if (seg * 8 + j < cols_ok) dst[j] = e[j];
+      }
+    }
+  }
+  __syncwarp();
+}
+
+// fp32 variant: thread `lane` writes its row (32 floats) swizzled; afterwards piece i of a lane is
+// row i*4 + lane/8, columns (lane%8)*4 .. +3 — 8 lanes cover 128 contiguous bytes of one row.
+__device__ __forceinline__ void stage_write_f32(uint8_t* stg, int lane, const float (&f)[32]) {
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const int qs = q ^ (lane & 7);
+    *reinterpret_cast<float4*>(stg + lane * 128 + qs * 16) = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
+  }
+  __syncwarp();
+}
+__device__ __forceinline__ float4 stage_read_f32(const uint8_t* stg, int lane, int i) {
+  const int row = i * 4 + (lane >> 3);
+  return *reinterpret_cast<const float4*>(stg + row * 128 + ((lane & 7) ^ (row & 7)) * 16);
+}
+
 template <int EPI>
-__device__ __forceinline__ void epilogue_tile(const GemmKParams& p, const TileCoord& t,
-                                              uint32_t taddr, int r_in_tile) {
-  const bool row_ok = r_in_tile < t.rows_valid;
-  const long long row = t.row0 + r_in_tile;
+__device__ __forceinline__ void epilogue_tile(const GemmKParams& p, const TileCoord& t, uint32_t taddr,
+                                              int sub, int half, int lane, uint8_t* stg) {
+  const int rows_ok = t.rows_valid - sub * 32;  // rows of this warp's 32-row slab that are real
+  const long long row_base = t.row0 + sub * 32;
   const int n0 = t.n_tile * BN;
 
   if constexpr (EPI == G2VLM_EPI_SWIGLU_BF16) {
     // columns [0,128) of the tile = gate, [128,256) = up, for output columns n_tile*128 + [0,128)
-    __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out) + row * p.ldo + t.n_tile * 128;
+    __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out) + row_base * p.ldo + t.n_tile * 128;
 #pragma unroll 1
-    for (int c = 0; c < 4; ++c) {
+    for (int c = half * 2; c < half * 2 + 2; ++c) {
       uint32_t vg[32], vu[32];
       tmem_ld32(taddr + c * 32, vg);
       tmem_ld32(taddr + 128 + c * 32, vu);
       tmem_wait_ld();
-      if (row_ok) {
-        uint32_t packed[16];
+      uint32_t pk[16];
 #pragma unroll
-        for (int j = 0; j < 32; j += 2) {
-          float o[2];
+      for (int j = 0; j < 32; j += 2) {
+        float o[2];
 #pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            // reference rounding points: gate_proj -> bf16, silu -> bf16, up_proj -> bf16, mul -> bf16
-            const float g = bf16_round(__uint_as_float(vg[j + e]));
-            const float u = bf16_round(__uint_as_float(vu[j + e]));
-            const float s = bf16_round(g / (1.0f + __expf(-g)));
-            o[e] = s * u;
-          }
-          packed[j >> 1] = pack_bf16x2(o[0], o[1]);
+        for (int e = 0; e < 2; ++e) {
+          // reference rounding points: gate_proj -> bf16, silu -> bf16, up_proj -> bf16, mul -> bf16
+          const float g = bf16_round(__uint_as_float(vg[j + e]));
+          const float u = bf16_round(__uint_as_float(vu[j + e]));
+          const float sg = bf16_round(g / (1.0f + __expf(-g)));
+          o[e] = sg * u;
         }
-        uint4* dst = reinterpret_cast<uint4*>(out + c * 32);
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-          dst[q] = make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
+        pk[j >> 1] = pack_bf16x2(o[0], o[1]);
       }
+      stage_store_bf16(stg, lane, pk, out + c * 32, p.ldo, rows_ok, 32);
     }
     return;
   } else {
     const float* bias = p.bias ? p.bias + (long long)t.g * p.N : nullptr;
     const bool use_scale = p.scale != nullptr && ((p.scale_groups >> t.g) & 1u);
 #pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
+    for (int c = half * 4; c < half * 4 + 4; ++c) {
       const int col0 = n0 + c * 32;
       if (col0 >= p.N) break;  // warp-uniform
+      const int cols_ok = min(32, p.N - col0);
+      const int c4 = (lane & 7) * 4;  // this lane's 4 columns in the transposed (coalesced) domain
+      [[maybe_unused]] float4 old[8];
+      [[maybe_unused]] float* out_piece = nullptr;
+      if constexpr (EPI == G2VLM_EPI_RESID_F32) {
+        out_piece = reinterpret_cast<float*>(p.out) + (row_base + (lane >> 3)) * p.ldo + col0 + c4;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          old[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (i * 4 + (lane >> 3) < rows_ok && c4 + 4 <= cols_ok)
+            old[i] = *reinterpret_cast<const float4*>(out_piece + (long long)i * 4 * p.ldo);
+        }
+      }
       uint32_t v[32];
       tmem_ld32(taddr + c * 32, v);
       tmem_wait_ld();
-      if (!row_ok) continue;
-      const bool full = (col0 + 32 <= p.N);
       float f[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
       if (bias) {
-        if (full) {
+        if (cols_ok == 32) {
           const float4* b4 = reinterpret_cast<const float4*>(bias + col0);
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
@@ -136,7 +195,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, const TileCo
         } else {
 #pragma unroll
           for (int j = 0; j < 32; ++j)
-            if (col0 + j < p.N) f[j] += __ldg(bias + col0 + j);
+            if (j < cols_ok) f[j] += __ldg(bias + col0 + j);
         }
       }
 
@@ -145,93 +204,99 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, const TileCo
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = gelu_erf(bf16_round(f[j]));
         }
-        __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out) + row * p.ldo + col0;
-        if (full) {
-          uint4* dst = reinterpret_cast<uint4*>(out);
+        uint32_t pk[16];
 #pragma unroll
-          for (int q = 0; q < 4; ++q)
-            dst[q] = make_uint4(pack_bf16x2(f[8 * q], f[8 * q + 1]), pack_bf16x2(f[8 * q + 2], f[8 * q + 3]),
-                                pack_bf16x2(f[8 * q + 4], f[8 * q + 5]), pack_bf16x2(f[8 * q + 6], f[8 * q + 7]));
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (col0 + j < p.N) out[j] = __float2bfloat16_rn(f[j]);
-        }
+        for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(f[2 * j], f[2 * j + 1]);
+        stage_store_bf16(stg, lane, pk, reinterpret_cast<__nv_bfloat16*>(p.out) + row_base * p.ldo + col0, p.ldo,
+                         rows_ok, cols_ok);
       } else if constexpr (EPI == G2VLM_EPI_RESID_F32) {
         // x += [bf16]( gamma * bf16(acc + bias) )   (reference: g2vlm/qwen2vl.py:885-887, 907-909)
 #pragma unroll
         for (int j = 0; j < 32; ++j) f[j] = bf16_round(f[j]);
         if (use_scale) {
-          if (full) {
+          if (cols_ok == 32) {
             const float4* s4 = reinterpret_cast<const float4*>(p.scale + col0);
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
-              const float4 s = __ldg(s4 + q);
-              f[4 * q] *= s.x; f[4 * q + 1] *= s.y; f[4 * q + 2] *= s.z; f[4 * q + 3] *= s.w;
+              const float4 sc = __ldg(s4 + q);
+              f[4 * q] *= sc.x; f[4 * q + 1] *= sc.y; f[4 * q + 2] *= sc.z; f[4 * q + 3] *= sc.w;
             }
           } else {
 #pragma unroll
             for (int j = 0; j < 32; ++j)
-              if (col0 + j < p.N) f[j] *= __ldg(p.scale + col0 + j);
+              if (j < cols_ok) f[j] *= __ldg(p.scale + col0 + j);
           }
           if (p.flags & G2VLM_GEMM_ROUND_AFTER_SCALE) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) f[j] = bf16_round(f[j]);
           }
         }
-        float* out = reinterpret_cast<float*>(p.out) + row * p.ldo + col0;
-        if (full) {
-          float4* o4 = reinterpret_cast<float4*>(out);
+        // RMW of the fp32 residual stream in the transposed (coalesced) domain. The 8 old values were
+        // loaded BEFORE the accumulator chunk was read (`old`, below), so their latency is hidden.
+        stage_write_f32(stg, lane, f);
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            float4 x = o4[q];
-            x.x += f[4 * q]; x.y += f[4 * q + 1]; x.z += f[4 * q + 2]; x.w += f[4 * q + 3];
-            o4[q] = x;
+        for (int i = 0; i < 8; ++i) {
+          const float4 a = stage_read_f32(stg, lane, i);
+          const int row = i * 4 + (lane >> 3);
+          float* d = out_piece + (long long)i * 4 * p.ldo;
+          if (row < rows_ok) {
+            if (c4 + 4 <= cols_ok) {
+              float4 x = old[i];
+              x.x += a.x; x.y += a.y; x.z += a.z; x.w += a.w;
+              *reinterpret_cast<float4*>(d) = x;
+            } else {
+              const float av[4] = {a.x, a.y, a.z, a.w};
+              for (int j = 0; j < 4; ++j)
+                if (c4 + j < cols_ok) d[j] += av[j];
+            }
           }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (col0 + j < p.N) out[j] += f[j];
         }
+        __syncwarp();
       } else {  // G2VLM_EPI_STORE_F32
         if (p.flags & G2VLM_GEMM_ROUND_BF16) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = bf16_round(f[j]);
         }
-        float* out = reinterpret_cast<float*>(p.out) + row * p.ldo + col0;
-        const float* res = p.residual ? p.residual + row * p.ldr + col0 : nullptr;
         const bool accum = (p.flags & G2VLM_GEMM_ACCUMULATE) != 0;
         const bool relu = (p.flags & G2VLM_GEMM_RELU) != 0;
-        if (full) {
-          float4* o4 = reinterpret_cast<float4*>(out);
+        float* outp = reinterpret_cast<float*>(p.out) + (row_base + (lane >> 3)) * p.ldo + col0 + c4;
+        const float* resp = p.residual ? p.residual + (row_base + (lane >> 3)) * p.ldr + col0 + c4 : nullptr;
+        stage_write_f32(stg, lane, f);
+        float4 po[8], pr[8];
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            float4 x = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
-            if (accum) {
-              const float4 o = o4[q];
-              x.x += o.x; x.y += o.y; x.z += o.z; x.w += o.w;
-            }
-            if (relu) {
-              x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f);
-            }
-            if (res) {
-              const float4 rr = *reinterpret_cast<const float4*>(res + 4 * q);
-              x.x += rr.x; x.y += rr.y; x.z += rr.z; x.w += rr.w;
-            }
-            o4[q] = x;
-          }
-        } else {
+        for (int i = 0; i < 8; ++i) {  // batch the loads (accumulate / residual operands)
+          const bool ok = i * 4 + (lane >> 3) < rows_ok && c4 + 4 <= cols_ok;
+          po[i] = (ok && accum) ? *reinterpret_cast<const float4*>(outp + (long long)i * 4 * p.ldo) : make_float4(0.f, 0.f, 0.f, 0.f);
+          pr[i] = (ok && resp) ? *reinterpret_cast<const float4*>(resp + (long long)i * 4 * p.ldr) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            if (col0 + j < p.N) {
-              float x = f[j];
-              if (accum) x += out[j];
-              if (relu) x = fmaxf(x, 0.f);
-              if (res) x += res[j];
-              out[j] = x;
+        for (int i = 0; i < 8; ++i) {
+          const float4 a = stage_read_f32(stg, lane, i);
+          const int row = i * 4 + (lane >> 3);
+          float* d = outp + (long long)i * 4 * p.ldo;
+          if (row < rows_ok) {
+            if (c4 + 4 <= cols_ok) {
+              float xv[4] = {a.x + po[i].x, a.y + po[i].y, a.z + po[i].z, a.w + po[i].w};
+              if (relu) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) xv[j] = fmaxf(xv[j], 0.f);
+              }
+              *reinterpret_cast<float4*>(d) = make_float4(xv[0] + pr[i].x, xv[1] + pr[i].y, xv[2] + pr[i].z, xv[3] + pr[i].w);
+            } else {
+              const float av[4] = {a.x, a.y, a.z, a.w};
+              for (int j = 0; j < 4; ++j) {
+                if (c4 + j < cols_ok) {
+                  float x = av[j];
+                  if (accum) x += d[j];
+                  if (relu) x = fmaxf(x, 0.f);
+                  if (resp) x += resp[(long long)i * 4 * p.ldr + j];
+                  d[j] = x;
+                }
+              }
             }
           }
         }
+        __syncwarp();
       }
     }
   }
@@ -244,7 +309,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ GemmKParams p) {
   // 128-byte swizzle atoms are 1024 B: align the operand ring on the SHARED address
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint8_t* staging = smem + STAGES * STAGE_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + STAGING_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full_bar = empty_bar + STAGES;
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;
@@ -265,7 +331,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ GemmKParams p) {
       }
       for (int s = 0; s < 2; ++s) {
         mbar_init(&tmem_full_bar[s], 1);
-        mbar_init(&tmem_empty_bar[s], 128);
+        mbar_init(&tmem_empty_bar[s], EPI_WARPS * 32);
       }
       fence_barrier_init();
     }
@@ -327,7 +393,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ GemmKParams p) {
     }
   } else {
     // ------------------------------- epilogue warps -------------------------------------------
-    const int sub = warp & 3;  // TMEM sub-partition this warp may access: lanes [32*sub, 32*sub+32)
+    const int sub = warp & 3;          // TMEM sub-partition this warp may access: lanes [32*sub, 32*sub+32)
+    const int half = (warp - 2) >> 2;  // which half of the tile's columns
+    uint8_t* stg = staging + (warp - 2) * 4096;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
@@ -335,7 +403,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ GemmKParams p) {
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(sub * 32) << 16) + acc * BN;
-      epilogue_tile<EPI>(p, t, taddr, sub * 32 + lane);
+      epilogue_tile<EPI>(p, t, taddr, sub, half, lane, stg);
       tc_fence_before();
       mbar_arrive(&tmem_empty_bar[acc]);
       acc ^= 1;
