@@ -790,11 +790,17 @@ class G2VLMFast:
         gi, newlens, new_rope = self.prepare_prompts_addbos([0], [0], ["Reconstruct the 3D scene."], tokenizer,
                                                             new_token_ids)
         past = self.forward_cache_update_text(past, **{k: v.to(dev) for k, v in gi.items()})  # replicated prefix
-        gi, _, _ = self.prepare_dino_images_pi3(newlens, new_rope, images, None, new_token_ids)
+        gi, _, _ = self.prepare_dino_images_pi3(newlens, new_rope, images, None, new_token_ids,
+                                                normalize_on_host=False)  # normalised on the device
         N, _, Hh, Ww = gi["packed_dino_images"].shape
         P = (Hh // self.cfg.dino_patch) * (Ww // self.cfg.dino_patch)
         shard = shard_views(N, P, rank, world, 1 + self.cfg.dino_registers)
-        past, last = self.forward_cache_update_dino(past, update_past_key_values=False, shard=shard, group=group, **gi)
+        self._raw_images = True
+        try:
+            past, last = self.forward_cache_update_dino(past, update_past_key_values=False, shard=shard, group=group,
+                                                        **gi)
+        finally:
+            self._raw_images = False
         pred = self.reconstruct(selected_hidden_states=last, shard=shard, group=group, **gi)
         poses_all = torch.empty(world, shard.n_local, 4, 4, dtype=torch.float32, device=dev)
         dist.all_gather_into_tensor(poses_all, pred["camera_poses"][0].contiguous(), group=group)
