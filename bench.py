@@ -387,6 +387,13 @@ def main():
 
     pk = peaks()
     fl = algorithmic_flops(cfg, n_views, P)
+    traffic = None
+    try:  # dram bytes per launch of the dominant kernel from the committed ncu --set full capture
+        tr = json.load(open(os.path.join(ROOT, "profiles", "kernel_traffic.json")))
+        if n_views == 16 and size == 518 and not args.tiny:
+            traffic = tr["attention_tcgen05_kernel<128>@T=21936"]["traffic_bytes"]
+    except Exception:
+        traffic = None
     ms_per_step = ms_total / args.steps
     value = world * n_views / (ms_per_step / 1e3)
     e2e_value = world * n_views / (ms_e2e / args.steps / 1e3)
@@ -409,7 +416,7 @@ def main():
                  ms_per_step=ms_e2e / args.steps),
         gpu_launches=launches,
         roofline=dict(bound="tensor", kernel="attention_tcgen05_kernel<128> (MoT shared attention)", achieved=achieved,
-                      peak=pk["tflops"], unit="TFLOP/s", frac=achieved / pk["tflops"], traffic=None,
+                      peak=pk["tflops"], unit="TFLOP/s", frac=achieved / pk["tflops"], traffic=traffic,
                       peak_source=pk["src"] + " sustained bf16", launch_ms=att_mean_ms, launches_timed=len(att_ms)),
         mot_layer_ms=stage.get("mot_ms", 0.0) / cfg.num_layers,
         stage_ms=stage,

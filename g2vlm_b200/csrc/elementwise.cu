@@ -348,6 +348,10 @@ __global__ void points_epilogue_kernel(const float* __restrict__ feat, long long
     const long long row = (long long)v * gh * gw + (Y / patch) * gw + X / patch;
     const int sub = (Y % patch) * patch + X % patch;
     const float* f = feat + row * ld_feat + sub;
+    if (mode == 2) {  // single-channel pixel shuffle (conf head)
+      out0[i] = f[0];
+      continue;
+    }
     const float a = f[0], b = f[pp], c = f[2 * pp];
     if (mode == 0) {
       out0[3 * i] = a; out0[3 * i + 1] = b; out0[3 * i + 2] = c;
@@ -644,7 +648,8 @@ extern "C" int g2vlm_points_epilogue(const float* feat, int64_t ld_feat, const f
                                      float* out1, int32_t n, int32_t H, int32_t W, int32_t patch, int32_t mode,
                                      void* stream) {
   G2_REQUIRE(feat && out0, "points_epilogue: null tensor");
-  G2_REQUIRE(mode == 0 || (poses && out1), "points_epilogue: mode 1 needs poses and out1");
+  G2_REQUIRE(mode >= 0 && mode <= 2, "points_epilogue: mode must be 0, 1 or 2");
+  G2_REQUIRE(mode != 1 || (poses && out1), "points_epilogue: mode 1 needs poses and out1");
   G2_REQUIRE(patch > 0 && H % patch == 0 && W % patch == 0, "points_epilogue: bad geometry");
   if (n <= 0) return G2VLM_OK;
   points_epilogue_kernel<<<blocks_for((long long)n * H * W, EW_THREADS * 2), EW_THREADS, 0, (cudaStream_t)stream>>>(

@@ -119,8 +119,6 @@ class G2VLMFast:
         _lib.load()  # fail loudly if the kernel library is missing
         if cfg.head_dim != 128:
             raise ValueError("LLM head_dim must be 128 (mrope_section is hard-coded to [16,24,24])")
-        if cfg.train_conf_pi3:
-            raise NotImplementedError("conf branch (train_conf_pi3) is not built yet")
         self.cfg = cfg
         self.device = torch.device(device)
         self.buf = _Buffers(self.device)
@@ -250,13 +248,18 @@ class G2VLMFast:
             return B
 
         self.decoders = {}
-        for name, cross in (("point_decoder", False), ("camera_decoder", False), ("global_points_decoder", True)):
+        dec_names = [("point_decoder", False), ("camera_decoder", False), ("global_points_decoder", True)]
+        head_names = ["point_head", "global_point_head"]
+        if cfg.train_conf_pi3:  # confidence branch (g2vlm.py:209-226): a copy of the point decoder + 1-channel head
+            dec_names.append(("conf_decoder", False))
+            head_names.append("conf_head")
+        for name, cross in dec_names:
             blocks = [pack_block(f"{name}.blocks.{i}.", cross) for i in range(cfg.dec_depth)]
             self.decoders[name] = dict(blocks=blocks, cross=cross,
                                        wout=_bf16(g(f"{name}.linear_out.weight"), dev),
                                        bout=_bias_bf16(g(f"{name}.linear_out.bias"), dev))
         # fp32 heads (autocast disabled in the reference): split-bf16 weights, exact fp32 biases
-        for hname in ("point_head", "global_point_head"):
+        for hname in head_names:
             w = g(hname + ".proj.weight")
             hi = w.to(torch.bfloat16)
             setattr(self, hname + "_whi", _bf16(hi, dev))
@@ -769,9 +772,19 @@ class G2VLMFast:
         ops.points_epilogue(feat_pts, None, global_points, None, N, Hh, Ww, p, 0)
 
         self._mark("heads_end")
+        conf = None
+        if cfg.train_conf_pi3:
+            conf_hidden = self.buf.get("rec.conf_hidden", (rows, cfg.point_dim), torch.bfloat16)
+            self._decoder("conf_decoder", hidden, N, P, gh, gw, conf_hidden)
+            feat_conf = self.buf.get("rec.feat_conf", (rows, p * p), torch.float32)
+            ops.gemm(conf_hidden, self.conf_head_whi, feat_conf, epilogue=ops.EPI_STORE_F32, bias=self.conf_head_b)
+            ops.gemm(conf_hidden, self.conf_head_wlo, feat_conf, epilogue=ops.EPI_STORE_F32, flags=ops.GEMM_ACCUMULATE)
+            conf = torch.empty(N, Hh, Ww, 1, dtype=torch.float32, device=dev)
+            ops.points_epilogue(feat_conf, None, conf, None, N, Hh, Ww, p, 2)
+            conf = conf[None]
         if original_images is not None and original_images.dim() == 4:
             original_images = original_images.unsqueeze(0)
-        return dict(points=points[None], local_points=local_points[None], conf=None, camera_poses=poses[None],
+        return dict(points=points[None], local_points=local_points[None], conf=conf, camera_poses=poses[None],
                     global_points=global_points[None], images=original_images)
 
     @torch.no_grad()

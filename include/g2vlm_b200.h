@@ -208,7 +208,8 @@ int g2vlm_rope2d(void* buf, int64_t ld, int64_t rows, int32_t n_heads_total, int
  * (g2vlm.py:1203-1205, 1226; homogenize_points pi3/utils/geometry.py:108-113).
  * feat fp32 [n*gh*gw, 3*p*p]. mode 0: out0 = pixel-shuffled (n,H,W,3) (global_points);
  * mode 1: out0 = local_points = (x*e^z, y*e^z, e^z), out1 = points = R*local + t with poses fp32
- * [n,4,4]. */
+ * [n,4,4]; mode 2: feat fp32 [n*gh*gw, p*p], out0 = single-channel pixel shuffle (n,H,W,1) (conf_head,
+ * g2vlm.py:1208-1212). */
 int g2vlm_points_epilogue(const float* feat, int64_t ld_feat, const float* poses, float* out0,
                           float* out1, int32_t n, int32_t H, int32_t W, int32_t patch, int32_t mode,
                           void* stream);

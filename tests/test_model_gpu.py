@@ -166,3 +166,21 @@ def test_full_depth_full_width_reference_layerscale_regime():
     assert all(e < TOL for e in errs.values()), errs
     del model
     torch.cuda.empty_cache()
+
+
+def test_conf_branch_matches_oracle():
+    """train_conf_pi3=True (off in the released config): conf_decoder + 1-channel conf_head (g2vlm.py:209-226)."""
+    from dataclasses import replace
+
+    from g2vlm_b200.model import G2VLMFast
+    from oracle import restate
+    cfg = replace(schema.TINY, train_conf_pi3=True)
+    sd = schema.init_synthetic(cfg, seed=2)
+    assert "conf_head.proj.weight" in sd and sd["conf_head.proj.weight"].shape == (196, 1024)
+    model = G2VLMFast(cfg, sd)
+    v = _views(dict(n=2, h=56, w=518, seed=8))
+    out = model.recon(StubTokenizer(), dict(TOKENS), None, v)
+    ref = restate.recon(sd, cfg, v, mode="bf16")
+    assert out["conf"].shape == (1, 2, 56, 518, 1) == tuple(ref["conf"].shape)
+    assert _maxrel(out["conf"], ref["conf"]) < TOL
+    assert _maxrel(out["points"], ref["points"]) < TOL
