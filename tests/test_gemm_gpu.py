@@ -158,3 +158,20 @@ def test_full_size_mot_qkv_timing():
     idx = torch.randint(0, rows, (512,), device="cuda")
     ref = _ref_linear(a, w, bias, groups, N)
     assert _relerr(out[idx], ref[idx]) < 1e-2
+
+
+@pytest.mark.parametrize("epi", ["bf16", "f32", "resid"])
+def test_guard_bands_are_never_written(epi):
+    """compute-sanitizer is closed on this pool, so out-of-bounds writes are hunted with guard bands: rows
+    past the last group row and columns past N (inside the leading dimension) must keep their sentinel."""
+    from g2vlm_b200 import ops
+    rows, K, N, pad_r, pad_c = 333, 192, 600, 70, 40
+    a, w, bias = _mk(rows + pad_r, K, N, 1, seed=11)
+    dt = torch.bfloat16 if epi == "bf16" else torch.float32
+    out = torch.full((rows + pad_r, N + pad_c), 3.0, device="cuda", dtype=dt)
+    e = {"bf16": ops.EPI_STORE_BF16, "f32": ops.EPI_STORE_F32, "resid": ops.EPI_RESID_F32}[epi]
+    ops.gemm(a, w, out, epilogue=e, groups=[(0, rows)], bias=bias)
+    torch.cuda.synchronize()
+    assert (out[rows:] == 3.0).all() and (out[:, N:] == 3.0).all()
+    ref = _ref_linear(a, w, bias, [(0, rows)], N)[:rows] + (3.0 if epi == "resid" else 0.0)
+    assert _relerr(out[:rows, :N], ref) < 1e-2

@@ -184,3 +184,52 @@ def test_conf_branch_matches_oracle():
     assert out["conf"].shape == (1, 2, 56, 518, 1) == tuple(ref["conf"].shape)
     assert _maxrel(out["conf"], ref["conf"]) < TOL
     assert _maxrel(out["points"], ref["points"]) < TOL
+
+
+@pytest.mark.parametrize("case", [
+    dict(n=1, h=518, w=518, seed=21),    # single view: context == the view itself, native 37x37 grid
+    dict(n=2, h=700, w=518, seed=22),    # portrait: gh (50) > gw (37): rope step uses max(gh, gw); pos-embed upsampled
+    dict(n=5, h=14, w=518, seed=23),     # one patch row per view: P = 37 < one attention tile, odd view count
+    dict(n=3, h=294, w=518, seed=24),    # examples/dl3dv geometry (960x540 -> 294x518), BASELINE configs[0]
+])
+def test_recon_edge_geometries(tiny, case):
+    from oracle import restate
+    sd, model = tiny
+    v = _views(case)
+    ref = restate.recon(sd, schema.TINY, v, mode="bf16")
+    out = model.recon(StubTokenizer(), dict(TOKENS), None, v)
+    for k in ("local_points", "points", "global_points", "camera_poses"):
+        assert out[k].shape == ref[k].shape, k
+        assert _maxrel(out[k], ref[k]) < TOL, (k, _maxrel(out[k], ref[k]))
+
+
+def test_recon_from_image_files(tiny, tmp_path):
+    """The reference entry point takes image PATHS (inference_recon.py:33-42): PIL load + LANCZOS resize to
+    518 wide + /14 rounding happen in host_prep.load_and_resize14 (tested equal to the reference loader)."""
+    from PIL import Image
+
+    from g2vlm_b200 import host_prep
+    from oracle import restate
+    sd, model = tiny
+    u8 = (schema.synthetic_views(2, 90, 160, seed=31) * 255).round().to(torch.uint8)
+    paths = []
+    for i in range(2):
+        p = tmp_path / f"view{i}.png"
+        Image.fromarray(u8[i].permute(1, 2, 0).numpy()).save(p)
+        paths.append(str(p))
+    out = model.recon(StubTokenizer(), dict(TOKENS), None, paths)
+    loaded = host_prep.load_and_resize14(paths, 518)
+    assert out["images"].shape == (1, 2, 3, 294, 518) and torch.equal(out["images"][0].cpu(), loaded)
+    ref = restate.recon(sd, schema.TINY, loaded, mode="bf16")
+    for k in ("points", "global_points", "camera_poses"):
+        assert _maxrel(out[k], ref[k]) < TOL, k
+
+
+def test_unsupported_calls_fail_loudly(tiny):
+    from g2vlm_b200.model import G2VLMFast, NaiveCache
+    sd, model = tiny
+    with pytest.raises(KeyError, match="missing"):
+        G2VLMFast(schema.TINY, {k: v for k, v in sd.items() if "ls1" not in k})
+    gi, _, _ = model.prepare_prompts_addbos([3], [3], ["x"], StubTokenizer(), TOKENS)
+    with pytest.raises(NotImplementedError):
+        model.forward_cache_update_text(NaiveCache(schema.TINY.num_layers), **gi)   # non-empty cache = chat path
