@@ -505,6 +505,95 @@ __global__ void camera_pose_kernel(const float* __restrict__ feat, long long ldf
   P[12] = 0.f; P[13] = 0.f; P[14] = 0.f; P[15] = 1.f;
 }
 
+// ------------------------------------------------------------------------------------------------
+// PLY packing: order-preserving compaction of finite points (3 passes: count, scan, scatter)
+// ------------------------------------------------------------------------------------------------
+constexpr int PLY_BLOCK = 1024;
+
+__device__ __forceinline__ bool point_finite(const float* p) {
+  return isfinite(p[0]) && isfinite(p[1]) && isfinite(p[2]);
+}
+
+__global__ void ply_count_kernel(const float* __restrict__ pts, long long n, int* __restrict__ block_counts) {
+  const long long i = blockIdx.x * (long long)PLY_BLOCK + threadIdx.x;
+  const int ok = (i < n) && point_finite(pts + 3 * i);
+  const int c = __syncthreads_count(ok);
+  if (threadIdx.x == 0) block_counts[blockIdx.x] = c;
+}
+
+// exclusive scan of the per-block counts by ONE block (<= a few thousand entries), total -> n_valid
+__global__ void ply_scan_kernel(int* __restrict__ block_counts, int n_blocks, long long* __restrict__ n_valid) {
+  __shared__ long long carry;
+  __shared__ int warp_tot[32];
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int base = 0; base < n_blocks; base += blockDim.x) {
+    const int i = base + threadIdx.x;
+    const int v = i < n_blocks ? block_counts[i] : 0;
+    int x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int y = __shfl_up_sync(0xffffffffu, x, o);
+      if ((threadIdx.x & 31) >= o) x += y;
+    }
+    if ((threadIdx.x & 31) == 31) warp_tot[threadIdx.x >> 5] = x;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      int w = threadIdx.x < (blockDim.x >> 5) ? warp_tot[threadIdx.x] : 0;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, w, o);
+        if (threadIdx.x >= o) w += y;
+      }
+      warp_tot[threadIdx.x] = w;  // inclusive scan of warp totals
+    }
+    __syncthreads();
+    const int warp_off = (threadIdx.x >> 5) ? warp_tot[(threadIdx.x >> 5) - 1] : 0;
+    const long long excl = carry + warp_off + x - v;
+    const int chunk_total = warp_tot[(blockDim.x >> 5) - 1];
+    __syncthreads();
+    // block offsets fit in int32 for any scene this path can hold (< 2^31 points)
+    if (i < n_blocks) block_counts[i] = static_cast<int>(excl);
+    if (threadIdx.x == 0) carry += chunk_total;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *n_valid = carry;
+}
+
+__global__ void ply_scatter_kernel(const float* __restrict__ pts, const float* __restrict__ img, long long n,
+                                   int hw, const int* __restrict__ block_offsets, uint8_t* __restrict__ out) {
+  __shared__ int warp_cnt[32];
+  const long long i = blockIdx.x * (long long)PLY_BLOCK + threadIdx.x;
+  const int ok = (i < n) && point_finite(pts + 3 * i);
+  const unsigned ballot = __ballot_sync(0xffffffffu, ok);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) warp_cnt[warp] = __popc(ballot);
+  __syncthreads();
+  if (warp == 0) {
+    int w = warp_cnt[lane];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int y = __shfl_up_sync(0xffffffffu, w, o);
+      if (lane >= o) w += y;
+    }
+    warp_cnt[lane] = w;
+  }
+  __syncthreads();
+  if (!ok) return;
+  const long long dst = block_offsets[blockIdx.x] + (warp ? warp_cnt[warp - 1] : 0) + __popc(ballot & ((1u << lane) - 1));
+  uint8_t* rec = out + dst * 27;
+  const float* p = pts + 3 * i;
+  const long long v = i / hw, pix = i - v * hw;
+  const float* c = img + v * 3 * hw + pix;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const double d = static_cast<double>(p[k]);
+    memcpy(rec + 8 * k, &d, 8);  // records are 27 bytes: unaligned doubles
+    const double col = fmin(255.0, fmax(0.0, static_cast<double>(c[(long long)k * hw]) * 255.0));
+    rec[24 + k] = static_cast<uint8_t>(col);
+  }
+}
+
 }  // namespace g2
 
 // =================================================================================================
@@ -695,5 +784,26 @@ extern "C" int g2vlm_camera_pose(const float* feat, int64_t ldf, const float* w_
   if (n <= 0) return G2VLM_OK;
   camera_pose_kernel<<<blocks_for(n, 4), 128, 0, (cudaStream_t)stream>>>(feat, ldf, w_t, b_t, w_r, b_r, poses, n, dim);
   G2_LAUNCH_CHECK();
+  return G2VLM_OK;
+}
+
+extern "C" int g2vlm_ply_pack(const float* points, const float* images, int32_t n_views, int32_t H, int32_t W,
+                              void* out, int32_t* block_counts, int64_t* n_valid, void* stream) {
+  G2_REQUIRE(points && images && out && block_counts && n_valid, "ply_pack: null tensor");
+  G2_REQUIRE(n_views >= 0 && H > 0 && W > 0, "ply_pack: bad geometry");
+  const long long n = (long long)n_views * H * W;
+  G2_REQUIRE(n < (1LL << 31), "ply_pack: too many points");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int n_blocks = static_cast<int>((n + PLY_BLOCK - 1) / PLY_BLOCK);
+  if (n_blocks > 0) {
+    ply_count_kernel<<<n_blocks, PLY_BLOCK, 0, st>>>(points, n, block_counts);
+    G2_LAUNCH_CHECK();
+  }
+  ply_scan_kernel<<<1, 1024, 0, st>>>(block_counts, n_blocks, (long long*)n_valid);
+  G2_LAUNCH_CHECK();
+  if (n_blocks > 0) {
+    ply_scatter_kernel<<<n_blocks, PLY_BLOCK, 0, st>>>(points, images, n, H * W, block_counts, (uint8_t*)out);
+    G2_LAUNCH_CHECK();
+  }
   return G2VLM_OK;
 }

@@ -292,3 +292,21 @@ def camera_pose(feat, w_t, b_t, w_r, b_r, poses):
           _vp(b_t.data_ptr()), _vp(w_r.data_ptr()), _vp(b_r.data_ptr()), _vp(poses.data_ptr()),
           _i32(feat.shape[0]), _i32(feat.shape[1]))
     return poses
+
+
+def ply_pack(points: torch.Tensor, images: torch.Tensor):
+    """points fp32 [N,H,W,3], images fp32 [N,3,H,W] (device) -> (uint8 [n_valid*27] packed PLY vertex
+    records on the device, n_valid).  Order-preserving; points with a NaN/Inf coordinate are dropped."""
+    _req(points, torch.float32, "points")
+    _req(images, torch.float32, "images")
+    n, H, W, _ = points.shape
+    if not points.is_contiguous() or not images.is_contiguous() or images.shape != (n, 3, H, W):
+        raise G2Error("ply_pack: contiguous points [N,H,W,3] and images [N,3,H,W] required")
+    total = n * H * W
+    out = torch.empty(max(total, 1) * 27, dtype=torch.uint8, device=points.device)
+    counts = torch.empty((total + 1023) // 1024 + 1, dtype=torch.int32, device=points.device)
+    n_valid = torch.zeros(1, dtype=torch.int64, device=points.device)
+    _call("g2vlm_ply_pack", _vp(points.data_ptr()), _vp(images.data_ptr()), _i32(n), _i32(H), _i32(W),
+          _vp(out.data_ptr()), _vp(counts.data_ptr()), _vp(n_valid.data_ptr()))
+    k = int(n_valid.item())
+    return out[: k * 27], k

@@ -234,6 +234,19 @@ int g2vlm_camera_pose(const float* feat, int64_t ldf, const float* w_t, const fl
                       const float* w_r, const float* b_r, float* poses, int32_t n, int32_t dim,
                       void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Output side of the path ("next" row f3): device-side replacement of the numpy stage of
+ * save_ply_visualization (g2vlm_utils.py:84-149): drop points with a NaN/Inf coordinate (:126-143),
+ * keep the original order, and pack binary-little-endian PLY vertex records
+ *   double x, y, z ; uchar red, green, blue          (27 bytes, the layout Open3D writes)
+ * points fp32 [n_views*H*W, 3] (= pred["points"]), images fp32 [n_views, 3, H, W] in [0,1]
+ * (= pred["images"]; colour of point (v,y,x) is images[v,:,y,x], :121). out must hold n*27 bytes;
+ * block_counts is an int32 workspace of ceil(n/1024)+1 entries; *n_valid (device int64) receives the
+ * number of records written. colour byte = (uchar) min(255, max(0, c*255)) (truncation).
+ * ---------------------------------------------------------------------------------------------- */
+int g2vlm_ply_pack(const float* points, const float* images, int32_t n_views, int32_t H, int32_t W,
+                   void* out, int32_t* block_counts, int64_t* n_valid, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

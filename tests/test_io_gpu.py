@@ -1,0 +1,54 @@
+"""PLY export (row f3): GPU filtering + packing against a numpy restatement of the reference's
+save_ply_visualization post-processing (g2vlm_utils.py:119-143)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def test_ply_pack_matches_numpy_filtering(tmp_path):
+    from g2vlm_b200 import io
+    g = torch.Generator().manual_seed(0)
+    N, H, W = 3, 70, 98                                   # 20580 points: > 20 scan blocks, ragged last block
+    pts = torch.randn(N, H, W, 3, generator=g) * 5
+    img = (torch.randint(0, 256, (N, 3, H, W), generator=g).float() / 255.0)
+    bad = torch.rand(N, H, W, generator=g) < 0.1
+    pts[bad] = torch.tensor([float("nan"), 1.0, 2.0])
+    pts[0, 0, 0] = torch.tensor([float("inf"), 0.0, 0.0])
+    pts[2, 69, 97] = torch.tensor([0.0, float("-inf"), 0.0])
+    pred = dict(points=pts[None].cuda(), images=img[None].cuda())
+    path = str(tmp_path / "out" / "scene.ply")
+    n = io.save_ply_visualization(pred, path)
+    # numpy restatement of the reference
+    p = pts.numpy().reshape(-1, 3)
+    c = img.permute(0, 2, 3, 1).numpy().reshape(-1, 3)
+    valid = ~(np.any(np.isnan(p), axis=1) | np.any(np.isinf(p), axis=1))
+    p, c = p[valid], c[valid]
+    assert n == len(p)
+    rec = io.read_ply(path)
+    assert len(rec) == n
+    got = np.stack([rec["x"], rec["y"], rec["z"]], 1)
+    assert np.array_equal(got, p.astype(np.float64))      # order preserved, fp32 -> double exact
+    col = np.stack([rec["red"], rec["green"], rec["blue"]], 1)
+    expect = np.minimum(255.0, np.maximum(0.0, c.astype(np.float64) * 255.0)).astype(np.uint8)
+    assert np.array_equal(col, expect)
+    head = open(path, "rb").read(200).decode("ascii", "ignore")
+    assert head.startswith("ply\nformat binary_little_endian 1.0") and f"element vertex {n}" in head
+
+
+def test_ply_pack_all_invalid_and_large():
+    from g2vlm_b200 import ops
+    pts = torch.full((1, 4, 5, 3), float("nan"), device="cuda")
+    img = torch.zeros(1, 3, 4, 5, device="cuda")
+    rec, n = ops.ply_pack(pts, img)
+    assert n == 0 and rec.numel() == 0
+    # config-2 sized output: 16 x 518 x 518 points, all valid
+    pts = torch.randn(16, 518, 518, 3, device="cuda")
+    img = torch.rand(16, 3, 518, 518, device="cuda")
+    rec, n = ops.ply_pack(pts, img)
+    assert n == 16 * 518 * 518
+    a = np.frombuffer(rec[:27 * 1000].cpu().numpy().tobytes(), dtype=np.dtype([("x", "<f8"), ("y", "<f8"), ("z", "<f8"), ("r", "u1"), ("g", "u1"), ("b", "u1")]))
+    assert np.array_equal(a["x"], pts.view(-1, 3)[:1000, 0].double().cpu().numpy())
+    tail = np.frombuffer(rec[-27:].cpu().numpy().tobytes(), dtype=a.dtype)
+    assert tail["z"][0] == float(pts.view(-1, 3)[-1, 2])
