@@ -506,6 +506,41 @@ __global__ void camera_pose_kernel(const float* __restrict__ feat, long long ldf
 }
 
 // ------------------------------------------------------------------------------------------------
+// argmax over the vocabulary (greedy decode): one block per row, lowest index wins ties
+// ------------------------------------------------------------------------------------------------
+__global__ void argmax_bf16_kernel(const __nv_bfloat16* __restrict__ logits, long long ld, int vocab,
+                                   long long* __restrict__ out) {
+  const __nv_bfloat16* row = logits + blockIdx.x * ld;
+  float best = -INFINITY;
+  int idx = 0x7fffffff;
+  for (int i = threadIdx.x; i < vocab; i += blockDim.x) {
+    const float v = __bfloat162float(row[i]);
+    if (v > best || (v == best && i < idx)) { best = v; idx = i; }
+  }
+  __shared__ float sb[32];
+  __shared__ int si[32];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+    if (ob > best || (ob == best && oi < idx)) { best = ob; idx = oi; }
+  }
+  if ((threadIdx.x & 31) == 0) { sb[threadIdx.x >> 5] = best; si[threadIdx.x >> 5] = idx; }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    best = threadIdx.x < (blockDim.x >> 5) ? sb[threadIdx.x] : -INFINITY;
+    idx = threadIdx.x < (blockDim.x >> 5) ? si[threadIdx.x] : 0x7fffffff;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+      if (ob > best || (ob == best && oi < idx)) { best = ob; idx = oi; }
+    }
+    if (threadIdx.x == 0) out[blockIdx.x] = idx == 0x7fffffff ? 0 : idx;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // PLY packing: order-preserving compaction of finite points (3 passes: count, scan, scatter)
 // ------------------------------------------------------------------------------------------------
 constexpr int PLY_BLOCK = 1024;
@@ -805,5 +840,15 @@ extern "C" int g2vlm_ply_pack(const float* points, const float* images, int32_t 
     ply_scatter_kernel<<<n_blocks, PLY_BLOCK, 0, st>>>(points, images, n, H * W, block_counts, (uint8_t*)out);
     G2_LAUNCH_CHECK();
   }
+  return G2VLM_OK;
+}
+
+extern "C" int g2vlm_argmax_bf16(const void* logits, int64_t ld, int64_t rows, int32_t vocab, int64_t* out,
+                                 void* stream) {
+  G2_REQUIRE(logits && out && vocab > 0, "argmax: bad arguments");
+  if (rows <= 0) return G2VLM_OK;
+  argmax_bf16_kernel<<<static_cast<unsigned>(rows), 1024, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)logits, ld, vocab, (long long*)out);
+  G2_LAUNCH_CHECK();
   return G2VLM_OK;
 }

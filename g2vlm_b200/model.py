@@ -42,6 +42,71 @@ class NaiveCache:
         return self.key_cache[0].shape[0] if self.key_cache[0] is not None else 0
 
 
+class _CacheView:
+    """`cache.key_cache[layer]` / `cache.value_cache[layer]` of a KVCache: (L, n_kv, head_dim) bf16 views."""
+
+    def __init__(self, cache, half):
+        self._c, self._h = cache, half
+
+    def __len__(self):
+        return self._c._layers
+
+    def __getitem__(self, layer):
+        c = self._c
+        if c.len == 0 or c.buf[layer] is None:
+            return None
+        w = c.kvw // 2
+        return c.buf[layer][: c.len, self._h * w:(self._h + 1) * w].unflatten(1, (c.n_kv, c.hd))
+
+
+class KVCache(NaiveCache):
+    """Append-style KV cache with the NaiveCache read contract (row f1): one preallocated bf16 buffer
+    [capacity, 2*n_kv*head_dim] (K | V) per layer; a step appends its rows in place instead of the reference's
+    per-step re-allocation + index scatter of the whole cache (g2vlm/qwen2vl.py:621-638, O(L) per token)."""
+
+    def __init__(self, num_layers, n_kv, hd, device):
+        self._layers, self.n_kv, self.hd, self.kvw = num_layers, n_kv, hd, 2 * n_kv * hd
+        self.device = device
+        self.buf = [None] * num_layers
+        self.len, self.cap = 0, 0
+        self.key_cache, self.value_cache = _CacheView(self, 0), _CacheView(self, 1)
+
+    @property
+    def num_layers(self):
+        return self._layers
+
+    @property
+    def seq_lens(self):
+        return self.len
+
+    def reserve(self, rows: int) -> None:
+        if rows <= self.cap:
+            return
+        cap = max(rows, int(self.cap * 1.5), 256)
+        for i in range(self._layers):
+            nb = torch.empty(cap, self.kvw, dtype=torch.bfloat16, device=self.device)
+            if self.buf[i] is not None and self.len:
+                ops.gather_rows(self.buf[i], nb, None, self.len)
+            self.buf[i] = nb
+        self.cap = cap
+
+    @classmethod
+    def adopt(cls, past, cfg, device) -> "KVCache":
+        """Accept a reference-style NaiveCache (possibly filled by reference code) or a KVCache."""
+        if isinstance(past, KVCache):
+            return past
+        c = cls(cfg.num_layers, cfg.num_kv_heads, cfg.head_dim, device)
+        if past is not None and past.key_cache[0] is not None:
+            L = past.key_cache[0].shape[0]
+            c.reserve(L)
+            w = c.kvw // 2
+            for i in range(cfg.num_layers):
+                c.buf[i][:L, :w] = past.key_cache[i].reshape(L, w).to(device, torch.bfloat16)
+                c.buf[i][:L, w:] = past.value_cache[i].reshape(L, w).to(device, torch.bfloat16)
+            c.len = L
+        return c
+
+
 def _pad_dim(hd: int) -> int:
     if hd <= 64:
         return 64
@@ -122,7 +187,7 @@ class G2VLMFast:
         self.cfg = cfg
         self.device = torch.device(device)
         self.buf = _Buffers(self.device)
-        missing = [k for k in state_dict_schema(cfg) if k not in state_dict]
+        missing = [k for k in state_dict_schema(cfg) if k not in state_dict and k != "language_model.lm_head.weight"]
         if missing:
             raise KeyError(f"state_dict is missing {len(missing)} keys, e.g. {missing[:4]}")
         self._pack(state_dict)
@@ -175,6 +240,8 @@ class G2VLMFast:
             L["ls1"] = _f32(g(p + "ls1.gamma"), dev)
             L["ls2"] = _f32(g(p + "ls2.gamma"), dev)
             self.layers.append(L)
+        self.lm_head = (_bf16(g("language_model.lm_head.weight"), dev)
+                        if "language_model.lm_head.weight" in sd else None)
         self.norm_geo = _f32(g(lm + "norm_moe_geo.weight"), dev)
         self.norm_und = _f32(g(lm + "norm.weight"), dev)
         hd = cfg.head_dim
@@ -368,31 +435,93 @@ class G2VLMFast:
         hbuf = self.buf.get("mot.h", (rows_q, cfg.hidden_size), torch.bfloat16)
         return qkv, attn, act, hbuf
 
+    def _und_forward(self, x, position_ids, cache: KVCache, causal: bool, update: bool = True):
+        """Qwen2VLModel.forward_inference(mode='und') on top of an append-style cache, single sample
+        (reference g2vlm/qwen2vl.py:1267-1337 with the und branches :570-576, 859-860, 891-893, 1322-1323):
+        text prefill (causal), the ViT step (non-causal) and every decode step.  x: fp32 [T,H] on the device in
+        packed order (all rows belong to the und expert); returns the `norm`-ed hidden states fp32 [T,H]."""
+        cfg, dev = self.cfg, self.device
+        nq, nkv, hd, H = cfg.num_heads, cfg.num_kv_heads, cfg.head_dim, cfg.hidden_size
+        T, L = x.shape[0], cache.len
+        cache.reserve(L + T)
+        pos = position_ids.to(dev, torch.long).contiguous()
+        cos = self.buf.get("und.cos", (T, hd // 2), torch.float32)
+        sin = self.buf.get("und.sin", (T, hd // 2), torch.float32)
+        ops.mrope_table(pos, self.inv_freq, cos, sin, cfg.mrope_section)
+        qkv, attn, act, hbuf = self._mot_buffers(T, T)
+        if T <= ops.ATTN_ROWS_PER_ITEM:   # one work item whose key range grows with the cache (decode loop)
+            work = self.buf.get("und.work", (1, 8), torch.int32)
+            work.copy_(torch.tensor([[0, 0, T, 0, L + T, 0, 0, 0]], dtype=torch.int32))
+        else:
+            work = self._work([0, T], [0, L + T], "und")
+        xs = self.buf.get("und.x", (T, H), torch.float32)
+        ops.gather_rows(x, xs, None, T)
+        w = nkv * hd
+        for i, Lw in enumerate(self.layers):
+            kvbuf = cache.buf[i]
+
+            def kv_append(qkv_, kvbuf=kvbuf):
+                ops.gather_rows(qkv_[:T, nq * hd:], kvbuf[L:], None, T)      # append this step's K|V rows
+                return kvbuf[: L + T, :w], kvbuf[: L + T, w:]
+            # all rows belong to the und expert: group 0 (geo) is empty
+            self._mot_layer(Lw, xs, T, 0, qkv, attn, act, hbuf, cos, sin, work, L + T, causal, True,
+                            kv_exchange=kv_append)
+        y = torch.empty(T, H, dtype=torch.float32, device=dev)
+        ops.rmsnorm_routed(xs, y, self.norm_geo, self.norm_und, 0, cfg.rms_norm_eps, rows=T)
+        if update:
+            cache.len = L + T
+        return y
+
     @torch.no_grad()
     def forward_cache_update_text(self, past_key_values: NaiveCache, packed_text_ids, packed_text_position_ids,
                                   text_token_lens, packed_text_indexes, packed_key_value_indexes, key_values_lens):
-        """Text prefill, mode='und', causal, empty cache (reference g2vlm.py:701-733)."""
+        """Text prefill, mode='und', causal, on top of whatever the cache holds (reference g2vlm.py:701-733).
+        Returns a KVCache (NaiveCache-compatible)."""
         cfg, dev = self.cfg, self.device
-        if int(key_values_lens.sum()) != 0 or len(text_token_lens) != 1:
-            raise NotImplementedError("prefill supports a single prompt on an empty cache (the recon path)")
-        K0 = int(packed_text_ids.numel())
-        nq, nkv, hd = cfg.num_heads, cfg.num_kv_heads, cfg.head_dim
-        ids = packed_text_ids.to(dev, torch.long)
-        x = torch.empty(K0, cfg.hidden_size, dtype=torch.float32, device=dev)
-        ops.gather_rows(self.embed, x, ids, K0)
-        pos = packed_text_position_ids.to(dev, torch.long).contiguous()
-        cos = torch.empty(K0, hd // 2, dtype=torch.float32, device=dev)
-        sin = torch.empty_like(cos)
-        ops.mrope_table(pos, self.inv_freq, cos, sin, cfg.mrope_section)
-        qkv, attn, act, hbuf = self._mot_buffers(K0, K0)
-        work = self._work([0, K0], [0, K0], "text")
-        for i, L in enumerate(self.layers):
-            # all rows belong to the und expert: group 0 (geo) is empty
-            self._mot_layer(L, x, K0, 0, qkv, attn, act, hbuf, cos, sin, work, K0, True, True)
-            kv = qkv[:K0, nq * hd:].clone()
-            past_key_values.key_cache[i] = kv[:, : nkv * hd].view(K0, nkv, hd)
-            past_key_values.value_cache[i] = kv[:, nkv * hd:].view(K0, nkv, hd)
-        return past_key_values
+        if len(text_token_lens) != 1:
+            raise NotImplementedError("single-sample path only (the reference's inference drivers use batch 1)")
+        cache = KVCache.adopt(past_key_values, cfg, dev)
+        if int(key_values_lens.sum()) != cache.len:
+            raise ValueError("key_values_lens does not match the cache length")
+        n = int(packed_text_ids.numel())
+        x = torch.empty(n, cfg.hidden_size, dtype=torch.float32, device=dev)
+        ops.gather_rows(self.embed, x, packed_text_ids.to(dev, torch.long), n)
+        self._und_forward(x, packed_text_position_ids, cache, causal=True)
+        return cache
+
+    @torch.no_grad()
+    def generate_text(self, past_key_values, packed_key_value_indexes, key_values_lens, packed_start_tokens,
+                      packed_query_position_ids, max_length: int, do_sample: bool = False, temperature: float = 1.0,
+                      end_token_id: Optional[int] = None, return_logits: bool = False):
+        """Greedy decode loop of the reference (g2vlm.py:1070-1141), batch 1: returns the generated ids
+        [steps, 1] INCLUDING the start token, like the reference.  The KV cache is appended in place."""
+        cfg, dev = self.cfg, self.device
+        if do_sample:
+            raise NotImplementedError("only greedy decoding (do_sample=False) is implemented")
+        if self.lm_head is None:
+            raise RuntimeError("generate_text needs language_model.lm_head.weight in the state_dict")
+        cache = KVCache.adopt(past_key_values, cfg, dev)
+        cur = packed_start_tokens.to(dev, torch.long).reshape(1).clone()
+        pos = packed_query_position_ids.to(dev, torch.long).reshape(3, 1).clone()
+        H, V = cfg.hidden_size, self.lm_head.shape[0]
+        x = torch.empty(1, H, dtype=torch.float32, device=dev)
+        yb = torch.empty(1, H, dtype=torch.bfloat16, device=dev)
+        logits = torch.empty(1, (V + 7) // 8 * 8, dtype=torch.bfloat16, device=dev)
+        out, all_logits = [], []
+        for _ in range(max_length):
+            out.append(cur.clone())
+            ops.gather_rows(self.embed, x, cur, 1)
+            y = self._und_forward(x, pos, cache, causal=True)
+            ops.cast_bf16(y, yb)
+            ops.gemm(yb, self.lm_head, logits, epilogue=ops.EPI_STORE_BF16)
+            ops.argmax_bf16(logits[:, :V], cur)
+            if return_logits:
+                all_logits.append(logits[0, :V].float().clone())
+            pos += 1
+            if end_token_id is not None and int(cur.item()) == int(end_token_id):
+                break
+        ids = torch.stack(out, dim=0)
+        return (ids, all_logits) if return_logits else ids
 
     @torch.no_grad()
     def language_model_forward_geo(self, packed_sequence, packed_position_ids, packed_geo_token_indexes,
@@ -410,7 +539,8 @@ class G2VLMFast:
         perm = torch.cat([geo, und]).contiguous()  # internal row i <- packed row perm[i]
         if int(perm.numel()) != T:
             raise ValueError("geo + text indexes must cover every packed row exactly once")
-        K0 = past_key_values.seq_lens
+        past_key_values = KVCache.adopt(past_key_values, cfg, dev)
+        K0 = past_key_values.len
         x = self.buf.get("mot.x", (T, H), torch.float32)
         ops.gather_rows(packed_sequence, x, perm, T)
         cos_p = self.buf.get("mot.cos_p", (T, hd // 2), torch.float32)
@@ -423,6 +553,8 @@ class G2VLMFast:
         ops.gather_rows(sin_p, sin, perm, T)
         qkv, attn, act, hbuf = self._mot_buffers(T, T + K0)
         kvw = 2 * nkv * hd
+        if update_past_key_values:
+            past_key_values.reserve(K0 + T)
         kv_exchange = None
         if group is not None:
             # view-sharded sequence parallelism: this rank holds T of world*T rows (equal shards); per layer
@@ -444,29 +576,22 @@ class G2VLMFast:
             work = self._work([0, T], [0, T + K0], "geo")
         for i, L in enumerate(self.layers):
             if K0:
-                # prefix K/V of the und prefill become key rows [T, T+K0) (KV merge, qwen2vl.py:621-638)
-                pk = past_key_values.key_cache[i].reshape(K0, nkv * hd)
-                pv = past_key_values.value_cache[i].reshape(K0, nkv * hd)
+                # cached K|V rows (text prefill) become key rows [T, T+K0) (KV merge, qwen2vl.py:621-638)
                 if group is None:
-                    ops.gather_rows(pk, qkv[T:, nq * hd:(nq + nkv) * hd], None, K0)
-                    ops.gather_rows(pv, qkv[T:, (nq + nkv) * hd:], None, K0)
+                    ops.gather_rows(past_key_values.buf[i], qkv[T:, nq * hd:], None, K0)
                 else:
-                    ops.gather_rows(pk, kv_all[T_all:, : nkv * hd], None, K0)
-                    ops.gather_rows(pv, kv_all[T_all:, nkv * hd:], None, K0)
+                    ops.gather_rows(past_key_values.buf[i], kv_all[T_all:], None, K0)
             self._mot_layer(L, x, T, n_geo, qkv, attn, act, hbuf, cos, sin, work, T + K0, False, False,
                             kv_exchange=kv_exchange)
             if update_past_key_values:
-                # reference order of the merged cache: prefix rows, then the packed query rows
-                merged = torch.empty(T + K0, kvw, dtype=torch.bfloat16, device=dev)
-                if K0:
-                    ops.gather_rows(qkv[T:, nq * hd:], merged, None, K0)
-                ops.gather_rows(qkv[:T, nq * hd:], merged[K0:], perm, T, scatter=True)
-                past_key_values.key_cache[i] = merged[:, : nkv * hd].view(T + K0, nkv, hd)
-                past_key_values.value_cache[i] = merged[:, nkv * hd:].view(T + K0, nkv, hd)
+                # append in the reference's merged order: cached rows, then the PACKED query rows
+                ops.gather_rows(qkv[:T, nq * hd:], past_key_values.buf[i][K0:], perm, T, scatter=True)
             if collect is not None:
                 y = torch.empty(T, H, dtype=torch.float32, device=dev)
                 ops.gather_rows(x, y, perm, T, scatter=True)
                 collect.append(y)
+        if update_past_key_values:
+            past_key_values.len = K0 + T
         y_int = self.buf.get("mot.y", (T, H), torch.float32)
         ops.rmsnorm_routed(x, y_int, self.norm_geo, self.norm_und, n_geo, cfg.rms_norm_eps, rows=T)
         last = torch.empty(T, H, dtype=torch.float32, device=dev)
@@ -838,7 +963,7 @@ class G2VLMFast:
         reference, `dino_image_transform` and `prompt` are ignored (the prompt is hard-coded, :1264).
         `images`: list of paths / PIL images, or an (N,3,H,W) tensor in [0,1] (H, W multiples of 14)."""
         dev = self.device
-        past = NaiveCache(self.cfg.num_layers)
+        past = KVCache(self.cfg.num_layers, self.cfg.num_kv_heads, self.cfg.head_dim, dev)
         self._mark("start")
         gi, newlens, new_rope = self.prepare_prompts_addbos([0], [0], ["Reconstruct the 3D scene."], tokenizer,
                                                             new_token_ids)

@@ -310,3 +310,11 @@ def ply_pack(points: torch.Tensor, images: torch.Tensor):
           _vp(out.data_ptr()), _vp(counts.data_ptr()), _vp(n_valid.data_ptr()))
     k = int(n_valid.item())
     return out[: k * 27], k
+
+
+def argmax_bf16(logits: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+    _req(logits, torch.bfloat16, "logits")
+    _req(out, torch.int64, "out")
+    _call("g2vlm_argmax_bf16", _vp(logits.data_ptr()), _i64(logits.stride(0)), _i64(logits.shape[0]),
+          _i32(logits.shape[1]), _vp(out.data_ptr()))
+    return out

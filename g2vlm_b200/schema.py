@@ -99,6 +99,7 @@ def state_dict_schema(cfg: G2Config) -> "OrderedDict[str, Tuple[int, ...]]":
             s[p + n + ".weight"] = (H,)
     s[lm + "norm.weight"] = (H,)
     s[lm + "norm_moe_geo.weight"] = (H,)
+    s["language_model.lm_head.weight"] = (cfg.vocab_size, H)  # only read by generate_text (chat path)
 
     D, g = cfg.dino_hidden, cfg.dino_grid
     d = "dino_model."
@@ -173,7 +174,7 @@ def init_synthetic(cfg: G2Config, seed: int = 0, embed_rows: int | None = None,
     the same weights)."""
     sd: Dict[str, torch.Tensor] = {}
     for idx, (name, shape) in enumerate(state_dict_schema(cfg).items()):
-        if name.endswith("embed_tokens.weight") and embed_rows is not None:
+        if (name.endswith("embed_tokens.weight") or name.endswith("lm_head.weight")) and embed_rows is not None:
             shape = (embed_rows, shape[1])
         g = torch.Generator(device=device).manual_seed(seed * 1000003 + idx)
         leaf = name.rsplit(".", 2)

@@ -234,6 +234,11 @@ int g2vlm_camera_pose(const float* feat, int64_t ldf, const float* w_t, const fl
                       const float* w_r, const float* b_r, float* poses, int32_t n, int32_t dim,
                       void* stream);
 
+/* Greedy token selection of generate_text (g2vlm.py:1122-1126, `torch.argmax(pred_logits, dim=-1)`):
+ * logits bf16 [rows, vocab] (leading dim ld) -> int64 [rows]; ties resolve to the lowest index. */
+int g2vlm_argmax_bf16(const void* logits, int64_t ld, int64_t rows, int32_t vocab, int64_t* out,
+                      void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Output side of the path ("next" row f3): device-side replacement of the numpy stage of
  * save_ply_visualization (g2vlm_utils.py:84-149): drop points with a NaN/Inf coordinate (:126-143),

@@ -77,6 +77,44 @@ def run_case(model, case):
     return out
 
 
+class ChatTokenizer:
+    """Deterministic stand-in for the Qwen2 tokenizer on the chat path (tiny vocab)."""
+
+    def encode(self, prompt, add_special_tokens=True):
+        if "your text" in prompt:          # the template of prepare_start_tokens (g2vlm.py:1046)
+            return [21, 22, 23]
+        if "system" in prompt:
+            return [31, 32, 33, 34]
+        return [41, 42, 43, 44, 45]
+
+
+CHAT_CASE = dict(n=2, h=28, w=518, seed=3, max_length=8)
+
+
+def run_chat_case(model):
+    """Text-only slice of chat_with_recon (g2vlm.py:1305-1410): system-prompt prefill (und, causal) -> geo
+    step on the views with cache update -> question prefill on top of the cache -> greedy generate_text."""
+    from modeling.g2vlm.qwen2vl import NaiveCache
+    c = CHAT_CASE
+    tok, ids = ChatTokenizer(), dict(rh.NEW_TOKEN_IDS)
+    pil = to_pil(views_u8(c["n"], c["h"], c["w"], c["seed"]))
+    with torch.no_grad(), torch.amp.autocast("cuda", dtype=torch.bfloat16):
+        past = NaiveCache(model.config.llm_config.num_hidden_layers)
+        gi, nl, nr = model.prepare_prompts_pure_text([0], [0], ["system prompt"], tok, ids)
+        past = model.forward_cache_update_text(past, **gi)
+        gi, nl, nr = model.prepare_dino_images_pi3(nl, nr, pil, None, ids)
+        past, last = model.forward_cache_update_dino(past, **gi)
+        gi, nl, nr = model.prepare_prompts_pure_text(nl, nr, ["question"], tok, ids)
+        past = model.forward_cache_update_text(past, **gi)
+        st = model.prepare_start_tokens(nl, nr, tok, ids)
+        cache_len = past.key_cache[0].shape[0]
+        k_probe = past.key_cache[1].float().clone()
+        out = model.generate_text(past_key_values=past, max_length=c["max_length"], end_token_id=ids["eos_token_id"], **st)
+    return dict(case=c, tokens=out[:, 0].clone(), start_token=st["packed_start_tokens"].clone(),
+                start_position=st["packed_query_position_ids"][:, 0].clone(), cache_len_before_decode=cache_len,
+                newlens=nl, key_cache_layer1=k_probe[::7].clone(), last_hidden=last.float()[::STRIDE_T].clone())
+
+
 def main():
     os.makedirs(GOLDEN, exist_ok=True)
     torch.manual_seed(0)
@@ -89,6 +127,9 @@ def main():
         out = run_case(model, case)
         torch.save(out, os.path.join(GOLDEN, f"recon_tiny_{name}.pt"))
         print("wrote", name, {k: tuple(v.shape) for k, v in out.items() if torch.is_tensor(v) and v.dim() > 0})
+    chat = run_chat_case(model)
+    torch.save(chat, os.path.join(GOLDEN, "chat_tiny.pt"))
+    print("wrote chat", chat["tokens"].tolist(), chat["cache_len_before_decode"])
     # full-size key schema: build on the meta device (no 18 GB allocation)
     with torch.device("meta"):
         full = rh.build_reference_model(rh.FULL, visual_und=False)

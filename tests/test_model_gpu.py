@@ -231,5 +231,55 @@ def test_unsupported_calls_fail_loudly(tiny):
     with pytest.raises(KeyError, match="missing"):
         G2VLMFast(schema.TINY, {k: v for k, v in sd.items() if "ls1" not in k})
     gi, _, _ = model.prepare_prompts_addbos([3], [3], ["x"], StubTokenizer(), TOKENS)
+    with pytest.raises(ValueError, match="cache length"):
+        model.forward_cache_update_text(NaiveCache(schema.TINY.num_layers), **gi)   # kv lens != cache contents
     with pytest.raises(NotImplementedError):
-        model.forward_cache_update_text(NaiveCache(schema.TINY.num_layers), **gi)   # non-empty cache = chat path
+        model.generate_text(None, None, None, torch.tensor([1]), torch.zeros(3, 1, dtype=torch.long), 2, do_sample=True)
+
+
+def test_chat_prefill_and_greedy_decode_match_reference(tiny):
+    """Row f1 (text-only slice of chat_with_recon, g2vlm.py:1305-1410): system-prompt prefill -> geo step with
+    cache update -> question prefill on top of the cache -> greedy generate_text with the append-style KV
+    cache.  Generated ids must equal the unmodified reference's (tests/golden/chat_tiny.pt)."""
+    from g2vlm_b200.model import KVCache, NaiveCache
+    from tests.test_oracle import _oracle_chat
+    sd, model = tiny
+    cfg = schema.TINY
+    g = torch.load(os.path.join(GOLDEN, "chat_tiny.pt"))
+    case = g["case"]
+    v = _views(case)
+
+    class ChatTok:
+        def encode(self, prompt, add_special_tokens=True):
+            if "your text" in prompt:
+                return [21, 22, 23]
+            return [31, 32, 33, 34] if "system" in prompt else [41, 42, 43, 44, 45]
+
+    def text_inputs(ids_, kvlen, rope):
+        n = len(ids_)
+        return dict(text_token_lens=torch.tensor([n], dtype=torch.int), packed_text_ids=torch.tensor(ids_),
+                    packed_text_position_ids=(rope + torch.arange(n)).expand(3, -1),
+                    packed_text_indexes=kvlen + torch.arange(n), packed_key_value_indexes=torch.arange(kvlen),
+                    key_values_lens=torch.tensor([kvlen], dtype=torch.int)), kvlen + n, rope + n
+
+    past = NaiveCache(cfg.num_layers)
+    gi, kvlen, rope = text_inputs([31, 32, 33, 34], 0, 0)
+    past = model.forward_cache_update_text(past, **gi)
+    assert isinstance(past, KVCache) and past.seq_lens == 4
+    gi, nl, nr = model.prepare_dino_images_pi3([kvlen], [rope], v, None, TOKENS)
+    past, last = model.forward_cache_update_dino(past, **gi)
+    assert past.seq_lens == nl[0]
+    gi, kvlen, rope = text_inputs([41, 42, 43, 44, 45], nl[0], nr[0])
+    past = model.forward_cache_update_text(past, **gi)
+    assert past.seq_lens == g["cache_len_before_decode"] and rope == int(g["start_position"][0])
+    assert _maxrel(past.key_cache[1][::7], g["key_cache_layer1"]) < TOL
+    assert _maxrel(last[::13], g["last_hidden"]) < TOL
+    ids, logits = model.generate_text(past, torch.arange(kvlen), torch.tensor([kvlen], dtype=torch.int),
+                                      torch.tensor([23]), torch.full((3, 1), rope), case["max_length"],
+                                      end_token_id=2, return_logits=True)
+    assert ids.shape == (case["max_length"], 1)
+    assert ids[:, 0].tolist() == g["tokens"].tolist()
+    assert past.seq_lens == g["cache_len_before_decode"] + case["max_length"]
+    toks, ref_logits, _, _ = _oracle_chat(sd, cfg, case)
+    for a, b in zip(logits, ref_logits):
+        assert _maxrel(a, b) < TOL
