@@ -45,6 +45,9 @@ int make_tmap_2d_bf16(CUtensorMap* map, const void* base, uint64_t rows, uint64_
 
 int num_sms();
 
+// decode.cu: bandwidth-bound GEMV path of g2vlm_gemm_bf16 for calls with <= 8 rows in one group
+int launch_gemv(const g2vlm_gemm_args* a, int group, cudaStream_t stream);
+
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 
 #if defined(__CUDACC__)

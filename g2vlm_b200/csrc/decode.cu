@@ -1,0 +1,288 @@
+// g2vlm_b200 — decode-shaped kernels of the chat path: with ONE query token per step the
+// work is HBM-bound (3.1 GB of bf16 weights + the KV cache stream through per token), so these are plain
+// bandwidth kernels, not tensor-core tiles:
+//   gemv_bf16_kernel<EPI>     out[m, n] = epilogue(sum_k x[m,k] * w[n,k]), m <= 8 rows, one warp per output
+//                             column, 16-byte loads of the weight row; same epilogues / rounding points as the
+//                             tcgen05 GEMM (g2vlm_gemm_bf16 routes here when the call has <= 8 rows)
+//   attn_decode_split_kernel  one query token, GQA: keys split across CTAs (flash-decoding); per CTA
+//                             scores -> softmax statistics -> P.V for the 6 query heads of a KV head
+//   attn_decode_merge_kernel  log-sum-exp merge of the splits
+#include "common.cuh"
+
+namespace g2 {
+
+constexpr int GEMV_MAX_ROWS = 8;
+constexpr int GEMV_WARPS = 8;
+
+struct GemvParams {
+  const __nv_bfloat16* x;  // [rows, K]
+  long long ldx;
+  const __nv_bfloat16* w;  // [N(, interleaved), K] rows of the selected expert
+  long long ldw;
+  int rows, N, K;
+  uint32_t flags;
+  int use_scale;
+  void* out;
+  long long ldo;
+  const float* bias;   // already offset to the expert
+  const float* scale;
+  const float* residual;
+  long long ldr;
+  long long row0;      // first output row
+};
+
+__device__ __forceinline__ float gelu_erf_d(float x) {
+  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+}
+
+__device__ __forceinline__ void dot8(const uint4& a, const uint4& b, float& acc) {
+  const __nv_bfloat162* pa = reinterpret_cast<const __nv_bfloat162*>(&a);
+  const __nv_bfloat162* pb = reinterpret_cast<const __nv_bfloat162*>(&b);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 fa = __bfloat1622float2(pa[i]);
+    const float2 fb = __bfloat1622float2(pb[i]);
+    acc = fmaf(fa.x, fb.x, acc);
+    acc = fmaf(fa.y, fb.y, acc);
+  }
+}
+
+template <int EPI>
+__global__ void __launch_bounds__(GEMV_WARPS * 32) gemv_bf16_kernel(const GemvParams p) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_out = (EPI == G2VLM_EPI_SWIGLU_BF16) ? p.N / 2 : p.N;
+  const int n = blockIdx.x * GEMV_WARPS + warp;  // output column
+  if (n >= n_out) return;
+  // weight row(s): SwiGLU weights interleave gate/up in blocks of 128 rows
+  long long r0 = n, r1 = -1;
+  if constexpr (EPI == G2VLM_EPI_SWIGLU_BF16) {
+    r0 = (long long)(n >> 7) * 256 + (n & 127);
+    r1 = r0 + 128;
+  }
+  const uint4* w0 = reinterpret_cast<const uint4*>(p.w + r0 * p.ldw);
+  const uint4* w1 = reinterpret_cast<const uint4*>(p.w + (r1 < 0 ? r0 : r1) * p.ldw);
+  float acc0[GEMV_MAX_ROWS], acc1[GEMV_MAX_ROWS];
+#pragma unroll
+  for (int m = 0; m < GEMV_MAX_ROWS; ++m) { acc0[m] = 0.f; acc1[m] = 0.f; }
+  const int k8 = p.K >> 3;
+  for (int c = lane; c < k8; c += 32) {
+    const uint4 a = __ldg(w0 + c);
+    uint4 b = make_uint4(0, 0, 0, 0);
+    if constexpr (EPI == G2VLM_EPI_SWIGLU_BF16) b = __ldg(w1 + c);
+#pragma unroll
+    for (int m = 0; m < GEMV_MAX_ROWS; ++m) {
+      if (m < p.rows) {
+        const uint4 xv = __ldg(reinterpret_cast<const uint4*>(p.x + m * p.ldx) + c);
+        dot8(a, xv, acc0[m]);
+        if constexpr (EPI == G2VLM_EPI_SWIGLU_BF16) dot8(b, xv, acc1[m]);
+      }
+    }
+  }
+#pragma unroll
+  for (int m = 0; m < GEMV_MAX_ROWS; ++m) {
+    if (m < p.rows) {
+      acc0[m] = warp_sum(acc0[m]);
+      if constexpr (EPI == G2VLM_EPI_SWIGLU_BF16) acc1[m] = warp_sum(acc1[m]);
+    }
+  }
+  if (lane != 0) return;
+  for (int m = 0; m < p.rows; ++m) {
+    const long long row = p.row0 + m;
+    float f = acc0[m];
+    if constexpr (EPI == G2VLM_EPI_SWIGLU_BF16) {
+      const float g = bf16_round(f), u = bf16_round(acc1[m]);
+      const float sg = bf16_round(g / (1.0f + __expf(-g)));
+      reinterpret_cast<__nv_bfloat16*>(p.out)[row * p.ldo + n] = __float2bfloat16_rn(sg * u);
+    } else {
+      if (p.bias) f += p.bias[n];
+      if constexpr (EPI == G2VLM_EPI_STORE_BF16) {
+        if (p.flags & G2VLM_GEMM_GELU) f = gelu_erf_d(bf16_round(f));
+        reinterpret_cast<__nv_bfloat16*>(p.out)[row * p.ldo + n] = __float2bfloat16_rn(f);
+      } else if constexpr (EPI == G2VLM_EPI_RESID_F32) {
+        f = bf16_round(f);
+        if (p.use_scale) {
+          f *= p.scale[n];
+          if (p.flags & G2VLM_GEMM_ROUND_AFTER_SCALE) f = bf16_round(f);
+        }
+        reinterpret_cast<float*>(p.out)[row * p.ldo + n] += f;
+      } else {
+        if (p.flags & G2VLM_GEMM_ROUND_BF16) f = bf16_round(f);
+        float* o = reinterpret_cast<float*>(p.out) + row * p.ldo + n;
+        if (p.flags & G2VLM_GEMM_ACCUMULATE) f += *o;
+        if (p.flags & G2VLM_GEMM_RELU) f = fmaxf(f, 0.f);
+        if (p.residual) f += p.residual[row * p.ldr + n];
+        *o = f;
+      }
+    }
+  }
+}
+
+// Called by g2vlm_gemm_bf16 when the call has <= GEMV_MAX_ROWS rows, all in ONE group.
+int launch_gemv(const g2vlm_gemm_args* a, int group, cudaStream_t stream) {
+  GemvParams p;
+  p.x = reinterpret_cast<const __nv_bfloat16*>(a->A) + (long long)a->group_row0[group] * a->lda;
+  p.ldx = a->lda;
+  p.w = reinterpret_cast<const __nv_bfloat16*>(a->B) + (long long)group * a->N * a->ldb;
+  p.ldw = a->ldb;
+  p.rows = a->group_rows[group];
+  p.N = a->N;
+  p.K = a->K;
+  p.flags = a->flags;
+  p.use_scale = a->scale != nullptr && ((a->scale_groups >> group) & 1u);
+  p.out = a->out;
+  p.ldo = a->ldo;
+  p.bias = a->bias ? a->bias + (long long)group * a->N : nullptr;
+  p.scale = a->scale;
+  p.residual = a->residual;
+  p.ldr = a->ldr;
+  p.row0 = a->group_row0[group];
+  const int n_out = a->epilogue == G2VLM_EPI_SWIGLU_BF16 ? a->N / 2 : a->N;
+  const unsigned grid = (n_out + GEMV_WARPS - 1) / GEMV_WARPS;
+  switch (a->epilogue) {
+    case G2VLM_EPI_STORE_BF16: gemv_bf16_kernel<G2VLM_EPI_STORE_BF16><<<grid, GEMV_WARPS * 32, 0, stream>>>(p); break;
+    case G2VLM_EPI_SWIGLU_BF16: gemv_bf16_kernel<G2VLM_EPI_SWIGLU_BF16><<<grid, GEMV_WARPS * 32, 0, stream>>>(p); break;
+    case G2VLM_EPI_RESID_F32: gemv_bf16_kernel<G2VLM_EPI_RESID_F32><<<grid, GEMV_WARPS * 32, 0, stream>>>(p); break;
+    default: gemv_bf16_kernel<G2VLM_EPI_STORE_F32><<<grid, GEMV_WARPS * 32, 0, stream>>>(p); break;
+  }
+  G2_CUDA_OK(cudaGetLastError());
+  return G2VLM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// decode attention (one query token, head_dim 128)
+// ------------------------------------------------------------------------------------------------
+constexpr int DEC_THREADS = 256;
+constexpr int DEC_MAX_CHUNK = 512;  // keys per split
+constexpr int DEC_MAX_G = 8;        // query heads per KV head
+
+__global__ void __launch_bounds__(DEC_THREADS)
+attn_decode_split_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ k, long long ldk,
+                         const __nv_bfloat16* __restrict__ v, long long ldv, int L, int G, int chunk,
+                         float scale_log2, float* __restrict__ part /*[splits][heads][130]*/, int n_heads) {
+  __shared__ float sq[DEC_MAX_G][128];
+  __shared__ float ss[DEC_MAX_G][DEC_MAX_CHUNK];
+  __shared__ float red[4][DEC_MAX_G][128];
+  __shared__ float sm[DEC_MAX_G], sl[DEC_MAX_G];
+  const int split = blockIdx.x, kvh = blockIdx.y, tid = threadIdx.x;
+  const int k0 = split * chunk, k1 = min(L, k0 + chunk), nk = max(0, k1 - k0);
+  for (int i = tid; i < G * 128; i += DEC_THREADS)
+    sq[i >> 7][i & 127] = __bfloat162float(q[(kvh * G + (i >> 7)) * 128 + (i & 127)]) * scale_log2;
+  __syncthreads();
+  // phase 1: scores (one key per thread, the 256-byte key row is read with 16-byte loads)
+  for (int j = tid; j < nk; j += DEC_THREADS) {
+    const uint4* kr = reinterpret_cast<const uint4*>(k + (long long)(k0 + j) * ldk + kvh * 128);
+    float acc[DEC_MAX_G];
+#pragma unroll
+    for (int h = 0; h < DEC_MAX_G; ++h) acc[h] = 0.f;
+#pragma unroll 4
+    for (int c = 0; c < 16; ++c) {
+      const uint4 kv = __ldg(kr + c);
+      const __nv_bfloat162* pk = reinterpret_cast<const __nv_bfloat162*>(&kv);
+      float kf[8];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 f = __bfloat1622float2(pk[i]);
+        kf[2 * i] = f.x; kf[2 * i + 1] = f.y;
+      }
+#pragma unroll
+      for (int h = 0; h < DEC_MAX_G; ++h)
+        if (h < G) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc[h] = fmaf(kf[i], sq[h][c * 8 + i], acc[h]);
+        }
+    }
+#pragma unroll
+    for (int h = 0; h < DEC_MAX_G; ++h)
+      if (h < G) ss[h][j] = acc[h];
+  }
+  __syncthreads();
+  // phase 2: per-head max / exp2 / sum over the chunk (one warp per head)
+  const int warp = tid >> 5, lane = tid & 31;
+  if (warp < G) {
+    float m = -INFINITY;
+    for (int j = lane; j < nk; j += 32) m = fmaxf(m, ss[warp][j]);
+    m = warp_max(m);
+    float l = 0.f;
+    for (int j = lane; j < nk; j += 32) {
+      const float pj = nk > 0 ? exp2f(ss[warp][j] - m) : 0.f;
+      ss[warp][j] = pj;
+      l += pj;
+    }
+    l = warp_sum(l);
+    if (lane == 0) { sm[warp] = m; sl[warp] = l; }
+  }
+  __syncthreads();
+  // phase 3: o[h][d] = sum_j p[h][j] * v[j][d]; thread = (pair of d, key quarter)
+  const int dp = tid & 63, kq = tid >> 6;
+  float o[DEC_MAX_G][2];
+#pragma unroll
+  for (int h = 0; h < DEC_MAX_G; ++h) { o[h][0] = 0.f; o[h][1] = 0.f; }
+  for (int j = kq; j < nk; j += 4) {
+    const __nv_bfloat162 vv = *reinterpret_cast<const __nv_bfloat162*>(v + (long long)(k0 + j) * ldv + kvh * 128 + dp * 2);
+    const float2 vf = __bfloat1622float2(vv);
+#pragma unroll
+    for (int h = 0; h < DEC_MAX_G; ++h)
+      if (h < G) {
+        const float pj = ss[h][j];
+        o[h][0] = fmaf(pj, vf.x, o[h][0]);
+        o[h][1] = fmaf(pj, vf.y, o[h][1]);
+      }
+  }
+#pragma unroll
+  for (int h = 0; h < DEC_MAX_G; ++h)
+    if (h < G) { red[kq][h][dp * 2] = o[h][0]; red[kq][h][dp * 2 + 1] = o[h][1]; }
+  __syncthreads();
+  for (int i = tid; i < G * 128; i += DEC_THREADS) {
+    const int h = i >> 7, d = i & 127;
+    float* dst = part + ((long long)split * n_heads + kvh * G + h) * 130;
+    dst[d] = red[0][h][d] + red[1][h][d] + red[2][h][d] + red[3][h][d];
+    if (d == 0) { dst[128] = sm[h]; dst[129] = sl[h]; }
+  }
+}
+
+__global__ void attn_decode_merge_kernel(const float* __restrict__ part, int n_splits, int n_heads,
+                                         __nv_bfloat16* __restrict__ out) {
+  const int h = blockIdx.x, d = threadIdx.x;  // 128 threads
+  float M = -INFINITY;
+  for (int s = 0; s < n_splits; ++s) M = fmaxf(M, part[((long long)s * n_heads + h) * 130 + 128]);
+  float acc = 0.f, l = 0.f;
+  for (int s = 0; s < n_splits; ++s) {
+    const float* p = part + ((long long)s * n_heads + h) * 130;
+    const float w = p[129] > 0.f ? exp2f(p[128] - M) : 0.f;
+    acc = fmaf(w, p[d], acc);
+    l = fmaf(w, p[129], l);
+  }
+  out[h * 128 + d] = __float2bfloat16_rn(l > 0.f ? acc / l : 0.f);
+}
+
+}  // namespace g2
+
+extern "C" int g2vlm_attention_decode(const void* q, const void* k, int64_t ldk, const void* v, int64_t ldv,
+                                      int64_t kv_len, void* out, int32_t num_q_heads, int32_t num_kv_heads,
+                                      int32_t head_dim, float softmax_scale, float* workspace,
+                                      int64_t workspace_floats, void* stream) {
+  using namespace g2;
+  G2_REQUIRE(q && k && v && out && workspace, "attention_decode: null tensor");
+  G2_REQUIRE(head_dim == 128, "attention_decode: head_dim must be 128");
+  G2_REQUIRE(num_kv_heads > 0 && num_q_heads % num_kv_heads == 0 && num_q_heads / num_kv_heads <= DEC_MAX_G,
+             "attention_decode: at most 8 query heads per KV head");
+  G2_REQUIRE(kv_len > 0 && kv_len < (1LL << 31), "attention_decode: bad kv_len");
+  G2_REQUIRE(ldk % 8 == 0 && ldv % 2 == 0, "attention_decode: leading dimensions");
+  const int L = static_cast<int>(kv_len);
+  int n_splits = (L + 127) / 128;
+  if (n_splits > 148) n_splits = 148;
+  int chunk = (L + n_splits - 1) / n_splits;
+  if (chunk > DEC_MAX_CHUNK) {
+    chunk = DEC_MAX_CHUNK;
+    n_splits = (L + chunk - 1) / chunk;
+  }
+  G2_REQUIRE((long long)n_splits * num_q_heads * 130 <= workspace_floats, "attention_decode: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  attn_decode_split_kernel<<<dim3(n_splits, num_kv_heads), DEC_THREADS, 0, st>>>(
+      (const __nv_bfloat16*)q, (const __nv_bfloat16*)k, ldk, (const __nv_bfloat16*)v, ldv, L,
+      num_q_heads / num_kv_heads, chunk, softmax_scale * 1.4426950408889634f, workspace, num_q_heads);
+  G2_CUDA_OK(cudaGetLastError());
+  attn_decode_merge_kernel<<<num_q_heads, 128, 0, st>>>(workspace, n_splits, num_q_heads, (__nv_bfloat16*)out);
+  G2_CUDA_OK(cudaGetLastError());
+  return G2VLM_OK;
+}

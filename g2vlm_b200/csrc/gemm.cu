@@ -475,6 +475,15 @@ extern "C" int g2vlm_gemm_bf16(const g2vlm_gemm_args* a, void* stream_) {
   if (a->n_groups == 1) kp.grp_mtile0[2] = mt;
   G2_REQUIRE(max_row <= a->a_rows, "gemm: group rows exceed a_rows");
   if (mt == 0) return G2VLM_OK;  // empty input: nothing to do
+  {
+    // decode-shaped calls (<= 8 rows, one non-empty group): HBM-bound -> GEMV kernel, not a 128-row MMA tile
+    int total = 0, nonempty = 0, grp = 0;
+    for (int g = 0; g < a->n_groups; ++g)
+      if (a->group_rows[g] > 0) { total += a->group_rows[g]; ++nonempty; grp = g; }
+    if (nonempty == 1 && total <= 8 && (reinterpret_cast<uintptr_t>(a->A) & 15) == 0 &&
+        (reinterpret_cast<uintptr_t>(a->B) & 15) == 0)
+      return launch_gemv(a, grp, stream);
+  }
   kp.n_groups = a->n_groups;
   kp.N = a->N;
   kp.K = a->K;

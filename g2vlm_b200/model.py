@@ -416,8 +416,15 @@ class G2VLMFast:
             k_all, v_all = qkv[:kv_rows, nq * hd:(nq + nkv) * hd], qkv[:kv_rows, (nq + nkv) * hd:]
         else:  # view-sharded: all ranks' K/V rows (+ prefix) gathered over NVLink
             k_all, v_all = kv_exchange(qkv)
-        ops.attention(qkv[:T, : nq * hd], k_all, v_all, attn, work, num_q_heads=nq, num_kv_heads=nkv, head_dim=hd,
-                      scale=1.0 / math.sqrt(hd), causal=causal)
+        if T == 1 and nq // nkv <= 8:
+            # decode step: one query row sees every cached key -> flash-decoding split over the keys
+            ws = self.buf.get("und.dec_ws", (ops.attention_decode_workspace_floats(k_all.shape[0], nq) + 148 * nq * 130,),
+                              torch.float32)
+            ops.attention_decode(qkv[0, : nq * hd], k_all, v_all, attn[0], ws, num_q_heads=nq, num_kv_heads=nkv,
+                                 head_dim=hd, scale=1.0 / math.sqrt(hd))
+        else:
+            ops.attention(qkv[:T, : nq * hd], k_all, v_all, attn, work, num_q_heads=nq, num_kv_heads=nkv, head_dim=hd,
+                          scale=1.0 / math.sqrt(hd), causal=causal)
         ops.gemm(attn[:T], L["wo"], x, epilogue=ops.EPI_RESID_F32, groups=groups, scale=L["ls1"], scale_groups=1,
                  flags=ops.GEMM_ROUND_AFTER_SCALE)
         ops.rmsnorm_routed(x, hbuf, L["post_attention_layernorm_geo"], L["post_attention_layernorm_und"], n_geo,

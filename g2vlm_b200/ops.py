@@ -318,3 +318,21 @@ def argmax_bf16(logits: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
     _call("g2vlm_argmax_bf16", _vp(logits.data_ptr()), _i64(logits.stride(0)), _i64(logits.shape[0]),
           _i32(logits.shape[1]), _vp(out.data_ptr()))
     return out
+
+
+def attention_decode(q, k, v, out, workspace, *, num_q_heads, num_kv_heads, head_dim, scale):
+    """One query token against kv_len = k.shape[0] cached keys (see g2vlm_attention_decode)."""
+    for t, n in ((q, "q"), (k, "k"), (v, "v"), (out, "out")):
+        _req(t, torch.bfloat16, n)
+    _req(workspace, torch.float32, "workspace")
+    _call("g2vlm_attention_decode", _vp(q.data_ptr()), _vp(k.data_ptr()), _i64(k.stride(0)), _vp(v.data_ptr()),
+          _i64(v.stride(0)), _i64(k.shape[0]), _vp(out.data_ptr()), _i32(num_q_heads), _i32(num_kv_heads),
+          _i32(head_dim), _f32(scale), _vp(workspace.data_ptr()), _i64(workspace.numel()))
+    return out
+
+
+def attention_decode_workspace_floats(kv_len: int, num_q_heads: int) -> int:
+    splits = min((kv_len + 127) // 128, 148)
+    if (kv_len + splits - 1) // splits > 512:
+        splits = (kv_len + 511) // 512
+    return splits * num_q_heads * 130

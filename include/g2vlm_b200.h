@@ -51,7 +51,8 @@ const char* g2vlm_last_error(void);
  * B is [n_groups * N, K] bf16 = the experts' nn.Linear weights stacked along rows. Group g owns A
  * rows [group_row0[g], group_row0[g] + group_rows[g]) and weight rows [g*N, (g+1)*N). Output rows
  * are the A rows (same index). fp32 accumulation in TMEM; the epilogue applies the reference's
- * rounding points (autocast returns bf16 from every Linear).
+ * rounding points (autocast returns bf16 from every Linear). Calls with <= 8 rows in a single group (the
+ * decode steps of generate_text) are HBM-bound and run a warp-per-column GEMV kernel with the same epilogues.
  * ---------------------------------------------------------------------------------------------- */
 #define G2VLM_EPI_STORE_BF16 0  /* out_bf16 = bf16(acc + bias) [; gelu] */
 #define G2VLM_EPI_SWIGLU_BF16 1 /* B rows interleave gate/up in blocks of 128; out[:, N/2] */
@@ -233,6 +234,16 @@ int g2vlm_cast_f32_to_bf16(const float* x, int64_t ldx, void* out, int64_t ldo, 
 int g2vlm_camera_pose(const float* feat, int64_t ldf, const float* w_t, const float* b_t,
                       const float* w_r, const float* b_r, float* poses, int32_t n, int32_t dim,
                       void* stream);
+
+/* Decode-shaped attention (ONE query token, head_dim 128, GQA): flash-decoding split over the keys + merge.
+ * Replaces flash_attn_varlen_func at g2vlm/qwen2vl.py:643-652 for the decode steps of generate_text
+ * (g2vlm.py:1100-1113; with one query row the bottom-right causal mask hides nothing).
+ * q bf16 [num_q_heads*128]; k / v bf16 [kv_len, num_kv_heads*128] (ldk / ldv); out bf16 [num_q_heads*128];
+ * workspace fp32, at least ceil(kv_len/128) (max 148, or kv_len/512 if larger) * num_q_heads * 130 floats. */
+int g2vlm_attention_decode(const void* q, const void* k, int64_t ldk, const void* v, int64_t ldv,
+                           int64_t kv_len, void* out, int32_t num_q_heads, int32_t num_kv_heads,
+                           int32_t head_dim, float softmax_scale, float* workspace,
+                           int64_t workspace_floats, void* stream);
 
 /* Greedy token selection of generate_text (g2vlm.py:1122-1126, `torch.argmax(pred_logits, dim=-1)`):
  * logits bf16 [rows, vocab] (leading dim ld) -> int64 [rows]; ties resolve to the lowest index. */
