@@ -157,13 +157,17 @@ constexpr int DEC_MAX_G = 8;        // query heads per KV head
 
 __global__ void __launch_bounds__(DEC_THREADS)
 attn_decode_split_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ k, long long ldk,
-                         const __nv_bfloat16* __restrict__ v, long long ldv, int L, int G, int chunk,
+                         const __nv_bfloat16* __restrict__ v, long long ldv, int L_static,
+                         const int* __restrict__ kv_len_dev, int kv_len_extra, int G, int chunk_static,
                          float scale_log2, float* __restrict__ part /*[splits][heads][130]*/, int n_heads) {
   __shared__ float sq[DEC_MAX_G][128];
   __shared__ float ss[DEC_MAX_G][DEC_MAX_CHUNK];
   __shared__ float red[4][DEC_MAX_G][128];
   __shared__ float sm[DEC_MAX_G], sl[DEC_MAX_G];
   const int split = blockIdx.x, kvh = blockIdx.y, tid = threadIdx.x;
+  // the key count may live on the device (CUDA-graph replay of the decode step: same launch, growing cache)
+  const int L = kv_len_dev ? (*kv_len_dev + kv_len_extra) : L_static;
+  const int chunk = kv_len_dev ? (L + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x) : chunk_static;
   const int k0 = split * chunk, k1 = min(L, k0 + chunk), nk = max(0, k1 - k0);
   for (int i = tid; i < G * 128; i += DEC_THREADS)
     sq[i >> 7][i & 127] = __bfloat162float(q[(kvh * G + (i >> 7)) * 128 + (i & 127)]) * scale_log2;
@@ -255,12 +259,44 @@ __global__ void attn_decode_merge_kernel(const float* __restrict__ part, int n_s
   out[h * 128 + d] = __float2bfloat16_rn(l > 0.f ? acc / l : 0.f);
 }
 
+// dst[(*len_dev or static_row) + i, :] = src[i, :] — the in-place append of a step's K|V rows
+__global__ void kv_append_kernel(const uint8_t* __restrict__ src, long long src_pitch, uint8_t* __restrict__ dst,
+                                 long long dst_pitch, const int* __restrict__ len_dev, long long static_row,
+                                 long long rows, int chunks) {
+  const long long base = len_dev ? *len_dev : static_row;
+  const long long total = rows * chunks;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / chunks;
+    const int c = static_cast<int>(i - r * chunks);
+    *reinterpret_cast<uint4*>(dst + (base + r) * dst_pitch + c * 16LL) =
+        *reinterpret_cast<const uint4*>(src + r * src_pitch + c * 16LL);
+  }
+}
+
 }  // namespace g2
 
+extern "C" int g2vlm_kv_append(const void* src, int64_t src_pitch_bytes, void* dst, int64_t dst_pitch_bytes,
+                               const int32_t* len_dev, int64_t static_row, int64_t rows, int64_t row_bytes,
+                               void* stream) {
+  using namespace g2;
+  G2_REQUIRE(src && dst && row_bytes > 0 && row_bytes % 16 == 0 && src_pitch_bytes % 16 == 0 && dst_pitch_bytes % 16 == 0,
+             "kv_append: bad arguments");
+  if (rows <= 0) return G2VLM_OK;
+  const int chunks = static_cast<int>(row_bytes / 16);
+  long long blocks = (rows * chunks + 255) / 256;
+  if (blocks > 4096) blocks = 4096;
+  kv_append_kernel<<<static_cast<unsigned>(blocks), 256, 0, (cudaStream_t)stream>>>(
+      (const uint8_t*)src, src_pitch_bytes, (uint8_t*)dst, dst_pitch_bytes, len_dev, static_row, rows, chunks);
+  G2_CUDA_OK(cudaGetLastError());
+  return G2VLM_OK;
+}
+
 extern "C" int g2vlm_attention_decode(const void* q, const void* k, int64_t ldk, const void* v, int64_t ldv,
-                                      int64_t kv_len, void* out, int32_t num_q_heads, int32_t num_kv_heads,
-                                      int32_t head_dim, float softmax_scale, float* workspace,
-                                      int64_t workspace_floats, void* stream) {
+                                      int64_t kv_len, const int32_t* kv_len_dev, int32_t kv_len_extra, void* out,
+                                      int32_t num_q_heads, int32_t num_kv_heads, int32_t head_dim,
+                                      float softmax_scale, float* workspace, int64_t workspace_floats,
+                                      void* stream) {
   using namespace g2;
   G2_REQUIRE(q && k && v && out && workspace, "attention_decode: null tensor");
   G2_REQUIRE(head_dim == 128, "attention_decode: head_dim must be 128");
@@ -268,6 +304,8 @@ extern "C" int g2vlm_attention_decode(const void* q, const void* k, int64_t ldk,
              "attention_decode: at most 8 query heads per KV head");
   G2_REQUIRE(kv_len > 0 && kv_len < (1LL << 31), "attention_decode: bad kv_len");
   G2_REQUIRE(ldk % 8 == 0 && ldv % 2 == 0, "attention_decode: leading dimensions");
+  // with kv_len_dev the actual key count is *kv_len_dev + kv_len_extra (read on the device, <= kv_len);
+  // kv_len then only sizes the split grid, so one captured launch serves a growing cache
   const int L = static_cast<int>(kv_len);
   int n_splits = (L + 127) / 128;
   if (n_splits > 148) n_splits = 148;
@@ -279,8 +317,8 @@ extern "C" int g2vlm_attention_decode(const void* q, const void* k, int64_t ldk,
   G2_REQUIRE((long long)n_splits * num_q_heads * 130 <= workspace_floats, "attention_decode: workspace too small");
   cudaStream_t st = (cudaStream_t)stream;
   attn_decode_split_kernel<<<dim3(n_splits, num_kv_heads), DEC_THREADS, 0, st>>>(
-      (const __nv_bfloat16*)q, (const __nv_bfloat16*)k, ldk, (const __nv_bfloat16*)v, ldv, L,
-      num_q_heads / num_kv_heads, chunk, softmax_scale * 1.4426950408889634f, workspace, num_q_heads);
+      (const __nv_bfloat16*)q, (const __nv_bfloat16*)k, ldk, (const __nv_bfloat16*)v, ldv, L, kv_len_dev,
+      kv_len_extra, num_q_heads / num_kv_heads, chunk, softmax_scale * 1.4426950408889634f, workspace, num_q_heads);
   G2_CUDA_OK(cudaGetLastError());
   attn_decode_merge_kernel<<<num_q_heads, 128, 0, st>>>(workspace, n_splits, num_q_heads, (__nv_bfloat16*)out);
   G2_CUDA_OK(cudaGetLastError());

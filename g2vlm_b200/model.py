@@ -82,7 +82,8 @@ class KVCache(NaiveCache):
     def reserve(self, rows: int) -> None:
         if rows <= self.cap:
             return
-        cap = max(rows, int(self.cap * 1.5), 256)
+        # headroom so the question prefill + decode steps that follow a big step never re-allocate
+        cap = (max(rows + 1024, int(self.cap * 1.25)) + 1023) // 1024 * 1024
         for i in range(self._layers):
             nb = torch.empty(cap, self.kvw, dtype=torch.bfloat16, device=self.device)
             if self.buf[i] is not None and self.len:
@@ -403,7 +404,7 @@ class G2VLMFast:
     # MoT language model
     # ------------------------------------------------------------------------------------------
     def _mot_layer(self, L, x, T, n_geo, qkv, attn, act, hbuf, cos, sin, work, kv_rows, causal, round_normed,
-                   kv_exchange=None):
+                   kv_exchange=None, kv_len_dev=None):
         cfg = self.cfg
         H, I = cfg.hidden_size, cfg.intermediate_size
         nq, nkv, hd = cfg.num_heads, cfg.num_kv_heads, cfg.head_dim
@@ -421,7 +422,7 @@ class G2VLMFast:
             ws = self.buf.get("und.dec_ws", (ops.attention_decode_workspace_floats(k_all.shape[0], nq) + 148 * nq * 130,),
                               torch.float32)
             ops.attention_decode(qkv[0, : nq * hd], k_all, v_all, attn[0], ws, num_q_heads=nq, num_kv_heads=nkv,
-                                 head_dim=hd, scale=1.0 / math.sqrt(hd))
+                                 head_dim=hd, scale=1.0 / math.sqrt(hd), kv_len_dev=kv_len_dev, kv_len_extra=1)
         else:
             ops.attention(qkv[:T, : nq * hd], k_all, v_all, attn, work, num_q_heads=nq, num_kv_heads=nkv, head_dim=hd,
                           scale=1.0 / math.sqrt(hd), causal=causal)
@@ -442,7 +443,8 @@ class G2VLMFast:
         hbuf = self.buf.get("mot.h", (rows_q, cfg.hidden_size), torch.bfloat16)
         return qkv, attn, act, hbuf
 
-    def _und_forward(self, x, position_ids, cache: KVCache, causal: bool, update: bool = True):
+    def _und_forward(self, x, position_ids, cache: KVCache, causal: bool, update: bool = True, len_dev=None,
+                     kv_bound: int = 0):
         """Qwen2VLModel.forward_inference(mode='und') on top of an append-style cache, single sample
         (reference g2vlm/qwen2vl.py:1267-1337 with the und branches :570-576, 859-860, 891-893, 1322-1323):
         text prefill (causal), the ViT step (non-causal) and every decode step.  x: fp32 [T,H] on the device in
@@ -451,12 +453,16 @@ class G2VLMFast:
         nq, nkv, hd, H = cfg.num_heads, cfg.num_kv_heads, cfg.head_dim, cfg.hidden_size
         T, L = x.shape[0], cache.len
         cache.reserve(L + T)
+        if len_dev is not None and T != 1:
+            raise ValueError("device-resident cache length is only supported for single-token steps")
         pos = position_ids.to(dev, torch.long).contiguous()
         cos = self.buf.get("und.cos", (T, hd // 2), torch.float32)
         sin = self.buf.get("und.sin", (T, hd // 2), torch.float32)
         ops.mrope_table(pos, self.inv_freq, cos, sin, cfg.mrope_section)
         qkv, attn, act, hbuf = self._mot_buffers(T, T)
-        if T <= ops.ATTN_ROWS_PER_ITEM:   # one work item whose key range grows with the cache (decode loop)
+        if T == 1:
+            work = None                   # single-token steps use the split-K decode attention
+        elif T <= ops.ATTN_ROWS_PER_ITEM:  # one work item whose key range grows with the cache
             work = self.buf.get("und.work", (1, 8), torch.int32)
             work.copy_(torch.tensor([[0, 0, T, 0, L + T, 0, 0, 0]], dtype=torch.int32))
         else:
@@ -468,14 +474,18 @@ class G2VLMFast:
             kvbuf = cache.buf[i]
 
             def kv_append(qkv_, kvbuf=kvbuf):
-                ops.gather_rows(qkv_[:T, nq * hd:], kvbuf[L:], None, T)      # append this step's K|V rows
-                return kvbuf[: L + T, :w], kvbuf[: L + T, w:]
+                if len_dev is None:
+                    ops.kv_append(qkv_[:T, nq * hd:], kvbuf, T, static_row=L)   # append this step's K|V rows
+                    return kvbuf[: L + T, :w], kvbuf[: L + T, w:]
+                # graph-replayable decode step: the row index and the key count are read on the device
+                ops.kv_append(qkv_[:1, nq * hd:], kvbuf, 1, len_dev=len_dev)
+                return kvbuf[:kv_bound, :w], kvbuf[:kv_bound, w:]
             # all rows belong to the und expert: group 0 (geo) is empty
             self._mot_layer(Lw, xs, T, 0, qkv, attn, act, hbuf, cos, sin, work, L + T, causal, True,
-                            kv_exchange=kv_append)
-        y = torch.empty(T, H, dtype=torch.float32, device=dev)
+                            kv_exchange=kv_append, kv_len_dev=len_dev)
+        y = self.buf.get("und.y1", (1, H), torch.float32) if T == 1 else torch.empty(T, H, dtype=torch.float32, device=dev)
         ops.rmsnorm_routed(xs, y, self.norm_geo, self.norm_und, 0, cfg.rms_norm_eps, rows=T)
-        if update:
+        if update and len_dev is None:
             cache.len = L + T
         return y
 
@@ -499,7 +509,7 @@ class G2VLMFast:
     @torch.no_grad()
     def generate_text(self, past_key_values, packed_key_value_indexes, key_values_lens, packed_start_tokens,
                       packed_query_position_ids, max_length: int, do_sample: bool = False, temperature: float = 1.0,
-                      end_token_id: Optional[int] = None, return_logits: bool = False):
+                      end_token_id: Optional[int] = None, return_logits: bool = False, use_cuda_graph: bool = True):
         """Greedy decode loop of the reference (g2vlm.py:1070-1141), batch 1: returns the generated ids
         [steps, 1] INCLUDING the start token, like the reference.  The KV cache is appended in place."""
         cfg, dev = self.cfg, self.device
@@ -508,25 +518,56 @@ class G2VLMFast:
         if self.lm_head is None:
             raise RuntimeError("generate_text needs language_model.lm_head.weight in the state_dict")
         cache = KVCache.adopt(past_key_values, cfg, dev)
+        L0 = cache.len
+        cache.reserve(L0 + max_length)           # no re-allocation while the step graph holds buffer pointers
+        bound = L0 + max_length
         cur = packed_start_tokens.to(dev, torch.long).reshape(1).clone()
         pos = packed_query_position_ids.to(dev, torch.long).reshape(3, 1).clone()
+        len_dev = torch.tensor([L0], dtype=torch.int32, device=dev)
         H, V = cfg.hidden_size, self.lm_head.shape[0]
-        x = torch.empty(1, H, dtype=torch.float32, device=dev)
-        yb = torch.empty(1, H, dtype=torch.bfloat16, device=dev)
-        logits = torch.empty(1, (V + 7) // 8 * 8, dtype=torch.bfloat16, device=dev)
-        out, all_logits = [], []
-        for _ in range(max_length):
-            out.append(cur.clone())
+        x = self.buf.get("gen.x", (1, H), torch.float32)
+        yb = self.buf.get("gen.yb", (1, H), torch.bfloat16)
+        logits = self.buf.get("gen.logits", (1, (V + 7) // 8 * 8), torch.bfloat16)
+        tokens = torch.empty(max_length, dtype=torch.long, device=dev)
+
+        def step():
+            # everything a step depends on (token, position, cache length) lives on the device, so the SAME
+            # launches serve every step: capture once, replay (row f1: no per-token host work)
             ops.gather_rows(self.embed, x, cur, 1)
-            y = self._und_forward(x, pos, cache, causal=True)
+            y = self._und_forward(x, pos, cache, causal=True, len_dev=len_dev, kv_bound=bound)
             ops.cast_bf16(y, yb)
             ops.gemm(yb, self.lm_head, logits, epilogue=ops.EPI_STORE_BF16)
             ops.argmax_bf16(logits[:, :V], cur)
+            pos.add_(1)
+            len_dev.add_(1)
+
+        graph = None
+        n_done, all_logits = 0, []
+        check_every = 8
+        while n_done < max_length:
+            tokens[n_done].copy_(cur[0])
+            if use_cuda_graph and n_done == 1 and graph is None and not return_logits:
+                torch.cuda.synchronize()
+                graph = torch.cuda.CUDAGraph()
+                # capture WITHOUT executing: the captured launches read token / position / length from device
+                # memory, so state is only advanced by replays
+                with torch.cuda.graph(graph):
+                    step()
+            if graph is not None:
+                graph.replay()
+            else:
+                step()
             if return_logits:
                 all_logits.append(logits[0, :V].float().clone())
-            pos += 1
-            if end_token_id is not None and int(cur.item()) == int(end_token_id):
-                break
+            n_done += 1
+            if end_token_id is not None and (n_done % check_every == 0 or n_done == max_length):
+                # `cur` after step i is token i+1; the reference stops when the NEW token is eos (g2vlm.py:1137)
+                produced = torch.cat([tokens[1:n_done], cur]).tolist()
+                if int(end_token_id) in produced:
+                    n_done = produced.index(int(end_token_id)) + 1
+                    break
+        cache.len = L0 + n_done
+        out = [tokens[i:i + 1] for i in range(n_done)]
         ids = torch.stack(out, dim=0)
         return (ids, all_logits) if return_logits else ids
 

@@ -320,15 +320,31 @@ def argmax_bf16(logits: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
     return out
 
 
-def attention_decode(q, k, v, out, workspace, *, num_q_heads, num_kv_heads, head_dim, scale):
-    """One query token against kv_len = k.shape[0] cached keys (see g2vlm_attention_decode)."""
+def attention_decode(q, k, v, out, workspace, *, num_q_heads, num_kv_heads, head_dim, scale, kv_len_dev=None,
+                     kv_len_extra: int = 0):
+    """One query token against the cached keys (see g2vlm_attention_decode).  Without kv_len_dev the key count
+    is k.shape[0]; with it (device int32) the count is *kv_len_dev + kv_len_extra and k.shape[0] is the bound."""
     for t, n in ((q, "q"), (k, "k"), (v, "v"), (out, "out")):
         _req(t, torch.bfloat16, n)
     _req(workspace, torch.float32, "workspace")
+    if kv_len_dev is not None:
+        _req(kv_len_dev, torch.int32, "kv_len_dev")
     _call("g2vlm_attention_decode", _vp(q.data_ptr()), _vp(k.data_ptr()), _i64(k.stride(0)), _vp(v.data_ptr()),
-          _i64(v.stride(0)), _i64(k.shape[0]), _vp(out.data_ptr()), _i32(num_q_heads), _i32(num_kv_heads),
-          _i32(head_dim), _f32(scale), _vp(workspace.data_ptr()), _i64(workspace.numel()))
+          _i64(v.stride(0)), _i64(k.shape[0]), _ptr(kv_len_dev), _i32(kv_len_extra), _vp(out.data_ptr()),
+          _i32(num_q_heads), _i32(num_kv_heads), _i32(head_dim), _f32(scale), _vp(workspace.data_ptr()),
+          _i64(workspace.numel()))
     return out
+
+
+def kv_append(src, dst, rows: int, len_dev=None, static_row: int = 0):
+    """dst[(*len_dev | static_row) + i] = src[i] for i < rows (2-D views, same dtype)."""
+    if src.dtype != dst.dtype or src.stride(-1) != 1 or dst.stride(-1) != 1:
+        raise G2Error("kv_append: same dtype, contiguous rows")
+    if len_dev is not None:
+        _req(len_dev, torch.int32, "len_dev")
+    _call("g2vlm_kv_append", _vp(src.data_ptr()), _i64(src.stride(0) * src.element_size()), _vp(dst.data_ptr()),
+          _i64(dst.stride(0) * dst.element_size()), _ptr(len_dev), _i64(static_row), _i64(rows),
+          _i64(min(src.shape[1], dst.shape[1]) * src.element_size()))
 
 
 def attention_decode_workspace_floats(kv_len: int, num_q_heads: int) -> int:

@@ -239,11 +239,21 @@ int g2vlm_camera_pose(const float* feat, int64_t ldf, const float* w_t, const fl
  * Replaces flash_attn_varlen_func at g2vlm/qwen2vl.py:643-652 for the decode steps of generate_text
  * (g2vlm.py:1100-1113; with one query row the bottom-right causal mask hides nothing).
  * q bf16 [num_q_heads*128]; k / v bf16 [kv_len, num_kv_heads*128] (ldk / ldv); out bf16 [num_q_heads*128];
- * workspace fp32, at least ceil(kv_len/128) (max 148, or kv_len/512 if larger) * num_q_heads * 130 floats. */
+ * workspace fp32, at least ceil(kv_len/128) (max 148, or kv_len/512 if larger) * num_q_heads * 130 floats.
+ * kv_len_dev (DEVICE int32, or NULL): if given, the number of keys is *kv_len_dev + kv_len_extra, read on
+ * the device, and kv_len is only an upper bound that sizes the split grid — one captured launch (CUDA graph)
+ * then serves every step of a growing cache. */
 int g2vlm_attention_decode(const void* q, const void* k, int64_t ldk, const void* v, int64_t ldv,
-                           int64_t kv_len, void* out, int32_t num_q_heads, int32_t num_kv_heads,
-                           int32_t head_dim, float softmax_scale, float* workspace,
-                           int64_t workspace_floats, void* stream);
+                           int64_t kv_len, const int32_t* kv_len_dev, int32_t kv_len_extra, void* out,
+                           int32_t num_q_heads, int32_t num_kv_heads, int32_t head_dim,
+                           float softmax_scale, float* workspace, int64_t workspace_floats, void* stream);
+
+/* In-place append of a step's rows to a cache buffer: dst[base + i, :] = src[i, :], base = *len_dev (DEVICE
+ * int32) if len_dev != NULL else static_row. Replaces the per-step re-allocation + index scatter of the whole
+ * cache in the reference (g2vlm/qwen2vl.py:621-638). row_bytes and pitches multiples of 16. */
+int g2vlm_kv_append(const void* src, int64_t src_pitch_bytes, void* dst, int64_t dst_pitch_bytes,
+                    const int32_t* len_dev, int64_t static_row, int64_t rows, int64_t row_bytes,
+                    void* stream);
 
 /* Greedy token selection of generate_text (g2vlm.py:1122-1126, `torch.argmax(pred_logits, dim=-1)`):
  * logits bf16 [rows, vocab] (leading dim ld) -> int64 [rows]; ties resolve to the lowest index. */

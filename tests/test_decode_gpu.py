@@ -83,3 +83,30 @@ def test_attention_decode(L):
     work = ops.attention_work_table([0, 1], [0, L]).cuda()
     ops.attention(q.view(1, -1), k, v, out2, work, num_q_heads=nq, num_kv_heads=nkv, head_dim=hd, scale=scale)
     assert (out.float() - out2[0].float()).abs().max().item() < 1e-2
+
+
+def test_attention_decode_device_resident_length_and_kv_append():
+    """The graph-replayable form: the key count and the append row are read from device memory."""
+    from g2vlm_b200 import ops
+    g = torch.Generator().manual_seed(7)
+    nq, nkv, hd, cap = 12, 2, 128, 3000
+    kvbuf = torch.randn(cap, 2 * nkv * hd, generator=g).to(torch.bfloat16).cuda()
+    q = torch.randn(nq * hd, generator=g).to(torch.bfloat16).cuda()
+    new = torch.randn(1, 2 * nkv * hd, generator=g).to(torch.bfloat16).cuda()
+    len_dev = torch.tensor([1234], dtype=torch.int32, device="cuda")
+    ws = torch.empty(ops.attention_decode_workspace_floats(cap, nq), device="cuda")
+    out = torch.empty(nq * hd, device="cuda", dtype=torch.bfloat16)
+    scale = 1 / math.sqrt(hd)
+    for step in range(3):
+        before = kvbuf.clone()
+        ops.kv_append(new, kvbuf, 1, len_dev=len_dev)
+        L = 1234 + step
+        assert torch.equal(kvbuf[L], new[0]) and torch.equal(kvbuf[:L], before[:L]) and torch.equal(kvbuf[L + 1:], before[L + 1:])
+        ops.attention_decode(q, kvbuf[:cap, : nkv * hd], kvbuf[:cap, nkv * hd:], out, ws, num_q_heads=nq,
+                             num_kv_heads=nkv, head_dim=hd, scale=scale, kv_len_dev=len_dev, kv_len_extra=1)
+        k, v = kvbuf[:L + 1, : nkv * hd], kvbuf[:L + 1, nkv * hd:]
+        ks = k.float().view(L + 1, nkv, hd).transpose(0, 1).repeat_interleave(nq // nkv, 0)
+        vs = v.float().view(L + 1, nkv, hd).transpose(0, 1).repeat_interleave(nq // nkv, 0)
+        ref = (torch.softmax(q.float().view(nq, 1, hd) @ ks.transpose(1, 2) * scale, -1) @ vs).reshape(-1)
+        assert (out.float() - ref).abs().max().item() < 1e-2
+        len_dev += 1

@@ -283,3 +283,22 @@ def test_chat_prefill_and_greedy_decode_match_reference(tiny):
     toks, ref_logits, _, _ = _oracle_chat(sd, cfg, case)
     for a, b in zip(logits, ref_logits):
         assert _maxrel(a, b) < TOL
+
+    # same flow, decode through the captured CUDA graph (device-resident token / position / cache length)
+    past = model.forward_cache_update_text(NaiveCache(cfg.num_layers), **text_inputs([31, 32, 33, 34], 0, 0)[0])
+    gi, nl, nr = model.prepare_dino_images_pi3([4], [4], v, None, TOKENS)
+    past, _ = model.forward_cache_update_dino(past, **gi)
+    past = model.forward_cache_update_text(past, **text_inputs([41, 42, 43, 44, 45], nl[0], nr[0])[0])
+    ids_g = model.generate_text(past, None, None, torch.tensor([23]), torch.full((3, 1), rope), case["max_length"],
+                                end_token_id=2, use_cuda_graph=True)
+    assert ids_g[:, 0].tolist() == g["tokens"].tolist()
+    assert past.seq_lens == g["cache_len_before_decode"] + case["max_length"]
+    # early stop: the reference breaks when the NEW token is eos and does not append it (g2vlm.py:1137)
+    past = model.forward_cache_update_text(NaiveCache(cfg.num_layers), **text_inputs([31, 32, 33, 34], 0, 0)[0])
+    past, _ = model.forward_cache_update_dino(past, **gi)
+    past = model.forward_cache_update_text(past, **text_inputs([41, 42, 43, 44, 45], nl[0], nr[0])[0])
+    eos = g["tokens"].tolist()[2]          # pretend the 2nd generated token is the end token
+    ids_e = model.generate_text(past, None, None, torch.tensor([23]), torch.full((3, 1), rope), case["max_length"],
+                                end_token_id=eos)
+    assert ids_e[:, 0].tolist() == g["tokens"].tolist()[:2]
+    assert past.seq_lens == g["cache_len_before_decode"] + 2
