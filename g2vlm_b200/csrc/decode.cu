@@ -47,46 +47,78 @@ __device__ __forceinline__ void dot8(const uint4& a, const uint4& b, float& acc)
   }
 }
 
-template <int EPI>
+// ROWS: 1 (the decode step) or 8; KSPLIT: warps that share one output column (long rows, few columns:
+// the down projection K = 8960, N = 1536 would otherwise run on 1536 warps only)
+template <int EPI, int ROWS, int KSPLIT>
 __global__ void __launch_bounds__(GEMV_WARPS * 32) gemv_bf16_kernel(const GemvParams p) {
+  constexpr int COLS = GEMV_WARPS / KSPLIT;  // output columns per block
+  __shared__ float part[COLS][KSPLIT][2][ROWS];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_out = (EPI == G2VLM_EPI_SWIGLU_BF16) ? p.N / 2 : p.N;
-  const int n = blockIdx.x * GEMV_WARPS + warp;  // output column
-  if (n >= n_out) return;
+  const int cl = warp / KSPLIT, ks = warp % KSPLIT;
+  const int n = blockIdx.x * COLS + cl;  // output column
+  const bool active = n < n_out;
   // weight row(s): SwiGLU weights interleave gate/up in blocks of 128 rows
-  long long r0 = n, r1 = -1;
+  long long r0 = active ? n : 0, r1 = r0;
   if constexpr (EPI == G2VLM_EPI_SWIGLU_BF16) {
-    r0 = (long long)(n >> 7) * 256 + (n & 127);
+    r0 = (long long)((active ? n : 0) >> 7) * 256 + ((active ? n : 0) & 127);
     r1 = r0 + 128;
   }
   const uint4* w0 = reinterpret_cast<const uint4*>(p.w + r0 * p.ldw);
-  const uint4* w1 = reinterpret_cast<const uint4*>(p.w + (r1 < 0 ? r0 : r1) * p.ldw);
-  float acc0[GEMV_MAX_ROWS], acc1[GEMV_MAX_ROWS];
+  const uint4* w1 = reinterpret_cast<const uint4*>(p.w + r1 * p.ldw);
+  float acc0[ROWS], acc1[ROWS];
 #pragma unroll
-  for (int m = 0; m < GEMV_MAX_ROWS; ++m) { acc0[m] = 0.f; acc1[m] = 0.f; }
+  for (int m = 0; m < ROWS; ++m) { acc0[m] = 0.f; acc1[m] = 0.f; }
   const int k8 = p.K >> 3;
-  for (int c = lane; c < k8; c += 32) {
-    const uint4 a = __ldg(w0 + c);
-    uint4 b = make_uint4(0, 0, 0, 0);
-    if constexpr (EPI == G2VLM_EPI_SWIGLU_BF16) b = __ldg(w1 + c);
+  const int per = (k8 + KSPLIT - 1) / KSPLIT;
+  const int kbeg = ks * per, kend = min(k8, kbeg + per);
+  constexpr int U = (ROWS == 1) ? 8 : 4;  // independent 16-byte weight loads in flight per lane
+  if (active) {
+    for (int c0 = kbeg + lane; c0 < kend; c0 += 32 * U) {
+      uint4 a[U], b[U];
 #pragma unroll
-    for (int m = 0; m < GEMV_MAX_ROWS; ++m) {
-      if (m < p.rows) {
-        const uint4 xv = __ldg(reinterpret_cast<const uint4*>(p.x + m * p.ldx) + c);
-        dot8(a, xv, acc0[m]);
-        if constexpr (EPI == G2VLM_EPI_SWIGLU_BF16) dot8(b, xv, acc1[m]);
+      for (int u = 0; u < U; ++u) {
+        const int c = c0 + 32 * u;
+        a[u] = c < kend ? __ldg(w0 + c) : make_uint4(0, 0, 0, 0);
+        if constexpr (EPI == G2VLM_EPI_SWIGLU_BF16) b[u] = c < kend ? __ldg(w1 + c) : make_uint4(0, 0, 0, 0);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int c = c0 + 32 * u;
+        if (c < kend) {
+#pragma unroll
+          for (int m = 0; m < ROWS; ++m) {
+            if (m < p.rows) {
+              const uint4 xv = __ldg(reinterpret_cast<const uint4*>(p.x + m * p.ldx) + c);
+              dot8(a[u], xv, acc0[m]);
+              if constexpr (EPI == G2VLM_EPI_SWIGLU_BF16) dot8(b[u], xv, acc1[m]);
+            }
+          }
+        }
       }
     }
   }
 #pragma unroll
-  for (int m = 0; m < GEMV_MAX_ROWS; ++m) {
-    if (m < p.rows) {
-      acc0[m] = warp_sum(acc0[m]);
-      if constexpr (EPI == G2VLM_EPI_SWIGLU_BF16) acc1[m] = warp_sum(acc1[m]);
+  for (int m = 0; m < ROWS; ++m) {
+    acc0[m] = warp_sum(acc0[m]);
+    if constexpr (EPI == G2VLM_EPI_SWIGLU_BF16) acc1[m] = warp_sum(acc1[m]);
+  }
+  if constexpr (KSPLIT > 1) {
+    if (lane == 0) {
+#pragma unroll
+      for (int m = 0; m < ROWS; ++m) { part[cl][ks][0][m] = acc0[m]; part[cl][ks][1][m] = acc1[m]; }
+    }
+    __syncthreads();
+    if (ks != 0) return;
+#pragma unroll
+    for (int m = 0; m < ROWS; ++m) {
+      acc0[m] = 0.f; acc1[m] = 0.f;
+#pragma unroll
+      for (int q = 0; q < KSPLIT; ++q) { acc0[m] += part[cl][q][0][m]; acc1[m] += part[cl][q][1][m]; }
     }
   }
-  if (lane != 0) return;
-  for (int m = 0; m < p.rows; ++m) {
+  if (lane != 0 || !active) return;
+  for (int m = 0; m < p.rows && m < ROWS; ++m) {
     const long long row = p.row0 + m;
     float f = acc0[m];
     if constexpr (EPI == G2VLM_EPI_SWIGLU_BF16) {
@@ -117,6 +149,18 @@ __global__ void __launch_bounds__(GEMV_WARPS * 32) gemv_bf16_kernel(const GemvPa
   }
 }
 
+template <int EPI>
+static void launch_gemv_epi(const GemvParams& p, int n_out, cudaStream_t stream) {
+  const bool one = p.rows == 1;
+  const bool split = p.K >= 4096;
+  const int cols = split ? GEMV_WARPS / 4 : GEMV_WARPS;
+  const unsigned grid = (n_out + cols - 1) / cols;
+  if (one && split) gemv_bf16_kernel<EPI, 1, 4><<<grid, GEMV_WARPS * 32, 0, stream>>>(p);
+  else if (one) gemv_bf16_kernel<EPI, 1, 1><<<grid, GEMV_WARPS * 32, 0, stream>>>(p);
+  else if (split) gemv_bf16_kernel<EPI, GEMV_MAX_ROWS, 4><<<grid, GEMV_WARPS * 32, 0, stream>>>(p);
+  else gemv_bf16_kernel<EPI, GEMV_MAX_ROWS, 1><<<grid, GEMV_WARPS * 32, 0, stream>>>(p);
+}
+
 // Called by g2vlm_gemm_bf16 when the call has <= GEMV_MAX_ROWS rows, all in ONE group.
 int launch_gemv(const g2vlm_gemm_args* a, int group, cudaStream_t stream) {
   GemvParams p;
@@ -137,12 +181,11 @@ int launch_gemv(const g2vlm_gemm_args* a, int group, cudaStream_t stream) {
   p.ldr = a->ldr;
   p.row0 = a->group_row0[group];
   const int n_out = a->epilogue == G2VLM_EPI_SWIGLU_BF16 ? a->N / 2 : a->N;
-  const unsigned grid = (n_out + GEMV_WARPS - 1) / GEMV_WARPS;
   switch (a->epilogue) {
-    case G2VLM_EPI_STORE_BF16: gemv_bf16_kernel<G2VLM_EPI_STORE_BF16><<<grid, GEMV_WARPS * 32, 0, stream>>>(p); break;
-    case G2VLM_EPI_SWIGLU_BF16: gemv_bf16_kernel<G2VLM_EPI_SWIGLU_BF16><<<grid, GEMV_WARPS * 32, 0, stream>>>(p); break;
-    case G2VLM_EPI_RESID_F32: gemv_bf16_kernel<G2VLM_EPI_RESID_F32><<<grid, GEMV_WARPS * 32, 0, stream>>>(p); break;
-    default: gemv_bf16_kernel<G2VLM_EPI_STORE_F32><<<grid, GEMV_WARPS * 32, 0, stream>>>(p); break;
+    case G2VLM_EPI_STORE_BF16: launch_gemv_epi<G2VLM_EPI_STORE_BF16>(p, n_out, stream); break;
+    case G2VLM_EPI_SWIGLU_BF16: launch_gemv_epi<G2VLM_EPI_SWIGLU_BF16>(p, n_out, stream); break;
+    case G2VLM_EPI_RESID_F32: launch_gemv_epi<G2VLM_EPI_RESID_F32>(p, n_out, stream); break;
+    default: launch_gemv_epi<G2VLM_EPI_STORE_F32>(p, n_out, stream); break;
   }
   G2_CUDA_OK(cudaGetLastError());
   return G2VLM_OK;
@@ -160,55 +203,83 @@ attn_decode_split_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat1
                          const __nv_bfloat16* __restrict__ v, long long ldv, int L_static,
                          const int* __restrict__ kv_len_dev, int kv_len_extra, int G, int chunk_static,
                          float scale_log2, float* __restrict__ part /*[splits][heads][130]*/, int n_heads) {
-  __shared__ float sq[DEC_MAX_G][128];
   __shared__ float ss[DEC_MAX_G][DEC_MAX_CHUNK];
   __shared__ float red[4][DEC_MAX_G][128];
   __shared__ float sm[DEC_MAX_G], sl[DEC_MAX_G];
   const int split = blockIdx.x, kvh = blockIdx.y, tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
   // the key count may live on the device (CUDA-graph replay of the decode step: same launch, growing cache)
   const int L = kv_len_dev ? (*kv_len_dev + kv_len_extra) : L_static;
-  const int chunk = kv_len_dev ? (L + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x) : chunk_static;
+  int chunk = chunk_static;
+  if (kv_len_dev) chunk = min(DEC_MAX_CHUNK, (L + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x));
   const int k0 = split * chunk, k1 = min(L, k0 + chunk), nk = max(0, k1 - k0);
-  for (int i = tid; i < G * 128; i += DEC_THREADS)
-    sq[i >> 7][i & 127] = __bfloat162float(q[(kvh * G + (i >> 7)) * 128 + (i & 127)]) * scale_log2;
-  __syncthreads();
-  // phase 1: scores (one key per thread, the 256-byte key row is read with 16-byte loads)
-  for (int j = tid; j < nk; j += DEC_THREADS) {
-    const uint4* kr = reinterpret_cast<const uint4*>(k + (long long)(k0 + j) * ldk + kvh * 128);
-    float acc[DEC_MAX_G];
+
+  // phase 1: scores. A warp reads 4 key rows per step: lane = (key kk = lane/8, 16-byte chunks cp and cp+8 of
+  // the 256-byte row) -> fully coalesced; the query (pre-scaled) sits in registers; 8-lane shuffle reduce.
+  const int kk = lane >> 3, cp = lane & 7;
+  float qr[DEC_MAX_G][16];
 #pragma unroll
-    for (int h = 0; h < DEC_MAX_G; ++h) acc[h] = 0.f;
-#pragma unroll 4
-    for (int c = 0; c < 16; ++c) {
-      const uint4 kv = __ldg(kr + c);
-      const __nv_bfloat162* pk = reinterpret_cast<const __nv_bfloat162*>(&kv);
-      float kf[8];
+  for (int h = 0; h < DEC_MAX_G; ++h) {
+    if (h < G) {
+      const uint4* qp = reinterpret_cast<const uint4*>(q + (kvh * G + h) * 128);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float2 f = __bfloat1622float2(pk[i]);
-        kf[2 * i] = f.x; kf[2 * i + 1] = f.y;
-      }
+      for (int half = 0; half < 2; ++half) {
+        const uint4 qv = __ldg(qp + cp + 8 * half);
+        const __nv_bfloat162* pq = reinterpret_cast<const __nv_bfloat162*>(&qv);
 #pragma unroll
-      for (int h = 0; h < DEC_MAX_G; ++h)
-        if (h < G) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) acc[h] = fmaf(kf[i], sq[h][c * 8 + i], acc[h]);
+        for (int i = 0; i < 4; ++i) {
+          const float2 f = __bfloat1622float2(pq[i]);
+          qr[h][half * 8 + 2 * i] = f.x * scale_log2;
+          qr[h][half * 8 + 2 * i + 1] = f.y * scale_log2;
         }
+      }
+    }
+  }
+  for (int j0 = warp * 4; j0 < nk; j0 += (DEC_THREADS / 32) * 4 * 2) {
+    uint4 kv[2][2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {  // two independent 4-key groups in flight
+      const int j = j0 + u * (DEC_THREADS / 32) * 4 + kk;
+      const uint4* kr = reinterpret_cast<const uint4*>(k + (long long)(k0 + min(j, nk - 1)) * ldk + kvh * 128);
+      kv[u][0] = __ldg(kr + cp);
+      kv[u][1] = __ldg(kr + cp + 8);
     }
 #pragma unroll
-    for (int h = 0; h < DEC_MAX_G; ++h)
-      if (h < G) ss[h][j] = acc[h];
+    for (int u = 0; u < 2; ++u) {
+      const int j = j0 + u * (DEC_THREADS / 32) * 4 + kk;
+      float kf[16];
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const __nv_bfloat162* pk = reinterpret_cast<const __nv_bfloat162*>(&kv[u][half]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float2 f = __bfloat1622float2(pk[i]);
+          kf[half * 8 + 2 * i] = f.x; kf[half * 8 + 2 * i + 1] = f.y;
+        }
+      }
+#pragma unroll
+      for (int h = 0; h < DEC_MAX_G; ++h) {
+        if (h < G) {
+          float a = 0.f;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) a = fmaf(kf[i], qr[h][i], a);
+          a += __shfl_xor_sync(0xffffffffu, a, 1);
+          a += __shfl_xor_sync(0xffffffffu, a, 2);
+          a += __shfl_xor_sync(0xffffffffu, a, 4);
+          if (cp == 0 && j < nk) ss[h][j] = a;
+        }
+      }
+    }
   }
   __syncthreads();
   // phase 2: per-head max / exp2 / sum over the chunk (one warp per head)
-  const int warp = tid >> 5, lane = tid & 31;
   if (warp < G) {
     float m = -INFINITY;
     for (int j = lane; j < nk; j += 32) m = fmaxf(m, ss[warp][j]);
     m = warp_max(m);
     float l = 0.f;
     for (int j = lane; j < nk; j += 32) {
-      const float pj = nk > 0 ? exp2f(ss[warp][j] - m) : 0.f;
+      const float pj = exp2f(ss[warp][j] - m);
       ss[warp][j] = pj;
       l += pj;
     }
@@ -216,21 +287,33 @@ attn_decode_split_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat1
     if (lane == 0) { sm[warp] = m; sl[warp] = l; }
   }
   __syncthreads();
-  // phase 3: o[h][d] = sum_j p[h][j] * v[j][d]; thread = (pair of d, key quarter)
+  // phase 3: o[h][d] = sum_j p[h][j] * v[j][d]; thread = (pair of d, key quarter); 8 value loads in flight
   const int dp = tid & 63, kq = tid >> 6;
   float o[DEC_MAX_G][2];
 #pragma unroll
   for (int h = 0; h < DEC_MAX_G; ++h) { o[h][0] = 0.f; o[h][1] = 0.f; }
-  for (int j = kq; j < nk; j += 4) {
-    const __nv_bfloat162 vv = *reinterpret_cast<const __nv_bfloat162*>(v + (long long)(k0 + j) * ldv + kvh * 128 + dp * 2);
-    const float2 vf = __bfloat1622float2(vv);
+  const __nv_bfloat16* vbase = v + (long long)k0 * ldv + kvh * 128 + dp * 2;
+  for (int j0 = kq; j0 < nk; j0 += 4 * 8) {
+    __nv_bfloat162 vv[8];
 #pragma unroll
-    for (int h = 0; h < DEC_MAX_G; ++h)
-      if (h < G) {
-        const float pj = ss[h][j];
-        o[h][0] = fmaf(pj, vf.x, o[h][0]);
-        o[h][1] = fmaf(pj, vf.y, o[h][1]);
+    for (int u = 0; u < 8; ++u) {
+      const int j = j0 + 4 * u;
+      vv[u] = *reinterpret_cast<const __nv_bfloat162*>(vbase + (long long)min(j, nk - 1) * ldv);
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int j = j0 + 4 * u;
+      if (j < nk) {
+        const float2 vf = __bfloat1622float2(vv[u]);
+#pragma unroll
+        for (int h = 0; h < DEC_MAX_G; ++h)
+          if (h < G) {
+            const float pj = ss[h][j];
+            o[h][0] = fmaf(pj, vf.x, o[h][0]);
+            o[h][1] = fmaf(pj, vf.y, o[h][1]);
+          }
       }
+    }
   }
 #pragma unroll
   for (int h = 0; h < DEC_MAX_G; ++h)
@@ -240,21 +323,36 @@ attn_decode_split_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat1
     const int h = i >> 7, d = i & 127;
     float* dst = part + ((long long)split * n_heads + kvh * G + h) * 130;
     dst[d] = red[0][h][d] + red[1][h][d] + red[2][h][d] + red[3][h][d];
-    if (d == 0) { dst[128] = sm[h]; dst[129] = sl[h]; }
+    if (d == 0) { dst[128] = nk > 0 ? sm[h] : -INFINITY; dst[129] = nk > 0 ? sl[h] : 0.f; }
   }
 }
 
 __global__ void attn_decode_merge_kernel(const float* __restrict__ part, int n_splits, int n_heads,
                                          __nv_bfloat16* __restrict__ out) {
   const int h = blockIdx.x, d = threadIdx.x;  // 128 threads
+  __shared__ float wgt[1024];
   float M = -INFINITY;
-  for (int s = 0; s < n_splits; ++s) M = fmaxf(M, part[((long long)s * n_heads + h) * 130 + 128]);
+  for (int s = d; s < n_splits; s += 128) M = fmaxf(M, part[((long long)s * n_heads + h) * 130 + 128]);
+  M = warp_max(M);
+  __shared__ float wm[4];
+  if ((d & 31) == 0) wm[d >> 5] = M;
+  __syncthreads();
+  M = fmaxf(fmaxf(wm[0], wm[1]), fmaxf(wm[2], wm[3]));
   float acc = 0.f, l = 0.f;
-  for (int s = 0; s < n_splits; ++s) {
-    const float* p = part + ((long long)s * n_heads + h) * 130;
-    const float w = p[129] > 0.f ? exp2f(p[128] - M) : 0.f;
-    acc = fmaf(w, p[d], acc);
-    l = fmaf(w, p[129], l);
+  for (int base = 0; base < n_splits; base += 1024) {
+    const int cnt = min(1024, n_splits - base);
+    __syncthreads();
+    for (int s = d; s < cnt; s += 128) {
+      const float* p = part + ((long long)(base + s) * n_heads + h) * 130;
+      wgt[s] = p[129] > 0.f ? exp2f(p[128] - M) * 1.0f : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int s = 0; s < cnt; ++s) {
+      const float* p = part + ((long long)(base + s) * n_heads + h) * 130;
+      acc = fmaf(wgt[s], p[d], acc);
+      l = fmaf(wgt[s], p[129], l);
+    }
   }
   out[h * 128 + d] = __float2bfloat16_rn(l > 0.f ? acc / l : 0.f);
 }
@@ -307,13 +405,8 @@ extern "C" int g2vlm_attention_decode(const void* q, const void* k, int64_t ldk,
   // with kv_len_dev the actual key count is *kv_len_dev + kv_len_extra (read on the device, <= kv_len);
   // kv_len then only sizes the split grid, so one captured launch serves a growing cache
   const int L = static_cast<int>(kv_len);
-  int n_splits = (L + 127) / 128;
-  if (n_splits > 148) n_splits = 148;
+  int n_splits = (L + 255) / 256;  // ~256 keys per CTA: enough CTAs to saturate HBM, little merge work
   int chunk = (L + n_splits - 1) / n_splits;
-  if (chunk > DEC_MAX_CHUNK) {
-    chunk = DEC_MAX_CHUNK;
-    n_splits = (L + chunk - 1) / chunk;
-  }
   G2_REQUIRE((long long)n_splits * num_q_heads * 130 <= workspace_floats, "attention_decode: workspace too small");
   cudaStream_t st = (cudaStream_t)stream;
   attn_decode_split_kernel<<<dim3(n_splits, num_kv_heads), DEC_THREADS, 0, st>>>(

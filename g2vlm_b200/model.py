@@ -419,8 +419,7 @@ class G2VLMFast:
             k_all, v_all = kv_exchange(qkv)
         if T == 1 and nq // nkv <= 8:
             # decode step: one query row sees every cached key -> flash-decoding split over the keys
-            ws = self.buf.get("und.dec_ws", (ops.attention_decode_workspace_floats(k_all.shape[0], nq) + 148 * nq * 130,),
-                              torch.float32)
+            ws = self.buf.get("und.dec_ws", (ops.attention_decode_workspace_floats(k_all.shape[0], nq),), torch.float32)
             ops.attention_decode(qkv[0, : nq * hd], k_all, v_all, attn[0], ws, num_q_heads=nq, num_kv_heads=nkv,
                                  head_dim=hd, scale=1.0 / math.sqrt(hd), kv_len_dev=kv_len_dev, kv_len_extra=1)
         else:

@@ -348,7 +348,4 @@ def kv_append(src, dst, rows: int, len_dev=None, static_row: int = 0):
 
 
 def attention_decode_workspace_floats(kv_len: int, num_q_heads: int) -> int:
-    splits = min((kv_len + 127) // 128, 148)
-    if (kv_len + splits - 1) // splits > 512:
-        splits = (kv_len + 511) // 512
-    return splits * num_q_heads * 130
+    return ((kv_len + 255) // 256) * num_q_heads * 130

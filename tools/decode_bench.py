@@ -13,7 +13,7 @@ from g2vlm_b200.model import G2VLMFast, NaiveCache
 
 steps = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 cfg = schema.FULL
-sd = schema.init_synthetic(cfg, seed=0, embed_rows=4096, device="cuda")
+sd = schema.init_synthetic(cfg, seed=0, device="cuda")  # full 151936-row embedding and lm_head
 model = G2VLMFast(cfg, sd)
 del sd
 torch.cuda.empty_cache()
