@@ -195,27 +195,44 @@ int launch_gemv(const g2vlm_gemm_args* a, int group, cudaStream_t stream) {
 // decode attention (one query token, head_dim 128)
 // ------------------------------------------------------------------------------------------------
 constexpr int DEC_THREADS = 256;
-constexpr int DEC_MAX_CHUNK = 512;  // keys per split
-constexpr int DEC_MAX_G = 8;        // query heads per KV head
+constexpr int DEC_CHUNK = 160;   // keys per CTA: K and V chunks (2 x 40 KB) are staged in shared memory
+constexpr int DEC_MAX_G = 8;     // query heads per KV head
+constexpr int DEC_SMEM = 2 * DEC_CHUNK * 256 + DEC_MAX_G * DEC_CHUNK * 4 + 4 * DEC_MAX_G * 128 * 4 + 64;
 
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+
+// One CTA = one KV head x one chunk of <= 160 keys. The whole K and V chunk is pulled into shared memory by
+// ONE round of cp.async issued up front (a decode step is latency-bound: the point is to have every byte in
+// flight at once), then scores / softmax statistics / P.V run out of shared memory.
 __global__ void __launch_bounds__(DEC_THREADS)
 attn_decode_split_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ k, long long ldk,
                          const __nv_bfloat16* __restrict__ v, long long ldv, int L_static,
-                         const int* __restrict__ kv_len_dev, int kv_len_extra, int G, int chunk_static,
+                         const int* __restrict__ kv_len_dev, int kv_len_extra, int G,
                          float scale_log2, float* __restrict__ part /*[splits][heads][130]*/, int n_heads) {
-  __shared__ float ss[DEC_MAX_G][DEC_MAX_CHUNK];
-  __shared__ float red[4][DEC_MAX_G][128];
-  __shared__ float sm[DEC_MAX_G], sl[DEC_MAX_G];
+  extern __shared__ __align__(16) uint8_t dsm[];
+  uint8_t* sK = dsm;                                   // [chunk][256 B]
+  uint8_t* sV = dsm + DEC_CHUNK * 256;                 // [chunk][256 B]
+  float (*ss)[DEC_CHUNK] = reinterpret_cast<float (*)[DEC_CHUNK]>(dsm + 2 * DEC_CHUNK * 256);
+  float (*red)[DEC_MAX_G][128] = reinterpret_cast<float (*)[DEC_MAX_G][128]>(dsm + 2 * DEC_CHUNK * 256 + DEC_MAX_G * DEC_CHUNK * 4);
+  float* sm = reinterpret_cast<float*>(dsm + 2 * DEC_CHUNK * 256 + DEC_MAX_G * DEC_CHUNK * 4 + 4 * DEC_MAX_G * 128 * 4);
+  float* sl = sm + DEC_MAX_G;
   const int split = blockIdx.x, kvh = blockIdx.y, tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
   // the key count may live on the device (CUDA-graph replay of the decode step: same launch, growing cache)
   const int L = kv_len_dev ? (*kv_len_dev + kv_len_extra) : L_static;
-  int chunk = chunk_static;
-  if (kv_len_dev) chunk = min(DEC_MAX_CHUNK, (L + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x));
+  const int chunk = min(DEC_CHUNK, (L + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x));
   const int k0 = split * chunk, k1 = min(L, k0 + chunk), nk = max(0, k1 - k0);
 
-  // phase 1: scores. A warp reads 4 key rows per step: lane = (key kk = lane/8, 16-byte chunks cp and cp+8 of
-  // the 256-byte row) -> fully coalesced; the query (pre-scaled) sits in registers; 8-lane shuffle reduce.
+  for (int i = tid; i < nk * 16; i += DEC_THREADS) {   // 16 x 16 B per 256-byte row
+    const int r = i >> 4, c = i & 15;
+    cp_async16(sK + r * 256 + c * 16, k + (long long)(k0 + r) * ldk + kvh * 128 + c * 8);
+    cp_async16(sV + r * 256 + c * 16, v + (long long)(k0 + r) * ldv + kvh * 128 + c * 8);
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+
+  // the query (pre-scaled by scale*log2e): lane = (key slot kk = lane/8, 16-byte chunks cp and cp+8)
   const int kk = lane >> 3, cp = lane & 7;
   float qr[DEC_MAX_G][16];
 #pragma unroll
@@ -235,39 +252,34 @@ attn_decode_split_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat1
       }
     }
   }
-  for (int j0 = warp * 4; j0 < nk; j0 += (DEC_THREADS / 32) * 4 * 2) {
-    uint4 kv[2][2];
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+
+  // phase 1: scores; a warp handles 4 keys per step, 8 lanes per key, shuffle-reduced
+  for (int j0 = warp * 4; j0 < nk; j0 += (DEC_THREADS / 32) * 4) {
+    const int j = j0 + kk;
+    const uint8_t* kr = sK + min(j, nk - 1) * 256;
+    float kf[16];
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {  // two independent 4-key groups in flight
-      const int j = j0 + u * (DEC_THREADS / 32) * 4 + kk;
-      const uint4* kr = reinterpret_cast<const uint4*>(k + (long long)(k0 + min(j, nk - 1)) * ldk + kvh * 128);
-      kv[u][0] = __ldg(kr + cp);
-      kv[u][1] = __ldg(kr + cp + 8);
+    for (int half = 0; half < 2; ++half) {
+      const uint4 kv = *reinterpret_cast<const uint4*>(kr + (cp + 8 * half) * 16);
+      const __nv_bfloat162* pk = reinterpret_cast<const __nv_bfloat162*>(&kv);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 f = __bfloat1622float2(pk[i]);
+        kf[half * 8 + 2 * i] = f.x; kf[half * 8 + 2 * i + 1] = f.y;
+      }
     }
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      const int j = j0 + u * (DEC_THREADS / 32) * 4 + kk;
-      float kf[16];
+    for (int h = 0; h < DEC_MAX_G; ++h) {
+      if (h < G) {
+        float a = 0.f;
 #pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        const __nv_bfloat162* pk = reinterpret_cast<const __nv_bfloat162*>(&kv[u][half]);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float2 f = __bfloat1622float2(pk[i]);
-          kf[half * 8 + 2 * i] = f.x; kf[half * 8 + 2 * i + 1] = f.y;
-        }
-      }
-#pragma unroll
-      for (int h = 0; h < DEC_MAX_G; ++h) {
-        if (h < G) {
-          float a = 0.f;
-#pragma unroll
-          for (int i = 0; i < 16; ++i) a = fmaf(kf[i], qr[h][i], a);
-          a += __shfl_xor_sync(0xffffffffu, a, 1);
-          a += __shfl_xor_sync(0xffffffffu, a, 2);
-          a += __shfl_xor_sync(0xffffffffu, a, 4);
-          if (cp == 0 && j < nk) ss[h][j] = a;
-        }
+        for (int i = 0; i < 16; ++i) a = fmaf(kf[i], qr[h][i], a);
+        a += __shfl_xor_sync(0xffffffffu, a, 1);
+        a += __shfl_xor_sync(0xffffffffu, a, 2);
+        a += __shfl_xor_sync(0xffffffffu, a, 4);
+        if (cp == 0 && j < nk) ss[h][j] = a;
       }
     }
   }
@@ -287,33 +299,20 @@ attn_decode_split_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat1
     if (lane == 0) { sm[warp] = m; sl[warp] = l; }
   }
   __syncthreads();
-  // phase 3: o[h][d] = sum_j p[h][j] * v[j][d]; thread = (pair of d, key quarter); 8 value loads in flight
+  // phase 3: o[h][d] = sum_j p[h][j] * v[j][d]; thread = (pair of d, key quarter)
   const int dp = tid & 63, kq = tid >> 6;
   float o[DEC_MAX_G][2];
 #pragma unroll
   for (int h = 0; h < DEC_MAX_G; ++h) { o[h][0] = 0.f; o[h][1] = 0.f; }
-  const __nv_bfloat16* vbase = v + (long long)k0 * ldv + kvh * 128 + dp * 2;
-  for (int j0 = kq; j0 < nk; j0 += 4 * 8) {
-    __nv_bfloat162 vv[8];
+  for (int j = kq; j < nk; j += 4) {
+    const float2 vf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(sV + j * 256 + dp * 4));
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const int j = j0 + 4 * u;
-      vv[u] = *reinterpret_cast<const __nv_bfloat162*>(vbase + (long long)min(j, nk - 1) * ldv);
-    }
-#pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const int j = j0 + 4 * u;
-      if (j < nk) {
-        const float2 vf = __bfloat1622float2(vv[u]);
-#pragma unroll
-        for (int h = 0; h < DEC_MAX_G; ++h)
-          if (h < G) {
-            const float pj = ss[h][j];
-            o[h][0] = fmaf(pj, vf.x, o[h][0]);
-            o[h][1] = fmaf(pj, vf.y, o[h][1]);
-          }
+    for (int h = 0; h < DEC_MAX_G; ++h)
+      if (h < G) {
+        const float pj = ss[h][j];
+        o[h][0] = fmaf(pj, vf.x, o[h][0]);
+        o[h][1] = fmaf(pj, vf.y, o[h][1]);
       }
-    }
   }
 #pragma unroll
   for (int h = 0; h < DEC_MAX_G; ++h)
@@ -327,34 +326,37 @@ attn_decode_split_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat1
   }
 }
 
-__global__ void attn_decode_merge_kernel(const float* __restrict__ part, int n_splits, int n_heads,
-                                         __nv_bfloat16* __restrict__ out) {
-  const int h = blockIdx.x, d = threadIdx.x;  // 128 threads
-  __shared__ float wgt[1024];
+// log-sum-exp merge of the splits: one block per head, 4 groups of 128 threads stride over the splits
+__global__ void __launch_bounds__(512)
+attn_decode_merge_kernel(const float* __restrict__ part, int n_splits, int n_heads, __nv_bfloat16* __restrict__ out) {
+  const int h = blockIdx.x, d = threadIdx.x & 127, grp = threadIdx.x >> 7;
+  __shared__ float wmax[16];
+  __shared__ float racc[4][128], rl[4];
   float M = -INFINITY;
-  for (int s = d; s < n_splits; s += 128) M = fmaxf(M, part[((long long)s * n_heads + h) * 130 + 128]);
+  for (int s = threadIdx.x; s < n_splits; s += 512) M = fmaxf(M, part[((long long)s * n_heads + h) * 130 + 128]);
   M = warp_max(M);
-  __shared__ float wm[4];
-  if ((d & 31) == 0) wm[d >> 5] = M;
+  if ((threadIdx.x & 31) == 0) wmax[threadIdx.x >> 5] = M;
   __syncthreads();
-  M = fmaxf(fmaxf(wm[0], wm[1]), fmaxf(wm[2], wm[3]));
+  M = wmax[0];
+#pragma unroll
+  for (int i = 1; i < 16; ++i) M = fmaxf(M, wmax[i]);
   float acc = 0.f, l = 0.f;
-  for (int base = 0; base < n_splits; base += 1024) {
-    const int cnt = min(1024, n_splits - base);
-    __syncthreads();
-    for (int s = d; s < cnt; s += 128) {
-      const float* p = part + ((long long)(base + s) * n_heads + h) * 130;
-      wgt[s] = p[129] > 0.f ? exp2f(p[128] - M) * 1.0f : 0.f;
-    }
-    __syncthreads();
-#pragma unroll 8
-    for (int s = 0; s < cnt; ++s) {
-      const float* p = part + ((long long)(base + s) * n_heads + h) * 130;
-      acc = fmaf(wgt[s], p[d], acc);
-      l = fmaf(wgt[s], p[129], l);
-    }
+#pragma unroll 4
+  for (int s = grp; s < n_splits; s += 4) {
+    const float* p = part + ((long long)s * n_heads + h) * 130;
+    const float ps = p[129];
+    const float w = ps > 0.f ? exp2f(p[128] - M) : 0.f;
+    acc = fmaf(w, p[d], acc);
+    l = fmaf(w, ps, l);
   }
-  out[h * 128 + d] = __float2bfloat16_rn(l > 0.f ? acc / l : 0.f);
+  racc[grp][d] = acc;
+  if (d == 0) rl[grp] = l;
+  __syncthreads();
+  if (grp == 0) {
+    const float a = racc[0][d] + racc[1][d] + racc[2][d] + racc[3][d];
+    const float lt = rl[0] + rl[1] + rl[2] + rl[3];
+    out[h * 128 + d] = __float2bfloat16_rn(lt > 0.f ? a / lt : 0.f);
+  }
 }
 
 // dst[(*len_dev or static_row) + i, :] = src[i, :] — the in-place append of a step's K|V rows
@@ -401,19 +403,24 @@ extern "C" int g2vlm_attention_decode(const void* q, const void* k, int64_t ldk,
   G2_REQUIRE(num_kv_heads > 0 && num_q_heads % num_kv_heads == 0 && num_q_heads / num_kv_heads <= DEC_MAX_G,
              "attention_decode: at most 8 query heads per KV head");
   G2_REQUIRE(kv_len > 0 && kv_len < (1LL << 31), "attention_decode: bad kv_len");
-  G2_REQUIRE(ldk % 8 == 0 && ldv % 2 == 0, "attention_decode: leading dimensions");
+  G2_REQUIRE(ldk % 8 == 0 && ldv % 8 == 0 && (reinterpret_cast<uintptr_t>(k) & 15) == 0 &&
+                 (reinterpret_cast<uintptr_t>(v) & 15) == 0, "attention_decode: k / v must be 16-byte aligned rows");
   // with kv_len_dev the actual key count is *kv_len_dev + kv_len_extra (read on the device, <= kv_len);
   // kv_len then only sizes the split grid, so one captured launch serves a growing cache
   const int L = static_cast<int>(kv_len);
-  int n_splits = (L + 255) / 256;  // ~256 keys per CTA: enough CTAs to saturate HBM, little merge work
-  int chunk = (L + n_splits - 1) / n_splits;
+  const int n_splits = (L + DEC_CHUNK - 1) / DEC_CHUNK;
+  static bool attr_set = false;
+  if (!attr_set) {
+    G2_CUDA_OK(cudaFuncSetAttribute(attn_decode_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DEC_SMEM));
+    attr_set = true;
+  }
   G2_REQUIRE((long long)n_splits * num_q_heads * 130 <= workspace_floats, "attention_decode: workspace too small");
   cudaStream_t st = (cudaStream_t)stream;
-  attn_decode_split_kernel<<<dim3(n_splits, num_kv_heads), DEC_THREADS, 0, st>>>(
+  attn_decode_split_kernel<<<dim3(n_splits, num_kv_heads), DEC_THREADS, DEC_SMEM, st>>>(
       (const __nv_bfloat16*)q, (const __nv_bfloat16*)k, ldk, (const __nv_bfloat16*)v, ldv, L, kv_len_dev,
-      kv_len_extra, num_q_heads / num_kv_heads, chunk, softmax_scale * 1.4426950408889634f, workspace, num_q_heads);
+      kv_len_extra, num_q_heads / num_kv_heads, softmax_scale * 1.4426950408889634f, workspace, num_q_heads);
   G2_CUDA_OK(cudaGetLastError());
-  attn_decode_merge_kernel<<<num_q_heads, 128, 0, st>>>(workspace, n_splits, num_q_heads, (__nv_bfloat16*)out);
+  attn_decode_merge_kernel<<<num_q_heads, 512, 0, st>>>(workspace, n_splits, num_q_heads, (__nv_bfloat16*)out);
   G2_CUDA_OK(cudaGetLastError());
   return G2VLM_OK;
 }

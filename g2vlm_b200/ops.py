@@ -348,4 +348,4 @@ def kv_append(src, dst, rows: int, len_dev=None, static_row: int = 0):
 
 
 def attention_decode_workspace_floats(kv_len: int, num_q_heads: int) -> int:
-    return ((kv_len + 255) // 256) * num_q_heads * 130
+    return ((kv_len + 159) // 160) * num_q_heads * 130

@@ -239,7 +239,7 @@ int g2vlm_camera_pose(const float* feat, int64_t ldf, const float* w_t, const fl
  * Replaces flash_attn_varlen_func at g2vlm/qwen2vl.py:643-652 for the decode steps of generate_text
  * (g2vlm.py:1100-1113; with one query row the bottom-right causal mask hides nothing).
  * q bf16 [num_q_heads*128]; k / v bf16 [kv_len, num_kv_heads*128] (ldk / ldv); out bf16 [num_q_heads*128];
- * workspace fp32, at least ceil(kv_len/256) * num_q_heads * 130 floats.
+ * workspace fp32, at least ceil(kv_len/160) * num_q_heads * 130 floats.
  * kv_len_dev (DEVICE int32, or NULL): if given, the number of keys is *kv_len_dev + kv_len_extra, read on
  * the device, and kv_len is only an upper bound that sizes the split grid — one captured launch (CUDA graph)
  * then serves every step of a growing cache. */

@@ -110,3 +110,17 @@ def test_attention_decode_device_resident_length_and_kv_append():
         ref = (torch.softmax(q.float().view(nq, 1, hd) @ ks.transpose(1, 2) * scale, -1) @ vs).reshape(-1)
         assert (out.float() - ref).abs().max().item() < 1e-2
         len_dev += 1
+
+
+@pytest.mark.parametrize("rows,vocab", [(1, 151936), (3, 512), (2, 40000)])
+def test_argmax_lowest_index_on_ties(rows, vocab):
+    from g2vlm_b200 import ops
+    g = torch.Generator().manual_seed(vocab)
+    logits = torch.randn(rows, vocab, generator=g).to(torch.bfloat16)
+    logits[0, vocab // 3] = 100.0
+    logits[0, vocab // 3 + 777 if vocab > 2000 else vocab // 3 + 7] = 100.0      # tie: the lower index must win
+    out = torch.full((rows,), -1, dtype=torch.int64, device="cuda")
+    for _ in range(2):                                                            # twice: the ticket counter resets
+        ops.argmax_bf16(logits.cuda(), out)
+        assert out[0].item() == vocab // 3
+        assert torch.equal(out.cpu()[1:], logits[1:].float().argmax(-1))
