@@ -505,10 +505,51 @@ class G2VLMFast:
         self._und_forward(x, packed_text_position_ids, cache, causal=True)
         return cache
 
+    def _decode_args(self, cache: "KVCache", bound: int, cur, pos, len_dev):
+        """Plain-C argument block of g2vlm_und_decode_step for this generation (und-expert weight pointers)."""
+        import ctypes
+        cfg = self.cfg
+        H, I, nq, nkv, hd = cfg.hidden_size, cfg.intermediate_size, cfg.num_heads, cfg.num_kv_heads, cfg.head_dim
+        qkv_w = (nq + 2 * nkv) * hd
+        if not hasattr(self, "_und_layer_array"):
+            arr = (ops.UndLayerWeights * cfg.num_layers)()
+            for i, L in enumerate(self.layers):
+                w = arr[i]
+                # expert 1 (und) is the second half of every stacked [geo | und] tensor
+                w.wqkv = L["wqkv"].data_ptr() + qkv_w * H * 2
+                w.bqkv = L["bqkv"].data_ptr() + qkv_w * 4
+                w.wo = L["wo"].data_ptr() + H * nq * hd * 2
+                w.wgu = L["wgu"].data_ptr() + 2 * I * H * 2
+                w.wdown = L["wdown"].data_ptr() + H * I * 2
+                w.input_norm = L["input_layernorm_und"].data_ptr()
+                w.post_norm = L["post_attention_layernorm_und"].data_ptr()
+                w.q_norm = L["q_norm_und"].data_ptr()
+                w.k_norm = L["k_norm_und"].data_ptr()
+            self._und_layer_array = arr
+        V = self.lm_head.shape[0]
+        kv = (ctypes.c_void_p * cfg.num_layers)(*[b.data_ptr() for b in cache.buf])
+        g = self.buf.get
+        bufs = dict(x=g("dec.x", (H,), torch.float32), h=g("dec.h", (max(H, I),), torch.bfloat16),
+                    qkv=g("dec.qkv", (qkv_w,), torch.bfloat16), attn=g("dec.attn", (nq * hd,), torch.bfloat16),
+                    act=g("dec.act", (I,), torch.bfloat16), y=g("dec.y", (H,), torch.float32),
+                    cos_sin=g("dec.cs", (hd,), torch.float32),
+                    attn_ws=g("dec.ws", (ops.attention_decode_workspace_floats(bound, nq),), torch.float32),
+                    logits=g("dec.logits", ((V + 7) // 8 * 8,), torch.bfloat16))
+        a = ops.DecodeStepArgs()
+        a.num_layers, a.hidden, a.intermediate, a.n_q_heads, a.n_kv_heads, a.head_dim = cfg.num_layers, H, I, nq, nkv, hd
+        a.vocab, a.rms_eps, a.mrope_s0, a.mrope_s1 = V, cfg.rms_norm_eps, cfg.mrope_section[0], cfg.mrope_section[1]
+        a.layers, a.kv, a.kv_capacity, a.kv_bound = self._und_layer_array, kv, cache.cap, bound
+        a.embed, a.final_norm, a.lm_head = self.embed.data_ptr(), self.norm_und.data_ptr(), self.lm_head.data_ptr()
+        a.inv_freq, a.cur_token, a.position, a.cache_len = self.inv_freq.data_ptr(), cur.data_ptr(), pos.data_ptr(), len_dev.data_ptr()
+        for k, t in bufs.items():
+            setattr(a, k, t.data_ptr())
+        a.attn_ws_floats = bufs["attn_ws"].numel()
+        return a, (kv, bufs)
+
     @torch.no_grad()
     def generate_text(self, past_key_values, packed_key_value_indexes, key_values_lens, packed_start_tokens,
                       packed_query_position_ids, max_length: int, do_sample: bool = False, temperature: float = 1.0,
-                      end_token_id: Optional[int] = None, return_logits: bool = False, use_cuda_graph: bool = True):
+                      end_token_id: Optional[int] = None, return_logits: bool = False, use_cuda_graph: bool = False):
         """Greedy decode loop of the reference (g2vlm.py:1070-1141), batch 1: returns the generated ids
         [steps, 1] INCLUDING the start token, like the reference.  The KV cache is appended in place."""
         cfg, dev = self.cfg, self.device
@@ -540,6 +581,12 @@ class G2VLMFast:
             pos.add_(1)
             len_dev.add_(1)
 
+        if not return_logits:
+            # native driver: the whole step (~260 launches) is enqueued by ONE C-ABI call
+            args, keep = self._decode_args(cache, bound, cur, pos, len_dev)
+
+            def step():  # noqa: F811
+                ops.und_decode_step(args)
         graph = None
         n_done, all_logits = 0, []
         check_every = 8

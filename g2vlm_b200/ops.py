@@ -349,3 +349,29 @@ def kv_append(src, dst, rows: int, len_dev=None, static_row: int = 0):
 
 def attention_decode_workspace_floats(kv_len: int, num_q_heads: int) -> int:
     return ((kv_len + 159) // 160) * num_q_heads * 130
+
+
+class UndLayerWeights(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_void_p) for n in ("wqkv", "bqkv", "wo", "wgu", "wdown", "input_norm", "post_norm",
+                                               "q_norm", "k_norm")]
+
+
+class DecodeStepArgs(ctypes.Structure):
+    _fields_ = [
+        ("num_layers", ctypes.c_int32), ("hidden", ctypes.c_int32), ("intermediate", ctypes.c_int32),
+        ("n_q_heads", ctypes.c_int32), ("n_kv_heads", ctypes.c_int32), ("head_dim", ctypes.c_int32),
+        ("vocab", ctypes.c_int32), ("rms_eps", ctypes.c_float), ("mrope_s0", ctypes.c_int32), ("mrope_s1", ctypes.c_int32),
+        ("layers", ctypes.POINTER(UndLayerWeights)), ("kv", ctypes.POINTER(ctypes.c_void_p)),
+        ("kv_capacity", ctypes.c_int64), ("kv_bound", ctypes.c_int64),
+        ("embed", ctypes.c_void_p), ("final_norm", ctypes.c_void_p), ("lm_head", ctypes.c_void_p),
+        ("inv_freq", ctypes.c_void_p), ("cur_token", ctypes.c_void_p), ("position", ctypes.c_void_p),
+        ("cache_len", ctypes.c_void_p),
+        ("x", ctypes.c_void_p), ("h", ctypes.c_void_p), ("qkv", ctypes.c_void_p), ("attn", ctypes.c_void_p),
+        ("act", ctypes.c_void_p), ("y", ctypes.c_void_p), ("cos_sin", ctypes.c_void_p),
+        ("attn_ws", ctypes.c_void_p), ("attn_ws_floats", ctypes.c_int64), ("logits", ctypes.c_void_p),
+    ]
+
+
+def und_decode_step(args: DecodeStepArgs) -> None:
+    """One greedy decode step issued natively (see g2vlm_und_decode_step)."""
+    _check(_lib.load().g2vlm_und_decode_step(ctypes.byref(args), _stream()))

@@ -255,6 +255,52 @@ int g2vlm_kv_append(const void* src, int64_t src_pitch_bytes, void* dst, int64_t
                     const int32_t* len_dev, int64_t static_row, int64_t rows, int64_t row_bytes,
                     void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * One greedy decode step of generate_text (g2vlm.py:1086-1131), `und` expert, batch 1, enqueued as ONE call:
+ * embed(cur_token) -> L x [RMSNorm -> qkv GEMV -> q/k-norm + M-RoPE -> append K|V at row *cache_len ->
+ * split-K attention over *cache_len + 1 keys -> o_proj GEMV (+residual) -> RMSNorm -> gate/up GEMV + SwiGLU ->
+ * down GEMV (+residual)] -> final RMSNorm -> lm_head GEMV -> argmax -> cur_token; position += 1; cache_len += 1.
+ * Everything a step depends on (token, position, cache length) lives on the DEVICE, so the host issues the
+ * same ~260 launches per token from native code (no per-kernel Python / FFI overhead; graph-capturable).
+ * All pointers are device pointers except `layers` and `kv` (HOST arrays of num_layers entries).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct g2vlm_und_layer_weights {
+  const void* wqkv;  const float* bqkv;  /* bf16 [(nq+2nkv)*hd, H], fp32 bias (bf16-rounded values) */
+  const void* wo;                        /* bf16 [H, nq*hd] */
+  const void* wgu;                       /* bf16 [2I, H], gate/up interleaved in blocks of 128 rows */
+  const void* wdown;                     /* bf16 [H, I] */
+  const float* input_norm;  const float* post_norm;  const float* q_norm;  const float* k_norm;
+} g2vlm_und_layer_weights;
+
+typedef struct g2vlm_decode_step_args {
+  int32_t num_layers, hidden, intermediate, n_q_heads, n_kv_heads, head_dim, vocab;
+  float rms_eps;
+  int32_t mrope_s0, mrope_s1;
+  const g2vlm_und_layer_weights* layers; /* HOST array [num_layers] */
+  void* const* kv;                       /* HOST array [num_layers] of device bf16 [kv_capacity, 2*nkv*hd] (K|V) */
+  int64_t kv_capacity;                   /* rows available in every cache buffer */
+  int64_t kv_bound;                      /* upper bound of *cache_len + 1 during this generation (split sizing) */
+  const float* embed;                    /* fp32 [vocab_rows, H] */
+  const float* final_norm;               /* fp32 [H] */
+  const void* lm_head;                   /* bf16 [vocab, H] */
+  const float* inv_freq;                 /* fp32 [head_dim/2] */
+  int64_t* cur_token;                    /* in: token to process, out: next token */
+  int64_t* position;                     /* int64 [3] (t,h,w rope ids), incremented */
+  int32_t* cache_len;                    /* int32 [1], incremented */
+  /* workspaces */
+  float* x;        /* fp32 [H] residual stream */
+  void* h;         /* bf16 [max(H, I)] */
+  void* qkv;       /* bf16 [(nq+2nkv)*hd] */
+  void* attn;      /* bf16 [nq*hd] */
+  void* act;       /* bf16 [I] */
+  float* y;        /* fp32 [H] */
+  float* cos_sin;  /* fp32 [head_dim] (cos | sin) */
+  float* attn_ws;  int64_t attn_ws_floats;
+  void* logits;    /* bf16 [round_up(vocab, 8)] */
+} g2vlm_decode_step_args;
+
+int g2vlm_und_decode_step(const g2vlm_decode_step_args* args, void* stream);
+
 /* Greedy token selection of generate_text (g2vlm.py:1122-1126, `torch.argmax(pred_logits, dim=-1)`):
  * logits bf16 [rows, vocab] (leading dim ld) -> int64 [rows]; ties resolve to the lowest index. */
 int g2vlm_argmax_bf16(const void* logits, int64_t ld, int64_t rows, int32_t vocab, int64_t* out,

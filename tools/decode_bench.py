@@ -27,7 +27,7 @@ def text_inputs(n, kvlen, rope):
                 packed_key_value_indexes=torch.arange(kvlen), key_values_lens=torch.tensor([kvlen], dtype=torch.int)), kvlen + n, rope + n
 
 
-def run():
+def run(graph=True):
     past = NaiveCache(cfg.num_layers)
     gi, kvlen, rope = text_inputs(20, 0, 0)
     past = model.forward_cache_update_text(past, **gi)
@@ -38,12 +38,15 @@ def run():
     past = model.forward_cache_update_text(past, **gi)
     torch.cuda.synchronize(); t_prefill = time.perf_counter() - t0
     t0 = time.perf_counter()
-    out = model.generate_text(past, None, None, torch.tensor([7]), torch.full((3, 1), rope), steps, end_token_id=None)
+    out = model.generate_text(past, None, None, torch.tensor([7]), torch.full((3, 1), rope), steps, end_token_id=None,
+                              use_cuda_graph=graph)
     torch.cuda.synchronize(); t_dec = time.perf_counter() - t0
     return t_prefill, t_dec, past.seq_lens, out
 
 
 run()
+tp, td, L, out = run(graph=False)
+print(f"eager launches: {td / steps * 1e3:.3f} ms/token")
 tp, td, L, out = run()
 print(f"cache length {L}; 60-token question prefill {tp * 1e3:.2f} ms; decode {steps} tokens in {td * 1e3:.1f} ms = "
       f"{td / steps * 1e3:.3f} ms/token = {steps / td:.1f} tokens/s (batch 1, greedy, lm_head {cfg.vocab_size}-way)")
