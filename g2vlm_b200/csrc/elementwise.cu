@@ -71,6 +71,41 @@ __global__ void rmsnorm_routed_kernel(const float* __restrict__ x, long long ldx
   }
 }
 
+// few rows (decode steps, 7-token prefill): one BLOCK per row so every element is in flight at once — the
+// warp-per-row kernel above is latency-bound there (12 dependent-latency load rounds per lane for H = 1536)
+__global__ void __launch_bounds__(256)
+rmsnorm_routed_block_kernel(const float* __restrict__ x, long long ldx, void* __restrict__ out, long long ldo,
+                            int out_bf16, const float* __restrict__ w_a, const float* __restrict__ w_b,
+                            long long n_first, int dim, float eps) {
+  __shared__ float red[8];
+  const long long row = blockIdx.x;
+  const float4* xr = reinterpret_cast<const float4*>(x + row * ldx);
+  const int n4 = dim >> 2;
+  float4 v[4];  // dim <= 4096
+  float ss = 0.f;
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int i = threadIdx.x + 256 * u;
+    v[u] = i < n4 ? xr[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    ss += v[u].x * v[u].x + v[u].y * v[u].y + v[u].z * v[u].z + v[u].w * v[u].w;
+  }
+  ss = warp_sum(ss);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+  __syncthreads();
+  ss = red[0] + red[1] + red[2] + red[3] + red[4] + red[5] + red[6] + red[7];
+  const float r = rsqrtf(ss / dim + eps);
+  const float4* w = reinterpret_cast<const float4*>(row < n_first ? w_a : w_b);
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int i = threadIdx.x + 256 * u;
+    if (i < n4) {
+      const float4 g = __ldg(w + i);
+      store4(out, out_bf16, row * ldo + 4LL * i, g.x * (v[u].x * r), g.y * (v[u].y * r), g.z * (v[u].z * r),
+             g.w * (v[u].w * r));
+    }
+  }
+}
+
 __global__ void layernorm_kernel(const float* __restrict__ x, long long ldx, void* __restrict__ out,
                                  long long ldo, int out_bf16, const float* __restrict__ w,
                                  const float* __restrict__ b, long long rows, int dim, float eps, int seg_in,
@@ -692,6 +727,12 @@ extern "C" int g2vlm_rmsnorm_routed(const float* x, int64_t ldx, void* out, int6
   G2_REQUIRE(dim > 0 && dim % 4 == 0 && ldx % 4 == 0 && ldo % 4 == 0, "rmsnorm: dim/ld must be multiples of 4");
   G2_REQUIRE(G2_ALIGNED16(x) && G2_ALIGNED16(out) && G2_ALIGNED16(w_a) && G2_ALIGNED16(w_b), "rmsnorm: alignment");
   if (rows <= 0) return G2VLM_OK;
+  if (rows <= 64 && dim <= 4096) {
+    rmsnorm_routed_block_kernel<<<static_cast<unsigned>(rows), 256, 0, (cudaStream_t)stream>>>(
+        x, ldx, out, ldo, out_bf16, w_a, w_b, n_first, dim, eps);
+    G2_LAUNCH_CHECK();
+    return G2VLM_OK;
+  }
   rmsnorm_routed_kernel<<<blocks_for(rows, EW_THREADS / 32), EW_THREADS, 0, (cudaStream_t)stream>>>(
       x, ldx, out, ldo, out_bf16, w_a, w_b, rows, n_first, dim, eps);
   G2_LAUNCH_CHECK();
