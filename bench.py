@@ -162,11 +162,15 @@ def run_reference_arm(args):
     threads = os.cpu_count() or 1
     v, desc, per_step = cpu_sample(args.cpu_views, 518, max(1, args.steps), min(args.warmup, 1), threads,
                                    layer_frac=args.cpu_layer_frac)
+    P = (args.size // 14) ** 2
     line = dict(metric=METRIC, value=v, unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
                 ms_per_step=per_step * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16",
-                data="synthetic", impl="reference",
-                config=dict(workload="G2VLM-2B-MoT recon, 518px views, CPU sample (see cpu_baseline.sample)",
-                            views_per_scene=args.cpu_views, image_size=518),
+                data="synthetic (seeded random-init weights, blurred-noise views)", impl="reference",
+                # same workload as our arm; every step is a BOUNDED SAMPLE of it (cpu_baseline.sample): the
+                # 1-view sample under-counts the quadratic attention of the 16-view scene, i.e. it favours the CPU
+                config=dict(workload="G2VLM-2B-MoT recon bf16, 16 views 518px, single B200 (BASELINE configs[1]); one scene per GPU",
+                            views_per_scene=args.views, image_size=args.size, tokens=args.views * (P + 2),
+                            scenes_per_step=1, parallelism="host cores (reference algorithm, CPU)"),
                 cpu_baseline=dict(value=v, unit=UNIT, cores=threads, kind="port", sample=desc),
                 e2e=dict(value=v, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
     print(json.dumps(line))
