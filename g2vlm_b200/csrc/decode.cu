@@ -129,6 +129,7 @@ __global__ void __launch_bounds__(GEMV_WARPS * 32) gemv_bf16_kernel(const GemvPa
       if (p.bias) f += p.bias[n];
       if constexpr (EPI == G2VLM_EPI_STORE_BF16) {
         if (p.flags & G2VLM_GEMM_GELU) f = gelu_erf_d(bf16_round(f));
+        else if (p.flags & G2VLM_GEMM_QUICK_GELU) { const float xq = bf16_round(f); f = xq / (1.0f + __expf(-1.702f * xq)); }
         reinterpret_cast<__nv_bfloat16*>(p.out)[row * p.ldo + n] = __float2bfloat16_rn(f);
       } else if constexpr (EPI == G2VLM_EPI_RESID_F32) {
         f = bf16_round(f);
@@ -136,7 +137,9 @@ __global__ void __launch_bounds__(GEMV_WARPS * 32) gemv_bf16_kernel(const GemvPa
           f *= p.scale[n];
           if (p.flags & G2VLM_GEMM_ROUND_AFTER_SCALE) f = bf16_round(f);
         }
-        reinterpret_cast<float*>(p.out)[row * p.ldo + n] += f;
+        float* xo = reinterpret_cast<float*>(p.out) + row * p.ldo + n;
+        const float xs = *xo + f;
+        *xo = (p.flags & G2VLM_GEMM_ROUND_SUM) ? bf16_round(xs) : xs;
       } else {
         if (p.flags & G2VLM_GEMM_ROUND_BF16) f = bf16_round(f);
         float* o = reinterpret_cast<float*>(p.out) + row * p.ldo + n;

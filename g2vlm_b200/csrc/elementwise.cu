@@ -365,6 +365,26 @@ __global__ void rope2d_vec8_kernel(__nv_bfloat16* __restrict__ buf, long long ld
   }
 }
 
+// vision rotary (Qwen2-VL ViT): rotate_half over the whole head, per-token cos/sin; one thread per pair
+__global__ void rope_vision_kernel(__nv_bfloat16* __restrict__ buf, long long ld, long long rows, int n_heads,
+                                   int head_stride, int head_dim, const float* __restrict__ cos_tab,
+                                   const float* __restrict__ sin_tab) {
+  const int half = head_dim >> 1;
+  const long long total = rows * n_heads * half;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int j = static_cast<int>(i % half);
+    const long long rh = i / half;
+    const int head = static_cast<int>(rh % n_heads);
+    const long long row = rh / n_heads;
+    const float c = cos_tab[row * half + j], s = sin_tab[row * half + j];
+    __nv_bfloat16* p = buf + row * ld + (long long)head * head_stride + j;
+    const float a = __bfloat162float(p[0]), b = __bfloat162float(p[half]);
+    p[0] = __float2bfloat16_rn(a * c - b * s);
+    p[half] = __float2bfloat16_rn(b * c + a * s);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // heads
 // ------------------------------------------------------------------------------------------------
@@ -923,6 +943,18 @@ extern "C" int g2vlm_argmax_bf16(const void* logits, int64_t ld, int64_t rows, i
   const unsigned slices = vocab >= 16384 ? ARGMAX_SLICES : 1;
   argmax_bf16_kernel<<<dim3(static_cast<unsigned>(rows), slices), 256, 0, (cudaStream_t)stream>>>(
       (const __nv_bfloat16*)logits, ld, vocab, (long long*)out);
+  G2_LAUNCH_CHECK();
+  return G2VLM_OK;
+}
+
+extern "C" int g2vlm_rope_vision(void* buf, int64_t ld, int64_t rows, int32_t n_heads_total, int32_t head_stride,
+                                 int32_t head_dim, const float* cos_tab, const float* sin_tab, void* stream) {
+  G2_REQUIRE(buf && cos_tab && sin_tab, "rope_vision: null tensor");
+  G2_REQUIRE(head_dim > 0 && head_dim % 2 == 0 && head_dim <= head_stride, "rope_vision: bad head_dim");
+  if (rows <= 0) return G2VLM_OK;
+  const long long total = rows * n_heads_total * (head_dim / 2);
+  rope_vision_kernel<<<blocks_for(total, EW_THREADS * 4), EW_THREADS, 0, (cudaStream_t)stream>>>(
+      (__nv_bfloat16*)buf, ld, rows, n_heads_total, head_stride, head_dim, cos_tab, sin_tab);
   G2_LAUNCH_CHECK();
   return G2VLM_OK;
 }

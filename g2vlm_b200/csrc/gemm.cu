@@ -203,6 +203,12 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, const TileCo
         if (p.flags & G2VLM_GEMM_GELU) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = gelu_erf(bf16_round(f[j]));
+        } else if (p.flags & G2VLM_GEMM_QUICK_GELU) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float xq = bf16_round(f[j]);
+            f[j] = xq / (1.0f + __expf(-1.702f * xq));
+          }
         }
         uint32_t pk[16];
 #pragma unroll
@@ -243,11 +249,17 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, const TileCo
             if (c4 + 4 <= cols_ok) {
               float4 x = old[i];
               x.x += a.x; x.y += a.y; x.z += a.z; x.w += a.w;
+              if (p.flags & G2VLM_GEMM_ROUND_SUM) {
+                x.x = bf16_round(x.x); x.y = bf16_round(x.y); x.z = bf16_round(x.z); x.w = bf16_round(x.w);
+              }
               *reinterpret_cast<float4*>(d) = x;
             } else {
               const float av[4] = {a.x, a.y, a.z, a.w};
               for (int j = 0; j < 4; ++j)
-                if (c4 + j < cols_ok) d[j] += av[j];
+                if (c4 + j < cols_ok) {
+                  const float xs = d[j] + av[j];
+                  d[j] = (p.flags & G2VLM_GEMM_ROUND_SUM) ? bf16_round(xs) : xs;
+                }
             }
           }
         }

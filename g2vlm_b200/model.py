@@ -346,6 +346,32 @@ class G2VLMFast:
             self.cam[n + "w"] = _f32(g(f"camera_head.{n}.weight"), dev)
             self.cam[n + "b"] = _f32(g(f"camera_head.{n}.bias"), dev)
 
+        # ---- Qwen2-VL ViT (chat path, row f2) ----
+        self.vit = None
+        if cfg.vit_depth > 0 and "vit_model.patch_embed.proj.weight" in sd:
+            E, vh = cfg.vit_embed_dim, cfg.vit_heads
+            vhd = E // vh
+            self.vit_hp = _pad_dim(vhd)
+            v = "vit_model."
+            V = dict(wpatch=_bf16(g(v + "patch_embed.proj.weight").reshape(E, -1), dev), blocks=[])
+            for i in range(cfg.vit_depth):
+                p = f"{v}blocks.{i}."
+                qw = g(p + "attn.qkv.weight").reshape(3, vh * vhd, E)
+                qb = g(p + "attn.qkv.bias").reshape(3, vh * vhd)
+                B = dict(wqkv=_bf16(torch.cat([_pad_head_rows(qw[j], vh, vhd, self.vit_hp) for j in range(3)], 0), dev),
+                         bqkv=_bias_bf16(torch.cat([_pad_head_rows(qb[j], vh, vhd, self.vit_hp) for j in range(3)], 0), dev),
+                         wproj=_bf16(_pad_head_cols(g(p + "attn.proj.weight"), vh, vhd, self.vit_hp), dev),
+                         bproj=_bias_bf16(g(p + "attn.proj.bias"), dev),
+                         wfc1=_bf16(g(p + "mlp.fc1.weight"), dev), bfc1=_bias_bf16(g(p + "mlp.fc1.bias"), dev),
+                         wfc2=_bf16(g(p + "mlp.fc2.weight"), dev), bfc2=_bias_bf16(g(p + "mlp.fc2.bias"), dev))
+                for n in ("norm1", "norm2"):
+                    B[n + "w"] = _f32(g(p + n + ".weight"), dev); B[n + "b"] = _f32(g(p + n + ".bias"), dev)
+                V["blocks"].append(B)
+            V.update(lnw=_f32(g(v + "merger.ln_q.weight"), dev), lnb=_f32(g(v + "merger.ln_q.bias"), dev),
+                     wm0=_bf16(g(v + "merger.mlp.0.weight"), dev), bm0=_bias_bf16(g(v + "merger.mlp.0.bias"), dev),
+                     wm2=_bf16(g(v + "merger.mlp.2.weight"), dev), bm2=_bias_bf16(g(v + "merger.mlp.2.bias"), dev))
+            self.vit = V
+
     # ------------------------------------------------------------------------------------------
     # small cached host-built tables
     # ------------------------------------------------------------------------------------------
@@ -1039,6 +1065,187 @@ class G2VLMFast:
         pred["camera_poses_all"] = poses_all.view(1, N, 4, 4)
         pred["view_range"] = (shard.v0, shard.v1)
         return pred
+
+    # ------------------------------------------------------------------------------------------
+    # Qwen2-VL ViT + chat path (rows f1 / f2)
+    # ------------------------------------------------------------------------------------------
+    def _vit_rope_tables(self, grid_thw):
+        """cos / sin [T, head_dim/2] of rot_pos_emb (modeling_qwen2_vl.py:1024-1048), built on the host exactly
+        like the reference (positions in 2x2-merge-major patch order), cached per grid."""
+        key = ("vit_rope",) + tuple(int(x) for x in grid_thw.flatten().tolist())
+        t = self._rope2d_cache.get(key)
+        if t is None:
+            cfg = self.cfg
+            m, hd = cfg.vit_merge, cfg.vit_embed_dim // cfg.vit_heads
+            pos = []
+            for tt, h, w in grid_thw.tolist():
+                hp = torch.arange(h).unsqueeze(1).expand(-1, w).reshape(h // m, m, w // m, m).permute(0, 2, 1, 3).flatten()
+                wp = torch.arange(w).unsqueeze(0).expand(h, -1).reshape(h // m, m, w // m, m).permute(0, 2, 1, 3).flatten()
+                pos.append(torch.stack([hp, wp], dim=-1).repeat(tt, 1))
+            pos = torch.cat(pos, dim=0)
+            inv_freq = 1.0 / (10000.0 ** (torch.arange(0, hd // 2, 2, dtype=torch.float) / (hd // 2)))
+            freqs = torch.outer(torch.arange(int(grid_thw[:, 1:].max())).float(), inv_freq)
+            rot = freqs[pos].flatten(1)
+            t = (rot.cos().contiguous().to(self.device), rot.sin().contiguous().to(self.device))
+            self._rope2d_cache[key] = t
+        return t
+
+    @torch.no_grad()
+    def vit_forward(self, pixel_values, grid_thw, out=None):
+        """Qwen2VisionTransformerPretrainedModel.forward (modeling_qwen2_vl.py:1050-1072): flattened patches
+        [T, 3*2*14*14] + grid_thw [n_img, 3] -> merged tokens fp32 [T/4, hidden] (bf16-rounded values)."""
+        if self.vit is None:
+            raise RuntimeError("this model was built without the ViT (cfg.vit_depth == 0 or no vit_model.* weights)")
+        cfg, dev, V = self.cfg, self.device, self.vit
+        E, vh, hp = cfg.vit_embed_dim, cfg.vit_heads, self.vit_hp
+        hd = E // vh
+        grid_thw = grid_thw.cpu().long()
+        pix = pixel_values.to(dev, torch.float32)
+        T = pix.shape[0]
+        pb = self.buf.get("vit.pix", tuple(pix.shape), torch.bfloat16)
+        ops.cast_bf16(pix.contiguous(), pb)
+        x = self.buf.get("vit.x", (T, E), torch.float32)     # bf16 residual stream held in fp32 (ROUND_SUM)
+        ops.gemm(pb, V["wpatch"], x, epilogue=ops.EPI_STORE_F32, flags=ops.GEMM_ROUND_BF16)
+        cos, sin = self._vit_rope_tables(grid_thw)
+        cu = [0]
+        for tt, h, w in grid_thw.tolist():
+            for _ in range(tt):
+                cu.append(cu[-1] + h * w)
+        work = self._work(cu, cu, "vit")
+        h = self.buf.get("vit.h", (T, E), torch.bfloat16)
+        qkv = self.buf.get("vit.qkv", (T, 3 * vh * hp), torch.bfloat16)
+        attn = self.buf.get("vit.attn", (T, vh * hp), torch.bfloat16, zero=True)
+        mid = self.buf.get("vit.mid", (T, E * cfg.vit_mlp_ratio), torch.bfloat16)
+        for B in V["blocks"]:
+            ops.layernorm(x, h, B["norm1w"], B["norm1b"], 1e-6)
+            ops.gemm(h, B["wqkv"], qkv, epilogue=ops.EPI_STORE_BF16, bias=B["bqkv"])
+            ops.rope_vision(qkv, T, 2 * vh, hp, hd, cos, sin)
+            ops.attention(qkv[:, : vh * hp], qkv[:, vh * hp: 2 * vh * hp], qkv[:, 2 * vh * hp:], attn, work,
+                          num_q_heads=vh, num_kv_heads=vh, head_dim=hp, scale=1.0 / math.sqrt(hd))
+            ops.gemm(attn, B["wproj"], x, epilogue=ops.EPI_RESID_F32, bias=B["bproj"], flags=ops.GEMM_ROUND_SUM)
+            ops.layernorm(x, h, B["norm2w"], B["norm2b"], 1e-6)
+            ops.gemm(h, B["wfc1"], mid, epilogue=ops.EPI_STORE_BF16, bias=B["bfc1"], flags=ops.GEMM_QUICK_GELU)
+            ops.gemm(mid, B["wfc2"], x, epilogue=ops.EPI_RESID_F32, bias=B["bfc2"], flags=ops.GEMM_ROUND_SUM)
+        m2 = cfg.vit_merge ** 2
+        ops.layernorm(x, h, V["lnw"], V["lnb"], 1e-6)
+        hm = h.view(T // m2, m2 * E)                                  # PatchMerger: 2x2 neighbours are consecutive rows
+        mm = self.buf.get("vit.mm", (T // m2, m2 * E), torch.bfloat16)
+        ops.gemm(hm, V["wm0"], mm, epilogue=ops.EPI_STORE_BF16, bias=V["bm0"], flags=ops.GEMM_GELU)
+        if out is None:
+            out = torch.empty(T // m2, cfg.hidden_size, dtype=torch.float32, device=dev)
+        ops.gemm(mm, V["wm2"], out, epilogue=ops.EPI_STORE_F32, bias=V["bm2"], flags=ops.GEMM_ROUND_BF16)
+        return out
+
+    def prepare_vit_images(self, curr_kvlens, curr_rope, images, transforms, new_token_ids):
+        """Reference: g2vlm.py:735-808 (+ get_rope_index_image_3D, data/data_utils.py:142-206), one image per call
+        as chat_with_recon uses it. `transforms([image])` -> (pixel_values [T, C*2*14*14], grid_thw [1, 3])."""
+        if len(images) != 1:
+            raise NotImplementedError("one image per call (the reference's chat driver does the same)")
+        kvlen, rope = int(curr_kvlens[0]), int(curr_rope[0])
+        pix, grid = transforms([images[0]])
+        t, h, w = [int(x) for x in grid[0]]
+        m = self.cfg.vit_merge
+        gh, gw = h // m, w // m
+        n = t * gh * gw
+        if pix.shape[0] // (m * m) != n:
+            raise ValueError("pixel_values rows do not match grid_thw")
+        ti = torch.arange(t).view(-1, 1).expand(-1, gh * gw).flatten()
+        hi = torch.arange(gh).view(1, -1, 1).expand(t, -1, gw).flatten()
+        wi = torch.arange(gw).view(1, 1, -1).expand(t, gh, -1).flatten()
+        pid = torch.stack([ti, hi, wi]) + (rope + 1)
+        delta = int(pid.max() - pid.min())
+        pos = torch.cat([torch.full((3, 1), rope), pid, torch.full((3, 1), rope + delta + 2)], dim=1)
+        gi = {
+            "packed_text_ids": torch.tensor([int(new_token_ids["start_of_image"]), int(new_token_ids["end_of_image"])]),
+            "packed_text_indexes": torch.tensor([0, n + 1]),
+            "vit_token_seqlens": torch.tensor([n], dtype=torch.int),
+            "packed_image_grid_thw": grid[:1].clone(),
+            "packed_vit_images": pix[None],
+            "packed_vit_token_indexes": torch.arange(1, n + 1),
+            "packed_position_ids": pos,
+            "packed_seqlens": torch.tensor([n + 2], dtype=torch.int),
+            "packed_indexes": kvlen + torch.arange(n + 2),
+            "packed_key_value_indexes": torch.arange(kvlen),
+            "key_values_lens": torch.tensor([kvlen], dtype=torch.int),
+        }
+        return gi, [kvlen + n + 2], [rope + delta + 3]
+
+    @torch.no_grad()
+    def forward_cache_update_vit(self, past_key_values, packed_text_ids, packed_text_indexes, packed_vit_images,
+                                 packed_image_grid_thw, packed_vit_token_indexes, vit_token_seqlens, packed_position_ids,
+                                 packed_seqlens, packed_indexes, packed_key_value_indexes, key_values_lens,
+                                 packed_vit_tokens=None, packed_vit_position_ids=None):
+        """Reference: g2vlm.py:810-866 — ViT tokens between <start>/<end> through the und expert, NON-causal, on
+        top of the cache.  Returns the (appended) KVCache."""
+        cfg, dev = self.cfg, self.device
+        cache = KVCache.adopt(past_key_values, cfg, dev)
+        n = int(sum(packed_seqlens.tolist()))
+        x = torch.zeros(n, cfg.hidden_size, dtype=torch.float32, device=dev)
+        nt = int(packed_text_ids.numel())
+        txt = torch.empty(nt, cfg.hidden_size, dtype=torch.float32, device=dev)
+        ops.gather_rows(self.embed, txt, packed_text_ids.to(dev, torch.long), nt)
+        ops.gather_rows(txt, x, packed_text_indexes.to(dev, torch.long), nt, scatter=True)
+        pix = packed_vit_images.reshape(-1, packed_vit_images.shape[-1])
+        emb = self.vit_forward(pix, packed_image_grid_thw)
+        ops.gather_rows(emb, x, packed_vit_token_indexes.to(dev, torch.long), emb.shape[0], scatter=True)
+        self._und_forward(x, packed_position_ids, cache, causal=False)
+        return cache
+
+    def prepare_prompts_pure_text(self, curr_kvlens, curr_rope, prompts, tokenizer, new_token_ids):
+        """Reference: g2vlm.py:628-662 (no bos / eos added)."""
+        kvlen, rope = int(curr_kvlens[0]), int(curr_rope[0])
+        ids = list(tokenizer.encode(prompts[0]))
+        n = len(ids)
+        gi = {
+            "text_token_lens": torch.tensor([n], dtype=torch.int),
+            "packed_text_ids": torch.tensor(ids, dtype=torch.long),
+            "packed_text_position_ids": (rope + torch.arange(n)).expand(3, -1),
+            "packed_text_indexes": kvlen + torch.arange(n),
+            "packed_key_value_indexes": torch.arange(kvlen),
+            "key_values_lens": torch.tensor([kvlen], dtype=torch.int),
+        }
+        return gi, [kvlen + n], [rope + n]
+
+    def prepare_start_tokens(self, curr_kvlens, curr_rope, tokenizer, new_token_ids):
+        """Reference: g2vlm.py:1041-1068: the start token is the LAST id of the chat template."""
+        template = "<|im_start|>user\\your text<|im_end|>\n<|im_start|>assistant\n"
+        ids = tokenizer.encode(template, add_special_tokens=False)
+        start = ids[-1] if ids else (getattr(tokenizer, "eos_token_id", None) or 151643)
+        kvlen, rope = int(curr_kvlens[0]), int(curr_rope[0])
+        return {
+            "packed_start_tokens": torch.tensor([start], dtype=torch.long),
+            "packed_query_position_ids": torch.tensor([rope], dtype=torch.long).expand(3, -1),
+            "key_values_lens": torch.tensor([kvlen], dtype=torch.int),
+            "packed_key_value_indexes": torch.arange(kvlen),
+        }
+
+    @torch.no_grad()
+    def chat_with_recon(self, tokenizer, new_token_ids, image_transform, dino_image_transform, images, prompt,
+                        max_length: int, do_sample: bool = False, temperature: float = 1.0, return_ids: bool = False):
+        """Same call shape as the reference's chat_with_recon (g2vlm.py:1305-1410): system prompt (und, causal)
+        -> geo step over the views with cache update -> one ViT step per image (und, non-causal) -> question
+        (und, causal) -> greedy decode.  `images`: list of PIL images (or an (N,3,H,W) tensor for the geo branch
+        together with `image_transform` accepting its items)."""
+        dev = self.device
+        past = KVCache(self.cfg.num_layers, self.cfg.num_kv_heads, self.cfg.head_dim, dev)
+        system_prompt = "<|im_start|>system\nYou are a helpful assistant.<|im_end|>\n<|im_start|>user\n"
+        gi, newlens, new_rope = self.prepare_prompts_pure_text([0], [0], [system_prompt], tokenizer, new_token_ids)
+        past = self.forward_cache_update_text(past, **gi)
+        gi, newlens, new_rope = self.prepare_dino_images_pi3(newlens, new_rope, images if torch.is_tensor(images) else list(images),
+                                                             dino_image_transform, new_token_ids)
+        past, _ = self.forward_cache_update_dino(past, **gi)
+        for image in images:
+            gi, newlens, new_rope = self.prepare_vit_images(newlens, new_rope, [image], image_transform, new_token_ids)
+            past = self.forward_cache_update_vit(past, **gi)
+        gi, newlens, new_rope = self.prepare_prompts_pure_text(newlens, new_rope, [prompt + "<|im_end|>\n<|im_start|>assistant"],
+                                                               tokenizer, new_token_ids)
+        past = self.forward_cache_update_text(past, **gi)
+        st = self.prepare_start_tokens(newlens, new_rope, tokenizer, new_token_ids)
+        ids = self.generate_text(past_key_values=past, max_length=max_length, do_sample=do_sample, temperature=temperature,
+                                 end_token_id=new_token_ids["eos_token_id"], **st)
+        if return_ids:
+            return ids
+        return tokenizer.decode(ids[1:, 0])   # skip the start token, like the reference
 
     # ------------------------------------------------------------------------------------------
     # the public entry point

@@ -15,6 +15,7 @@ from . import _lib
 
 EPI_STORE_BF16, EPI_SWIGLU_BF16, EPI_RESID_F32, EPI_STORE_F32 = 0, 1, 2, 3
 GEMM_GELU, GEMM_ROUND_AFTER_SCALE, GEMM_RELU, GEMM_ACCUMULATE, GEMM_ROUND_BF16 = 1, 2, 4, 8, 16
+GEMM_QUICK_GELU, GEMM_ROUND_SUM = 32, 64
 
 
 class G2Error(RuntimeError):
@@ -375,3 +376,11 @@ class DecodeStepArgs(ctypes.Structure):
 def und_decode_step(args: DecodeStepArgs) -> None:
     """One greedy decode step issued natively (see g2vlm_und_decode_step)."""
     _check(_lib.load().g2vlm_und_decode_step(ctypes.byref(args), _stream()))
+
+
+def rope_vision(buf, rows, n_heads_total, head_stride, head_dim, cos, sin):
+    _req(buf, torch.bfloat16, "buf")
+    _req(cos, torch.float32, "cos")
+    _req(sin, torch.float32, "sin")
+    _call("g2vlm_rope_vision", _vp(buf.data_ptr()), _i64(buf.stride(0)), _i64(rows), _i32(n_heads_total),
+          _i32(head_stride), _i32(head_dim), _vp(cos.data_ptr()), _vp(sin.data_ptr()))

@@ -43,6 +43,14 @@ class G2Config:
     camera_dim: int = 512
     rope2d_base: float = 100.0  # 'rope100', g2vlm.py:152
     train_conf_pi3: bool = False
+    # Qwen2-VL ViT of the chat path (row f2; vit_depth = 0: recon-only model, no vit_model.* keys needed)
+    vit_depth: int = 0
+    vit_embed_dim: int = 1280
+    vit_heads: int = 16
+    vit_mlp_ratio: int = 4
+    vit_patch: int = 14
+    vit_merge: int = 2
+    vit_temporal: int = 2
 
     @property
     def head_dim(self) -> int:
@@ -64,6 +72,11 @@ class G2Config:
 FULL = G2Config()
 TINY = G2Config(hidden_size=256, num_layers=2, num_heads=2, num_kv_heads=1, intermediate_size=512,
                 vocab_size=512, dino_hidden=64, dino_layers=2, dino_heads=2)
+# the same models with the Qwen2-VL ViT (chat path)
+FULL_CHAT = G2Config(vit_depth=32)
+TINY_CHAT = G2Config(hidden_size=256, num_layers=2, num_heads=2, num_kv_heads=1, intermediate_size=512,
+                     vocab_size=512, dino_hidden=64, dino_layers=2, dino_heads=2, vit_depth=1, vit_embed_dim=64,
+                     vit_heads=2, vit_mlp_ratio=2)
 
 
 def state_dict_schema(cfg: G2Config) -> "OrderedDict[str, Tuple[int, ...]]":
@@ -157,6 +170,22 @@ def state_dict_schema(cfg: G2Config) -> "OrderedDict[str, Tuple[int, ...]]":
     s["camera_head.fc_rot.weight"] = (9, C); s["camera_head.fc_rot.bias"] = (9,)
     decoder("global_points_decoder", cfg.point_dim, cross=True)
     s["global_point_head.proj.weight"] = (3 * ps2, cfg.point_dim); s["global_point_head.proj.bias"] = (3 * ps2,)
+    if cfg.vit_depth > 0:
+        E, Fv = cfg.vit_embed_dim, cfg.vit_embed_dim * cfg.vit_mlp_ratio
+        v = "vit_model."
+        s[v + "patch_embed.proj.weight"] = (E, 3, cfg.vit_temporal, cfg.vit_patch, cfg.vit_patch)
+        for i in range(cfg.vit_depth):
+            p = f"{v}blocks.{i}."
+            s[p + "norm1.weight"] = (E,); s[p + "norm1.bias"] = (E,)
+            s[p + "norm2.weight"] = (E,); s[p + "norm2.bias"] = (E,)
+            s[p + "attn.qkv.weight"] = (3 * E, E); s[p + "attn.qkv.bias"] = (3 * E,)
+            s[p + "attn.proj.weight"] = (E, E); s[p + "attn.proj.bias"] = (E,)
+            s[p + "mlp.fc1.weight"] = (Fv, E); s[p + "mlp.fc1.bias"] = (Fv,)
+            s[p + "mlp.fc2.weight"] = (E, Fv); s[p + "mlp.fc2.bias"] = (E,)
+        Em = E * cfg.vit_merge ** 2
+        s[v + "merger.ln_q.weight"] = (E,); s[v + "merger.ln_q.bias"] = (E,)
+        s[v + "merger.mlp.0.weight"] = (Em, Em); s[v + "merger.mlp.0.bias"] = (Em,)
+        s[v + "merger.mlp.2.weight"] = (H, Em); s[v + "merger.mlp.2.bias"] = (H,)
     if cfg.train_conf_pi3:
         decoder("conf_decoder", cfg.point_dim)
         s["conf_head.proj.weight"] = (ps2, cfg.point_dim); s["conf_head.proj.bias"] = (ps2,)
@@ -178,7 +207,7 @@ def init_synthetic(cfg: G2Config, seed: int = 0, embed_rows: int | None = None,
             shape = (embed_rows, shape[1])
         g = torch.Generator(device=device).manual_seed(seed * 1000003 + idx)
         leaf = name.rsplit(".", 2)
-        is_norm_w = name.endswith(".weight") and ("norm" in leaf[-2] or leaf[-2] == "layernorm")
+        is_norm_w = name.endswith(".weight") and ("norm" in leaf[-2] or leaf[-2] in ("layernorm", "ln_q"))
         if is_norm_w or name.endswith(".gamma") or name.endswith(".lambda1"):
             t = torch.rand(shape, generator=g, device=device) + 0.5
         else:

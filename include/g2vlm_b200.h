@@ -64,6 +64,8 @@ const char* g2vlm_last_error(void);
 #define G2VLM_GEMM_RELU 4u              /* STORE_F32 */
 #define G2VLM_GEMM_ACCUMULATE 8u        /* STORE_F32: out += value (second pass of split-bf16) */
 #define G2VLM_GEMM_ROUND_BF16 16u       /* STORE_F32: round (acc+bias) to bf16 before storing */
+#define G2VLM_GEMM_QUICK_GELU 32u       /* STORE_BF16: x*sigmoid(1.702x) on the bf16-rounded value (Qwen2-VL ViT MLP) */
+#define G2VLM_GEMM_ROUND_SUM 64u        /* RESID_F32: round the updated stream value to bf16 (bf16 residual stream) */
 
 typedef struct g2vlm_gemm_args {
   const void* A; /* bf16 [a_rows, K], leading dimension lda */
@@ -204,6 +206,13 @@ int g2vlm_dino_embed(const void* patch_emb, int64_t ld_patch, const float* cls, 
 int g2vlm_rope2d(void* buf, int64_t ld, int64_t rows, int32_t n_heads_total, int32_t head_stride,
                  int32_t head_dim, int32_t tokens_per_view, int32_t grid_w, const float* cos_tab,
                  const float* sin_tab, int32_t bf16_ops, void* stream);
+
+/* apply_rotary_pos_emb_vision (modeling/qwen2vl/modeling_qwen2_vl.py:236-246) in place on the q and k heads of a
+ * fused bf16 buffer [rows, ld]: n_heads_total heads of `head_stride` columns from column 0, the first head_dim
+ * real; rotate_half over the whole head (pair d, d + head_dim/2); cos / sin fp32 [rows, head_dim/2] per token
+ * (built by the host from the 2-D patch positions like rot_pos_emb :1024-1048); fp32 math, one bf16 rounding. */
+int g2vlm_rope_vision(void* buf, int64_t ld, int64_t rows, int32_t n_heads_total, int32_t head_stride,
+                      int32_t head_dim, const float* cos_tab, const float* sin_tab, void* stream);
 
 /* Pi3LinearPts3d pixel-shuffle (transformer_head.py:77-81) fused with the recon epilogue
  * (g2vlm.py:1203-1205, 1226; homogenize_points pi3/utils/geometry.py:108-113).

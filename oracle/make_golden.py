@@ -115,6 +115,42 @@ def run_chat_case(model):
                 newlens=nl, key_cache_layer1=k_probe[::7].clone(), last_hidden=last.float()[::STRIDE_T].clone())
 
 
+class ChatTokenizerFull(ChatTokenizer):
+    def decode(self, ids):
+        return " ".join(str(int(i)) for i in ids)
+
+
+CHAT_VIT_CASE = dict(n=2, h=28, w=518, seed=4, max_length=6, vit_h=56, vit_w=84)
+
+
+def run_chat_vit_case():
+    """The reference's chat_with_recon end to end (g2vlm.py:1305-1410) on the tiny model WITH the Qwen2-VL ViT:
+    system prompt -> geo step -> one ViT step per image -> question -> greedy decode."""
+    from oracle.vit_stub import StubVitTransform
+    c = CHAT_VIT_CASE
+    model = rh.build_reference_model(rh.TINY, visual_und=True)
+    sd = schema.init_synthetic(schema.TINY_CHAT, seed=0)
+    msg = model.load_state_dict(sd, strict=False)
+    assert not msg.unexpected_keys and msg.missing_keys == ["dino_model.embeddings.mask_token"], msg
+    pil = to_pil(views_u8(c["n"], c["h"], c["w"], c["seed"]))
+    captured = {}
+    orig = model.generate_text
+
+    def spy(*a, **k):
+        captured["cache_len"] = k["past_key_values"].key_cache[0].shape[0]
+        captured["key_cache_layer1"] = k["past_key_values"].key_cache[1].float()[::7].clone()
+        out = orig(*a, **k)
+        captured["ids"] = out.clone()
+        return out
+
+    model.generate_text = spy
+    with torch.no_grad():
+        text = model.chat_with_recon(ChatTokenizerFull(), dict(rh.NEW_TOKEN_IDS), StubVitTransform(c["vit_h"], c["vit_w"]),
+                                     None, pil, "question", c["max_length"])
+    return dict(case=c, text=text, tokens=captured["ids"][:, 0].clone(), cache_len_before_decode=captured["cache_len"],
+                key_cache_layer1=captured["key_cache_layer1"])
+
+
 def main():
     os.makedirs(GOLDEN, exist_ok=True)
     torch.manual_seed(0)
@@ -130,6 +166,10 @@ def main():
     chat = run_chat_case(model)
     torch.save(chat, os.path.join(GOLDEN, "chat_tiny.pt"))
     print("wrote chat", chat["tokens"].tolist(), chat["cache_len_before_decode"])
+    chatv = run_chat_vit_case()
+    torch.save(chatv, os.path.join(GOLDEN, "chat_vit_tiny.pt"))
+    print("wrote chat+vit", chatv["tokens"].tolist(), chatv["cache_len_before_decode"], repr(chatv["text"]))
+    keys["tiny_chat"] = {k: list(v.shape) for k, v in rh.build_reference_model(rh.TINY, visual_und=True).state_dict().items()}
     # full-size key schema: build on the meta device (no 18 GB allocation)
     with torch.device("meta"):
         full = rh.build_reference_model(rh.FULL, visual_und=False)

@@ -168,6 +168,8 @@ def build_reference_model(dims=TINY, visual_und=True):
 
     _qm.flash_attn_varlen_func = varlen_sdpa
     _dm.flash_attn_varlen_func = varlen_sdpa
+    import modeling.qwen2vl.modeling_qwen2_vl as _vm
+    _vm.flash_attn_varlen_func = varlen_sdpa   # VisionFlashAttention2 (ViT of the chat path)
 
     llm = Qwen2VLConfig(pad_token_id=None, rope_scaling={"type": "mrope", "mrope_section": [16, 24, 24]},
                         qk_norm=True, layer_module="Qwen2VLMoTDecoderLayer", tie_word_embeddings=False,

@@ -302,3 +302,38 @@ def test_chat_prefill_and_greedy_decode_match_reference(tiny):
                                 end_token_id=eos)
     assert ids_e[:, 0].tolist() == g["tokens"].tolist()[:2]
     assert past.seq_lens == g["cache_len_before_decode"] + 2
+
+
+def test_vit_forward_matches_oracle():
+    """Row f2: Qwen2-VL ViT (patch-embed GEMM, 2-D rotary, per-image attention with head_dim padded to 64,
+    QuickGELU MLP, bf16 residual stream, 2x2 PatchMerger) against the restatement; two images, ragged grids."""
+    from g2vlm_b200.model import G2VLMFast
+    from oracle import restate
+    cfg = schema.TINY_CHAT
+    sd = schema.init_synthetic(cfg, seed=0)
+    model = G2VLMFast(cfg, sd)
+    g = torch.Generator().manual_seed(1)
+    grid = torch.tensor([[1, 6, 8], [1, 4, 10]])
+    pix = torch.randn(48 + 40, 3 * 2 * 14 * 14, generator=g)
+    ref = restate.vit_forward(sd, cfg, pix, grid, "bf16")
+    out = model.vit_forward(pix, grid)
+    assert out.shape == ref.shape == (22, cfg.hidden_size)
+    assert _maxrel(out, ref) < TOL
+
+
+def test_chat_with_recon_matches_reference_golden():
+    """Rows f1 + f2 end to end: same generated ids as the unmodified reference's chat_with_recon."""
+    from g2vlm_b200.model import G2VLMFast
+    from oracle.make_golden import ChatTokenizerFull, to_pil, views_u8
+    from oracle.vit_stub import StubVitTransform
+    g = torch.load(os.path.join(GOLDEN, "chat_vit_tiny.pt"))
+    c = g["case"]
+    cfg = schema.TINY_CHAT
+    model = G2VLMFast(cfg, schema.init_synthetic(cfg, seed=0))
+    pil = to_pil(views_u8(c["n"], c["h"], c["w"], c["seed"]))
+    text = model.chat_with_recon(ChatTokenizerFull(), dict(TOKENS), StubVitTransform(c["vit_h"], c["vit_w"]), None, pil,
+                                 "question", c["max_length"])
+    assert text == g["text"]
+    ids = model.chat_with_recon(ChatTokenizerFull(), dict(TOKENS), StubVitTransform(c["vit_h"], c["vit_w"]), None, pil,
+                                "question", c["max_length"], return_ids=True)
+    assert ids[:, 0].tolist() == g["tokens"].tolist()

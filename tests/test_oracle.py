@@ -119,3 +119,48 @@ def test_chat_restatement_reproduces_reference_tokens(tiny_sd):
     assert int(g["start_position"][0]) == 4 + (28 // 14 and 2) * (max(2, 37) + 2) + 5
     assert _maxrel(cache[1][0][::7], g["key_cache_layer1"]) < TOL_BF16
     assert _maxrel(last[::13], g["last_hidden"]) < TOL_BF16
+
+
+def _oracle_chat_vit(sd, cfg, case):
+    """chat_with_recon through the restatement (system prompt -> geo -> ViT per image -> question -> decode)."""
+    from oracle.vit_stub import StubVitTransform
+    from oracle.make_golden import to_pil, views_u8
+    u8 = views_u8(case["n"], case["h"], case["w"], case["seed"])
+    pil = to_pil(u8)
+    v = u8.float() / 255.0
+    W = restate._W(sd)
+    emb = W("language_model.model.embed_tokens.weight")
+    _, cache = restate.lm_forward_und(sd, cfg, emb[torch.tensor([31, 32, 33, 34])], torch.arange(4).expand(3, -1), None, True, "bf16")
+    gi, nl, nr = restate.prepare_dino_images(v, 4, 4, 3, 4)
+    geo, und = gi["packed_dino_token_indexes"], gi["packed_text_indexes"]
+    x = torch.zeros(int(gi["packed_seqlens"][0]), cfg.hidden_size)
+    x[und] = emb[gi["packed_text_ids"]]
+    d = restate.dino_forward(sd, cfg, gi["packed_dino_images"], gi["dino_token_seqlens"], "bf16")
+    x[geo] = restate.linear(d.reshape(-1, d.shape[-1]), W("dino2llm.weight"), W("dino2llm.bias"), "bf16")
+    _, cache = restate.lm_forward_geo(sd, cfg, x, gi["packed_position_ids"], geo, und, cache, "bf16")
+    kvlen, rope = nl[0], nr[0]
+    tf = StubVitTransform(case["vit_h"], case["vit_w"])
+    for im in pil:
+        pix, grid = tf([im])
+        cache, kvlen, rope = restate.vit_step(sd, cfg, pix, grid, cache, kvlen, rope, 3, 4, "bf16")
+    _, cache = restate.lm_forward_und(sd, cfg, emb[torch.tensor([41, 42, 43, 44, 45])], (rope + torch.arange(5)).expand(3, -1),
+                                      cache, True, "bf16")
+    toks, logits, _ = restate.generate_text_greedy(sd, cfg, cache, 23, rope + 5, case["max_length"], 2)
+    return toks, logits, cache
+
+
+def test_chat_with_vit_restatement_reproduces_reference():
+    """Rows f1 + f2: the whole chat_with_recon flow incl. the Qwen2-VL ViT step."""
+    g = torch.load(os.path.join(GOLDEN, "chat_vit_tiny.pt"))
+    sd = schema.init_synthetic(schema.TINY_CHAT, seed=0)
+    toks, _, cache = _oracle_chat_vit(sd, schema.TINY_CHAT, g["case"])
+    assert toks == g["tokens"].tolist()
+    assert cache[0][0].shape[0] == g["cache_len_before_decode"]
+    assert _maxrel(cache[1][0][::7], g["key_cache_layer1"]) < TOL_BF16
+
+
+def test_schema_with_vit_matches_reference_keys():
+    keys = json.load(open(os.path.join(GOLDEN, "state_dict_keys.json")))
+    ours = {k: list(v) for k, v in schema.state_dict_schema(schema.TINY_CHAT).items()}
+    ref = {k: v for k, v in keys["tiny_chat"].items() if k != "dino_model.embeddings.mask_token"}
+    assert ours == ref
