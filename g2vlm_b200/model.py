@@ -508,7 +508,7 @@ class G2VLMFast:
             # all rows belong to the und expert: group 0 (geo) is empty
             self._mot_layer(Lw, xs, T, 0, qkv, attn, act, hbuf, cos, sin, work, L + T, causal, True,
                             kv_exchange=kv_append, kv_len_dev=len_dev)
-        y = self.buf.get("und.y1", (1, H), torch.float32) if T == 1 else torch.empty(T, H, dtype=torch.float32, device=dev)
+        y = self.buf.get("und.y", (T, H), torch.float32)   # reused workspace (valid until the next und step)
         ops.rmsnorm_routed(xs, y, self.norm_geo, self.norm_und, 0, cfg.rms_norm_eps, rows=T)
         if update and len_dev is None:
             cache.len = L + T
@@ -526,7 +526,7 @@ class G2VLMFast:
         if int(key_values_lens.sum()) != cache.len:
             raise ValueError("key_values_lens does not match the cache length")
         n = int(packed_text_ids.numel())
-        x = torch.empty(n, cfg.hidden_size, dtype=torch.float32, device=dev)
+        x = self.buf.get("txt.x", (n, cfg.hidden_size), torch.float32)   # reused workspace: no allocator call per step
         ops.gather_rows(self.embed, x, packed_text_ids.to(dev, torch.long), n)
         self._und_forward(x, packed_text_position_ids, cache, causal=True)
         return cache
