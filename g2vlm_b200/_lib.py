@@ -18,7 +18,7 @@ PKG_DIR = Path(__file__).resolve().parent
 REPO_ROOT = PKG_DIR.parent
 CSRC = PKG_DIR / "csrc"
 HEADER = REPO_ROOT / "include" / "g2vlm_b200.h"
-LIB_PATH = PKG_DIR / "libg2vlm_b200.so"
+LIB_PATH = Path(os.environ.get("G2VLM_B200_LIB", PKG_DIR / "libg2vlm_b200.so"))
 
 NVCC_FLAGS = [
     "-shared", "-Xcompiler", "-fPIC", "-gencode", "arch=compute_100a,code=sm_100a",

@@ -13,6 +13,10 @@
 //                 tcgen05.ld S -> running max / exp2 / row sum -> bf16 P written back to TMEM over S
 //                 (tcgen05.st); lazy rescale of O in TMEM only when the running max grows by > 2^8
 //                 (exact: the stale max cancels in the final 1/l normalisation); final O/l -> global.
+//                 P reaches the MMA warp in 4 chunks of 32 keys (own mbarrier each) so PV starts while
+//                 the rest of the row is still in exp2.  Measured and rejected on B200 (r01): moving
+//                 25/50 % of the exp2 to a degree-3 FMA-pipe polynomial (-1 % / -6 %: the extra issue
+//                 slots cost more than the MUFU relief gains).
 // TMEM columns: S0/P0 [0,128)  S1/P1 [128,256)  O0 [256,256+D)  O1 [384,384+D).
 #include "common.cuh"
 
@@ -22,6 +26,7 @@ constexpr int ATT_BM = 128;       // query rows per tile
 constexpr int ATT_BN = 128;       // keys per block
 constexpr int ATT_THREADS = 384;  // 12 warps
 constexpr float ATT_RESCALE_TAU = 8.0f;
+constexpr int ATT_PCHUNKS = 4;    // P_t reaches the MMA warp in 4 chunks of 32 keys (PV overlaps the exp tail)
 
 struct AttnKParams {
   CUtensorMap tmQ, tmK, tmV;
@@ -47,6 +52,26 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
+// packed fp32 pairs (one FFMA2/FADD2 per two values on sm_100)
+__device__ __forceinline__ uint64_t pack2(float a, float b) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float& a, float& b) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+
 template <int D>
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 attention_tcgen05_kernel(const __grid_constant__ AttnKParams p) {
@@ -67,8 +92,8 @@ attention_tcgen05_kernel(const __grid_constant__ AttnKParams p) {
   uint64_t* k_empty = v_full + Cfg::kStages;
   uint64_t* v_empty = k_empty + Cfg::kStages;
   uint64_t* s_full = v_empty + Cfg::kStages;       // [2]
-  uint64_t* p_full = s_full + 2;                   // [2]
-  uint64_t* o_done = p_full + 2;                   // [2]
+  uint64_t* p_full = s_full + 2;                   // [2][ATT_PCHUNKS]: P handed over in key chunks
+  uint64_t* o_done = p_full + 2 * ATT_PCHUNKS;     // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 2);
 
   const int warp = threadIdx.x >> 5;
@@ -105,7 +130,7 @@ attention_tcgen05_kernel(const __grid_constant__ AttnKParams p) {
       }
       for (int t = 0; t < 2; ++t) {
         mbar_init(&s_full[t], 1);
-        mbar_init(&p_full[t], 128);
+        for (int c = 0; c < ATT_PCHUNKS; ++c) mbar_init(&p_full[t * ATT_PCHUNKS + c], 4);  // one arrive per warp
         mbar_init(&o_done[t], 1);
       }
       fence_barrier_init();
@@ -170,13 +195,20 @@ attention_tcgen05_kernel(const __grid_constant__ AttnKParams p) {
         }
         umma_commit(&s_full[t]);
       };
+      // O_t += P_t V, issued chunk by chunk as the softmax warps publish 32 keys of P at a time
       auto issue_pv = [&](int t, int s, int j) {
         const uint32_t va = kv_addr + s * 2 * Cfg::kTileBytes + Cfg::kTileBytes;
 #pragma unroll
-        for (int k = 0; k < KSTEPS_PV; ++k) {
-          // 16 keys = 16 rows of 128 B inside each 64-column box; boxes are BOX_BYTES apart (LBO)
-          umma_ts(tO(t), tS(t) + k * 8, umma_desc_mnmajor(va + k * 2048, BOX_BYTES), idesc_pv,
-                  (j | k) != 0);
+        for (int c = 0; c < ATT_PCHUNKS; ++c) {
+          mbar_wait(&p_full[t * ATT_PCHUNKS + c], j & 1);
+          tc_fence_after();
+#pragma unroll
+          for (int kk = 0; kk < KSTEPS_PV / ATT_PCHUNKS; ++kk) {
+            const int k = c * (KSTEPS_PV / ATT_PCHUNKS) + kk;
+            // 16 keys = 16 rows of 128 B inside each 64-column box; boxes are BOX_BYTES apart (LBO)
+            umma_ts(tO(t), tS(t) + k * 8, umma_desc_mnmajor(va + k * 2048, BOX_BYTES), idesc_pv,
+                    (j | k) != 0);
+          }
         }
         umma_commit(&o_done[t]);
       };
@@ -193,16 +225,12 @@ attention_tcgen05_kernel(const __grid_constant__ AttnKParams p) {
         const int s1 = (j + 1) % Cfg::kStages;
         const uint32_t par1 = ((j + 1) / Cfg::kStages) & 1;
         mbar_wait(&v_full[s], par);
-        mbar_wait(&p_full[0], j & 1);
-        tc_fence_after();
         issue_pv(0, s, j);
         if (j + 1 < nblk) {
           mbar_wait(&k_full[s1], par1);
           tc_fence_after();
           issue_qk(0, s1);
         }
-        mbar_wait(&p_full[1], j & 1);
-        tc_fence_after();
         issue_pv(1, s, j);
         umma_commit(&v_empty[s]);
         if (j + 1 < nblk) {
@@ -280,23 +308,35 @@ attention_tcgen05_kernel(const __grid_constant__ AttnKParams p) {
         }
       }
 
-      // P = 2^(s*scale - m), packed to bf16 pairs, written over S (columns [0,64) of the S region)
-      float sum0 = 0.f, sum1 = 0.f;
-      const float neg_m = -m_used;
+      // P = 2^(s*scale - m), packed to bf16 pairs, written over S (columns [0,64) of the S region) and
+      // handed to the MMA warp 32 keys at a time so PV starts while the rest of the row is still in exp
+      uint64_t sum2 = pack2(0.f, 0.f);
+      const uint64_t neg_m2 = pack2(-m_used, -m_used);
+      const uint64_t scale2 = pack2(p.scale_log2, p.scale_log2);
 #pragma unroll
-      for (int i = 0; i < 128; i += 2) {
-        const float p0 = ex2_approx(fmaf(__uint_as_float(sv[i]), p.scale_log2, neg_m));
-        const float p1 = ex2_approx(fmaf(__uint_as_float(sv[i + 1]), p.scale_log2, neg_m));
-        sum0 += p0;
-        sum1 += p1;
-        sv[i >> 1] = pack_bf16x2(p0, p1);  // in place: slot i/2 <= i is already consumed
+      for (int c = 0; c < ATT_PCHUNKS; ++c) {
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          float p0, p1;
+          const uint64_t x2 = fma2(pack2(__uint_as_float(sv[c * 32 + i]), __uint_as_float(sv[c * 32 + i + 1])),
+                                   scale2, neg_m2);
+          float x0, x1;
+          unpack2(x2, x0, x1);
+          p0 = ex2_approx(x0);
+          p1 = ex2_approx(x1);
+          sum2 = add2(sum2, pack2(p0, p1));
+          pk[i >> 1] = pack_bf16x2(p0, p1);
+        }
+        tmem_st16(tS_w + c * 16, pk);
+        tmem_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[t * ATT_PCHUNKS + c]);
       }
+      float sum0, sum1;
+      unpack2(sum2, sum0, sum1);
       l_run += sum0 + sum1;
-      tmem_st32(tS_w, *reinterpret_cast<uint32_t(*)[32]>(&sv[0]));
-      tmem_st32(tS_w + 32, *reinterpret_cast<uint32_t(*)[32]>(&sv[32]));
-      tmem_wait_st();
-      tc_fence_before();
-      mbar_arrive(&p_full[t]);
     }
 
     // epilogue: O / l -> bf16 -> global (each thread owns one output row of D contiguous values)
