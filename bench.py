@@ -299,9 +299,11 @@ def main():
 
     # ---- device-resident arm ("value") ---------------------------------------------------------
     gi_text, newlens, new_rope = model.prepare_prompts_addbos([0], [0], ["x"], tok, TOKENS)
-    gi_text = {k: v.cuda() for k, v in gi_text.items()}
+    # the *_lens tensors are host-side control metadata (reading them from the device would stall the host every step)
+    HOST_META = ("text_token_lens", "key_values_lens", "packed_seqlens", "dino_token_seqlens")
+    gi_text = {k: (v if k in HOST_META else v.cuda()) for k, v in gi_text.items()}
     gi, _, _ = model.prepare_dino_images_pi3(newlens, new_rope, views_host, None, TOKENS)
-    gi = {k: v.cuda() for k, v in gi.items()}
+    gi = {k: (v if k in HOST_META else v.cuda()) for k, v in gi.items()}
 
     att_events = []
     orig_attention = ops.attention

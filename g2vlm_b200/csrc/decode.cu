@@ -47,6 +47,40 @@ __device__ __forceinline__ void dot8(const uint4& a, const uint4& b, float& acc)
   }
 }
 
+// epilogue of one output element (row m of the call, output column n): same rounding points as the tcgen05 GEMM
+template <int EPI>
+__device__ __forceinline__ void gemv_store(const GemvParams& p, int n, int m, float f, float f_up) {
+  const long long row = p.row0 + m;
+  if constexpr (EPI == G2VLM_EPI_SWIGLU_BF16) {
+    const float g = bf16_round(f), u = bf16_round(f_up);
+    const float sg = bf16_round(g / (1.0f + __expf(-g)));
+    reinterpret_cast<__nv_bfloat16*>(p.out)[row * p.ldo + n] = __float2bfloat16_rn(sg * u);
+  } else {
+    if (p.bias) f += p.bias[n];
+    if constexpr (EPI == G2VLM_EPI_STORE_BF16) {
+      if (p.flags & G2VLM_GEMM_GELU) f = gelu_erf_d(bf16_round(f));
+      else if (p.flags & G2VLM_GEMM_QUICK_GELU) { const float xq = bf16_round(f); f = xq / (1.0f + __expf(-1.702f * xq)); }
+      reinterpret_cast<__nv_bfloat16*>(p.out)[row * p.ldo + n] = __float2bfloat16_rn(f);
+    } else if constexpr (EPI == G2VLM_EPI_RESID_F32) {
+      f = bf16_round(f);
+      if (p.use_scale) {
+        f *= p.scale[n];
+        if (p.flags & G2VLM_GEMM_ROUND_AFTER_SCALE) f = bf16_round(f);
+      }
+      float* xo = reinterpret_cast<float*>(p.out) + row * p.ldo + n;
+      const float xs = *xo + f;
+      *xo = (p.flags & G2VLM_GEMM_ROUND_SUM) ? bf16_round(xs) : xs;
+    } else {
+      if (p.flags & G2VLM_GEMM_ROUND_BF16) f = bf16_round(f);
+      float* o = reinterpret_cast<float*>(p.out) + row * p.ldo + n;
+      if (p.flags & G2VLM_GEMM_ACCUMULATE) f += *o;
+      if (p.flags & G2VLM_GEMM_RELU) f = fmaxf(f, 0.f);
+      if (p.residual) f += p.residual[row * p.ldr + n];
+      *o = f;
+    }
+  }
+}
+
 // ROWS: 1 (the decode step) or 8; KSPLIT: warps that share one output column (long rows, few columns:
 // the down projection K = 8960, N = 1536 would otherwise run on 1536 warps only)
 template <int EPI, int ROWS, int KSPLIT>
@@ -118,36 +152,91 @@ __global__ void __launch_bounds__(GEMV_WARPS * 32) gemv_bf16_kernel(const GemvPa
     }
   }
   if (lane != 0 || !active) return;
-  for (int m = 0; m < p.rows && m < ROWS; ++m) {
-    const long long row = p.row0 + m;
-    float f = acc0[m];
-    if constexpr (EPI == G2VLM_EPI_SWIGLU_BF16) {
-      const float g = bf16_round(f), u = bf16_round(acc1[m]);
-      const float sg = bf16_round(g / (1.0f + __expf(-g)));
-      reinterpret_cast<__nv_bfloat16*>(p.out)[row * p.ldo + n] = __float2bfloat16_rn(sg * u);
-    } else {
-      if (p.bias) f += p.bias[n];
-      if constexpr (EPI == G2VLM_EPI_STORE_BF16) {
-        if (p.flags & G2VLM_GEMM_GELU) f = gelu_erf_d(bf16_round(f));
-        else if (p.flags & G2VLM_GEMM_QUICK_GELU) { const float xq = bf16_round(f); f = xq / (1.0f + __expf(-1.702f * xq)); }
-        reinterpret_cast<__nv_bfloat16*>(p.out)[row * p.ldo + n] = __float2bfloat16_rn(f);
-      } else if constexpr (EPI == G2VLM_EPI_RESID_F32) {
-        f = bf16_round(f);
-        if (p.use_scale) {
-          f *= p.scale[n];
-          if (p.flags & G2VLM_GEMM_ROUND_AFTER_SCALE) f = bf16_round(f);
-        }
-        float* xo = reinterpret_cast<float*>(p.out) + row * p.ldo + n;
-        const float xs = *xo + f;
-        *xo = (p.flags & G2VLM_GEMM_ROUND_SUM) ? bf16_round(xs) : xs;
-      } else {
-        if (p.flags & G2VLM_GEMM_ROUND_BF16) f = bf16_round(f);
-        float* o = reinterpret_cast<float*>(p.out) + row * p.ldo + n;
-        if (p.flags & G2VLM_GEMM_ACCUMULATE) f += *o;
-        if (p.flags & G2VLM_GEMM_RELU) f = fmaxf(f, 0.f);
-        if (p.residual) f += p.residual[row * p.ldr + n];
-        *o = f;
+  for (int m = 0; m < p.rows && m < ROWS; ++m) gemv_store<EPI>(p, n, m, acc0[m], acc1[m]);
+}
+
+// 2..8 rows (the 7-token prompt prefill of every recon call, short chat prompts): still one pass over the weights,
+// but 8 scalar dot products per weight would make the kernel issue-bound (measured 0.9 TB/s), so the products go
+// through the legacy warp-level tensor-core MMA: D[16 weight rows x 8 x-rows] += W[16 x 16] . X^T[16 x 8]
+// (mma.sync m16n8k16 — the right tool for an HBM-bound skinny product; tcgen05 tiles would idle 121 of 128 rows).
+// One CTA = 16 output columns, its NW warps split K; lane (g = lane/4, t = lane%4) loads 16 contiguous bytes of
+// weight rows g and g+8 and of x row g per 32-element k block (full 32-byte sectors), and because a dot product
+// does not care about the order of k, those 8 elements are fed as the k slots {2t,2t+1,2t+8,2t+9} of two MMAs.
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                               uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+template <int EPI, int NW>
+__global__ void __launch_bounds__(NW * 32) gemv_skinny_mma_kernel(const GemvParams p) {
+  constexpr bool SW = EPI == G2VLM_EPI_SWIGLU_BF16;
+  constexpr int U = 4;  // k blocks in flight per warp
+  __shared__ float part[NW][SW ? 2 : 1][16][8];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int n0 = blockIdx.x * 16;  // first output column of this CTA
+  long long r0 = n0;
+  if constexpr (SW) r0 = (long long)(n0 >> 7) * 256 + (n0 & 127);  // gate rows; up rows sit 128 further
+  const uint4* wg0 = reinterpret_cast<const uint4*>(p.w + (r0 + g) * p.ldw) + t;
+  const uint4* wg1 = reinterpret_cast<const uint4*>(p.w + (r0 + g + 8) * p.ldw) + t;
+  const uint4* wu0 = reinterpret_cast<const uint4*>(p.w + (r0 + 128 + g) * p.ldw) + t;
+  const uint4* wu1 = reinterpret_cast<const uint4*>(p.w + (r0 + 128 + g + 8) * p.ldw) + t;
+  const bool xrow = g < p.rows;
+  const uint4* xp = reinterpret_cast<const uint4*>(p.x + (xrow ? g : 0) * p.ldx) + t;
+  const int kb_total = p.K >> 5;
+  const int per = (kb_total + NW - 1) / NW;
+  const int kb0 = warp * per, kb1 = min(kb_total, kb0 + per);
+  float dg[4] = {0.f, 0.f, 0.f, 0.f}, du[4] = {0.f, 0.f, 0.f, 0.f};
+  const uint4 zero = make_uint4(0, 0, 0, 0);
+  for (int kb = kb0; kb < kb1; kb += U) {
+    uint4 a0[U], a1[U], b0[U], b1[U], xv[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const bool ok = kb + u < kb1;
+      const int o = (kb + u) * 4;  // uint4 units: 32 elements = 64 B = 4 x 16 B per row
+      a0[u] = ok ? __ldg(wg0 + o) : zero;
+      a1[u] = ok ? __ldg(wg1 + o) : zero;
+      if constexpr (SW) {
+        b0[u] = ok ? __ldg(wu0 + o) : zero;
+        b1[u] = ok ? __ldg(wu1 + o) : zero;
       }
+      xv[u] = (ok && xrow) ? __ldg(xp + o) : zero;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      mma_bf16_16816(dg, a0[u].x, a1[u].x, a0[u].y, a1[u].y, xv[u].x, xv[u].y);
+      mma_bf16_16816(dg, a0[u].z, a1[u].z, a0[u].w, a1[u].w, xv[u].z, xv[u].w);
+      if constexpr (SW) {
+        mma_bf16_16816(du, b0[u].x, b1[u].x, b0[u].y, b1[u].y, xv[u].x, xv[u].y);
+        mma_bf16_16816(du, b0[u].z, b1[u].z, b0[u].w, b1[u].w, xv[u].z, xv[u].w);
+      }
+    }
+  }
+  // C fragment: d0,d1 = (weight row g, x rows 2t,2t+1), d2,d3 = (weight row g+8, x rows 2t,2t+1)
+  part[warp][0][g][2 * t] = dg[0];
+  part[warp][0][g][2 * t + 1] = dg[1];
+  part[warp][0][g + 8][2 * t] = dg[2];
+  part[warp][0][g + 8][2 * t + 1] = dg[3];
+  if constexpr (SW) {
+    part[warp][1][g][2 * t] = du[0];
+    part[warp][1][g][2 * t + 1] = du[1];
+    part[warp][1][g + 8][2 * t] = du[2];
+    part[warp][1][g + 8][2 * t + 1] = du[3];
+  }
+  __syncthreads();
+  if (threadIdx.x < 128) {
+    const int m = threadIdx.x >> 4, c = threadIdx.x & 15;  // 16 consecutive columns per row: coalesced stores
+    if (m < p.rows) {
+      float f = 0.f, fu = 0.f;
+#pragma unroll
+      for (int w = 0; w < NW; ++w) {
+        f += part[w][0][c][m];
+        if constexpr (SW) fu += part[w][1][c][m];
+      }
+      gemv_store<EPI>(p, n0 + c, m, f, fu);
     }
   }
 }
@@ -156,6 +245,11 @@ template <int EPI>
 static void launch_gemv_epi(const GemvParams& p, int n_out, cudaStream_t stream) {
   const bool one = p.rows == 1;
   const bool split = p.K >= 4096;
+  if (!one && n_out % 16 == 0 && p.K % 32 == 0 && p.ldw % 8 == 0 && p.ldx % 8 == 0) {
+    if (split) gemv_skinny_mma_kernel<EPI, 16><<<n_out / 16, 16 * 32, 0, stream>>>(p);
+    else gemv_skinny_mma_kernel<EPI, 8><<<n_out / 16, 8 * 32, 0, stream>>>(p);
+    return;
+  }
   const int cols = split ? GEMV_WARPS / 4 : GEMV_WARPS;
   const unsigned grid = (n_out + cols - 1) / cols;
   if (one && split) gemv_bf16_kernel<EPI, 1, 4><<<grid, GEMV_WARPS * 32, 0, stream>>>(p);

@@ -188,6 +188,7 @@ class G2VLMFast:
         self.cfg = cfg
         self.device = torch.device(device)
         self.buf = _Buffers(self.device)
+        self._stage: Dict[str, dict] = {}
         missing = [k for k in state_dict_schema(cfg) if k not in state_dict and k != "language_model.lm_head.weight"]
         if missing:
             raise KeyError(f"state_dict is missing {len(missing)} keys, e.g. {missing[:4]}")
@@ -373,6 +374,32 @@ class G2VLMFast:
             self.vit = V
 
     # ------------------------------------------------------------------------------------------
+    # host -> device staging of the per-call index tensors
+    # ------------------------------------------------------------------------------------------
+    def _idx(self, name: str, t: torch.Tensor, dtype=torch.long) -> torch.Tensor:
+        """Device copy of a host-built index tensor WITHOUT stalling the host: the values go through one of two
+        reusable pinned staging buffers (guarded by an event) into a reusable device buffer, so the copy is a true
+        async H2D in stream order — a pageable `.to(device)` would block the host until the stream drains, which
+        stops it from enqueueing the next scene while this one computes.  Device tensors pass through."""
+        if t.is_cuda:
+            return t.to(dtype).contiguous()
+        slot = self._stage.setdefault(name, dict(i=0, pin=[None, None], ev=[None, None]))
+        i = slot["i"]
+        slot["i"] = i ^ 1
+        pin = slot["pin"][i]
+        if pin is None or pin.shape != t.shape or pin.dtype != dtype:
+            pin = slot["pin"][i] = torch.empty(t.shape, dtype=dtype, pin_memory=True)
+        elif slot["ev"][i] is not None:
+            slot["ev"][i].synchronize()       # the upload issued two calls ago has left this buffer (long done)
+        pin.copy_(t)
+        d = self.buf.get("idx." + name, tuple(t.shape), dtype)
+        d.copy_(pin, non_blocking=True)
+        if slot["ev"][i] is None:
+            slot["ev"][i] = torch.cuda.Event()
+        slot["ev"][i].record()
+        return d
+
+    # ------------------------------------------------------------------------------------------
     # small cached host-built tables
     # ------------------------------------------------------------------------------------------
     def _work(self, cu_q: Sequence[int], cu_k: Sequence[int], tag: str) -> torch.Tensor:
@@ -480,7 +507,7 @@ class G2VLMFast:
         cache.reserve(L + T)
         if len_dev is not None and T != 1:
             raise ValueError("device-resident cache length is only supported for single-token steps")
-        pos = position_ids.to(dev, torch.long).contiguous()
+        pos = self._idx("und.pos", position_ids)
         cos = self.buf.get("und.cos", (T, hd // 2), torch.float32)
         sin = self.buf.get("und.sin", (T, hd // 2), torch.float32)
         ops.mrope_table(pos, self.inv_freq, cos, sin, cfg.mrope_section)
@@ -488,8 +515,7 @@ class G2VLMFast:
         if T == 1:
             work = None                   # single-token steps use the split-K decode attention
         elif T <= ops.ATTN_ROWS_PER_ITEM:  # one work item whose key range grows with the cache
-            work = self.buf.get("und.work", (1, 8), torch.int32)
-            work.copy_(torch.tensor([[0, 0, T, 0, L + T, 0, 0, 0]], dtype=torch.int32))
+            work = self._idx("und.work", torch.tensor([[0, 0, T, 0, L + T, 0, 0, 0]], dtype=torch.int32), torch.int32)
         else:
             work = self._work([0, T], [0, L + T], "und")
         xs = self.buf.get("und.x", (T, H), torch.float32)
@@ -523,11 +549,12 @@ class G2VLMFast:
         if len(text_token_lens) != 1:
             raise NotImplementedError("single-sample path only (the reference's inference drivers use batch 1)")
         cache = KVCache.adopt(past_key_values, cfg, dev)
-        if int(key_values_lens.sum()) != cache.len:
+        # (a device-resident key_values_lens is not validated: reading it would stall the host on the stream)
+        if not key_values_lens.is_cuda and int(key_values_lens.sum()) != cache.len:
             raise ValueError("key_values_lens does not match the cache length")
         n = int(packed_text_ids.numel())
         x = self.buf.get("txt.x", (n, cfg.hidden_size), torch.float32)   # reused workspace: no allocator call per step
-        ops.gather_rows(self.embed, x, packed_text_ids.to(dev, torch.long), n)
+        ops.gather_rows(self.embed, x, self._idx("txt.ids", packed_text_ids), n)
         self._und_forward(x, packed_text_position_ids, cache, causal=True)
         return cache
 
@@ -653,10 +680,11 @@ class G2VLMFast:
         cfg, dev = self.cfg, self.device
         nq, nkv, hd, H = cfg.num_heads, cfg.num_kv_heads, cfg.head_dim, cfg.hidden_size
         T = packed_sequence.shape[0]
-        geo = packed_geo_token_indexes.to(dev, torch.long)
-        und = packed_text_indexes.to(dev, torch.long)
-        n_geo = int(geo.numel())
-        perm = torch.cat([geo, und]).contiguous()  # internal row i <- packed row perm[i]
+        n_geo = int(packed_geo_token_indexes.numel())
+        if packed_geo_token_indexes.is_cuda or packed_text_indexes.is_cuda:
+            perm = torch.cat([packed_geo_token_indexes.to(dev, torch.long), packed_text_indexes.to(dev, torch.long)])
+        else:  # internal row i <- packed row perm[i]
+            perm = self._idx("mot.perm", torch.cat([packed_geo_token_indexes.long(), packed_text_indexes.long()]))
         if int(perm.numel()) != T:
             raise ValueError("geo + text indexes must cover every packed row exactly once")
         past_key_values = KVCache.adopt(past_key_values, cfg, dev)
@@ -665,7 +693,7 @@ class G2VLMFast:
         ops.gather_rows(packed_sequence, x, perm, T)
         cos_p = self.buf.get("mot.cos_p", (T, hd // 2), torch.float32)
         sin_p = self.buf.get("mot.sin_p", (T, hd // 2), torch.float32)
-        ops.mrope_table(packed_position_ids.to(dev, torch.long).contiguous(), self.inv_freq, cos_p, sin_p,
+        ops.mrope_table(self._idx("mot.pos", packed_position_ids.contiguous()), self.inv_freq, cos_p, sin_p,
                         cfg.mrope_section)
         cos = self.buf.get("mot.cos", (T, hd // 2), torch.float32)
         sin = self.buf.get("mot.sin", (T, hd // 2), torch.float32)
@@ -864,9 +892,9 @@ class G2VLMFast:
         packed = self.buf.get("mot.packed", (T, H), torch.float32)
         n_und = int(packed_text_ids.numel())
         txt = self.buf.get("mot.txt", (n_und, H), torch.float32)
-        ops.gather_rows(self.embed, txt, packed_text_ids.to(dev, torch.long), n_und)
-        ops.gather_rows(txt, packed, packed_text_indexes.to(dev, torch.long), n_und, scatter=True)
-        ops.gather_rows(geo_emb, packed, packed_dino_token_indexes.to(dev, torch.long), n_geo, scatter=True)
+        ops.gather_rows(self.embed, txt, self._idx("dino.txt_ids", packed_text_ids), n_und)
+        ops.gather_rows(txt, packed, self._idx("dino.txt_idx", packed_text_indexes), n_und, scatter=True)
+        ops.gather_rows(geo_emb, packed, self._idx("dino.geo_idx", packed_dino_token_indexes), n_geo, scatter=True)
         if collect is not None:
             collect["dino_tokens"] = tokens.float().clone()
             collect["packed_sequence"] = packed.clone()
@@ -951,7 +979,7 @@ class G2VLMFast:
         p = cfg.dino_patch
         gh, gw = Hh // p, Ww // p
         P, H = gh * gw, cfg.hidden_size
-        geo = packed_dino_token_indexes.to(dev, torch.long)
+        geo = self._idx("recon.geo_idx", packed_dino_token_indexes)
         if shard is not None:
             p0, p1 = shard.packed_rows
             geo = geo[(geo >= p0) & (geo < p1)] - p0
@@ -1268,16 +1296,14 @@ class G2VLMFast:
         self._mark("start")
         gi, newlens, new_rope = self.prepare_prompts_addbos([0], [0], ["Reconstruct the 3D scene."], tokenizer,
                                                             new_token_ids)
-        gi = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in gi.items()}
-        past = self.forward_cache_update_text(past, **gi)
+        past = self.forward_cache_update_text(past, **gi)   # index tensors stay on the host: _idx stages them
         # the raw views cross PCIe once; normalisation happens on the device (bit-identical to the host op)
         gi, newlens, new_rope = self.prepare_dino_images_pi3(newlens, new_rope, images, dino_image_transform,
                                                              new_token_ids, normalize_on_host=False)
         if collect is not None:
             collect["generation_input"] = {k: v.clone() for k, v in gi.items() if torch.is_tensor(v)}
         raw = gi["original_images"].to(dev, non_blocking=True)
-        gi = {k: (v.to(dev, non_blocking=True) if torch.is_tensor(v) and k not in ("packed_dino_images", "original_images")
-                  else v) for k, v in gi.items()}
+        gi = dict(gi)
         gi["packed_dino_images"] = gi["original_images"] = raw
         self._raw_images = True
         try:

@@ -12,7 +12,7 @@ def _relerr(a, b):
     return ((a.float() - b.float()).abs().max() / b.float().abs().max().clamp_min(1e-30)).item()
 
 
-@pytest.mark.parametrize("rows", [1, 3, 8])
+@pytest.mark.parametrize("rows", [1, 2, 3, 7, 8])
 def test_gemv_epilogues_match_reference(rows):
     from g2vlm_b200 import ops
     g = torch.Generator().manual_seed(rows)
@@ -45,6 +45,20 @@ def test_gemv_epilogues_match_reference(rows):
     ops.gemm(x, wi, o, epilogue=ops.EPI_SWIGLU_BF16)
     gt, up = (x.float() @ wg.float().T).to(torch.bfloat16), (x.float() @ wu.float().T).to(torch.bfloat16)
     assert _relerr(o, torch.nn.functional.silu(gt.float()).to(torch.bfloat16).float() * up.float()) < 1.5e-2
+
+
+@pytest.mark.parametrize("rows,K,N", [(5, 1536, 648), (7, 1552, 640), (4, 8960, 1536), (7, 4096, 48)])
+def test_gemv_skinny_shapes(rows, K, N):
+    """2..8 rows: the mma.sync kernel (N % 16 == 0, K % 32 == 0; 8 or 16 warps split K, ragged K split) and the
+    scalar fallback for the other shapes."""
+    from g2vlm_b200 import ops
+    g = torch.Generator().manual_seed(K + N + rows)
+    x = (torch.randn(rows, K, generator=g) * 0.5).to(torch.bfloat16).cuda()
+    w = (torch.randn(N, K, generator=g) * 0.05).to(torch.bfloat16).cuda()
+    out = torch.full((rows + 1, N), 7.0, device="cuda")
+    ops.gemm(x, w, out[:rows], epilogue=ops.EPI_STORE_F32)
+    assert _relerr(out[:rows], x.float() @ w.float().T) < 1e-4
+    assert bool((out[rows] == 7.0).all())
 
 
 def test_gemv_agrees_with_tensor_core_path():

@@ -25,9 +25,9 @@ class Tok:
 
 ids = dict(bos_token_id=1, eos_token_id=2, start_of_image=3, end_of_image=4)
 gi_t, nl, nr = model.prepare_prompts_addbos([0], [0], ["x"], Tok(), ids)
-gi_t = {k: v.cuda() for k, v in gi_t.items()}
+gi_t = {k: (v if k.endswith('lens') else v.cuda()) for k, v in gi_t.items()}
 gi, _, _ = model.prepare_dino_images_pi3(nl, nr, views, None, ids)
-gi = {k: v.cuda() for k, v in gi.items()}
+gi = {k: (v if k.endswith('lens') else v.cuda()) for k, v in gi.items()}
 
 
 def step():
