@@ -188,6 +188,7 @@ def run_view_sharded(args, cfg, dist, rank, world, local_rank):
     P = (size // 14) ** 2
     sd = schema.init_synthetic(cfg, seed=0, embed_rows=32, device="cuda")
     model = G2VLMFast(cfg, sd)
+    model.fuse_prompt = not args.no_fuse_prompt
     del sd
     torch.cuda.empty_cache()
     views_host = schema.synthetic_views(n_views, size, size, seed=1)
@@ -257,6 +258,8 @@ def main():
     ap.add_argument("--cpu-views", type=int, default=1)
     ap.add_argument("--cpu-layer-frac", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-fuse-prompt", action="store_true",
+                    help="run the 7-token prompt prefill as a separate und pass (reference order) instead of fused into the geo step")
     ap.add_argument("--profile", action="store_true",
                     help="profiling run under ncu: skip the e2e arm and the CPU baseline, allow warmup < 3 (not a bench value)")
     ap.add_argument("--tiny", action="store_true", help="tiny model dims (smoke / debugging only; INVALID as a benchmark)")
@@ -292,6 +295,7 @@ def main():
     P = (size // 14) ** 2
     sd = schema.init_synthetic(cfg, seed=0, embed_rows=32, device="cuda")
     model = G2VLMFast(cfg, sd)
+    model.fuse_prompt = not args.no_fuse_prompt
     del sd
     torch.cuda.empty_cache()
     views_host = schema.synthetic_views(n_views, size, size, seed=1 + rank).pin_memory()
@@ -320,8 +324,13 @@ def main():
         return orig_attention(q, *a, **k)
 
     def step_resident():
-        past = model.forward_cache_update_text(NaiveCache(cfg.num_layers), **gi_text)
-        past, last = model.forward_cache_update_dino(past, update_past_key_values=False, **gi)
+        # same sequence as G2VLMFast.recon(): the 7-token prompt prefill rides along with the geo step
+        # (model.fuse_prompt; --no-fuse-prompt runs it as the reference's separate und pass first)
+        past = NaiveCache(cfg.num_layers)
+        if not model.fuse_prompt:
+            past = model.forward_cache_update_text(past, **gi_text)
+        past, last = model.forward_cache_update_dino(past, update_past_key_values=False,
+                                                     prompt=gi_text if model.fuse_prompt else None, **gi)
         return model.reconstruct(past_key_values=past, selected_hidden_states=last, **gi)
 
     out_host = {}

@@ -101,6 +101,7 @@ attention_tcgen05_kernel(const __grid_constant__ AttnKParams p) {
 
   const int* w = p.work + blockIdx.x * 8;
   const int q_tile_begin = w[0], q_seg_begin = w[1], q_seg_end = w[2], k_begin = w[3], k_end = w[4];
+  const bool causal = p.causal != 0 || w[5] != 0;  // per launch, or per work item
   const int head = blockIdx.y;
   const int kv_head = head / p.q_heads_per_kv;
   const int len_q = q_seg_end - q_seg_begin;
@@ -108,7 +109,7 @@ attention_tcgen05_kernel(const __grid_constant__ AttnKParams p) {
   const int rows_here = min(2 * ATT_BM, q_seg_end - q_tile_begin);
   // keys needed by this CTA (causal: bottom-right aligned, as flash-attn)
   int k_needed = len_k;
-  if (p.causal) {
+  if (causal) {
     const int last_row = q_tile_begin + rows_here - 1 - q_seg_begin;
     k_needed = max(0, min(len_k, last_row + (len_k - len_q) + 1));
   }
@@ -254,7 +255,7 @@ attention_tcgen05_kernel(const __grid_constant__ AttnKParams p) {
     const uint32_t tO_w = tO(t) + lane_off;
     // number of keys this row may see
     int limit = len_k;
-    if (p.causal) limit = max(0, min(len_k, (row - q_seg_begin) + (len_k - len_q) + 1));
+    if (causal) limit = max(0, min(len_k, (row - q_seg_begin) + (len_k - len_q) + 1));
 
     float m_used = 0.f;  // running max in the scaled log2 domain (possibly stale by <= TAU)
     float l_run = 0.f;

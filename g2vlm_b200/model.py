@@ -189,6 +189,7 @@ class G2VLMFast:
         self.device = torch.device(device)
         self.buf = _Buffers(self.device)
         self._stage: Dict[str, dict] = {}
+        self.fuse_prompt = True   # recon(): run the prompt prefill inside the geo step (language_model_forward_geo)
         missing = [k for k in state_dict_schema(cfg) if k not in state_dict and k != "language_model.lm_head.weight"]
         if missing:
             raise KeyError(f"state_dict is missing {len(missing)} keys, e.g. {missing[:4]}")
@@ -457,15 +458,21 @@ class G2VLMFast:
     # MoT language model
     # ------------------------------------------------------------------------------------------
     def _mot_layer(self, L, x, T, n_geo, qkv, attn, act, hbuf, cos, sin, work, kv_rows, causal, round_normed,
-                   kv_exchange=None, kv_len_dev=None):
+                   kv_exchange=None, kv_len_dev=None, prompt_rows=0):
+        # prompt_rows: the LAST prompt_rows of the T rows are the causal text prefill riding along with the geo
+        # step (fused recon path); they take the und branch's rounding of the normed q/k (round_normed=True)
         cfg = self.cfg
         H, I = cfg.hidden_size, cfg.intermediate_size
         nq, nkv, hd = cfg.num_heads, cfg.num_kv_heads, cfg.head_dim
         groups = [(0, n_geo), (n_geo, T - n_geo)]
         ops.rmsnorm_routed(x, hbuf, L["input_layernorm_geo"], L["input_layernorm_und"], n_geo, cfg.rms_norm_eps, rows=T)
         ops.gemm(hbuf[:T], L["wqkv"], qkv, epilogue=ops.EPI_STORE_BF16, groups=groups, bias=L["bqkv"])
-        ops.qknorm_mrope(qkv, T, n_geo, nq, nkv, hd, L["q_norm_geo"], L["k_norm_geo"], L["q_norm_und"],
+        Tm = T - prompt_rows
+        ops.qknorm_mrope(qkv, Tm, n_geo, nq, nkv, hd, L["q_norm_geo"], L["k_norm_geo"], L["q_norm_und"],
                          L["k_norm_und"], cos, sin, cfg.rms_norm_eps, round_normed=round_normed)
+        if prompt_rows:
+            ops.qknorm_mrope(qkv[Tm:], prompt_rows, 0, nq, nkv, hd, L["q_norm_geo"], L["k_norm_geo"], L["q_norm_und"],
+                             L["k_norm_und"], cos[Tm:], sin[Tm:], cfg.rms_norm_eps, round_normed=True)
         if kv_exchange is None:
             k_all, v_all = qkv[:kv_rows, nq * hd:(nq + nkv) * hd], qkv[:kv_rows, (nq + nkv) * hd:]
         else:  # view-sharded: all ranks' K/V rows (+ prefix) gathered over NVLink
@@ -674,9 +681,18 @@ class G2VLMFast:
     def language_model_forward_geo(self, packed_sequence, packed_position_ids, packed_geo_token_indexes,
                                    packed_text_indexes, past_key_values: NaiveCache,
                                    update_past_key_values: bool = True, collect: Optional[list] = None,
-                                   group=None):
+                                   group=None, prompt: Optional[dict] = None):
         """Qwen2VLModel.forward_inference(mode='geo', is_causal=False) incl. the routed final norm
-        (reference g2vlm/qwen2vl.py:1267-1337).  packed_sequence: fp32 [T, H] in packed order."""
+        (reference g2vlm/qwen2vl.py:1267-1337).  packed_sequence: fp32 [T, H] in packed order.
+
+        prompt (fused recon path): dict(packed_text_ids, packed_text_position_ids) of the text prefill the
+        reference runs as a separate und pass before this step (g2vlm.py:1262-1272).  Layer i of that prefill only
+        needs its own layer i-1, and this step only needs the prefill's layer-i K/V, so the Kp prompt rows ride
+        along as extra und rows [T, T+Kp): their K/V land exactly where the merged prefix is expected (key rows
+        [T, T+Kp)), their attention is one extra causal work item over those keys, and the und-expert weights are
+        streamed once per layer instead of twice.  Per-row arithmetic is unchanged (same rounding points); only
+        the fp32 accumulation order of the prompt rows' Linear layers differs (tensor-core tiles instead of the
+        skinny-row kernel).  Requires an empty cache and update_past_key_values=False."""
         cfg, dev = self.cfg, self.device
         nq, nkv, hd, H = cfg.num_heads, cfg.num_kv_heads, cfg.head_dim, cfg.hidden_size
         T = packed_sequence.shape[0]
@@ -689,17 +705,26 @@ class G2VLMFast:
             raise ValueError("geo + text indexes must cover every packed row exactly once")
         past_key_values = KVCache.adopt(past_key_values, cfg, dev)
         K0 = past_key_values.len
-        x = self.buf.get("mot.x", (T, H), torch.float32)
+        Kp = 0
+        if prompt is not None:
+            if K0 or update_past_key_values or group is not None:
+                raise ValueError("the fused prompt needs an empty cache, no cache update and no view sharding")
+            Kp = int(prompt["packed_text_ids"].numel())
+        x = self.buf.get("mot.x", (T + Kp, H), torch.float32)
         ops.gather_rows(packed_sequence, x, perm, T)
         cos_p = self.buf.get("mot.cos_p", (T, hd // 2), torch.float32)
         sin_p = self.buf.get("mot.sin_p", (T, hd // 2), torch.float32)
         ops.mrope_table(self._idx("mot.pos", packed_position_ids.contiguous()), self.inv_freq, cos_p, sin_p,
                         cfg.mrope_section)
-        cos = self.buf.get("mot.cos", (T, hd // 2), torch.float32)
-        sin = self.buf.get("mot.sin", (T, hd // 2), torch.float32)
+        cos = self.buf.get("mot.cos", (T + Kp, hd // 2), torch.float32)
+        sin = self.buf.get("mot.sin", (T + Kp, hd // 2), torch.float32)
         ops.gather_rows(cos_p, cos, perm, T)
         ops.gather_rows(sin_p, sin, perm, T)
-        qkv, attn, act, hbuf = self._mot_buffers(T, T + K0)
+        if Kp:
+            ops.gather_rows(self.embed, x[T:], self._idx("mot.prompt_ids", prompt["packed_text_ids"]), Kp)
+            ops.mrope_table(self._idx("mot.prompt_pos", prompt["packed_text_position_ids"].contiguous()), self.inv_freq,
+                            cos[T:], sin[T:], cfg.mrope_section)
+        qkv, attn, act, hbuf = self._mot_buffers(T + Kp, T + K0 + Kp)
         kvw = 2 * nkv * hd
         if update_past_key_values:
             past_key_values.reserve(K0 + T)
@@ -720,6 +745,13 @@ class G2VLMFast:
                 ops.gather_rows(qkv_[:T, nq * hd:], kv_send, None, T)
                 dist.all_gather_into_tensor(kv_all[:T_all], kv_send, group=group)
                 return kv_all[:, : nkv * hd], kv_all[:, nkv * hd:]
+        elif Kp:
+            key = ("geo_fused", T, Kp)
+            work = self._work_cache.get(key)
+            if work is None:   # the geo rows see every key incl. the prompt's; the prompt rows are causal among themselves
+                items = ops.attention_work_table([0, T], [0, T + Kp]).tolist()
+                items += [[t0, T, T + Kp, T, T + Kp, 1, 0, 0] for t0 in range(T, T + Kp, ops.ATTN_ROWS_PER_ITEM)]
+                work = self._work_cache[key] = torch.tensor(items, dtype=torch.int32).to(dev)
         else:
             work = self._work([0, T], [0, T + K0], "geo")
         for i, L in enumerate(self.layers):
@@ -729,8 +761,8 @@ class G2VLMFast:
                     ops.gather_rows(past_key_values.buf[i], qkv[T:, nq * hd:], None, K0)
                 else:
                     ops.gather_rows(past_key_values.buf[i], kv_all[T_all:], None, K0)
-            self._mot_layer(L, x, T, n_geo, qkv, attn, act, hbuf, cos, sin, work, T + K0, False, False,
-                            kv_exchange=kv_exchange)
+            self._mot_layer(L, x, T + Kp, n_geo, qkv, attn, act, hbuf, cos, sin, work, T + K0 + Kp, False, False,
+                            kv_exchange=kv_exchange, prompt_rows=Kp)
             if update_past_key_values:
                 # append in the reference's merged order: cached rows, then the PACKED query rows
                 ops.gather_rows(qkv[:T, nq * hd:], past_key_values.buf[i][K0:], perm, T, scatter=True)
@@ -861,8 +893,10 @@ class G2VLMFast:
                                   packed_dino_token_indexes, dino_token_seqlens, packed_position_ids, packed_seqlens,
                                   packed_indexes, packed_key_value_indexes, key_values_lens, packed_dino_images,
                                   original_images, update_past_key_values: bool = True, collect: Optional[dict] = None,
-                                  shard=None, group=None):
+                                  shard=None, group=None, prompt: Optional[dict] = None):
         """Reference: g2vlm.py:968-1039.  Returns (past_key_values, last_hidden_state [T, H] fp32).
+        `prompt`: generation input of the text prefill to fuse into this step instead of running it as a separate
+        pass first (see language_model_forward_geo); the index tensors are the ones built on top of that prefill.
         With `shard` (sharding.ViewShard) the index tensors describe the WHOLE scene and this rank processes
         the packed rows of its views only (last_hidden_state then has the local rows)."""
         cfg, dev = self.cfg, self.device
@@ -901,7 +935,7 @@ class G2VLMFast:
         last, past_key_values = self.language_model_forward_geo(
             packed, packed_position_ids, packed_dino_token_indexes, packed_text_indexes, past_key_values,
             update_past_key_values=update_past_key_values,
-            collect=None if collect is None else collect.setdefault("mot_layers", []), group=group)
+            collect=None if collect is None else collect.setdefault("mot_layers", []), group=group, prompt=prompt)
         self._mark("mot_end")
         return past_key_values, last
 
@@ -1296,7 +1330,11 @@ class G2VLMFast:
         self._mark("start")
         gi, newlens, new_rope = self.prepare_prompts_addbos([0], [0], ["Reconstruct the 3D scene."], tokenizer,
                                                             new_token_ids)
-        past = self.forward_cache_update_text(past, **gi)   # index tensors stay on the host: _idx stages them
+        prompt = None
+        if self.fuse_prompt:
+            prompt = gi                                     # the 7 prompt rows ride along with the geo step
+        else:
+            past = self.forward_cache_update_text(past, **gi)   # index tensors stay on the host: _idx stages them
         # the raw views cross PCIe once; normalisation happens on the device (bit-identical to the host op)
         gi, newlens, new_rope = self.prepare_dino_images_pi3(newlens, new_rope, images, dino_image_transform,
                                                              new_token_ids, normalize_on_host=False)
@@ -1307,7 +1345,8 @@ class G2VLMFast:
         gi["packed_dino_images"] = gi["original_images"] = raw
         self._raw_images = True
         try:
-            past, last = self.forward_cache_update_dino(past, update_past_key_values=False, collect=collect, **gi)
+            past, last = self.forward_cache_update_dino(past, update_past_key_values=False, collect=collect,
+                                                        prompt=prompt, **gi)
         finally:
             self._raw_images = False
         if collect is not None:

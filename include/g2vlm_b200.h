@@ -104,12 +104,13 @@ int g2vlm_gemm_bf16(const g2vlm_gemm_args* args, void* stream);
  * num_kv_heads*head_dim] (ldk / ldv), out is [q_rows, num_q_heads*head_dim] (ldo). The segment
  * structure (cu_seqlens_q / cu_seqlens_k of flash-attn; per-view batches of SDPA) is given as a
  * DEVICE table of work items, 8 int32 each:
- *   {q_tile_begin, q_seg_begin, q_seg_end, k_begin, k_end, 0, 0, 0}
+ *   {q_tile_begin, q_seg_begin, q_seg_end, k_begin, k_end, item_causal, 0, 0}
  * one item per <= 256 consecutive query rows [q_tile_begin, min(q_tile_begin+256, q_seg_end)) of a
  * segment whose queries are rows [q_seg_begin, q_seg_end) and whose keys are rows [k_begin, k_end).
  * Query rows covered by no item are NOT written (flash-attn leaves them uninitialised, SURVEY.md
  * quirk Q1; the caller defines them, the host mirror zero-fills). causal = bottom-right aligned
- * mask as in flash-attn. K/V rows in [k_end, round_up(k_end,128)) that lie inside kv_rows must hold
+ * mask as in flash-attn, for the whole launch (args.causal) or for one item (item_causal != 0: lets
+ * the causal prompt rows ride in the same launch as the non-causal geo step). K/V rows in [k_end, round_up(k_end,128)) that lie inside kv_rows must hold
  * finite values. head_dim in {64, 128} (the 96-wide Pi3 heads are zero-padded to 128 by the caller).
  * ---------------------------------------------------------------------------------------------- */
 typedef struct g2vlm_attn_args {

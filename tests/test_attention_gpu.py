@@ -131,3 +131,23 @@ def test_strided_fused_qkv_buffer_and_timing():
     vs = v.float().view(-1, 2, 128).transpose(0, 1).repeat_interleave(6, 0)
     ref = (torch.softmax(qs @ ks.transpose(1, 2) * scale, -1) @ vs).transpose(0, 1).reshape(-1, 1536)
     assert (out[rows].float() - ref).abs().max().item() < 2e-2
+
+
+def test_per_item_causal_flag_mixes_masks_in_one_launch():
+    """Work items carry their own causal flag (column 5): a non-causal segment over all keys and a causal segment
+    over the last keys in ONE launch (the fused prompt prefill of the recon path)."""
+    from g2vlm_b200 import ops
+    hq, hk, d, T, Kp = 12, 2, 128, 300, 7
+    g = torch.Generator().manual_seed(5)
+    q = torch.randn(T + Kp, hq * d, generator=g).to(torch.bfloat16).cuda()
+    k = torch.randn(T + Kp, hk * d, generator=g).to(torch.bfloat16).cuda()
+    v = torch.randn(T + Kp, hk * d, generator=g).to(torch.bfloat16).cuda()
+    items = ops.attention_work_table([0, T], [0, T + Kp]).tolist() + [[T, T, T + Kp, T, T + Kp, 1, 0, 0]]
+    work = torch.tensor(items, dtype=torch.int32).cuda()
+    out = torch.zeros(T + Kp, hq * d, device="cuda", dtype=torch.bfloat16)
+    scale = 1 / math.sqrt(d)
+    ops.attention(q, k, v, out, work, num_q_heads=hq, num_kv_heads=hk, head_dim=d, scale=scale)
+    ref_a = _ref_attention(q[:T], k, v, [0, T], [0, T + Kp], hq, hk, d, scale, False)
+    ref_b = _ref_attention(q[T:], k[T:], v[T:], [0, Kp], [0, Kp], hq, hk, d, scale, True)
+    assert (out[:T].float() - ref_a).abs().max() < 2e-2
+    assert (out[T:].float() - ref_b).abs().max() < 2e-2

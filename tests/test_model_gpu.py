@@ -362,3 +362,22 @@ def test_recon_server_matches_direct_calls():
     for a, b in zip(direct, got):
         for k in a:
             assert torch.equal(a[k], b[k]), k
+
+
+def test_fused_prompt_prefill_matches_separate_pass():
+    """recon() runs the prompt prefill as extra causal und rows of the geo step; the reference order (separate und
+    pass first, K/V merged as a prefix) must give the same result up to the accumulation order of 7 rows."""
+    from g2vlm_b200.model import G2VLMFast
+    cfg = schema.TINY
+    model = G2VLMFast(cfg, schema.init_synthetic(cfg, seed=0, device="cuda"))
+    v = schema.synthetic_views(3, 70, 98, seed=11)
+    keys = ("points", "local_points", "global_points", "camera_poses")
+    model.fuse_prompt = True
+    c1 = {}
+    a = {k: x.float().clone() for k, x in model.recon(StubTokenizer(), dict(TOKENS), None, v, collect=c1).items() if k in keys}
+    model.fuse_prompt = False
+    c2 = {}
+    b = {k: x.float().clone() for k, x in model.recon(StubTokenizer(), dict(TOKENS), None, v, collect=c2).items() if k in keys}
+    assert _maxrel(c1["last_hidden"], c2["last_hidden"]) < 2e-3
+    for k in keys:
+        assert _maxrel(a[k], b[k]) < 2e-3, k
