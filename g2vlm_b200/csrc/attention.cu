@@ -3,9 +3,11 @@
 // Replaces flash_attn_varlen_func (modeling/g2vlm/qwen2vl.py:643-652, dinov2_model.py:49-58) and the
 // per-view SDPA calls of the Pi3 decoders (modeling/pi3/models/layers/attention.py:255-259,370-372).
 //
-// One CTA = one work item (<= 256 query rows of one segment) x one query head, two 128-row query
-// tiles in flight ("ping-pong"): while the softmax warps of tile 0 turn S0 into P0, the tensor core
-// runs tile 1's MMAs and vice versa.
+// Persistent kernel, one CTA per SM.  A unit of work = one work item (<= 256 query rows of one segment) x
+// one query head; a CTA walks units blockIdx.x, +gridDim.x, ... with TMEM, barriers and the K/V ring kept
+// alive across units (the producer prefetches the next unit while this one drains).  Inside a unit two
+// 128-row query tiles are in flight ("ping-pong"): while the softmax warps of tile 0 turn S0 into P0, the
+// tensor core runs tile 1's MMAs and vice versa.
 //   warp 0        TMA producer: Q tiles once, K/V blocks of 128 keys through an mbarrier ring
 //   warp 1        MMA issuer:   S_t = Q_t K^T (SS, K-major operands) ; O_t += P_t V (TS: P read from
 //                               TMEM, V is an MN-major B operand straight from the [key][d] layout)
@@ -26,7 +28,10 @@ constexpr int ATT_BM = 128;       // query rows per tile
 constexpr int ATT_BN = 128;       // keys per block
 constexpr int ATT_THREADS = 384;  // 12 warps
 constexpr float ATT_RESCALE_TAU = 8.0f;
-constexpr int ATT_PCHUNKS = 4;    // P_t reaches the MMA warp in 4 chunks of 32 keys (PV overlaps the exp tail)
+#ifndef ATT_PCHUNKS_N
+#define ATT_PCHUNKS_N 4
+#endif
+constexpr int ATT_PCHUNKS = ATT_PCHUNKS_N;    // P_t reaches the MMA warp in 4 chunks of 32 keys (PV overlaps the exp tail)
 
 struct AttnKParams {
   CUtensorMap tmQ, tmK, tmV;
@@ -36,6 +41,7 @@ struct AttnKParams {
   int q_heads_per_kv;
   int causal;
   float scale_log2;
+  int n_items, n_heads;
 };
 
 template <int D>
@@ -72,6 +78,12 @@ __device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
   return d;
 }
 
+// One (work item, head) unit of a persistent CTA, decoded identically by every role.
+struct AttnUnit {
+  int q_tile_begin, q_seg_begin, q_seg_end, k_begin, len_q, len_k, head, kv_head, nblk;
+  bool causal;
+};
+
 template <int D>
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 attention_tcgen05_kernel(const __grid_constant__ AttnKParams p) {
@@ -79,41 +91,56 @@ attention_tcgen05_kernel(const __grid_constant__ AttnKParams p) {
   constexpr int KSTEPS_QK = D / 16;       // MMAs per S tile (K = head dim)
   constexpr int KSTEPS_PV = ATT_BN / 16;  // MMAs per PV block (K = keys)
   constexpr int BOX_BYTES = ATT_BM * 128; // one 64-col box of 128 rows
+  constexpr int KS = Cfg::kStages;
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
   uint8_t* sQ = smem;                              // 2 tiles
   uint8_t* sKV = smem + 2 * Cfg::kTileBytes;       // kStages x (K tile, V tile)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sKV + Cfg::kStages * 2 * Cfg::kTileBytes);
-  uint64_t* q_full = bars;                         // [1]
-  uint64_t* k_full = bars + 1;                     // [kStages]
-  uint64_t* v_full = k_full + Cfg::kStages;
-  uint64_t* k_empty = v_full + Cfg::kStages;
-  uint64_t* v_empty = k_empty + Cfg::kStages;
-  uint64_t* s_full = v_empty + Cfg::kStages;       // [2]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sKV + KS * 2 * Cfg::kTileBytes);
+  uint64_t* q_full = bars;                         // [1]  Q tiles of the current unit landed
+  uint64_t* q_empty = bars + 1;                    // [1]  every QK^T of the unit has read them
+  uint64_t* k_full = bars + 2;                     // [kStages]
+  uint64_t* v_full = k_full + KS;
+  uint64_t* k_empty = v_full + KS;
+  uint64_t* v_empty = k_empty + KS;
+  uint64_t* s_full = v_empty + KS;                 // [2]
   uint64_t* p_full = s_full + 2;                   // [2][ATT_PCHUNKS]: P handed over in key chunks
-  uint64_t* o_done = p_full + 2 * ATT_PCHUNKS;     // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 2);
+  uint64_t* o_done = p_full + 2 * ATT_PCHUNKS;     // [2]  PV of a block finished
+  uint64_t* o_free = o_done + 2;                   // [2]  the epilogue has read O_t out of TMEM
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_free + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const int total_units = p.n_items * p.n_heads;
 
-  const int* w = p.work + blockIdx.x * 8;
-  const int q_tile_begin = w[0], q_seg_begin = w[1], q_seg_end = w[2], k_begin = w[3], k_end = w[4];
-  const bool causal = p.causal != 0 || w[5] != 0;  // per launch, or per work item
-  const int head = blockIdx.y;
-  const int kv_head = head / p.q_heads_per_kv;
-  const int len_q = q_seg_end - q_seg_begin;
-  const int len_k = k_end - k_begin;
-  const int rows_here = min(2 * ATT_BM, q_seg_end - q_tile_begin);
-  // keys needed by this CTA (causal: bottom-right aligned, as flash-attn)
-  int k_needed = len_k;
-  if (causal) {
-    const int last_row = q_tile_begin + rows_here - 1 - q_seg_begin;
-    k_needed = max(0, min(len_k, last_row + (len_k - len_q) + 1));
-  }
-  const int nblk = (k_needed + ATT_BN - 1) / ATT_BN;
+  // Persistent CTA: units blockIdx.x, blockIdx.x + gridDim.x, ... (item index fastest, so CTAs that run
+  // side by side work on neighbouring query tiles of the same head and share its K/V in L2).  TMEM, the
+  // barriers and the K/V ring live across units: the producer prefetches the next unit's Q/K/V while the
+  // softmax warps still drain this one, which hides the per-unit prologue/epilogue (5-7 us of ~25 us per unit
+  // on the 11-block DINO / Pi3-decoder segments when every unit was its own CTA).
+  auto decode = [&](int u) {
+    AttnUnit a;
+    const int* w = p.work + (u % p.n_items) * 8;
+    a.q_tile_begin = w[0];
+    a.q_seg_begin = w[1];
+    a.q_seg_end = w[2];
+    a.k_begin = w[3];
+    a.len_k = w[4] - w[3];
+    a.causal = p.causal != 0 || w[5] != 0;  // per launch, or per work item
+    a.head = u / p.n_items;
+    a.kv_head = a.head / p.q_heads_per_kv;
+    a.len_q = a.q_seg_end - a.q_seg_begin;
+    const int rows_here = min(2 * ATT_BM, a.q_seg_end - a.q_tile_begin);
+    int k_needed = a.len_k;  // keys needed by this unit (causal: bottom-right aligned, as flash-attn)
+    if (a.causal) {
+      const int last_row = a.q_tile_begin + rows_here - 1 - a.q_seg_begin;
+      k_needed = max(0, min(a.len_k, last_row + (a.len_k - a.len_q) + 1));
+    }
+    a.nblk = (k_needed + ATT_BN - 1) / ATT_BN;
+    return a;
+  };
 
   if (warp == 0 && elect_one()) {
     tma_prefetch_desc(&p.tmQ);
@@ -123,7 +150,8 @@ attention_tcgen05_kernel(const __grid_constant__ AttnKParams p) {
   if (warp == 1) {
     if (elect_one()) {
       mbar_init(q_full, 1);
-      for (int s = 0; s < Cfg::kStages; ++s) {
+      mbar_init(q_empty, 1);
+      for (int s = 0; s < KS; ++s) {
         mbar_init(&k_full[s], 1);
         mbar_init(&v_full[s], 1);
         mbar_init(&k_empty[s], 1);
@@ -133,6 +161,7 @@ attention_tcgen05_kernel(const __grid_constant__ AttnKParams p) {
         mbar_init(&s_full[t], 1);
         for (int c = 0; c < ATT_PCHUNKS; ++c) mbar_init(&p_full[t * ATT_PCHUNKS + c], 4);  // one arrive per warp
         mbar_init(&o_done[t], 1);
+        mbar_init(&o_free[t], 4);
       }
       fence_barrier_init();
     }
@@ -147,40 +176,49 @@ attention_tcgen05_kernel(const __grid_constant__ AttnKParams p) {
   auto tS = [&](int t) { return tmem_base + static_cast<uint32_t>(t) * 128u; };
   auto tO = [&](int t) { return tmem_base + 256u + static_cast<uint32_t>(t) * 128u; };
 
+  // Every role walks the same unit sequence and keeps the same two running counters, from which all mbarrier
+  // parities follow:  g = key blocks processed so far by this CTA,  n = units (with >= 1 block) so far.
   // Register budget (setmaxnreg must sit INSIDE each role branch so ptxas knows which budget governs
   // which code): 4 control warps x 32 x 80 + 8 softmax warps x 32 x 208 = 63488 <= 65536.
   if (warp == 0) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
     // ------------------------------------ TMA producer ----------------------------------------
-    if (elect_one() && nblk > 0) {
-      mbar_arrive_expect_tx(q_full, 2 * Cfg::kTileBytes);
+    if (elect_one()) {
+      uint32_t g = 0, n = 0;
+      for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
+        const AttnUnit a = decode(u);
+        if (a.nblk == 0) continue;
+        mbar_wait(q_empty, (n & 1) ^ 1);  // the previous unit's QK^T are done with the Q tiles
+        mbar_arrive_expect_tx(q_full, 2 * Cfg::kTileBytes);
 #pragma unroll
-      for (int t = 0; t < 2; ++t)
+        for (int t = 0; t < 2; ++t)
 #pragma unroll
-        for (int b = 0; b < Cfg::kBoxes; ++b)
-          tma_load_2d(sQ + t * Cfg::kTileBytes + b * BOX_BYTES, &p.tmQ, q_full, head * D + b * 64,
-                      q_tile_begin + t * ATT_BM);
-      for (int j = 0; j < nblk; ++j) {
-        const int s = j % Cfg::kStages;
-        const uint32_t par = ((j / Cfg::kStages) & 1) ^ 1;
-        uint8_t* sk = sKV + s * 2 * Cfg::kTileBytes;
-        uint8_t* sv = sk + Cfg::kTileBytes;
-        mbar_wait(&k_empty[s], par);
-        mbar_arrive_expect_tx(&k_full[s], Cfg::kTileBytes);
+          for (int b = 0; b < Cfg::kBoxes; ++b)
+            tma_load_2d(sQ + t * Cfg::kTileBytes + b * BOX_BYTES, &p.tmQ, q_full, a.head * D + b * 64,
+                        a.q_tile_begin + t * ATT_BM);
+        for (int j = 0; j < a.nblk; ++j, ++g) {
+          const int s = g % KS;
+          const uint32_t par = ((g / KS) & 1) ^ 1;
+          uint8_t* sk = sKV + s * 2 * Cfg::kTileBytes;
+          uint8_t* sv = sk + Cfg::kTileBytes;
+          mbar_wait(&k_empty[s], par);
+          mbar_arrive_expect_tx(&k_full[s], Cfg::kTileBytes);
 #pragma unroll
-        for (int b = 0; b < Cfg::kBoxes; ++b)
-          tma_load_2d(sk + b * BOX_BYTES, &p.tmK, &k_full[s], kv_head * D + b * 64, k_begin + j * ATT_BN);
-        mbar_wait(&v_empty[s], par);
-        mbar_arrive_expect_tx(&v_full[s], Cfg::kTileBytes);
+          for (int b = 0; b < Cfg::kBoxes; ++b)
+            tma_load_2d(sk + b * BOX_BYTES, &p.tmK, &k_full[s], a.kv_head * D + b * 64, a.k_begin + j * ATT_BN);
+          mbar_wait(&v_empty[s], par);
+          mbar_arrive_expect_tx(&v_full[s], Cfg::kTileBytes);
 #pragma unroll
-        for (int b = 0; b < Cfg::kBoxes; ++b)
-          tma_load_2d(sv + b * BOX_BYTES, &p.tmV, &v_full[s], kv_head * D + b * 64, k_begin + j * ATT_BN);
+          for (int b = 0; b < Cfg::kBoxes; ++b)
+            tma_load_2d(sv + b * BOX_BYTES, &p.tmV, &v_full[s], a.kv_head * D + b * 64, a.k_begin + j * ATT_BN);
+        }
+        ++n;
       }
     }
   } else if (warp == 1) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
     // ------------------------------------ MMA issuer ------------------------------------------
-    if (elect_one() && nblk > 0) {
+    if (elect_one()) {
       constexpr uint32_t idesc_qk = umma_idesc_bf16(ATT_BM, ATT_BN, 0, 0);
       constexpr uint32_t idesc_pv = umma_idesc_bf16(ATT_BM, D, 0, 1);  // B (= V) is MN-major
       const uint32_t q_addr = smem_u32(sQ);
@@ -197,47 +235,65 @@ attention_tcgen05_kernel(const __grid_constant__ AttnKParams p) {
         umma_commit(&s_full[t]);
       };
       // O_t += P_t V, issued chunk by chunk as the softmax warps publish 32 keys of P at a time
-      auto issue_pv = [&](int t, int s, int j) {
+      auto issue_pv = [&](int t, int s, uint32_t par, bool first_block) {
         const uint32_t va = kv_addr + s * 2 * Cfg::kTileBytes + Cfg::kTileBytes;
 #pragma unroll
         for (int c = 0; c < ATT_PCHUNKS; ++c) {
-          mbar_wait(&p_full[t * ATT_PCHUNKS + c], j & 1);
+          mbar_wait(&p_full[t * ATT_PCHUNKS + c], par);
           tc_fence_after();
 #pragma unroll
           for (int kk = 0; kk < KSTEPS_PV / ATT_PCHUNKS; ++kk) {
             const int k = c * (KSTEPS_PV / ATT_PCHUNKS) + kk;
             // 16 keys = 16 rows of 128 B inside each 64-column box; boxes are BOX_BYTES apart (LBO)
             umma_ts(tO(t), tS(t) + k * 8, umma_desc_mnmajor(va + k * 2048, BOX_BYTES), idesc_pv,
-                    (j | k) != 0);
+                    !(first_block && k == 0));
           }
         }
         umma_commit(&o_done[t]);
       };
 
-      mbar_wait(q_full, 0);
-      mbar_wait(&k_full[0], 0);
-      tc_fence_after();
-      issue_qk(0, 0);
-      issue_qk(1, 0);
-      umma_commit(&k_empty[0]);
-      for (int j = 0; j < nblk; ++j) {
-        const int s = j % Cfg::kStages;
-        const uint32_t par = (j / Cfg::kStages) & 1;
-        const int s1 = (j + 1) % Cfg::kStages;
-        const uint32_t par1 = ((j + 1) / Cfg::kStages) & 1;
-        mbar_wait(&v_full[s], par);
-        issue_pv(0, s, j);
-        if (j + 1 < nblk) {
-          mbar_wait(&k_full[s1], par1);
-          tc_fence_after();
-          issue_qk(0, s1);
+      uint32_t g = 0, n = 0;
+      for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
+        const AttnUnit a = decode(u);
+        if (a.nblk == 0) continue;
+        mbar_wait(q_full, n & 1);
+        mbar_wait(&k_full[g % KS], (g / KS) & 1);
+        tc_fence_after();
+        // S_t is free: the previous unit's last PV_t (which read P_t out of the same columns) is ahead in the pipe
+        issue_qk(0, g % KS);
+        issue_qk(1, g % KS);
+        umma_commit(&k_empty[g % KS]);
+        if (a.nblk == 1) umma_commit(q_empty);
+        for (int j = 0; j < a.nblk; ++j, ++g) {
+          const int s = g % KS;
+          const uint32_t par = (g / KS) & 1;
+          const int s1 = (g + 1) % KS;
+          const uint32_t par1 = ((g + 1) / KS) & 1;
+          const bool more = j + 1 < a.nblk;
+          mbar_wait(&v_full[s], par);
+          if (j == 0 && n > 0) {  // the first PV overwrites O_t: the previous unit's epilogue must have read it
+            mbar_wait(&o_free[0], (n - 1) & 1);
+            tc_fence_after();
+          }
+          issue_pv(0, s, g & 1, j == 0);
+          if (more) {
+            mbar_wait(&k_full[s1], par1);
+            tc_fence_after();
+            issue_qk(0, s1);
+          }
+          if (j == 0 && n > 0) {
+            mbar_wait(&o_free[1], (n - 1) & 1);
+            tc_fence_after();
+          }
+          issue_pv(1, s, g & 1, j == 0);
+          umma_commit(&v_empty[s]);
+          if (more) {
+            issue_qk(1, s1);
+            umma_commit(&k_empty[s1]);
+            if (j + 2 == a.nblk) umma_commit(q_empty);  // that was the unit's last QK^T
+          }
         }
-        issue_pv(1, s, j);
-        umma_commit(&v_empty[s]);
-        if (j + 1 < nblk) {
-          issue_qk(1, s1);
-          umma_commit(&k_empty[s1]);
-        }
+        ++n;
       }
     }
   } else if (warp < 4) {
@@ -248,126 +304,143 @@ attention_tcgen05_kernel(const __grid_constant__ AttnKParams p) {
     const int t = (warp - 4) >> 2;              // query tile 0 or 1
     const int sub = warp & 3;                   // TMEM sub-partition
     const int r_in_tile = sub * 32 + lane;
-    const int row = q_tile_begin + t * ATT_BM + r_in_tile;  // global query row
-    const bool row_ok = row < q_seg_end;
     const uint32_t lane_off = static_cast<uint32_t>(sub * 32) << 16;
     const uint32_t tS_w = tS(t) + lane_off;
     const uint32_t tO_w = tO(t) + lane_off;
-    // number of keys this row may see
-    int limit = len_k;
-    if (causal) limit = max(0, min(len_k, (row - q_seg_begin) + (len_k - len_q) + 1));
+    uint32_t g = 0, n = 0;
 
-    float m_used = 0.f;  // running max in the scaled log2 domain (possibly stale by <= TAU)
-    float l_run = 0.f;
-
-    for (int j = 0; j < nblk; ++j) {
-      mbar_wait(&s_full[t], j & 1);
-      tc_fence_after();
-      uint32_t sv[128];
+    for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
+      const AttnUnit a = decode(u);
+      const int row = a.q_tile_begin + t * ATT_BM + r_in_tile;  // global query row
+      const bool row_ok = row < a.q_seg_end;
+      if (a.nblk == 0) {
+        if (row_ok) {  // no visible keys at all: flash-attn writes zeros
+          uint4* dst = reinterpret_cast<uint4*>(p.out + (long long)row * p.ldo + a.head * D);
 #pragma unroll
-      for (int c = 0; c < 4; ++c) tmem_ld32(tS_w + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&sv[c * 32]));
-      tmem_wait_ld();
-
-      const int col_base = j * ATT_BN;
-      if (col_base + ATT_BN > limit) {
-#pragma unroll
-        for (int i = 0; i < 128; ++i)
-          if (col_base + i >= limit) sv[i] = 0xff800000u;  // -inf
+          for (int q = 0; q < D / 8; ++q) dst[q] = make_uint4(0, 0, 0, 0);
+        }
+        continue;
       }
-      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
-#pragma unroll
-      for (int i = 0; i < 128; i += 4) {
-        mx0 = fmaxf(mx0, __uint_as_float(sv[i]));
-        mx1 = fmaxf(mx1, __uint_as_float(sv[i + 1]));
-        mx2 = fmaxf(mx2, __uint_as_float(sv[i + 2]));
-        mx3 = fmaxf(mx3, __uint_as_float(sv[i + 3]));
-      }
-      const float m_blk = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * p.scale_log2;  // may be -inf
+      // number of keys this row may see
+      int limit = a.len_k;
+      if (a.causal) limit = max(0, min(a.len_k, (row - a.q_seg_begin) + (a.len_k - a.len_q) + 1));
 
-      if (j == 0) {
-        m_used = (m_blk == -INFINITY) ? 0.f : m_blk;
-      } else {
-        const bool need = m_blk > m_used + ATT_RESCALE_TAU;
-        if (__any_sync(0xffffffffu, need)) {
-          // rare path: O_t must be multiplied by 2^(m_used - m_new) before the next PV accumulates
-          mbar_wait(&o_done[t], (j - 1) & 1);
-          tc_fence_after();
-          const float m_new = need ? m_blk : m_used;
-          const float alpha = ex2_approx(m_used - m_new);
+      float m_used = 0.f;  // running max in the scaled log2 domain (possibly stale by <= TAU)
+      float l_run = 0.f;
+
+      for (int j = 0; j < a.nblk; ++j, ++g) {
+        mbar_wait(&s_full[t], g & 1);
+        tc_fence_after();
+        uint32_t sv[128];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) tmem_ld32(tS_w + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&sv[c * 32]));
+        tmem_wait_ld();
+
+        const int col_base = j * ATT_BN;
+        if (col_base + ATT_BN > limit) {
+#pragma unroll
+          for (int i = 0; i < 128; ++i)
+            if (col_base + i >= limit) sv[i] = 0xff800000u;  // -inf
+        }
+        float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < 128; i += 4) {
+          mx0 = fmaxf(mx0, __uint_as_float(sv[i]));
+          mx1 = fmaxf(mx1, __uint_as_float(sv[i + 1]));
+          mx2 = fmaxf(mx2, __uint_as_float(sv[i + 2]));
+          mx3 = fmaxf(mx3, __uint_as_float(sv[i + 3]));
+        }
+        const float m_blk = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * p.scale_log2;  // may be -inf
+
+        if (j == 0) {
+          m_used = (m_blk == -INFINITY) ? 0.f : m_blk;
+        } else {
+          const bool need = m_blk > m_used + ATT_RESCALE_TAU;
+          if (__any_sync(0xffffffffu, need)) {
+            // rare path: O_t must be multiplied by 2^(m_used - m_new) before the next PV accumulates
+            mbar_wait(&o_done[t], (g - 1) & 1);
+            tc_fence_after();
+            const float m_new = need ? m_blk : m_used;
+            const float alpha = ex2_approx(m_used - m_new);
 #pragma unroll 1
-          for (int c = 0; c < D / 32; ++c) {
-            uint32_t ov[32];
-            tmem_ld32(tO_w + c * 32, ov);
-            tmem_wait_ld();
+            for (int c = 0; c < D / 32; ++c) {
+              uint32_t ov[32];
+              tmem_ld32(tO_w + c * 32, ov);
+              tmem_wait_ld();
 #pragma unroll
-            for (int i = 0; i < 32; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * alpha);
-            tmem_st32(tO_w + c * 32, ov);
+              for (int i = 0; i < 32; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * alpha);
+              tmem_st32(tO_w + c * 32, ov);
+            }
+            tmem_wait_st();
+            l_run *= alpha;
+            m_used = m_new;
           }
-          tmem_wait_st();
-          l_run *= alpha;
-          m_used = m_new;
         }
-      }
 
-      // P = 2^(s*scale - m), packed to bf16 pairs, written over S (columns [0,64) of the S region) and
-      // handed to the MMA warp 32 keys at a time so PV starts while the rest of the row is still in exp
-      uint64_t sum2 = pack2(0.f, 0.f);
-      const uint64_t neg_m2 = pack2(-m_used, -m_used);
-      const uint64_t scale2 = pack2(p.scale_log2, p.scale_log2);
+        // P = 2^(s*scale - m), packed to bf16 pairs, written over S (columns [0,64) of the S region) and
+        // handed to the MMA warp 32 keys at a time so PV starts while the rest of the row is still in exp
+        uint64_t sum2 = pack2(0.f, 0.f);
+        const uint64_t neg_m2 = pack2(-m_used, -m_used);
+        const uint64_t scale2 = pack2(p.scale_log2, p.scale_log2);
 #pragma unroll
-      for (int c = 0; c < ATT_PCHUNKS; ++c) {
-        uint32_t pk[16];
+        for (int c = 0; c < ATT_PCHUNKS; ++c) {
+          constexpr int CW = ATT_BN / ATT_PCHUNKS;  // keys per chunk
+          uint32_t pk[CW / 2];
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          float p0, p1;
-          const uint64_t x2 = fma2(pack2(__uint_as_float(sv[c * 32 + i]), __uint_as_float(sv[c * 32 + i + 1])),
-                                   scale2, neg_m2);
-          float x0, x1;
-          unpack2(x2, x0, x1);
-          p0 = ex2_approx(x0);
-          p1 = ex2_approx(x1);
-          sum2 = add2(sum2, pack2(p0, p1));
-          pk[i >> 1] = pack_bf16x2(p0, p1);
+          for (int i = 0; i < CW; i += 2) {
+            const uint64_t x2 = fma2(pack2(__uint_as_float(sv[c * CW + i]), __uint_as_float(sv[c * CW + i + 1])),
+                                     scale2, neg_m2);
+            float x0, x1;
+            unpack2(x2, x0, x1);
+            const float p0 = ex2_approx(x0);
+            const float p1 = ex2_approx(x1);
+            sum2 = add2(sum2, pack2(p0, p1));
+            pk[i >> 1] = pack_bf16x2(p0, p1);
+          }
+          // the store of chunk c-1 has had a whole chunk of exp2 to land: publishing it here keeps the
+          // tcgen05.wait::st latency off the critical path
+          if (c > 0) {
+            tmem_wait_st();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&p_full[t * ATT_PCHUNKS + c - 1]);
+          }
+          if constexpr (CW == 32) tmem_st16(tS_w + c * 16, pk);
+          else tmem_st32(tS_w + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&pk[0]));
         }
-        tmem_st16(tS_w + c * 16, pk);
         tmem_wait_st();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&p_full[t * ATT_PCHUNKS + c]);
+        if (lane == 0) mbar_arrive(&p_full[t * ATT_PCHUNKS + ATT_PCHUNKS - 1]);
+        float sum0, sum1;
+        unpack2(sum2, sum0, sum1);
+        l_run += sum0 + sum1;
       }
-      float sum0, sum1;
-      unpack2(sum2, sum0, sum1);
-      l_run += sum0 + sum1;
-    }
 
-    // epilogue: O / l -> bf16 -> global (each thread owns one output row of D contiguous values)
-    if (nblk > 0) {
-      mbar_wait(&o_done[t], (nblk - 1) & 1);
+      // epilogue: O_t leaves TMEM in one go (so the next unit's first PV may overwrite it), then
+      // O / l -> bf16 -> global (each thread owns one output row of D contiguous values)
+      mbar_wait(&o_done[t], (g - 1) & 1);
       tc_fence_after();
-      const float inv_l = l_run > 0.f ? 1.0f / l_run : 0.f;
-      __nv_bfloat16* orow = p.out + (long long)row * p.ldo + head * D;
-#pragma unroll 1
-      for (int c = 0; c < D / 32; ++c) {
-        uint32_t ov[32];
-        tmem_ld32(tO_w + c * 32, ov);
-        tmem_wait_ld();
-        if (row_ok) {
-          uint4* dst = reinterpret_cast<uint4*>(orow + c * 32);
+      uint32_t ov[D];
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            dst[q] = make_uint4(
-                pack_bf16x2(__uint_as_float(ov[8 * q]) * inv_l, __uint_as_float(ov[8 * q + 1]) * inv_l),
-                pack_bf16x2(__uint_as_float(ov[8 * q + 2]) * inv_l, __uint_as_float(ov[8 * q + 3]) * inv_l),
-                pack_bf16x2(__uint_as_float(ov[8 * q + 4]) * inv_l, __uint_as_float(ov[8 * q + 5]) * inv_l),
-                pack_bf16x2(__uint_as_float(ov[8 * q + 6]) * inv_l, __uint_as_float(ov[8 * q + 7]) * inv_l));
-          }
+      for (int c = 0; c < D / 32; ++c) tmem_ld32(tO_w + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&ov[c * 32]));
+      tmem_wait_ld();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&o_free[t]);
+      if (row_ok) {
+        const float inv_l = l_run > 0.f ? 1.0f / l_run : 0.f;
+        uint4* dst = reinterpret_cast<uint4*>(p.out + (long long)row * p.ldo + a.head * D);
+#pragma unroll
+        for (int q = 0; q < D / 8; ++q) {
+          dst[q] = make_uint4(
+              pack_bf16x2(__uint_as_float(ov[8 * q]) * inv_l, __uint_as_float(ov[8 * q + 1]) * inv_l),
+              pack_bf16x2(__uint_as_float(ov[8 * q + 2]) * inv_l, __uint_as_float(ov[8 * q + 3]) * inv_l),
+              pack_bf16x2(__uint_as_float(ov[8 * q + 4]) * inv_l, __uint_as_float(ov[8 * q + 5]) * inv_l),
+              pack_bf16x2(__uint_as_float(ov[8 * q + 6]) * inv_l, __uint_as_float(ov[8 * q + 7]) * inv_l));
         }
       }
-    } else if (row_ok) {
-      // no visible keys at all: flash-attn writes zeros
-      uint4* dst = reinterpret_cast<uint4*>(p.out + (long long)row * p.ldo + head * D);
-#pragma unroll
-      for (int q = 0; q < D / 8; ++q) dst[q] = make_uint4(0, 0, 0, 0);
+      ++n;
     }
   }
 
@@ -380,14 +453,16 @@ attention_tcgen05_kernel(const __grid_constant__ AttnKParams p) {
 }
 
 template <int D>
-static int launch_attention(const AttnKParams& kp, int n_items, int n_heads, cudaStream_t stream) {
+static int launch_attention(const AttnKParams& kp, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
     G2_CUDA_OK(cudaFuncSetAttribute(attention_tcgen05_kernel<D>,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg<D>::kSmem));
     attr_set = true;
   }
-  attention_tcgen05_kernel<D><<<dim3(n_items, n_heads), ATT_THREADS, AttnCfg<D>::kSmem, stream>>>(kp);
+  const long long units = (long long)kp.n_items * kp.n_heads;
+  const unsigned grid = (unsigned)(units < num_sms() ? units : num_sms());  // one persistent CTA per SM
+  attention_tcgen05_kernel<D><<<grid, ATT_THREADS, AttnCfg<D>::kSmem, stream>>>(kp);
   G2_CUDA_OK(cudaGetLastError());
   return G2VLM_OK;
 }
@@ -428,6 +503,8 @@ extern "C" int g2vlm_attention(const g2vlm_attn_args* a, void* stream_) {
   kp.q_heads_per_kv = a->num_q_heads / a->num_kv_heads;
   kp.causal = a->causal;
   kp.scale_log2 = a->softmax_scale * 1.4426950408889634f;
-  if (D == 128) return launch_attention<128>(kp, a->n_items, a->num_q_heads, stream);
-  return launch_attention<64>(kp, a->n_items, a->num_q_heads, stream);
+  kp.n_items = a->n_items;
+  kp.n_heads = a->num_q_heads;
+  if (D == 128) return launch_attention<128>(kp, stream);
+  return launch_attention<64>(kp, stream);
 }
