@@ -151,3 +151,26 @@ def test_per_item_causal_flag_mixes_masks_in_one_launch():
     ref_b = _ref_attention(q[T:], k[T:], v[T:], [0, Kp], [0, Kp], hq, hk, d, scale, True)
     assert (out[:T].float() - ref_a).abs().max() < 2e-2
     assert (out[T:].float() - ref_b).abs().max() < 2e-2
+
+
+@pytest.mark.parametrize("hot_key", [10, 100, 128 + 10, 128 + 100, 256 + 70, 383])
+def test_lazy_rescale_paths(hot_key):
+    """A score far above the running max (> 2^8 in the scaled log2 domain) appearing in the first half, the second
+    half, or a later block forces the O rescale through each of its code paths (early check on the first 64 keys,
+    late check after the first two P chunks were already computed)."""
+    from g2vlm_b200 import ops
+    hq, hk, d, T = 2, 1, 128, 384
+    g = torch.Generator().manual_seed(hot_key)
+    q = (torch.randn(T, hq * d, generator=g) * 0.3).to(torch.bfloat16)
+    k = (torch.randn(T, hk * d, generator=g) * 0.3).to(torch.bfloat16)
+    v = torch.randn(T, hk * d, generator=g).to(torch.bfloat16)
+    k[hot_key] = (q[5, :d].float() * 40).to(torch.bfloat16)          # row 5 (head 0) gets a huge score there
+    k[min(hot_key + 1, T - 1)] = (q[200, d:].float() * 25).to(torch.bfloat16)   # and row 200 (head 1) next to it
+    q, k, v = q.cuda(), k.cuda(), v.cuda()
+    work = ops.attention_work_table([0, T], [0, T]).cuda()
+    out = torch.zeros(T, hq * d, device="cuda", dtype=torch.bfloat16)
+    scale = 1 / math.sqrt(d)
+    ops.attention(q, k, v, out, work, num_q_heads=hq, num_kv_heads=hk, head_dim=d, scale=scale)
+    ref = _ref_attention(q, k, v, [0, T], [0, T], hq, hk, d, scale, False)
+    assert torch.isfinite(out.float()).all()
+    assert (out.float() - ref).abs().max() < 3e-2
