@@ -312,9 +312,10 @@ def main():
     att_events = []
     orig_attention = ops.attention
     T = n_views * (P + 2)
+    K_PROMPT = int(gi_text["packed_text_ids"].numel())   # prompt rows ride along in the fused path
 
     def timed_attention(q, *a, **k):
-        if q.shape[0] == T and k.get("num_kv_heads") == cfg.num_kv_heads and not k.get("causal", False):
+        if q.shape[0] in (T, T + K_PROMPT) and k.get("num_kv_heads") == cfg.num_kv_heads and not k.get("causal", False):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             r = orig_attention(q, *a, **k)

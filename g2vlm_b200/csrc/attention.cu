@@ -4,7 +4,7 @@
 // per-view SDPA calls of the Pi3 decoders (modeling/pi3/models/layers/attention.py:255-259,370-372).
 //
 // Persistent kernel, one CTA per SM.  A unit of work = one work item (<= 256 query rows of one segment) x
-// one query head; a CTA walks units blockIdx.x, +gridDim.x, ... with TMEM, barriers and the K/V ring kept
+// one query head; a CTA walks units blockIdx.x, +gridDim.x, ... (head fastest) with TMEM, barriers and the K/V ring kept
 // alive across units (the producer prefetches the next unit while this one drains).  Inside a unit two
 // 128-row query tiles are in flight ("ping-pong"): while the softmax warps of tile 0 turn S0 into P0, the
 // tensor core runs tile 1's MMAs and vice versa.
@@ -115,21 +115,23 @@ attention_tcgen05_kernel(const __grid_constant__ AttnKParams p) {
   const int lane = threadIdx.x & 31;
   const int total_units = p.n_items * p.n_heads;
 
-  // Persistent CTA: units blockIdx.x, blockIdx.x + gridDim.x, ... (item index fastest, so CTAs that run
-  // side by side work on neighbouring query tiles of the same head and share its K/V in L2).  TMEM, the
+  // Persistent CTA: units blockIdx.x, blockIdx.x + gridDim.x, ... (head index fastest, so CTAs that run
+  // side by side work on the heads of the same few query tiles and share their K/V in L2, and the cheap items a
+  // caller appends at the end of the work table — the fused prompt rows — land at the end of every CTA's list
+  // instead of unbalancing the static round-robin).  TMEM, the
   // barriers and the K/V ring live across units: the producer prefetches the next unit's Q/K/V while the
   // softmax warps still drain this one, which hides the per-unit prologue/epilogue (5-7 us of ~25 us per unit
   // on the 11-block DINO / Pi3-decoder segments when every unit was its own CTA).
   auto decode = [&](int u) {
     AttnUnit a;
-    const int* w = p.work + (u % p.n_items) * 8;
+    const int* w = p.work + (u / p.n_heads) * 8;
     a.q_tile_begin = w[0];
     a.q_seg_begin = w[1];
     a.q_seg_end = w[2];
     a.k_begin = w[3];
     a.len_k = w[4] - w[3];
     a.causal = p.causal != 0 || w[5] != 0;  // per launch, or per work item
-    a.head = u / p.n_items;
+    a.head = u % p.n_heads;
     a.kv_head = a.head / p.q_heads_per_kv;
     a.len_q = a.q_seg_end - a.q_seg_begin;
     const int rows_here = min(2 * ATT_BM, a.q_seg_end - a.q_tile_begin);
