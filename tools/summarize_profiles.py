@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Turns gpurun_out ncu artefacts into the committed text summaries under profiles/.
-usage: python tools/summarize_profiles.py launches <csv> <out.txt> "<title>"
+usage: python tools/summarize_profiles.py launches <csv> <out.txt> "<title>" [--last N]   (N = launches of one step)
        python tools/summarize_profiles.py kernel <ncu-rep> <out.txt> "<title>" """
 import collections
 import csv
@@ -13,7 +13,10 @@ if mode == "launches":
     lines = [l for l in open(src) if not l.startswith("==")]
     agg = collections.defaultdict(lambda: [0, 0.0])
     tot = 0.0
-    for row in csv.DictReader(lines):
+    rows = [r for r in csv.DictReader(lines) if r["Metric Name"] == "gpu__time_duration.sum"]
+    if "--last" in sys.argv:
+        rows = rows[-int(sys.argv[sys.argv.index("--last") + 1]):]
+    for row in rows:
         v = float(row["Metric Value"].replace(",", ""))
         v *= {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}[row["Metric Unit"]]
         name = re.sub(r"\(.*", "", row["Kernel Name"])
