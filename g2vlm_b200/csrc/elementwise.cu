@@ -71,6 +71,35 @@ __global__ void rmsnorm_routed_kernel(const float* __restrict__ x, long long ldx
   }
 }
 
+// Same arithmetic (same per-lane order), row held in registers: ONE global read per element with all NV float4
+// loads of a lane in flight at once.  NV = dim / 128 (8 for the 1024-wide DINO / 12 for the 1536-wide streams).
+template <int NV>
+__global__ void __launch_bounds__(EW_THREADS)
+rmsnorm_routed_reg_kernel(const float* __restrict__ x, long long ldx, void* __restrict__ out, long long ldo,
+                          int out_bf16, const float* __restrict__ w_a, const float* __restrict__ w_b,
+                          long long rows, long long n_first, float eps) {
+  const long long row = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const float4* xr = reinterpret_cast<const float4*>(x + row * ldx);
+  float4 v[NV];
+#pragma unroll
+  for (int u = 0; u < NV; ++u) v[u] = xr[lane + 32 * u];
+  float ss = 0.f;
+#pragma unroll
+  for (int u = 0; u < NV; ++u) ss += v[u].x * v[u].x + v[u].y * v[u].y + v[u].z * v[u].z + v[u].w * v[u].w;
+  ss = warp_sum(ss);
+  const float r = rsqrtf(ss / (NV * 128) + eps);
+  const float4* w = reinterpret_cast<const float4*>(row < n_first ? w_a : w_b);
+#pragma unroll
+  for (int u = 0; u < NV; ++u) {
+    const int i = lane + 32 * u;
+    const float4 g = __ldg(w + i);
+    store4(out, out_bf16, row * ldo + 4LL * i, g.x * (v[u].x * r), g.y * (v[u].y * r), g.z * (v[u].z * r),
+           g.w * (v[u].w * r));
+  }
+}
+
 // few rows (decode steps, 7-token prefill): one BLOCK per row so every element is in flight at once — the
 // warp-per-row kernel above is latency-bound there (12 dependent-latency load rounds per lane for H = 1536)
 __global__ void __launch_bounds__(256)
@@ -143,6 +172,50 @@ __global__ void layernorm_kernel(const float* __restrict__ x, long long ldx, voi
     const float4 bt = __ldg(b4 + i);
     store4(out, out_bf16, orow * ldo + 4LL * i, (v.x - mean) * rstd * g.x + bt.x, (v.y - mean) * rstd * g.y + bt.y,
            (v.z - mean) * rstd * g.z + bt.z, (v.w - mean) * rstd * g.w + bt.w);
+  }
+}
+
+// Register-cached variant (same arithmetic and per-lane order as above; one global read per element).
+template <int NV>
+__global__ void __launch_bounds__(EW_THREADS)
+layernorm_reg_kernel(const float* __restrict__ x, long long ldx, void* __restrict__ out, long long ldo, int out_bf16,
+                     const float* __restrict__ w, const float* __restrict__ b, long long rows, float eps, int seg_in,
+                     int seg_skip) {
+  constexpr int dim = NV * 128;
+  const long long row = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  long long orow = row;
+  if (seg_in > 0) {
+    const long long s = row / seg_in;
+    const int local = static_cast<int>(row - s * seg_in);
+    if (local < seg_skip) return;
+    orow = s * (seg_in - seg_skip) + (local - seg_skip);
+  }
+  const int lane = threadIdx.x & 31;
+  const float4* xr = reinterpret_cast<const float4*>(x + row * ldx);
+  float4 v[NV];
+#pragma unroll
+  for (int u = 0; u < NV; ++u) v[u] = xr[lane + 32 * u];
+  float s1 = 0.f;
+#pragma unroll
+  for (int u = 0; u < NV; ++u) s1 += (v[u].x + v[u].y) + (v[u].z + v[u].w);
+  const float mean = warp_sum(s1) / dim;
+  float s2 = 0.f;
+#pragma unroll
+  for (int u = 0; u < NV; ++u) {
+    const float a = v[u].x - mean, bb = v[u].y - mean, c = v[u].z - mean, d = v[u].w - mean;
+    s2 += a * a + bb * bb + c * c + d * d;
+  }
+  const float rstd = rsqrtf(warp_sum(s2) / dim + eps);
+  const float4* w4 = reinterpret_cast<const float4*>(w);
+  const float4* b4 = reinterpret_cast<const float4*>(b);
+#pragma unroll
+  for (int u = 0; u < NV; ++u) {
+    const int i = lane + 32 * u;
+    const float4 g = __ldg(w4 + i);
+    const float4 bt = __ldg(b4 + i);
+    store4(out, out_bf16, orow * ldo + 4LL * i, (v[u].x - mean) * rstd * g.x + bt.x, (v[u].y - mean) * rstd * g.y + bt.y,
+           (v[u].z - mean) * rstd * g.z + bt.z, (v[u].w - mean) * rstd * g.w + bt.w);
   }
 }
 
@@ -753,8 +826,16 @@ extern "C" int g2vlm_rmsnorm_routed(const float* x, int64_t ldx, void* out, int6
     G2_LAUNCH_CHECK();
     return G2VLM_OK;
   }
-  rmsnorm_routed_kernel<<<blocks_for(rows, EW_THREADS / 32), EW_THREADS, 0, (cudaStream_t)stream>>>(
-      x, ldx, out, ldo, out_bf16, w_a, w_b, rows, n_first, dim, eps);
+  const unsigned grid = blocks_for(rows, EW_THREADS / 32);
+  if (dim == 1536)
+    rmsnorm_routed_reg_kernel<12><<<grid, EW_THREADS, 0, (cudaStream_t)stream>>>(x, ldx, out, ldo, out_bf16, w_a, w_b,
+                                                                                rows, n_first, eps);
+  else if (dim == 1024)
+    rmsnorm_routed_reg_kernel<8><<<grid, EW_THREADS, 0, (cudaStream_t)stream>>>(x, ldx, out, ldo, out_bf16, w_a, w_b,
+                                                                               rows, n_first, eps);
+  else
+    rmsnorm_routed_kernel<<<grid, EW_THREADS, 0, (cudaStream_t)stream>>>(x, ldx, out, ldo, out_bf16, w_a, w_b, rows,
+                                                                        n_first, dim, eps);
   G2_LAUNCH_CHECK();
   return G2VLM_OK;
 }
@@ -767,8 +848,16 @@ extern "C" int g2vlm_layernorm(const float* x, int64_t ldx, void* out, int64_t l
   G2_REQUIRE(G2_ALIGNED16(x) && G2_ALIGNED16(out) && G2_ALIGNED16(w) && G2_ALIGNED16(b), "layernorm: alignment");
   G2_REQUIRE(seg_in >= 0 && seg_skip >= 0 && (seg_in == 0 || seg_skip < seg_in), "layernorm: bad segment spec");
   if (rows <= 0) return G2VLM_OK;
-  layernorm_kernel<<<blocks_for(rows, EW_THREADS / 32), EW_THREADS, 0, (cudaStream_t)stream>>>(
-      x, ldx, out, ldo, out_bf16, w, b, rows, dim, eps, seg_in, seg_skip);
+  const unsigned grid = blocks_for(rows, EW_THREADS / 32);
+  if (dim == 1024)
+    layernorm_reg_kernel<8><<<grid, EW_THREADS, 0, (cudaStream_t)stream>>>(x, ldx, out, ldo, out_bf16, w, b, rows, eps,
+                                                                          seg_in, seg_skip);
+  else if (dim == 1536)
+    layernorm_reg_kernel<12><<<grid, EW_THREADS, 0, (cudaStream_t)stream>>>(x, ldx, out, ldo, out_bf16, w, b, rows, eps,
+                                                                           seg_in, seg_skip);
+  else
+    layernorm_kernel<<<grid, EW_THREADS, 0, (cudaStream_t)stream>>>(x, ldx, out, ldo, out_bf16, w, b, rows, dim, eps,
+                                                                   seg_in, seg_skip);
   G2_LAUNCH_CHECK();
   return G2VLM_OK;
 }

@@ -30,7 +30,7 @@ def test_gather_scatter_rows_roundtrip_exact():
     assert torch.equal(wide[13:, 1536:1792], b) and wide[:13].abs().sum() == 0 and wide[:, :1536].abs().sum() == 0
 
 
-@pytest.mark.parametrize("rows,dim,n_first", [(777, 1536, 700), (33, 256, 0), (5, 1024, 5)])
+@pytest.mark.parametrize("rows,dim,n_first", [(777, 1536, 700), (300, 1024, 100), (33, 256, 0), (5, 1024, 5), (100, 2048, 40)])
 def test_rmsnorm_routed(rows, dim, n_first):
     from g2vlm_b200 import ops
     from oracle import restate
@@ -46,10 +46,11 @@ def test_rmsnorm_routed(rows, dim, n_first):
     assert (o16.float().cpu() - ref.to(torch.bfloat16).float()).abs().max() <= ref.abs().max() * 2 ** -8
 
 
-def test_layernorm_and_segment_drop():
+@pytest.mark.parametrize("D", [1024, 1536, 512])   # register-cached kernels (1024, 1536) and the generic one
+def test_layernorm_and_segment_drop(D):
     from g2vlm_b200 import ops
     g = torch.Generator().manual_seed(2)
-    n, S, D = 3, 190, 1024
+    n, S = 3, 190
     x = (torch.randn(n * S, D, generator=g) * 2 + 0.3).cuda()
     w, b = (torch.rand(D, generator=g) + 0.5).cuda(), (torch.randn(D, generator=g) * 0.1).cuda()
     ref = torch.nn.functional.layer_norm(x.cpu(), (D,), w.cpu(), b.cpu(), 1e-6)
