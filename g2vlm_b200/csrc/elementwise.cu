@@ -280,6 +280,69 @@ __global__ void qknorm_mrope_kernel(__nv_bfloat16* __restrict__ qkv, long long l
   *reinterpret_cast<uint2*>(p) = make_uint2(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]));
 }
 
+// Row-per-warp variant for an even number of heads (the full model: 12 q + 2 k heads -> NU = 7): lane l owns the
+// 16-byte chunks l, l+32, ... of the row's q|k columns, i.e. per round u the 8 elements 8k..8k+7 (k = l % 16) of head
+// 2u + l/16.  All NU loads of a lane are in flight at once, the row's cos/sin and the norm weights are read once per
+// row instead of once per head (that re-read made the per-head kernel above run at 46 % of the HBM roofline), the
+// per-head sum of squares is a half-warp reduction and the rotate_half partner (d +- 64) is lane ^ 8.
+template <int NU>
+__global__ void __launch_bounds__(EW_THREADS)
+qknorm_mrope_row_kernel(__nv_bfloat16* __restrict__ qkv, long long ld, long long rows, long long n_first, int n_q,
+                        const float* __restrict__ qw_a, const float* __restrict__ kw_a,
+                        const float* __restrict__ qw_b, const float* __restrict__ kw_b,
+                        const float* __restrict__ cos_tab, const float* __restrict__ sin_tab, float eps,
+                        int round_normed) {
+  const long long row = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const int k = lane & 15, hsel = lane >> 4;
+  uint4* p = reinterpret_cast<uint4*>(qkv + row * ld) + lane;
+  uint4 raw[NU];
+#pragma unroll
+  for (int u = 0; u < NU; ++u) raw[u] = p[32 * u];
+  const bool first = row < n_first;
+  const float4* qw = reinterpret_cast<const float4*>(first ? qw_a : qw_b) + 2 * k;
+  const float4* kw = reinterpret_cast<const float4*>(first ? kw_a : kw_b) + 2 * k;
+  const float4 q0 = __ldg(qw), q1 = __ldg(qw + 1), k0 = __ldg(kw), k1 = __ldg(kw + 1);
+  const float wq[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+  const float wk[8] = {k0.x, k0.y, k0.z, k0.w, k1.x, k1.y, k1.z, k1.w};
+  const float4* ct = reinterpret_cast<const float4*>(cos_tab + row * 64 + 8 * (k & 7));
+  const float4* st = reinterpret_cast<const float4*>(sin_tab + row * 64 + 8 * (k & 7));
+  const float4 c0 = __ldg(ct), c1 = __ldg(ct + 1), s0 = __ldg(st), s1 = __ldg(st + 1);
+  const float cs[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+  const float sn[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+#pragma unroll
+  for (int u = 0; u < NU; ++u) {
+    const bool is_q = 2 * u + hsel < n_q;
+    const uint32_t rw[4] = {raw[u].x, raw[u].y, raw[u].z, raw[u].w};
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const __nv_bfloat162 b2 = *reinterpret_cast<const __nv_bfloat162*>(&rw[e]);
+      v[2 * e] = __low2float(b2);
+      v[2 * e + 1] = __high2float(b2);
+    }
+    float ss = 0.f;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) ss += v[e] * v[e];
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);  // stays inside the half-warp
+    const float r = rsqrtf(ss / 128.0f + eps);
+    float o8[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      float n = v[e] * r;
+      if (round_normed) n = bf16_round(n);
+      n = (is_q ? wq[e] : wk[e]) * n;
+      const float partner = __shfl_xor_sync(0xffffffffu, n, 8);
+      const float rot = k < 8 ? -partner : partner;  // rotate_half: first half gets -x2, second half gets +x1
+      o8[e] = n * cs[e] + rot * sn[e];
+    }
+    p[32 * u] = make_uint4(pack_bf16x2(o8[0], o8[1]), pack_bf16x2(o8[2], o8[3]), pack_bf16x2(o8[4], o8[5]),
+                           pack_bf16x2(o8[6], o8[7]));
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // DINO input side
 // ------------------------------------------------------------------------------------------------
@@ -882,6 +945,12 @@ extern "C" int g2vlm_qknorm_mrope(void* qkv, int64_t ld, int64_t rows, int64_t n
   G2_REQUIRE(head_dim == 128, "qknorm_mrope: head_dim must be 128 (mrope_section sums to 64)");
   G2_REQUIRE(ld % 8 == 0 && G2_ALIGNED16(qkv) && G2_ALIGNED16(cos_tab) && G2_ALIGNED16(sin_tab), "qknorm_mrope: alignment");
   if (rows <= 0) return G2VLM_OK;
+  if (n_q_heads + n_kv_heads == 14) {
+    qknorm_mrope_row_kernel<7><<<blocks_for(rows, EW_THREADS / 32), EW_THREADS, 0, (cudaStream_t)stream>>>(
+        (__nv_bfloat16*)qkv, ld, rows, n_first, n_q_heads, qw_a, kw_a, qw_b, kw_b, cos_tab, sin_tab, eps, round_normed);
+    G2_LAUNCH_CHECK();
+    return G2VLM_OK;
+  }
   const long long warps = rows * (n_q_heads + n_kv_heads);
   qknorm_mrope_kernel<<<blocks_for(warps, EW_THREADS / 32), EW_THREADS, 0, (cudaStream_t)stream>>>(
       (__nv_bfloat16*)qkv, ld, rows, n_first, n_q_heads, n_kv_heads, qw_a, kw_a, qw_b, kw_b, cos_tab, sin_tab, eps,

@@ -63,11 +63,12 @@ def test_layernorm_and_segment_drop(D):
     assert _err(comp, ref_c) < 5e-3
 
 
-def test_mrope_table_and_qknorm_mrope():
+@pytest.mark.parametrize("nq,nkv", [(12, 2), (2, 1)])   # row-per-warp kernel (14 heads) and the per-head kernel
+def test_mrope_table_and_qknorm_mrope(nq, nkv):
     from g2vlm_b200 import ops
     from oracle import restate
     g = torch.Generator().manual_seed(3)
-    T, nq, nkv, hd, n_first = 600, 12, 2, 128, 550
+    T, hd, n_first = 600, 128, 550
     pos = torch.stack([torch.randint(0, 700, (T,), generator=g) for _ in range(3)])
     inv = (1.0 / (1e6 ** (torch.arange(0, hd, 2, dtype=torch.int64).float() / hd))).cuda()
     cos, sin = torch.empty(T, 64, device="cuda"), torch.empty(T, 64, device="cuda")
