@@ -42,6 +42,7 @@ struct AttnKParams {
   int causal;
   float scale_log2;
   int n_items, n_heads;
+  int out_head_cols;  // columns of each head written to `out` (= head stride in `out`); D unless compacted
 };
 
 template <int D>
@@ -317,9 +318,10 @@ attention_tcgen05_kernel(const __grid_constant__ AttnKParams p) {
       const bool row_ok = row < a.q_seg_end;
       if (a.nblk == 0) {
         if (row_ok) {  // no visible keys at all: flash-attn writes zeros
-          uint4* dst = reinterpret_cast<uint4*>(p.out + (long long)row * p.ldo + a.head * D);
+          uint4* dst = reinterpret_cast<uint4*>(p.out + (long long)row * p.ldo + a.head * p.out_head_cols);
 #pragma unroll
-          for (int q = 0; q < D / 8; ++q) dst[q] = make_uint4(0, 0, 0, 0);
+          for (int q = 0; q < D / 8; ++q)
+            if (q * 8 < p.out_head_cols) dst[q] = make_uint4(0, 0, 0, 0);
         }
         continue;
       }
@@ -432,10 +434,10 @@ attention_tcgen05_kernel(const __grid_constant__ AttnKParams p) {
       if (lane == 0) mbar_arrive(&o_free[t]);
       if (row_ok) {
         const float inv_l = l_run > 0.f ? 1.0f / l_run : 0.f;
-        uint4* dst = reinterpret_cast<uint4*>(p.out + (long long)row * p.ldo + a.head * D);
+        uint4* dst = reinterpret_cast<uint4*>(p.out + (long long)row * p.ldo + a.head * p.out_head_cols);
 #pragma unroll
         for (int q = 0; q < D / 8; ++q) {
-          dst[q] = make_uint4(
+          if (q * 8 < p.out_head_cols) dst[q] = make_uint4(
               pack_bf16x2(__uint_as_float(ov[8 * q]) * inv_l, __uint_as_float(ov[8 * q + 1]) * inv_l),
               pack_bf16x2(__uint_as_float(ov[8 * q + 2]) * inv_l, __uint_as_float(ov[8 * q + 3]) * inv_l),
               pack_bf16x2(__uint_as_float(ov[8 * q + 4]) * inv_l, __uint_as_float(ov[8 * q + 5]) * inv_l),
@@ -507,6 +509,9 @@ extern "C" int g2vlm_attention(const g2vlm_attn_args* a, void* stream_) {
   kp.scale_log2 = a->softmax_scale * 1.4426950408889634f;
   kp.n_items = a->n_items;
   kp.n_heads = a->num_q_heads;
+  G2_REQUIRE(a->out_head_cols >= 0 && a->out_head_cols <= D && a->out_head_cols % 8 == 0,
+             "attention: out_head_cols must be 0 or a multiple of 8 not above head_dim");
+  kp.out_head_cols = a->out_head_cols ? a->out_head_cols : D;
   if (D == 128) return launch_attention<128>(kp, stream);
   return launch_attention<64>(kp, stream);
 }

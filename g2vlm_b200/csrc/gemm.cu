@@ -46,6 +46,7 @@ struct GemmKParams {
   const float* scale;
   const float* residual;
   long long ldr;
+  int out_col_group, out_col_stride;  // STORE_BF16 column regrouping (0 = plain)
 };
 
 struct TileCoord {
@@ -213,7 +214,10 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, const TileCo
         uint32_t pk[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(f[2 * j], f[2 * j + 1]);
-        stage_store_bf16(stg, lane, pk, reinterpret_cast<__nv_bfloat16*>(p.out) + row_base * p.ldo + col0, p.ldo,
+        // optional regrouping of the output columns (heads of `group` columns into slots of `stride`); both are
+        // multiples of the 32-column chunk, so a chunk never straddles a slot
+        const int ocol = p.out_col_group ? col0 + (col0 / p.out_col_group) * (p.out_col_stride - p.out_col_group) : col0;
+        stage_store_bf16(stg, lane, pk, reinterpret_cast<__nv_bfloat16*>(p.out) + row_base * p.ldo + ocol, p.ldo,
                          rows_ok, cols_ok);
       } else if constexpr (EPI == G2VLM_EPI_RESID_F32) {
         // x += [bf16]( gamma * bf16(acc + bias) )   (reference: g2vlm/qwen2vl.py:885-887, 907-909)
@@ -466,6 +470,10 @@ extern "C" int g2vlm_gemm_bf16(const g2vlm_gemm_args* a, void* stream_) {
     G2_REQUIRE(a->residual == nullptr || a->ldr % 4 == 0, "gemm: ldr must be a multiple of 4");
   }
   G2_REQUIRE((reinterpret_cast<uintptr_t>(a->out) & 15) == 0, "gemm: out must be 16-byte aligned");
+  G2_REQUIRE(a->out_col_group == 0 ||
+                 (a->epilogue == G2VLM_EPI_STORE_BF16 && a->out_col_group > 0 && a->out_col_group % 32 == 0 &&
+                  a->out_col_stride % 32 == 0 && a->out_col_stride >= a->out_col_group && a->N % a->out_col_group == 0),
+             "gemm: out_col_group/out_col_stride need STORE_BF16, multiples of 32, stride >= group, N % group == 0");
   G2_REQUIRE(a->bias == nullptr || (reinterpret_cast<uintptr_t>(a->bias) & 15) == 0, "gemm: bias alignment");
   G2_REQUIRE(a->bias == nullptr || a->n_groups == 1 || a->N % 4 == 0, "gemm: stacked bias needs N % 4 == 0");
   G2_REQUIRE(a->scale == nullptr || (reinterpret_cast<uintptr_t>(a->scale) & 15) == 0, "gemm: scale alignment");
@@ -492,7 +500,7 @@ extern "C" int g2vlm_gemm_bf16(const g2vlm_gemm_args* a, void* stream_) {
     int total = 0, nonempty = 0, grp = 0;
     for (int g = 0; g < a->n_groups; ++g)
       if (a->group_rows[g] > 0) { total += a->group_rows[g]; ++nonempty; grp = g; }
-    if (nonempty == 1 && total <= 8 && (reinterpret_cast<uintptr_t>(a->A) & 15) == 0 &&
+    if (nonempty == 1 && total <= 8 && a->out_col_group == 0 && (reinterpret_cast<uintptr_t>(a->A) & 15) == 0 &&
         (reinterpret_cast<uintptr_t>(a->B) & 15) == 0)
       return launch_gemv(a, grp, stream);
   }
@@ -510,6 +518,8 @@ extern "C" int g2vlm_gemm_bf16(const g2vlm_gemm_args* a, void* stream_) {
   kp.scale = a->scale;
   kp.residual = a->residual;
   kp.ldr = a->ldr;
+  kp.out_col_group = a->out_col_group;
+  kp.out_col_stride = a->out_col_stride;
 
   int rc = make_tmap_2d_bf16(&kp.tmA, a->A, (uint64_t)a->a_rows, (uint64_t)a->K, (uint64_t)a->lda * 2, BM, BK);
   if (rc) return rc;

@@ -291,27 +291,33 @@ class G2VLMFast:
         # ---- Pi3 decoders ----
         H, dh, ehd = cfg.hidden_size, cfg.dec_heads, cfg.dec_head_dim
         self.dec_hp = _pad_dim(ehd)
+        # 96-wide Pi3 heads live in 128-wide q/k/v slots for the attention kernel.  When the head width is a multiple
+        # of 32 the Linear layers around it stay UNPADDED: the qkv GEMM scatters its columns into the slots
+        # (out_col_group/out_col_stride) and the attention kernel writes a compact [rows, heads*96] output, so no
+        # zero weight rows / columns are multiplied (25 % of the qkv and proj GEMMs otherwise).
+        self.dec_compact = ehd != self.dec_hp and ehd % 32 == 0
+        hp_w = ehd if self.dec_compact else self.dec_hp   # head width the packed weights use
 
         def pack_block(p, cross):
             B = {}
             qkv_w = g(p + "attn.qkv.weight").reshape(3, dh * ehd, H)
             qkv_b = g(p + "attn.qkv.bias").reshape(3, dh * ehd)
-            B["wqkv"] = _bf16(torch.cat([_pad_head_rows(qkv_w[j], dh, ehd, self.dec_hp) for j in range(3)], 0), dev)
-            B["bqkv"] = _bias_bf16(torch.cat([_pad_head_rows(qkv_b[j], dh, ehd, self.dec_hp) for j in range(3)], 0), dev)
-            B["wproj"] = _bf16(_pad_head_cols(g(p + "attn.proj.weight"), dh, ehd, self.dec_hp), dev)
+            B["wqkv"] = _bf16(torch.cat([_pad_head_rows(qkv_w[j], dh, ehd, hp_w) for j in range(3)], 0), dev)
+            B["bqkv"] = _bias_bf16(torch.cat([_pad_head_rows(qkv_b[j], dh, ehd, hp_w) for j in range(3)], 0), dev)
+            B["wproj"] = _bf16(_pad_head_cols(g(p + "attn.proj.weight"), dh, ehd, hp_w), dev)
             B["bproj"] = _bias_bf16(g(p + "attn.proj.bias"), dev)
             names = ["norm1", "norm2"] + (["norm3", "norm_y"] if cross else [])
             for n in names:
                 B[n + "w"] = _f32(g(p + n + ".weight"), dev); B[n + "b"] = _f32(g(p + n + ".bias"), dev)
             if cross:
                 c = p + "cross_attn."
-                B["wcq"] = _bf16(_pad_head_rows(g(c + "q_proj.weight"), dh, ehd, self.dec_hp), dev)
-                B["bcq"] = _bias_bf16(_pad_head_rows(g(c + "q_proj.bias"), dh, ehd, self.dec_hp), dev)
-                B["wckv"] = _bf16(torch.cat([_pad_head_rows(g(c + "k_proj.weight"), dh, ehd, self.dec_hp),
-                                             _pad_head_rows(g(c + "v_proj.weight"), dh, ehd, self.dec_hp)], 0), dev)
-                B["bckv"] = _bias_bf16(torch.cat([_pad_head_rows(g(c + "k_proj.bias"), dh, ehd, self.dec_hp),
-                                                  _pad_head_rows(g(c + "v_proj.bias"), dh, ehd, self.dec_hp)], 0), dev)
-                B["wcproj"] = _bf16(_pad_head_cols(g(c + "proj.weight"), dh, ehd, self.dec_hp), dev)
+                B["wcq"] = _bf16(_pad_head_rows(g(c + "q_proj.weight"), dh, ehd, hp_w), dev)
+                B["bcq"] = _bias_bf16(_pad_head_rows(g(c + "q_proj.bias"), dh, ehd, hp_w), dev)
+                B["wckv"] = _bf16(torch.cat([_pad_head_rows(g(c + "k_proj.weight"), dh, ehd, hp_w),
+                                             _pad_head_rows(g(c + "v_proj.weight"), dh, ehd, hp_w)], 0), dev)
+                B["bckv"] = _bias_bf16(torch.cat([_pad_head_rows(g(c + "k_proj.bias"), dh, ehd, hp_w),
+                                                  _pad_head_rows(g(c + "v_proj.bias"), dh, ehd, hp_w)], 0), dev)
+                B["wcproj"] = _bf16(_pad_head_cols(g(c + "proj.weight"), dh, ehd, hp_w), dev)
                 B["bcproj"] = _bias_bf16(g(c + "proj.bias"), dev)
             B["wfc1"] = _bf16(g(p + "mlp.fc1.weight"), dev); B["bfc1"] = _bias_bf16(g(p + "mlp.fc1.bias"), dev)
             B["wfc2"] = _bf16(g(p + "mlp.fc2.weight"), dev); B["bfc2"] = _bias_bf16(g(p + "mlp.fc2.bias"), dev)
@@ -950,8 +956,12 @@ class G2VLMFast:
         x = self.buf.get("dec.x", (rows, H), torch.float32)
         ops.gather_rows(hidden, x, None, rows)
         h = self.buf.get("dec.h", (rows, H), torch.bfloat16)
-        qkv = self.buf.get("dec.qkv", (rows, 3 * dh * hp), torch.bfloat16)
-        attn = self.buf.get("dec.attn", (rows, dh * hp), torch.bfloat16)
+        cmp_ = self.dec_compact
+        regroup = dict(out_col_group=ehd, out_col_stride=hp) if cmp_ else {}
+        ohc = ehd if cmp_ else 0
+        # zero-filled once: the pad columns of every head slot are never written afterwards
+        qkv = self.buf.get("dec.qkv", (rows, 3 * dh * hp), torch.bfloat16, zero=True)
+        attn = self.buf.get("dec.attn", (rows, dh * (ehd if cmp_ else hp)), torch.bfloat16)
         mid = self.buf.get("dec.mid", (rows, H * cfg.dec_mlp_ratio), torch.bfloat16)
         cos, sin = self._rope2d_tables(gh, gw)
         cu = [v * P for v in range(N + 1)]
@@ -959,26 +969,26 @@ class G2VLMFast:
         scale = 1.0 / math.sqrt(ehd)
         if dec["cross"]:
             yh = self.buf.get("dec.yh", (P, H), torch.bfloat16)
-            kvc = self.buf.get("dec.kvc", (P, 2 * dh * hp), torch.bfloat16)
-            qc = self.buf.get("dec.qc", (rows, dh * hp), torch.bfloat16)
+            kvc = self.buf.get("dec.kvc", (P, 2 * dh * hp), torch.bfloat16, zero=True)
+            qc = self.buf.get("dec.qc", (rows, dh * hp), torch.bfloat16, zero=True)
             cwork = self._cross_work(N, P)
         for B in dec["blocks"]:
             ops.layernorm(x, h, B["norm1w"], B["norm1b"], 1e-6)
-            ops.gemm(h, B["wqkv"], qkv, epilogue=ops.EPI_STORE_BF16, bias=B["bqkv"])
+            ops.gemm(h, B["wqkv"], qkv, epilogue=ops.EPI_STORE_BF16, bias=B["bqkv"], **regroup)
             ops.rope2d(qkv, rows, 2 * dh, hp, ehd, P, gw, cos, sin)
             ops.attention(qkv[:, : dh * hp], qkv[:, dh * hp: 2 * dh * hp], qkv[:, 2 * dh * hp:], attn, work,
-                          num_q_heads=dh, num_kv_heads=dh, head_dim=hp, scale=scale)
+                          num_q_heads=dh, num_kv_heads=dh, head_dim=hp, scale=scale, out_head_cols=ohc)
             ops.gemm(attn, B["wproj"], x, epilogue=ops.EPI_RESID_F32, bias=B["bproj"])
             if dec["cross"]:
                 # context = view 0's tokens for every view (g2vlm.py:1196): K/V projected ONCE per block
                 ops.layernorm(context, yh, B["norm_yw"], B["norm_yb"], 1e-6, rows=P)
-                ops.gemm(yh, B["wckv"], kvc, epilogue=ops.EPI_STORE_BF16, bias=B["bckv"])
+                ops.gemm(yh, B["wckv"], kvc, epilogue=ops.EPI_STORE_BF16, bias=B["bckv"], **regroup)
                 ops.rope2d(kvc, P, dh, hp, ehd, P, gw, cos, sin)
                 ops.layernorm(x, h, B["norm2w"], B["norm2b"], 1e-6)
-                ops.gemm(h, B["wcq"], qc, epilogue=ops.EPI_STORE_BF16, bias=B["bcq"])
+                ops.gemm(h, B["wcq"], qc, epilogue=ops.EPI_STORE_BF16, bias=B["bcq"], **regroup)
                 ops.rope2d(qc, rows, dh, hp, ehd, P, gw, cos, sin)
                 ops.attention(qc, kvc[:, : dh * hp], kvc[:, dh * hp:], attn, cwork, num_q_heads=dh, num_kv_heads=dh,
-                              head_dim=hp, scale=scale)
+                              head_dim=hp, scale=scale, out_head_cols=ohc)
                 ops.gemm(attn, B["wcproj"], x, epilogue=ops.EPI_RESID_F32, bias=B["bcproj"])
                 ops.layernorm(x, h, B["norm3w"], B["norm3b"], 1e-6)
             else:

@@ -60,14 +60,16 @@ class GemmArgs(ctypes.Structure):
         ("out", ctypes.c_void_p), ("ldo", ctypes.c_int64),
         ("bias", ctypes.c_void_p), ("scale", ctypes.c_void_p), ("scale_groups", ctypes.c_uint32),
         ("residual", ctypes.c_void_p), ("ldr", ctypes.c_int64),
+        ("out_col_group", ctypes.c_int32), ("out_col_stride", ctypes.c_int32),
     ]
 
 
 def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, epilogue: int,
          groups: Optional[Sequence[tuple]] = None, bias: Optional[torch.Tensor] = None,
          scale: Optional[torch.Tensor] = None, scale_groups: int = 0, flags: int = 0,
-         residual: Optional[torch.Tensor] = None) -> torch.Tensor:
+         residual: Optional[torch.Tensor] = None, out_col_group: int = 0, out_col_stride: int = 0) -> torch.Tensor:
     """out <- epilogue(a @ w_g.T) per token group; see g2vlm_gemm_bf16 in include/g2vlm_b200.h.
+    out_col_group / out_col_stride (STORE_BF16): output column c lands at (c // group) * stride + c % group.
 
     a: bf16 [rows, K]; w: bf16 [n_groups*N, K] (experts stacked); groups: [(row0, rows), ...]
     (default: one group covering all rows); bias: fp32 [n_groups*N]; scale: fp32 [N].
@@ -93,6 +95,9 @@ def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, epilogue: int,
     want = torch.bfloat16 if epilogue in (EPI_STORE_BF16, EPI_SWIGLU_BF16) else torch.float32
     _req(out, want, "out")
     n_out = N // 2 if epilogue == EPI_SWIGLU_BF16 else N
+    if out_col_group:
+        n_out = (N // out_col_group - 1) * out_col_stride + out_col_group
+        args.out_col_group, args.out_col_stride = out_col_group, out_col_stride
     if out.shape[0] < max(r0 + rows for r0, rows in groups) or out.shape[1] < n_out:
         raise G2Error(f"gemm: out shape {tuple(out.shape)} too small")
     args.out, args.ldo = out.data_ptr(), out.stride(0)
@@ -123,6 +128,7 @@ class AttnArgs(ctypes.Structure):
         ("head_dim", ctypes.c_int32), ("causal", ctypes.c_int32),
         ("softmax_scale", ctypes.c_float), ("n_items", ctypes.c_int32),
         ("work_items", ctypes.c_void_p),
+        ("out_head_cols", ctypes.c_int32),
     ]
 
 
@@ -145,9 +151,10 @@ def attention_work_table(cu_seqlens_q: Sequence[int], cu_seqlens_k: Sequence[int
 
 def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tensor, work: torch.Tensor,
               *, num_q_heads: int, num_kv_heads: int, head_dim: int, scale: float,
-              causal: bool = False) -> torch.Tensor:
+              causal: bool = False, out_head_cols: int = 0) -> torch.Tensor:
     """out[rows covered by `work`] = softmax(scale * q k^T) v, per segment; q/k/v/out are 2-D bf16
-    views [rows, heads*head_dim] (they may be column slices of one fused QKV buffer)."""
+    views [rows, heads*head_dim] (they may be column slices of one fused QKV buffer).  out_head_cols: write only
+    that many columns per head, heads packed at that stride (96-wide heads computed in 128-wide slots)."""
     for t, n in ((q, "q"), (k, "k"), (v, "v"), (out, "out")):
         _req(t, torch.bfloat16, n)
     _req(work, torch.int32, "work")
@@ -163,6 +170,7 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tens
     args.num_q_heads, args.num_kv_heads, args.head_dim = num_q_heads, num_kv_heads, head_dim
     args.causal, args.softmax_scale = int(causal), float(scale)
     args.n_items, args.work_items = work.shape[0], work.data_ptr()
+    args.out_head_cols = int(out_head_cols)
     _check(_lib.load().g2vlm_attention(ctypes.byref(args), _stream()))
     return out
 

@@ -25,7 +25,7 @@ extern "C" {
 #define G2VLM_ERR_INVALID 1 /* bad argument / unsupported shape */
 #define G2VLM_ERR_CUDA 2    /* a CUDA runtime / driver call failed */
 
-#define G2VLM_ABI_VERSION 1
+#define G2VLM_ABI_VERSION 2 /* 2: gemm out_col_group/out_col_stride, attention item_causal + out_head_cols */
 
 /* Version of this ABI (G2VLM_ABI_VERSION of the built library). */
 int g2vlm_abi_version(void);
@@ -87,6 +87,12 @@ typedef struct g2vlm_gemm_args {
   uint32_t scale_groups;   /* bit g set: group g rows are multiplied by `scale` */
   const float* residual;   /* STORE_F32: fp32 [rows, ldr] added to the result, or NULL */
   int64_t ldr;
+  /* STORE_BF16 only: output column c is written at (c / out_col_group) * out_col_stride + c % out_col_group
+   * (both multiples of 32, stride >= group; 0 = plain).  Lets a Linear whose outputs are heads of 96 write
+   * straight into the 128-wide head slots the attention kernel reads, without multiplying zero weight rows
+   * (Pi3 decoders: modeling/pi3/models/layers/attention.py:353-357). The pad columns are not written. */
+  int32_t out_col_group;
+  int32_t out_col_stride;
 } g2vlm_gemm_args;
 
 int g2vlm_gemm_bf16(const g2vlm_gemm_args* args, void* stream);
@@ -111,7 +117,8 @@ int g2vlm_gemm_bf16(const g2vlm_gemm_args* args, void* stream);
  * quirk Q1; the caller defines them, the host mirror zero-fills). causal = bottom-right aligned
  * mask as in flash-attn, for the whole launch (args.causal) or for one item (item_causal != 0: lets
  * the causal prompt rows ride in the same launch as the non-causal geo step). K/V rows in [k_end, round_up(k_end,128)) that lie inside kv_rows must hold
- * finite values. head_dim in {64, 128} (the 96-wide Pi3 heads are zero-padded to 128 by the caller).
+ * finite values. head_dim in {64, 128} (the 96-wide Pi3 heads sit zero-padded in 128-wide q/k/v slots; see
+ * out_head_cols for the compact output).
  * ---------------------------------------------------------------------------------------------- */
 typedef struct g2vlm_attn_args {
   const void* q;
@@ -131,6 +138,9 @@ typedef struct g2vlm_attn_args {
   float softmax_scale;
   int32_t n_items;
   const int32_t* work_items; /* DEVICE int32 [n_items][8] */
+  /* 0, or the number of columns of each head that are written to `out`, heads packed at that stride
+   * (multiple of 8, <= head_dim): a 96-wide head computed in a 128-wide slot leaves as [q_rows, heads*96]. */
+  int32_t out_head_cols;
 } g2vlm_attn_args;
 
 int g2vlm_attention(const g2vlm_attn_args* args, void* stream);

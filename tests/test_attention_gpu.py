@@ -174,3 +174,23 @@ def test_lazy_rescale_paths(hot_key):
     ref = _ref_attention(q, k, v, [0, T], [0, T], hq, hk, d, scale, False)
     assert torch.isfinite(out.float()).all()
     assert (out.float() - ref).abs().max() < 3e-2
+
+
+def test_compact_head_output():
+    """out_head_cols: 96-wide heads computed in zero-padded 128-wide slots leave as [rows, heads*96]."""
+    from g2vlm_b200 import ops
+    hq, d, dv, T = 4, 128, 96, 300
+    g = torch.Generator().manual_seed(9)
+    def padded():
+        x = torch.zeros(T, hq, d)
+        x[:, :, :dv] = torch.randn(T, hq, dv, generator=g)
+        return x.reshape(T, hq * d).to(torch.bfloat16).cuda()
+    q, k, v = padded(), padded(), padded()
+    work = ops.attention_work_table([0, 140, T], [0, 140, T]).cuda()
+    scale = 1 / math.sqrt(dv)
+    full = torch.zeros(T, hq * d, device="cuda", dtype=torch.bfloat16)
+    ops.attention(q, k, v, full, work, num_q_heads=hq, num_kv_heads=hq, head_dim=d, scale=scale)
+    compact = torch.full((T + 1, hq * dv), 5.0, device="cuda", dtype=torch.bfloat16)
+    ops.attention(q, k, v, compact[:T], work, num_q_heads=hq, num_kv_heads=hq, head_dim=d, scale=scale, out_head_cols=dv)
+    assert torch.equal(compact[:T].view(T, hq, dv), full.view(T, hq, d)[:, :, :dv])
+    assert bool((compact[T] == 5.0).all())

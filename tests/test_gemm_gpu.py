@@ -175,3 +175,21 @@ def test_guard_bands_are_never_written(epi):
     assert (out[rows:] == 3.0).all() and (out[:, N:] == 3.0).all()
     ref = _ref_linear(a, w, bias, [(0, rows)], N)[:rows] + (3.0 if epi == "resid" else 0.0)
     assert _relerr(out[:rows, :N], ref) < 1e-2
+
+
+def test_store_bf16_column_regroup():
+    """out_col_group / out_col_stride: heads of 96 output columns land in 128-wide slots; pad columns untouched."""
+    from g2vlm_b200 import ops
+    g = torch.Generator().manual_seed(11)
+    rows, K, heads = 300, 256, 6
+    a = (torch.randn(rows, K, generator=g) * 0.5).to(torch.bfloat16).cuda()
+    w = (torch.randn(heads * 96, K, generator=g) * 0.1).to(torch.bfloat16).cuda()
+    bias = torch.randn(heads * 96, generator=g).cuda()
+    out = torch.full((rows, heads * 128), 3.0, device="cuda", dtype=torch.bfloat16)
+    ops.gemm(a, w, out, epilogue=ops.EPI_STORE_BF16, bias=bias, out_col_group=96, out_col_stride=128)
+    ref = (a.float() @ w.float().T + bias).view(rows, heads, 96)
+    got = out.float().view(rows, heads, 128)
+    assert ((got[:, :, :96] - ref).abs().max() / ref.abs().max()) < 1e-2
+    assert bool((got[:, :, 96:] == 3.0).all())
+    with pytest.raises(Exception):
+        ops.gemm(a, w, out, epilogue=ops.EPI_STORE_BF16, out_col_group=48, out_col_stride=128)
