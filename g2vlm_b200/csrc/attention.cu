@@ -9,8 +9,8 @@
 // 128-row query tiles are in flight ("ping-pong"): while the softmax warps of tile 0 turn S0 into P0, the
 // tensor core runs tile 1's MMAs and vice versa.
 //   warp 0        TMA producer: Q tiles once, K/V blocks of 128 keys through an mbarrier ring
-//   warp 1        MMA issuer:   S_t = Q_t K^T (SS, K-major operands) ; O_t += P_t V (TS: P read from
-//                               TMEM, V is an MN-major B operand straight from the [key][d] layout)
+//   warps 1, 2    MMA issuers (one per query tile): S_t = Q_t K^T (SS, K-major operands) ; O_t += P_t V (TS: P
+//                               read from TMEM, V is an MN-major B operand straight from the [key][d] layout)
 //   warps 4-7     softmax of tile 0 (one thread per query row), warps 8-11 softmax of tile 1:
 //                 tcgen05.ld S -> running max / exp2 / row sum -> bf16 P written back to TMEM over S
 //                 (tcgen05.st); lazy rescale of O in TMEM only when the running max grows by > 2^8
@@ -93,6 +93,7 @@ attention_tcgen05_kernel(const __grid_constant__ AttnKParams p) {
   constexpr int KSTEPS_PV = ATT_BN / 16;  // MMAs per PV block (K = keys)
   constexpr int BOX_BYTES = ATT_BM * 128; // one 64-col box of 128 rows
   constexpr int KS = Cfg::kStages;
+  constexpr bool kSepP = D == 64;  // P_t in its own TMEM columns + one MMA issuer per tile (see the TMEM map below)
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -110,7 +111,8 @@ attention_tcgen05_kernel(const __grid_constant__ AttnKParams p) {
   uint64_t* p_full = s_full + 2;                   // [2][ATT_PCHUNKS]: P handed over in key chunks
   uint64_t* o_done = p_full + 2 * ATT_PCHUNKS;     // [2]  PV of a block finished
   uint64_t* o_free = o_done + 2;                   // [2]  the epilogue has read O_t out of TMEM
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_free + 2);
+  uint64_t* s_free = o_free + 2;                   // [2]  (kSepP) the softmax warps hold S_t in registers
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_free + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -153,18 +155,19 @@ attention_tcgen05_kernel(const __grid_constant__ AttnKParams p) {
   if (warp == 1) {
     if (elect_one()) {
       mbar_init(q_full, 1);
-      mbar_init(q_empty, 1);
+      mbar_init(q_empty, kSepP ? 2 : 1);   // every MMA issuer is done with the Q tiles
       for (int s = 0; s < KS; ++s) {
         mbar_init(&k_full[s], 1);
         mbar_init(&v_full[s], 1);
-        mbar_init(&k_empty[s], 1);
-        mbar_init(&v_empty[s], 1);
+        mbar_init(&k_empty[s], kSepP ? 2 : 1);  // released by every MMA issuer
+        mbar_init(&v_empty[s], kSepP ? 2 : 1);
       }
       for (int t = 0; t < 2; ++t) {
         mbar_init(&s_full[t], 1);
         for (int c = 0; c < ATT_PCHUNKS; ++c) mbar_init(&p_full[t * ATT_PCHUNKS + c], 4);  // one arrive per warp
         mbar_init(&o_done[t], 1);
         mbar_init(&o_free[t], 4);
+        mbar_init(&s_free[t], 4);
       }
       fence_barrier_init();
     }
@@ -175,9 +178,18 @@ attention_tcgen05_kernel(const __grid_constant__ AttnKParams p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  // TMEM columns of tile t: S/P at t*128, O at 256 + t*128 (plain arithmetic: no local arrays)
+  // TMEM columns of tile t (plain arithmetic: no local arrays).
+  //   D = 128: S_t at t*128 with P_t written over its first 64 columns, O_t at 256 + t*128 (all 512 columns used)
+  //   D =  64: O_t needs only 64 columns, which leaves room for P_t OUTSIDE S_t: S at t*128, P at 256 + t*64,
+  //            O at 384 + t*64.  Then the next QK^T of a tile no longer has to wait for the PV that reads P: it is
+  //            issued as soon as the softmax warps hold S_t in registers (s_free), S_{j+1} is ready before
+  //            softmax_j ends, and the softmax warps never idle (the per-tile chain QK -> softmax -> PV -> QK that
+  //            bounds the D = 128 case is broken).
   auto tS = [&](int t) { return tmem_base + static_cast<uint32_t>(t) * 128u; };
-  auto tO = [&](int t) { return tmem_base + 256u + static_cast<uint32_t>(t) * 128u; };
+  auto tP = [&](int t) { return kSepP ? tmem_base + 256u + static_cast<uint32_t>(t) * 64u : tS(t); };
+  auto tO = [&](int t) {
+    return kSepP ? tmem_base + 384u + static_cast<uint32_t>(t) * 64u : tmem_base + 256u + static_cast<uint32_t>(t) * 128u;
+  };
 
   // Every role walks the same unit sequence and keeps the same two running counters, from which all mbarrier
   // parities follow:  g = key blocks processed so far by this CTA,  n = units (with >= 1 block) so far.
@@ -218,9 +230,9 @@ attention_tcgen05_kernel(const __grid_constant__ AttnKParams p) {
         ++n;
       }
     }
-  } else if (warp == 1) {
+  } else if (!kSepP && warp == 1) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
-    // ------------------------------------ MMA issuer ------------------------------------------
+    // ------------------------------------ MMA issuer (D = 128: one thread issues both tiles) ----
     if (elect_one()) {
       constexpr uint32_t idesc_qk = umma_idesc_bf16(ATT_BM, ATT_BN, 0, 0);
       constexpr uint32_t idesc_pv = umma_idesc_bf16(ATT_BM, D, 0, 1);  // B (= V) is MN-major
@@ -299,6 +311,93 @@ attention_tcgen05_kernel(const __grid_constant__ AttnKParams p) {
         ++n;
       }
     }
+  } else if (kSepP && (warp == 1 || warp == 2)) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
+    // ------------------------------------ MMA issuers (D = 64): warp 1 -> query tile 0, warp 2 -> tile 1 ------
+    // One issuer per tile: each walks its own tile's sequence in order and is never held up by a barrier of the
+    // other tile; the tensor pipe interleaves the two instruction streams.  (Measured: -6.5 % on the DINO shape
+    // together with the separate P columns; for D = 128, where P must alias S, two issuers cost +5 %, so that case
+    // keeps the single issuer above.)
+    if (elect_one()) {
+      const int t = warp - 1;
+      constexpr uint32_t idesc_qk = umma_idesc_bf16(ATT_BM, ATT_BN, 0, 0);
+      constexpr uint32_t idesc_pv = umma_idesc_bf16(ATT_BM, D, 0, 1);  // B (= V) is MN-major
+      const uint32_t qa = smem_u32(sQ) + t * Cfg::kTileBytes;
+      const uint32_t kv_addr = smem_u32(sKV);
+      const uint32_t tS_t = tS(t), tP_t = tP(t), tO_t = tO(t);
+
+      auto issue_qk = [&](int s) {
+        const uint32_t ka = kv_addr + s * 2 * Cfg::kTileBytes;
+#pragma unroll
+        for (int k = 0; k < KSTEPS_QK; ++k) {
+          const uint32_t off = (k >> 2) * BOX_BYTES + (k & 3) * 32;
+          umma_ss(tS_t, umma_desc_kmajor(qa + off), umma_desc_kmajor(ka + off), idesc_qk, k != 0);
+        }
+        umma_commit(&s_full[t]);
+        umma_commit(&k_empty[s]);
+      };
+      // O_t += P_t V, issued chunk by chunk as the softmax warps publish 32 keys of P at a time
+      auto issue_pv = [&](int s, uint32_t par, bool first_block) {
+        const uint32_t va = kv_addr + s * 2 * Cfg::kTileBytes + Cfg::kTileBytes;
+#pragma unroll
+        for (int c = 0; c < ATT_PCHUNKS; ++c) {
+          mbar_wait(&p_full[t * ATT_PCHUNKS + c], par);
+          tc_fence_after();
+#pragma unroll
+          for (int kk = 0; kk < KSTEPS_PV / ATT_PCHUNKS; ++kk) {
+            const int k = c * (KSTEPS_PV / ATT_PCHUNKS) + kk;
+            // 16 keys = 16 rows of 128 B inside each 64-column box; boxes are BOX_BYTES apart (LBO)
+            umma_ts(tO_t, tP_t + k * 8, umma_desc_mnmajor(va + k * 2048, BOX_BYTES), idesc_pv,
+                    !(first_block && k == 0));
+          }
+        }
+        umma_commit(&o_done[t]);
+        umma_commit(&v_empty[s]);
+      };
+
+      uint32_t g = 0, n = 0;
+      for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
+        const AttnUnit a = decode(u);
+        if (a.nblk == 0) continue;
+        mbar_wait(q_full, n & 1);
+        mbar_wait(&k_full[g % KS], (g / KS) & 1);
+        tc_fence_after();
+        // S_t is free: the previous unit's last PV_t (which read P_t) is ahead in this thread's instruction stream
+        // (aliased P) / the softmax warps released it through s_free (separate P)
+        issue_qk(g % KS);
+        if (a.nblk == 1) umma_commit(q_empty);
+        for (int j = 0; j < a.nblk; ++j, ++g) {
+          const int s = g % KS;
+          const uint32_t par = (g / KS) & 1;
+          const int s1 = (g + 1) % KS;
+          const uint32_t par1 = ((g + 1) / KS) & 1;
+          const bool more = j + 1 < a.nblk;
+          if constexpr (kSepP) {
+            // S_t is free once the softmax warps have loaded it: the next QK^T goes ahead of this block's PV
+            mbar_wait(&s_free[t], g & 1);
+            if (more) {
+              mbar_wait(&k_full[s1], par1);
+              tc_fence_after();
+              issue_qk(s1);
+              if (j + 2 == a.nblk) umma_commit(q_empty);  // that was the unit's last QK^T
+            }
+          }
+          mbar_wait(&v_full[s], par);
+          if (j == 0 && n > 0) {  // the first PV overwrites O_t: the previous unit's epilogue must have read it
+            mbar_wait(&o_free[t], (n - 1) & 1);
+            tc_fence_after();
+          }
+          issue_pv(s, g & 1, j == 0);
+          if (!kSepP && more) {
+            mbar_wait(&k_full[s1], par1);
+            tc_fence_after();
+            issue_qk(s1);
+            if (j + 2 == a.nblk) umma_commit(q_empty);  // that was the unit's last QK^T
+          }
+        }
+        ++n;
+      }
+    }
   } else if (warp < 4) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
   } else {
@@ -309,6 +408,7 @@ attention_tcgen05_kernel(const __grid_constant__ AttnKParams p) {
     const int r_in_tile = sub * 32 + lane;
     const uint32_t lane_off = static_cast<uint32_t>(sub * 32) << 16;
     const uint32_t tS_w = tS(t) + lane_off;
+    const uint32_t tP_w = tP(t) + lane_off;
     const uint32_t tO_w = tO(t) + lane_off;
     uint32_t g = 0, n = 0;
 
@@ -339,6 +439,11 @@ attention_tcgen05_kernel(const __grid_constant__ AttnKParams p) {
 #pragma unroll
         for (int c = 0; c < 4; ++c) tmem_ld32(tS_w + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&sv[c * 32]));
         tmem_wait_ld();
+        if constexpr (kSepP) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&s_free[t]);
+        }
 
         const int col_base = j * ATT_BN;
         if (col_base + ATT_BN > limit) {
@@ -383,6 +488,12 @@ attention_tcgen05_kernel(const __grid_constant__ AttnKParams p) {
 
         // P = 2^(s*scale - m), packed to bf16 pairs, written over S (columns [0,64) of the S region) and
         // handed to the MMA warp 32 keys at a time so PV starts while the rest of the row is still in exp
+        if constexpr (kSepP) {
+          if (g > 0) {  // P_t has its own columns: the previous block's PV must be done reading them
+            mbar_wait(&o_done[t], (g - 1) & 1);
+            tc_fence_after();
+          }
+        }
         uint64_t sum2 = pack2(0.f, 0.f);
         const uint64_t neg_m2 = pack2(-m_used, -m_used);
         const uint64_t scale2 = pack2(p.scale_log2, p.scale_log2);
@@ -409,8 +520,8 @@ attention_tcgen05_kernel(const __grid_constant__ AttnKParams p) {
             __syncwarp();
             if (lane == 0) mbar_arrive(&p_full[t * ATT_PCHUNKS + c - 1]);
           }
-          if constexpr (CW == 32) tmem_st16(tS_w + c * 16, pk);
-          else tmem_st32(tS_w + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&pk[0]));
+          if constexpr (CW == 32) tmem_st16(tP_w + c * 16, pk);
+          else tmem_st32(tP_w + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&pk[0]));
         }
         tmem_wait_st();
         tc_fence_before();
