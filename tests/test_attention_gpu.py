@@ -194,3 +194,38 @@ def test_compact_head_output():
     ops.attention(q, k, v, compact[:T], work, num_q_heads=hq, num_kv_heads=hq, head_dim=d, scale=scale, out_head_cols=dv)
     assert torch.equal(compact[:T].view(T, hq, dv), full.view(T, hq, d)[:, :, :dv])
     assert bool((compact[T] == 5.0).all())
+
+
+@pytest.mark.parametrize("d,causal", [(128, False), (64, False), (128, True), (64, True)])
+def test_persistent_ctas_walk_many_ragged_units(d, causal):
+    """More (item, head) units than SMs, with segment lengths from 1 row to several tiles and key counts from one
+    block to many: every CTA chains units of different length through the same TMEM / barrier state (unit boundary
+    hand-offs: q_empty, o_free, s_free, running mbarrier parities)."""
+    lens_q = [1, 130, 700, 5, 1371, 256, 257, 64, 900, 3, 512, 129]
+    lens_k = [300, 130, 700, 40, 1371, 1, 257, 1000, 900, 3, 127, 2048] if not causal else lens_q
+    cu_q = [0]
+    cu_k = [0]
+    for a, b in zip(lens_q, lens_k):
+        cu_q.append(cu_q[-1] + a)
+        cu_k.append(cu_k[-1] + b)
+    err, mag = _run(cu_q, cu_k, 16, 16 if d == 64 else 4, d, causal=causal, seed=d + causal)
+    assert err < 2e-2 * max(mag, 1.0), (err, mag)
+
+
+@pytest.mark.parametrize("d", [64, 128])
+def test_causal_units_without_any_visible_key(d):
+    """Bottom-right causal mask with fewer keys than queries: the first query rows see no key at all (whole units
+    with zero key blocks are skipped by every role and written as zeros, like flash-attn)."""
+    from g2vlm_b200 import ops
+    lq, lk, hq = 700, 100, 2
+    g = torch.Generator().manual_seed(d)
+    q = torch.randn(lq, hq * d, generator=g).to(torch.bfloat16).cuda()
+    k = torch.randn(lk, hq * d, generator=g).to(torch.bfloat16).cuda()
+    v = torch.randn(lk, hq * d, generator=g).to(torch.bfloat16).cuda()
+    out = torch.full((lq, hq * d), 7.0, device="cuda", dtype=torch.bfloat16)
+    work = ops.attention_work_table([0, lq], [0, lk]).cuda()
+    scale = 1 / math.sqrt(d)
+    ops.attention(q, k, v, out, work, num_q_heads=hq, num_kv_heads=hq, head_dim=d, scale=scale, causal=True)
+    assert bool((out[: lq - lk] == 0).all())
+    ref = _ref_attention(q[lq - lk:], k, v, [0, lk], [0, lk], hq, hq, d, scale, True)
+    assert (out[lq - lk:].float() - ref).abs().max() < 2e-2
