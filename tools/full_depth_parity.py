@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """One-off check (too slow for the test suite): FULL-depth, FULL-width G2VLM-2B-MoT (28 MoT + 24 DINO layers,
 5 blocks per decoder) on N views of 518x518 — CUDA path vs the CPU oracle (bf16 mode), same weights.
-usage: python tools/full_depth_parity.py [n_views]   (N=1: ~6 TFLOP on the CPU)"""
+usage: python tools/full_depth_parity.py [n_views] [layerscale|-] [H W]   (N=1, 518x518: ~6 TFLOP on the CPU;
+       8 294 518 = BASELINE configs[0], the reference's CPU-runnable shape)"""
 import json
 import os
 import sys
@@ -15,7 +16,7 @@ from g2vlm_b200.model import G2VLMFast
 from oracle import restate
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 1
-ls_value = float(sys.argv[2]) if len(sys.argv) > 2 else None   # e.g. 0.01 = the reference's LayerScale init
+ls_value = float(sys.argv[2]) if len(sys.argv) > 2 and sys.argv[2] != "-" else None   # e.g. 0.01 = the reference's LayerScale init
 cfg = schema.FULL
 
 
@@ -35,7 +36,8 @@ model = G2VLMFast(cfg, sd)
 sd_cpu = {k: v.cpu() for k, v in sd.items()}
 del sd
 torch.cuda.empty_cache()
-v = (schema.synthetic_views(n, 518, 518, seed=1) * 255).round() / 255
+HH, WW = (int(sys.argv[3]), int(sys.argv[4])) if len(sys.argv) > 4 else (518, 518)
+v = (schema.synthetic_views(n, HH, WW, seed=1) * 255).round() / 255
 c_out, c_ref = {}, {}
 out = model.recon(Tok(), dict(ids), None, v, collect=c_out)
 torch.cuda.synchronize()
@@ -49,7 +51,7 @@ c32 = {}
 ref32 = restate.recon(sd_cpu, cfg, v, mode="fp32", collect=c32)
 print(f"oracle fp32 {time.time() - t0:.1f}s", flush=True)
 rel = lambda a, b: ((a.float().cpu() - b.float()).abs().max() / b.float().abs().max()).item()
-res = {"n_views": n, "layerscale": ls_value}
+res = {"n_views": n, "image_hw": [HH, WW], "layerscale": ls_value}
 # distance of each bf16 implementation from the fp32 ground truth (the reference never runs fp32)
 for k in ("local_points", "points", "global_points", "camera_poses"):
     res[f"cuda_vs_fp32.{k}"] = rel(out[k], ref32[k])

@@ -31,8 +31,8 @@ gi = {k: (v if k.endswith('lens') else v.cuda()) for k, v in gi.items()}
 
 
 def step():
-    past = model.forward_cache_update_text(NaiveCache(cfg.num_layers), **gi_t)
-    past, last = model.forward_cache_update_dino(past, update_past_key_values=False, **gi)
+    past, last = model.forward_cache_update_dino(NaiveCache(cfg.num_layers), update_past_key_values=False,
+                                                 prompt=gi_t, **gi)   # fused prompt prefill, as recon() does
     return model.reconstruct(past_key_values=past, selected_hidden_states=last, **gi)
 
 
