@@ -850,6 +850,74 @@ __global__ void ply_scatter_kernel(const float* __restrict__ pts, const float* _
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Pillow-exact 8-bit Lanczos resampling (two passes, 22-bit fixed-point coefficients)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint8_t clip8_fixed(int acc) {
+  const int v = acc >> 22;  // arithmetic shift: floor, like Pillow's clip8 lookup
+  return static_cast<uint8_t>(min(255, max(0, v)));
+}
+
+// horizontal pass: tmp[y][xx][c] from src[y][xmin .. xmin+n)[c]; one thread per (y, xx)
+__global__ void resize_h_u8_kernel(const uint8_t* __restrict__ src, long long pitch, int H, int out_w,
+                                   const int* __restrict__ bounds, const int* __restrict__ coef, int ksize,
+                                   uint8_t* __restrict__ tmp) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= (long long)H * out_w) return;
+  const int y = static_cast<int>(i / out_w), xx = static_cast<int>(i - (long long)y * out_w);
+  const int xmin = bounds[2 * xx], n = bounds[2 * xx + 1];
+  const int* k = coef + (long long)xx * ksize;
+  const uint8_t* row = src + y * pitch + 3LL * xmin;
+  int a0 = 1 << 21, a1 = 1 << 21, a2 = 1 << 21;
+  for (int x = 0; x < n; ++x) {
+    const int w = __ldg(k + x);
+    a0 += row[3 * x] * w;
+    a1 += row[3 * x + 1] * w;
+    a2 += row[3 * x + 2] * w;
+  }
+  uint8_t* o = tmp + 3 * i;
+  o[0] = clip8_fixed(a0);
+  o[1] = clip8_fixed(a1);
+  o[2] = clip8_fixed(a2);
+}
+
+// vertical pass: out[yy][xx][c] from in[ymin .. ymin+n)[xx][c]; one thread per (yy, xx); optional fp32 CHW output
+__global__ void resize_v_u8_kernel(const uint8_t* __restrict__ in, long long pitch, int out_h, int out_w,
+                                   const int* __restrict__ bounds, const int* __restrict__ coef, int ksize,
+                                   uint8_t* __restrict__ out_u8, float* __restrict__ out_f32) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= (long long)out_h * out_w) return;
+  const int yy = static_cast<int>(i / out_w), xx = static_cast<int>(i - (long long)yy * out_w);
+  uint8_t r, g, b;
+  if (bounds != nullptr) {
+    const int ymin = bounds[2 * yy], n = bounds[2 * yy + 1];
+    const int* k = coef + (long long)yy * ksize;
+    const uint8_t* col = in + ymin * pitch + 3LL * xx;
+    int a0 = 1 << 21, a1 = 1 << 21, a2 = 1 << 21;
+    for (int y = 0; y < n; ++y) {
+      const int w = __ldg(k + y);
+      const uint8_t* px = col + y * pitch;
+      a0 += px[0] * w;
+      a1 += px[1] * w;
+      a2 += px[2] * w;
+    }
+    r = clip8_fixed(a0); g = clip8_fixed(a1); b = clip8_fixed(a2);
+  } else {  // the height does not change: Pillow skips the vertical pass
+    const uint8_t* px = in + yy * pitch + 3LL * xx;
+    r = px[0]; g = px[1]; b = px[2];
+  }
+  if (out_u8 != nullptr) {
+    uint8_t* o = out_u8 + 3 * i;
+    o[0] = r; o[1] = g; o[2] = b;
+  }
+  if (out_f32 != nullptr) {  // ToTensor: uint8 -> float, / 255 (IEEE division, as torch)
+    const long long plane = (long long)out_h * out_w;
+    out_f32[i] = static_cast<float>(r) / 255.0f;
+    out_f32[plane + i] = static_cast<float>(g) / 255.0f;
+    out_f32[2 * plane + i] = static_cast<float>(b) / 255.0f;
+  }
+}
+
 }  // namespace g2
 
 // =================================================================================================
@@ -1113,6 +1181,36 @@ extern "C" int g2vlm_rope_vision(void* buf, int64_t ld, int64_t rows, int32_t n_
   const long long total = rows * n_heads_total * (head_dim / 2);
   rope_vision_kernel<<<blocks_for(total, EW_THREADS * 4), EW_THREADS, 0, (cudaStream_t)stream>>>(
       (__nv_bfloat16*)buf, ld, rows, n_heads_total, head_stride, head_dim, cos_tab, sin_tab);
+  G2_LAUNCH_CHECK();
+  return G2VLM_OK;
+}
+
+extern "C" int g2vlm_resize_lanczos_u8(const uint8_t* src, int32_t H, int32_t W, int64_t src_pitch,
+                                       const int32_t* hbounds, const int32_t* hcoef, int32_t hk,
+                                       const int32_t* vbounds, const int32_t* vcoef, int32_t vk, uint8_t* tmp,
+                                       int32_t out_h, int32_t out_w, uint8_t* out_u8, float* out_f32, void* stream) {
+  using namespace g2;
+  G2_REQUIRE(src != nullptr && H > 0 && W > 0 && out_h > 0 && out_w > 0, "resize: bad geometry");
+  G2_REQUIRE(src_pitch >= 3LL * W, "resize: src_pitch smaller than a row");
+  G2_REQUIRE((hbounds == nullptr) == (hcoef == nullptr) && (vbounds == nullptr) == (vcoef == nullptr),
+             "resize: bounds and coefficients must be given together");
+  G2_REQUIRE(hbounds != nullptr || W == out_w, "resize: the width changes but no horizontal tables were given");
+  G2_REQUIRE(vbounds != nullptr || H == out_h, "resize: the height changes but no vertical tables were given");
+  G2_REQUIRE(hbounds == nullptr || (tmp != nullptr && hk > 0), "resize: the horizontal pass needs tmp and hk > 0");
+  G2_REQUIRE(vbounds == nullptr || vk > 0, "resize: vk must be positive");
+  G2_REQUIRE(out_u8 != nullptr || out_f32 != nullptr, "resize: no output buffer");
+  cudaStream_t st = (cudaStream_t)stream;
+  const uint8_t* mid = src;
+  long long mid_pitch = src_pitch;
+  if (hbounds != nullptr) {
+    resize_h_u8_kernel<<<blocks_for((long long)H * out_w, EW_THREADS), EW_THREADS, 0, st>>>(src, src_pitch, H, out_w,
+                                                                                          hbounds, hcoef, hk, tmp);
+    G2_LAUNCH_CHECK();
+    mid = tmp;
+    mid_pitch = 3LL * out_w;
+  }
+  resize_v_u8_kernel<<<blocks_for((long long)out_h * out_w, EW_THREADS), EW_THREADS, 0, st>>>(
+      mid, mid_pitch, out_h, out_w, vbounds, vcoef, vk, out_u8, out_f32);
   G2_LAUNCH_CHECK();
   return G2VLM_OK;
 }

@@ -38,6 +38,95 @@ def load_and_resize14(images: Sequence, new_width: int = 518) -> torch.Tensor:
                                            antialias=True)
 
 
+def lanczos_tables(in_size: int, out_size: int):
+    """Pillow's 8-bit resampling tables for one axis (restates precompute_coeffs + normalize_coeffs_8bpc of
+    Pillow's Resample.c with the Lanczos-3 filter): bounds int32 [out,2] = (first input index, taps) and coef
+    int32 [out, ksize] in 22-bit fixed point.  Checked against PIL bit for bit (tests/test_host_prep_cpu.py)."""
+    import math
+
+    import numpy as np
+    scale = in_size / out_size
+    filterscale = max(scale, 1.0)
+    support = 3.0 * filterscale
+    ksize = int(math.ceil(support)) * 2 + 1
+    bounds = np.zeros((out_size, 2), np.int32)
+    kk = np.zeros((out_size, ksize), np.float64)
+    ss = 1.0 / filterscale
+    for xx in range(out_size):
+        center = (xx + 0.5) * scale
+        xmin = max(int(center - support + 0.5), 0)
+        xmax = min(int(center + support + 0.5), in_size) - xmin
+        t = (np.arange(xmax, dtype=np.float64) + xmin - center + 0.5) * ss
+
+        def sinc(v):
+            out = np.ones_like(v)
+            nz = v != 0.0
+            vv = v[nz] * math.pi
+            out[nz] = np.sin(vv) / vv
+            return out
+
+        w = np.where((t >= -3.0) & (t < 3.0), sinc(t) * sinc(t / 3.0), 0.0)
+        ww = 0.0
+        for v in w:          # sequential double sum, as the C loop
+            ww += float(v)
+        if ww != 0.0:
+            w = w / ww
+        kk[xx, :xmax] = w
+        bounds[xx] = (xmin, xmax)
+    coef = np.where(kk < 0, np.trunc(-0.5 + kk * (1 << 22)), np.trunc(0.5 + kk * (1 << 22))).astype(np.int32)
+    return bounds, coef
+
+
+_TABLE_CACHE: Dict[tuple, tuple] = {}
+_STAGING: Dict[object, object] = {}
+
+
+def load_and_resize14_device(images: Sequence, new_width: int = 518, device="cuda") -> torch.Tensor:
+    """Same result as load_and_resize14 (bit-identical, tests/test_io_gpu.py), but only the decoded uint8 pixels
+    cross PCIe and the LANCZOS resampling + ToTensor run on the device (g2vlm_resize_lanczos_u8).  The trailing
+    antialiased-bilinear resample of the reference is the identity here because the LANCZOS target is already a
+    multiple of 14 in both directions whenever new_width is.  Views that are not plain RGB take the host path."""
+    from PIL import Image
+    import numpy as np
+
+    from . import ops
+    pil = [Image.open(im) if isinstance(im, str) else im for im in images]
+    w0, h0 = pil[0].size
+    tw, th = new_width, round(h0 * (new_width / w0) / 14) * 14
+    if tw % 14 or th % 14 or th <= 0 or any(im.mode != "RGB" for im in pil):
+        return load_and_resize14(pil, new_width).to(device)
+    out = torch.empty(len(pil), 3, th, tw, dtype=torch.float32, device=device)
+
+    def tables(n_in, n_out):
+        if n_in == n_out:
+            return None
+        key = (n_in, n_out, str(device))
+        if key not in _TABLE_CACHE:
+            b, c = lanczos_tables(n_in, n_out)
+            _TABLE_CACHE[key] = (torch.from_numpy(b).to(device), torch.from_numpy(c).to(device))
+        return _TABLE_CACHE[key]
+
+    # one pinned + one device staging slot per view, kept across calls (pinning memory costs ~1 ms per image)
+    ev = _STAGING.get("event")
+    if ev is not None:
+        ev.synchronize()             # the previous call's uploads have left the pinned slots
+    for i, im in enumerate(pil):
+        a = np.asarray(im, dtype=np.uint8)                                    # [H, W, 3] view of the decoded pixels
+        key = (i, a.shape, str(device))
+        slot = _STAGING.get(key)
+        if slot is None:
+            slot = _STAGING[key] = (torch.empty(a.shape, dtype=torch.uint8, pin_memory=True),
+                                    torch.empty(a.shape, dtype=torch.uint8, device=device))
+        pin, src = slot
+        pin.numpy()[...] = a
+        src.copy_(pin, non_blocking=True)
+        ops.resize_lanczos_u8(src, tables(a.shape[1], tw), tables(a.shape[0], th), th, tw, out_f32=out[i])
+    if ev is None:
+        ev = _STAGING["event"] = torch.cuda.Event()
+    ev.record()
+    return out
+
+
 def prepare_prompts_addbos(curr_kvlens: List[int], curr_rope: List[int], prompts: List[str], tokenizer,
                            new_token_ids: Dict[str, int]) -> Tuple[Dict[str, torch.Tensor], List[int], List[int]]:
     """Same signature and outputs as the reference method (g2vlm.py:561-594)."""

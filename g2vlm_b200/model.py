@@ -189,6 +189,7 @@ class G2VLMFast:
         self.device = torch.device(device)
         self.buf = _Buffers(self.device)
         self._stage: Dict[str, dict] = {}
+        self.device_resize = True   # recon(): LANCZOS resize of path / PIL inputs on the device (host_prep)
         self.fuse_prompt = True   # recon(): run the prompt prefill inside the geo step (language_model_forward_geo)
         missing = [k for k in state_dict_schema(cfg) if k not in state_dict and k != "language_model.lm_head.weight"]
         if missing:
@@ -1345,6 +1346,10 @@ class G2VLMFast:
             prompt = gi                                     # the 7 prompt rows ride along with the geo step
         else:
             past = self.forward_cache_update_text(past, **gi)   # index tensors stay on the host: _idx stages them
+        if not torch.is_tensor(images) and self.device_resize:
+            # paths / PIL images: only the decoded uint8 pixels cross PCIe; Pillow-exact LANCZOS + ToTensor on the GPU
+            from .host_prep import load_and_resize14_device
+            images = load_and_resize14_device(images, 518, dev)
         # the raw views cross PCIe once; normalisation happens on the device (bit-identical to the host op)
         gi, newlens, new_rope = self.prepare_dino_images_pi3(newlens, new_rope, images, dino_image_transform,
                                                              new_token_ids, normalize_on_host=False)

@@ -392,3 +392,27 @@ def rope_vision(buf, rows, n_heads_total, head_stride, head_dim, cos, sin):
     _req(sin, torch.float32, "sin")
     _call("g2vlm_rope_vision", _vp(buf.data_ptr()), _i64(buf.stride(0)), _i64(rows), _i32(n_heads_total),
           _i32(head_stride), _i32(head_dim), _vp(cos.data_ptr()), _vp(sin.data_ptr()))
+
+
+def resize_lanczos_u8(src: torch.Tensor, htab, vtab, out_h: int, out_w: int, out_u8: Optional[torch.Tensor] = None,
+                      out_f32: Optional[torch.Tensor] = None):
+    """Pillow-exact LANCZOS resize of one uint8 [H, W, 3] image on the device (see g2vlm_resize_lanczos_u8).
+    htab / vtab: (bounds, coef) int32 device tensors from host_prep.lanczos_tables, or None when that axis keeps
+    its size.  out_u8 uint8 [out_h, out_w, 3] and/or out_f32 fp32 [3, out_h, out_w]."""
+    if src.dtype != torch.uint8 or not src.is_cuda or src.dim() != 3 or src.shape[2] != 3 or src.stride(2) != 1 \
+            or src.stride(1) != 3:
+        raise G2Error("resize_lanczos_u8: src must be a CUDA uint8 [H, W, 3] tensor with packed pixels")
+    H, W = int(src.shape[0]), int(src.shape[1])
+    for t, shape, dt, n in ((out_u8, (out_h, out_w, 3), torch.uint8, "out_u8"), (out_f32, (3, out_h, out_w), torch.float32, "out_f32")):
+        if t is not None and (tuple(t.shape) != shape or t.dtype != dt or not t.is_cuda or not t.is_contiguous()):
+            raise G2Error(f"resize_lanczos_u8: {n} must be a contiguous CUDA {dt} tensor of shape {shape}")
+    tmp = torch.empty(H, out_w, 3, dtype=torch.uint8, device=src.device) if htab is not None else None
+    hb, hc = htab if htab is not None else (None, None)
+    vb, vc = vtab if vtab is not None else (None, None)
+    for t in (hb, hc, vb, vc):
+        if t is not None and (t.dtype != torch.int32 or not t.is_cuda or not t.is_contiguous()):
+            raise G2Error("resize_lanczos_u8: tables must be contiguous CUDA int32 tensors")
+    _call("g2vlm_resize_lanczos_u8", _vp(src.data_ptr()), _i32(H), _i32(W), _i64(src.stride(0)), _ptr(hb), _ptr(hc),
+          _i32(hc.shape[1] if hc is not None else 0), _ptr(vb), _ptr(vc), _i32(vc.shape[1] if vc is not None else 0),
+          _ptr(tmp), _i32(out_h), _i32(out_w), _ptr(out_u8), _ptr(out_f32))
+    return out_f32 if out_f32 is not None else out_u8

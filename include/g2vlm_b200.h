@@ -339,6 +339,25 @@ int g2vlm_argmax_bf16(const void* logits, int64_t ld, int64_t rows, int32_t voca
 int g2vlm_ply_pack(const float* points, const float* images, int32_t n_views, int32_t H, int32_t W,
                    void* out, int32_t* block_counts, int64_t* n_valid, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Input side of the path ("next" row f3): device-side replacement of the per-view
+ *   img_pil.resize((TARGET_W, TARGET_H), Image.Resampling.LANCZOS) ; ToTensor()
+ * of load_images (data/transforms_vggt.py:437-441), bit-exact with Pillow's 8-bit two-pass resampler
+ * (horizontal pass into an 8-bit intermediate, then vertical; per output sample
+ *   clip8((2^21 + sum_k coef[k] * pixel[k]) >> 22),  coefficients = normalised Lanczos-3 weights in 22-bit fixed
+ * point).  The coefficient tables depend only on (input size, output size) and are built on the host
+ * (g2vlm_b200.host_prep.lanczos_tables restates Pillow's precompute_coeffs / normalize_coeffs_8bpc).
+ * src uint8 [H, W, 3] interleaved RGB (row pitch src_pitch bytes);
+ * hbounds int32 [out_w][2] = {first input column, taps}, hcoef int32 [out_w][hk]; vbounds/vcoef likewise for rows;
+ * pass NULL tables for an axis whose size does not change (Pillow skips that pass).
+ * tmp uint8 [H, out_w, 3] workspace (unused when hbounds is NULL);
+ * out_u8 uint8 [out_h, out_w, 3] and/or out_f32 fp32 [3, out_h, out_w] = value / 255 (ToTensor); either may be NULL.
+ * ---------------------------------------------------------------------------------------------- */
+int g2vlm_resize_lanczos_u8(const uint8_t* src, int32_t H, int32_t W, int64_t src_pitch, const int32_t* hbounds,
+                            const int32_t* hcoef, int32_t hk, const int32_t* vbounds, const int32_t* vcoef,
+                            int32_t vk, uint8_t* tmp, int32_t out_h, int32_t out_w, uint8_t* out_u8,
+                            float* out_f32, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -52,3 +52,36 @@ def test_ply_pack_all_invalid_and_large():
     assert np.array_equal(a["x"], pts.view(-1, 3)[:1000, 0].double().cpu().numpy())
     tail = np.frombuffer(rec[-27:].cpu().numpy().tobytes(), dtype=a.dtype)
     assert tail["z"][0] == float(pts.view(-1, 3)[-1, 2])
+
+
+@pytest.mark.parametrize("H,W", [(540, 960), (300, 518), (200, 300), (333, 777)])
+def test_device_lanczos_resize_is_bit_identical_to_pillow(H, W):
+    """g2vlm_resize_lanczos_u8 + ToTensor on the GPU == the reference's host path (PIL LANCZOS resize, ToTensor,
+    identity antialias-bilinear), bit for bit: down-scaling, up-scaling, width already 518 (no horizontal pass)."""
+    from PIL import Image
+
+    from g2vlm_b200 import host_prep
+    rng = np.random.default_rng(H + W)
+    views = []
+    for i in range(3):
+        a = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+        a[:, : W // 2] = np.linspace(0, 255, H)[:, None, None].astype(np.uint8) + i   # smooth half, noisy half
+        views.append(Image.fromarray(a))
+    ref = host_prep.load_and_resize14(views, 518)
+    got = host_prep.load_and_resize14_device(views, 518, "cuda")
+    assert got.shape == ref.shape and got.dtype == torch.float32
+    assert torch.equal(got.cpu(), ref)
+
+
+def test_device_resize_uint8_output_and_errors():
+    from g2vlm_b200 import host_prep, ops
+    from PIL import Image
+    rng = np.random.default_rng(5)
+    a = rng.integers(0, 256, (90, 130, 3), dtype=np.uint8)
+    ref = np.asarray(Image.fromarray(a).resize((56, 42), Image.Resampling.LANCZOS))
+    tabs = [tuple(torch.from_numpy(t).cuda() for t in host_prep.lanczos_tables(n_in, n_out)) for n_in, n_out in ((130, 56), (90, 42))]
+    out = torch.zeros(42, 56, 3, dtype=torch.uint8, device="cuda")
+    ops.resize_lanczos_u8(torch.from_numpy(a).cuda(), tabs[0], tabs[1], 42, 56, out_u8=out)
+    assert np.array_equal(out.cpu().numpy(), ref)
+    with pytest.raises(Exception):   # the width changes but no horizontal tables
+        ops.resize_lanczos_u8(torch.from_numpy(a).cuda(), None, tabs[1], 42, 56, out_u8=out)
