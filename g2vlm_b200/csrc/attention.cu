@@ -28,10 +28,7 @@ constexpr int ATT_BM = 128;       // query rows per tile
 constexpr int ATT_BN = 128;       // keys per block
 constexpr int ATT_THREADS = 384;  // 12 warps
 constexpr float ATT_RESCALE_TAU = 8.0f;
-#ifndef ATT_PCHUNKS_N
-#define ATT_PCHUNKS_N 4
-#endif
-constexpr int ATT_PCHUNKS = ATT_PCHUNKS_N;    // P_t reaches the MMA warp in 4 chunks of 32 keys (PV overlaps the exp tail)
+constexpr int ATT_PCHUNKS = 4;    // P_t reaches the MMA warp in 4 chunks of 32 keys (PV overlaps the exp tail)
 
 struct AttnKParams {
   CUtensorMap tmQ, tmK, tmV;
