@@ -47,6 +47,11 @@ struct GemmKParams {
   const float* residual;
   long long ldr;
   int out_col_group, out_col_stride;  // STORE_BF16 column regrouping (0 = plain)
+  // CTA-pair kernel: B tensor map with a 128-row box (each CTA of the pair loads half of the 256 N rows) and the
+  // tile list in units of M-tile PAIRS (every group padded to an even number of M tiles)
+  CUtensorMap tmBh;
+  int grp_mpair0[3];
+  int num_pair_tiles;
 };
 
 struct TileCoord {
@@ -435,6 +440,178 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ GemmKParams p) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// CTA-pair variant (cluster of 2, tcgen05 cta_group::2): the pair computes a 256 x 256 tile.  Each CTA loads its own
+// 128 A rows and HALF of the 256 B rows per k block (32 KB instead of 48 KB per CTA and per 128x256x64 of MMA work:
+// one third less TMA / L2 / shared-memory operand traffic per FLOP, and a 6-stage ring instead of 4), the leader CTA
+// issues one M = 256 MMA per k step that reads both CTAs' operands, and each CTA keeps the accumulator of its own
+// 128 rows in its own TMEM and runs the unchanged epilogue on it.
+//   full[s]        lives in the leader, whose producer announces the 64 KB of both CTAs; both CTAs' TMA loads
+//                  complete their bytes on it (cp.async.bulk.tensor .cta_group::2)
+//   empty[s], tmem_full[a]   one per CTA, signalled in both CTAs at once by the leader's multicast tcgen05.commit
+//   tmem_empty[a]  lives in the leader; the epilogue warps of both CTAs arrive on it (remote arrive from the peer)
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int PAIR_STAGES = 6;
+constexpr int PAIR_B_BYTES = (BN / 2) * BK * 2;
+constexpr int PAIR_STAGE_BYTES = A_BYTES + PAIR_B_BYTES;   // 32 KB
+constexpr int PAIR_PANEL = 8;                                // rasterisation: 8 M pairs x all N tiles per panel
+constexpr int PAIR_SMEM = PAIR_STAGES * PAIR_STAGE_BYTES + STAGING_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+
+__device__ __forceinline__ TileCoord decode_pair_tile(const GemmKParams& p, int tile, int rank) {
+  const int mp_total = p.grp_mpair0[p.n_groups];
+  const int per_panel = PAIR_PANEL * p.n_tiles_n;
+  const int panel = tile / per_panel;
+  const int r = tile - panel * per_panel;
+  const int panel_h = min(PAIR_PANEL, mp_total - panel * PAIR_PANEL);
+  const int n_tile = r / panel_h;
+  const int mp = panel * PAIR_PANEL + (r - n_tile * panel_h);
+  TileCoord t;
+  t.g = (p.n_groups > 1 && mp >= p.grp_mpair0[1]) ? 1 : 0;
+  const int m_local = 2 * (mp - p.grp_mpair0[t.g]) + rank;
+  t.row0 = p.grp_row0[t.g] + m_local * BM;
+  t.rows_valid = min(BM, p.grp_rows[t.g] - m_local * BM);  // <= 0: this CTA's half of the pair is padding
+  t.n_tile = n_tile;
+  return t;
+}
+
+template <int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ GemmKParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint8_t* staging = smem + PAIR_STAGES * PAIR_STAGE_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + STAGING_BYTES);
+  uint64_t* empty_bar = full_bar + PAIR_STAGES;
+  uint64_t* tmem_full_bar = empty_bar + PAIR_STAGES;
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int rank = static_cast<int>(cluster_ctarank());
+  const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&p.tmA);
+    tma_prefetch_desc(&p.tmBh);
+  }
+  if (warp == 1) {
+    if (elect_one()) {
+      for (int s = 0; s < PAIR_STAGES; ++s) {
+        mbar_init(&full_bar[s], 1);    // the leader announces the bytes of BOTH CTAs (only the leader's copy is used)
+        mbar_init(&empty_bar[s], 1);
+      }
+      for (int s = 0; s < 2; ++s) {
+        mbar_init(&tmem_full_bar[s], 1);
+        mbar_init(&tmem_empty_bar[s], 2 * EPI_WARPS);   // one arrive per epilogue warp of either CTA
+      }
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc_pair<512>(tmem_slot);
+  }
+  tc_fence_before();
+  cluster_sync_all();   // barriers initialised and TMEM allocated in BOTH CTAs before any remote arrive / MMA
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------- TMA producer (both CTAs) ---------------------------------
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = pair; tile < p.num_pair_tiles; tile += n_pairs) {
+        const TileCoord t = decode_pair_tile(p, tile, rank);
+        const int b_row = t.g * p.N + t.n_tile * BN + rank * (BN / 2);
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          const uint32_t full_leader = mapa_shared(smem_u32(&full_bar[stage]), 0);
+          // Only the leader arrives (with the byte count of both CTAs); the peer's bytes may complete on the barrier
+          // before that arrive — the transaction count is signed — but never in an earlier phase: the peer reuses a
+          // stage only after the leader's MMAs, which waited for that phase, have released it.  (A remote
+          // arrive.expect_tx.release.cluster per k block from the peer cost ~1000 cycles each.)
+          if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * PAIR_STAGE_BYTES);
+          uint8_t* sa = smem + stage * PAIR_STAGE_BYTES;
+          tma_load_2d_pair(sa, &p.tmA, full_leader, kb * BK, t.row0);
+          tma_load_2d_pair(sa + A_BYTES, &p.tmBh, full_leader, kb * BK, b_row);
+          if (++stage == PAIR_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------- MMA issuer (leader CTA only) -----------------------------
+    if (rank == 0 && elect_one()) {
+      constexpr uint32_t idesc = umma_idesc_bf16(2 * BM, BN, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = pair; tile < p.num_pair_tiles; tile += n_pairs) {
+        mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + stage * PAIR_STAGE_BYTES);
+          const uint32_t b_addr = a_addr + A_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            umma_ss_pair(d_tmem, umma_desc_kmajor(a_addr + k * 32), umma_desc_kmajor(b_addr + k * 32), idesc,
+                         (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit_pair(&empty_bar[stage]);  // frees the slot in both CTAs once these MMAs retire
+          if (++stage == PAIR_STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit_pair(&tmem_full_bar[acc]);  // accumulators complete -> both CTAs' epilogues
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else {
+    // ------------------------------- epilogue warps (both CTAs, own 128 rows) -----------------
+    const int sub = warp & 3;
+    const int half = (warp - 2) >> 2;
+    uint8_t* stg = staging + (warp - 2) * 4096;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = pair; tile < p.num_pair_tiles; tile += n_pairs) {
+      const TileCoord t = decode_pair_tile(p, tile, rank);
+      mbar_wait(&tmem_full_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(sub * 32) << 16) + acc * BN;
+      if (t.rows_valid > 0) epilogue_tile<EPI>(p, t, taddr, sub, half, lane, stg);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa_shared(smem_u32(&tmem_empty_bar[acc]), 0));
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();   // both CTAs are done with TMEM and with each other's shared memory
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_pair<512>(tmem_base);
+  }
+}
+
+template <int EPI>
+static int launch_gemm_pair(const GemmKParams& kp, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    G2_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_tcgen05_pair_kernel<EPI>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM));
+    attr_set = true;
+  }
+  const int pairs = min(kp.num_pair_tiles, num_sms() / 2);
+  gemm_bf16_tcgen05_pair_kernel<EPI><<<2 * pairs, GEMM_THREADS, PAIR_SMEM, stream>>>(kp);
+  G2_CUDA_OK(cudaGetLastError());
+  return G2VLM_OK;
+}
+
 template <int EPI>
 static int launch_gemm(const GemmKParams& kp, cudaStream_t stream) {
   static bool attr_set = false;
@@ -526,6 +703,32 @@ extern "C" int g2vlm_gemm_bf16(const g2vlm_gemm_args* a, void* stream_) {
   rc = make_tmap_2d_bf16(&kp.tmB, a->B, (uint64_t)a->n_groups * a->N, (uint64_t)a->K, (uint64_t)a->ldb * 2, BN, BK);
   if (rc) return rc;
 
+  // Large problems run on CTA pairs (256 x 256 tiles, cta_group::2); small ones keep one CTA per 128 x 256 tile,
+  // which gives twice as many independent tiles to spread over the SMs.  G2VLM_GEMM_PAIR=0/1 forces either (A/B runs).
+  int mp = 0;
+  for (int g = 0; g < a->n_groups; ++g) {
+    kp.grp_mpair0[g] = mp;
+    mp += cdiv(cdiv(a->group_rows[g], BM), 2);
+  }
+  kp.grp_mpair0[a->n_groups] = mp;
+  if (a->n_groups == 1) kp.grp_mpair0[2] = mp;
+  kp.num_pair_tiles = mp * kp.n_tiles_n;
+  static const int force_pair = [] {
+    const char* e = getenv("G2VLM_GEMM_PAIR");
+    return e == nullptr ? -1 : atoi(e);
+  }();
+  const bool use_pair = force_pair >= 0 ? force_pair != 0 : kp.num_pair_tiles >= num_sms();
+  if (use_pair) {
+    rc = make_tmap_2d_bf16(&kp.tmBh, a->B, (uint64_t)a->n_groups * a->N, (uint64_t)a->K, (uint64_t)a->ldb * 2, BN / 2,
+                           BK);
+    if (rc) return rc;
+    switch (a->epilogue) {
+      case G2VLM_EPI_STORE_BF16: return launch_gemm_pair<G2VLM_EPI_STORE_BF16>(kp, stream);
+      case G2VLM_EPI_SWIGLU_BF16: return launch_gemm_pair<G2VLM_EPI_SWIGLU_BF16>(kp, stream);
+      case G2VLM_EPI_RESID_F32: return launch_gemm_pair<G2VLM_EPI_RESID_F32>(kp, stream);
+      default: return launch_gemm_pair<G2VLM_EPI_STORE_F32>(kp, stream);
+    }
+  }
   switch (a->epilogue) {
     case G2VLM_EPI_STORE_BF16: return launch_gemm<G2VLM_EPI_STORE_BF16>(kp, stream);
     case G2VLM_EPI_SWIGLU_BF16: return launch_gemm<G2VLM_EPI_SWIGLU_BF16>(kp, stream);
