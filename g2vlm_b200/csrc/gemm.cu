@@ -1,6 +1,7 @@
 // g2vlm_b200 — grouped (token-type-routed) bf16 GEMM on tcgen05 tensor cores.
 //
-// One persistent, warp-specialised kernel per epilogue:
+// Two persistent, warp-specialised kernels per epilogue: gemm_bf16_tcgen05_pair_kernel (CTA pairs, cta_group::2,
+// 256x256 tiles; used whenever there are enough tiles, see its comment block below) and the 1-CTA kernel:
 //   warp 0      TMA producer   (cp.async.bulk.tensor, 128-byte swizzle, 4-stage mbarrier ring)
 //   warp 1      MMA issuer     (tcgen05.mma 128x256x16, fp32 accumulators in TMEM, 2 accumulator
 //                               stages so the epilogue of tile i overlaps the main loop of i+1)
