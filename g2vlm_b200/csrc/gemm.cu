@@ -132,9 +132,7 @@ __device__ __forceinline__ float4 stage_read_f32(const uint8_t* stg, int lane, i
   return *reinterpret_cast<const float4*>(stg + row * 128 + ((lane & 7) ^ (row & 7)) * 16);
 }
 
-// PREFETCH (RESID_F32 only): request the NEXT chunk's residual values one chunk ahead (long main loops) instead of
-// right before this chunk's accumulator load (short main loops, where the epilogue is the critical path).
-template <int EPI, bool PREFETCH = false>
+template <int EPI>
 __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, const TileCoord& t, uint32_t taddr,
                                               int sub, int half, int lane, uint8_t* stg) {
   const int rows_ok = t.rows_valid - sub * 32;  // rows of this warp's 32-row slab that are real
@@ -170,35 +168,22 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, const TileCo
   } else {
     const float* bias = p.bias ? p.bias + (long long)t.g * p.N : nullptr;
     const bool use_scale = p.scale != nullptr && ((p.scale_groups >> t.g) & 1u);
-    [[maybe_unused]] float4 old[8], old_next[8];
-    constexpr bool prefetch_old = PREFETCH;
-    [[maybe_unused]] auto load_old = [&](int cc, float4 (&dst)[8]) {
-      const int cb = n0 + cc * 32;
-      const int ok_cols = min(32, p.N - cb);   // <= 0 when the chunk lies beyond N
-      const int q4 = (lane & 7) * 4;
-      const float* src = reinterpret_cast<const float*>(p.out) + (row_base + (lane >> 3)) * p.ldo + cb + q4;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        dst[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (i * 4 + (lane >> 3) < rows_ok && q4 + 4 <= ok_cols)
-          dst[i] = *reinterpret_cast<const float4*>(src + (long long)i * 4 * p.ldo);
-      }
-    };
 #pragma unroll 1
     for (int c = half * 4; c < half * 4 + 4; ++c) {
       const int col0 = n0 + c * 32;
       if (col0 >= p.N) break;  // warp-uniform
       const int cols_ok = min(32, p.N - col0);
       const int c4 = (lane & 7) * 4;  // this lane's 4 columns in the transposed (coalesced) domain
+      [[maybe_unused]] float4 old[8];
       [[maybe_unused]] float* out_piece = nullptr;
       if constexpr (EPI == G2VLM_EPI_RESID_F32) {
-        // `old` holds this chunk's residual values: they were requested one chunk earlier (before the previous
-        // chunk's TMEM load / math / stores), so a full HBM round trip is hidden; now request the next chunk's.
         out_piece = reinterpret_cast<float*>(p.out) + (row_base + (lane >> 3)) * p.ldo + col0 + c4;
-        // (Only when the main loop is long: with K <= 2048 the epilogue is the critical path and requesting the
-        //  next chunk's rows right before this chunk's stores made o_proj / DINO dense 15-30 % slower.)
-        if (!prefetch_old || c == half * 4) load_old(c, old);
-        if (prefetch_old && c + 1 < half * 4 + 4) load_old(c + 1, old_next);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          old[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (i * 4 + (lane >> 3) < rows_ok && c4 + 4 <= cols_ok)
+            old[i] = *reinterpret_cast<const float4*>(out_piece + (long long)i * 4 * p.ldo);
+        }
       }
       uint32_t v[32];
       tmem_ld32(taddr + c * 32, v);
@@ -262,8 +247,8 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, const TileCo
             for (int j = 0; j < 32; ++j) f[j] = bf16_round(f[j]);
           }
         }
-        // RMW of the fp32 residual stream in the transposed (coalesced) domain; the 8 old values were requested
-        // one chunk ago (see the top of the loop).
+        // RMW of the fp32 residual stream in the transposed (coalesced) domain. The 8 old values were
+        // loaded BEFORE the accumulator chunk was read (`old`, below), so their latency is hidden.
         stage_write_f32(stg, lane, f);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -289,10 +274,6 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, const TileCo
           }
         }
         __syncwarp();
-        if (prefetch_old) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) old[i] = old_next[i];
-        }
       } else {  // G2VLM_EPI_STORE_F32
         if (p.flags & G2VLM_GEMM_ROUND_BF16) {
 #pragma unroll
@@ -444,8 +425,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ GemmKParams p) {
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(sub * 32) << 16) + acc * BN;
-      if (EPI == G2VLM_EPI_RESID_F32 && p.num_kb > 32) epilogue_tile<EPI, true>(p, t, taddr, sub, half, lane, stg);
-      else epilogue_tile<EPI, false>(p, t, taddr, sub, half, lane, stg);
+      epilogue_tile<EPI>(p, t, taddr, sub, half, lane, stg);
       tc_fence_before();
       mbar_arrive(&tmem_empty_bar[acc]);
       acc ^= 1;
@@ -602,10 +582,7 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ GemmKParams p) {
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(sub * 32) << 16) + acc * BN;
-      if (t.rows_valid > 0) {
-        if (EPI == G2VLM_EPI_RESID_F32 && p.num_kb > 32) epilogue_tile<EPI, true>(p, t, taddr, sub, half, lane, stg);
-        else epilogue_tile<EPI, false>(p, t, taddr, sub, half, lane, stg);
-      }
+      if (t.rows_valid > 0) epilogue_tile<EPI>(p, t, taddr, sub, half, lane, stg);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(mapa_shared(smem_u32(&tmem_empty_bar[acc]), 0));
