@@ -617,11 +617,14 @@ class G2VLMFast:
     def generate_text(self, past_key_values, packed_key_value_indexes, key_values_lens, packed_start_tokens,
                       packed_query_position_ids, max_length: int, do_sample: bool = False, temperature: float = 1.0,
                       end_token_id: Optional[int] = None, return_logits: bool = False, use_cuda_graph: bool = False):
-        """Greedy decode loop of the reference (g2vlm.py:1070-1141), batch 1: returns the generated ids
-        [steps, 1] INCLUDING the start token, like the reference.  The KV cache is appended in place."""
+        """Decode loop of the reference (g2vlm.py:1070-1141), batch 1: returns the generated ids [steps, 1]
+        INCLUDING the start token, like the reference.  The KV cache is appended in place.  Greedy decoding runs
+        the native one-call step; do_sample=True keeps the reference's sampling tail — softmax(logits /
+        temperature) in fp32 and torch.multinomial (g2vlm.py:1122-1124) — as torch ops after the lm_head GEMM
+        (it draws from torch's CUDA generator, so a seed reproduces a run; not bit-comparable to a CPU reference)."""
         cfg, dev = self.cfg, self.device
-        if do_sample:
-            raise NotImplementedError("only greedy decoding (do_sample=False) is implemented")
+        if do_sample and not temperature > 0:
+            raise ValueError("temperature must be positive")
         if self.lm_head is None:
             raise RuntimeError("generate_text needs language_model.lm_head.weight in the state_dict")
         cache = KVCache.adopt(past_key_values, cfg, dev)
@@ -644,11 +647,15 @@ class G2VLMFast:
             y = self._und_forward(x, pos, cache, causal=True, len_dev=len_dev, kv_bound=bound)
             ops.cast_bf16(y, yb)
             ops.gemm(yb, self.lm_head, logits, epilogue=ops.EPI_STORE_BF16)
-            ops.argmax_bf16(logits[:, :V], cur)
+            if do_sample:
+                probs = torch.softmax((logits[:, :V] / temperature).float(), dim=-1)   # bf16 divide, fp32 softmax
+                cur.copy_(torch.multinomial(probs, num_samples=1).squeeze(1))
+            else:
+                ops.argmax_bf16(logits[:, :V], cur)
             pos.add_(1)
             len_dev.add_(1)
 
-        if not return_logits:
+        if not return_logits and not do_sample:
             # native driver: the whole step (~260 launches) is enqueued by ONE C-ABI call
             args, keep = self._decode_args(cache, bound, cur, pos, len_dev)
 
@@ -659,7 +666,7 @@ class G2VLMFast:
         check_every = 8
         while n_done < max_length:
             tokens[n_done].copy_(cur[0])
-            if use_cuda_graph and n_done == 1 and graph is None and not return_logits:
+            if use_cuda_graph and n_done == 1 and graph is None and not return_logits and not do_sample:
                 torch.cuda.synchronize()
                 graph = torch.cuda.CUDAGraph()
                 # capture WITHOUT executing: the captured launches read token / position / length from device

@@ -233,8 +233,9 @@ def test_unsupported_calls_fail_loudly(tiny):
     gi, _, _ = model.prepare_prompts_addbos([3], [3], ["x"], StubTokenizer(), TOKENS)
     with pytest.raises(ValueError, match="cache length"):
         model.forward_cache_update_text(NaiveCache(schema.TINY.num_layers), **gi)   # kv lens != cache contents
-    with pytest.raises(NotImplementedError):
-        model.generate_text(None, None, None, torch.tensor([1]), torch.zeros(3, 1, dtype=torch.long), 2, do_sample=True)
+    with pytest.raises(ValueError, match="temperature"):
+        model.generate_text(None, None, None, torch.tensor([1]), torch.zeros(3, 1, dtype=torch.long), 2, do_sample=True,
+                            temperature=0.0)
 
 
 def test_chat_prefill_and_greedy_decode_match_reference(tiny):
@@ -381,3 +382,33 @@ def test_fused_prompt_prefill_matches_separate_pass():
     assert _maxrel(c1["last_hidden"], c2["last_hidden"]) < 2e-3
     for k in keys:
         assert _maxrel(a[k], b[k]) < 2e-3, k
+
+
+def test_generate_text_sampling_tail(tiny):
+    """do_sample=True (reference g2vlm.py:1122-1124): at a vanishing temperature the sampled ids equal the greedy
+    ids; at temperature 1 a fixed torch seed reproduces the run and ids stay inside the vocabulary."""
+    from g2vlm_b200.model import NaiveCache
+    sd, model = tiny
+    cfg = schema.TINY
+
+    def prefill():
+        n = 5
+        gi = dict(text_token_lens=torch.tensor([n], dtype=torch.int), packed_text_ids=torch.tensor([31, 32, 33, 34, 35]),
+                  packed_text_position_ids=torch.arange(n).expand(3, -1), packed_text_indexes=torch.arange(n),
+                  packed_key_value_indexes=torch.arange(0), key_values_lens=torch.tensor([0], dtype=torch.int))
+        return model.forward_cache_update_text(NaiveCache(cfg.num_layers), **gi), n
+
+    def run(**kw):
+        past, n = prefill()
+        return model.generate_text(past, torch.arange(n), torch.tensor([n], dtype=torch.int), torch.tensor([23]),
+                                   torch.full((3, 1), n), 6, **kw)[:, 0].tolist()
+
+    greedy = run()
+    assert run(do_sample=True, temperature=1e-3) == greedy
+    torch.manual_seed(7)
+    a = run(do_sample=True, temperature=1.0)
+    torch.manual_seed(7)
+    b = run(do_sample=True, temperature=1.0)
+    assert a == b and len(a) == 6 and all(0 <= t < cfg.vocab_size for t in a)
+    with pytest.raises(ValueError):
+        run(do_sample=True, temperature=0.0)
