@@ -53,6 +53,7 @@ struct GemmKParams {
   CUtensorMap tmBh;
   int grp_mpair0[3];
   int num_pair_tiles;
+  int pair_panel;   // rasterisation: pair_panel M pairs x all N tiles per panel
 };
 
 struct TileCoord {
@@ -455,17 +456,16 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ GemmKParams p) {
 constexpr int PAIR_STAGES = 6;
 constexpr int PAIR_B_BYTES = (BN / 2) * BK * 2;
 constexpr int PAIR_STAGE_BYTES = A_BYTES + PAIR_B_BYTES;   // 32 KB
-constexpr int PAIR_PANEL = 8;                                // rasterisation: 8 M pairs x all N tiles per panel
 constexpr int PAIR_SMEM = PAIR_STAGES * PAIR_STAGE_BYTES + STAGING_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 
 __device__ __forceinline__ TileCoord decode_pair_tile(const GemmKParams& p, int tile, int rank) {
   const int mp_total = p.grp_mpair0[p.n_groups];
-  const int per_panel = PAIR_PANEL * p.n_tiles_n;
+  const int per_panel = p.pair_panel * p.n_tiles_n;
   const int panel = tile / per_panel;
   const int r = tile - panel * per_panel;
-  const int panel_h = min(PAIR_PANEL, mp_total - panel * PAIR_PANEL);
+  const int panel_h = min(p.pair_panel, mp_total - panel * p.pair_panel);
   const int n_tile = r / panel_h;
-  const int mp = panel * PAIR_PANEL + (r - n_tile * panel_h);
+  const int mp = panel * p.pair_panel + (r - n_tile * panel_h);
   TileCoord t;
   t.g = (p.n_groups > 1 && mp >= p.grp_mpair0[1]) ? 1 : 0;
   const int m_local = 2 * (mp - p.grp_mpair0[t.g]) + rank;
@@ -714,6 +714,15 @@ extern "C" int g2vlm_gemm_bf16(const g2vlm_gemm_args* a, void* stream_) {
   kp.grp_mpair0[a->n_groups] = mp;
   if (a->n_groups == 1) kp.grp_mpair0[2] = mp;
   kp.num_pair_tiles = mp * kp.n_tiles_n;
+  // Panel height: the A rows of a panel stay in L2 while every N tile sweeps over them, so short-K problems want
+  // tall panels (B = the weights stream from HBM once per panel) and long-K problems short ones (the A panel
+  // itself must fit next to B).  Target ~24 MB of A per panel (same-box sweep: gate/up K=1536 857 us at 32 pairs
+  // vs 906 at 4; down K=8960 431 us at 4 vs 459 at 32).
+  {
+    const long long per_pair_bytes = 2LL * BM * a->K * 2;
+    long long ph = (24LL << 20) / per_pair_bytes;
+    kp.pair_panel = (int)(ph < 4 ? 4 : (ph > 32 ? 32 : ph));
+  }
   static const int force_pair = [] {
     const char* e = getenv("G2VLM_GEMM_PAIR");
     return e == nullptr ? -1 : atoi(e);
