@@ -18,7 +18,7 @@ permutation invariant, and the result is scattered back to the packed order at t
 from __future__ import annotations
 
 import math
-from typing import Dict, List, Optional, Sequence
+from typing import Dict, Optional, Sequence
 
 import torch
 

@@ -8,7 +8,7 @@ The JSON configs of the released checkpoint are not in the reference repo, so di
 from __future__ import annotations
 
 from collections import OrderedDict
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 from typing import Dict, Tuple
 
 import torch

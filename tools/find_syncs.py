@@ -10,7 +10,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 
 from g2vlm_b200 import schema
-from g2vlm_b200.model import G2VLMFast, NaiveCache
+from g2vlm_b200.model import G2VLMFast
 from g2vlm_b200.serving import ReconServer
 
 
