@@ -412,3 +412,17 @@ def test_generate_text_sampling_tail(tiny):
     assert a == b and len(a) == 6 and all(0 <= t < cfg.vocab_size for t in a)
     with pytest.raises(ValueError):
         run(do_sample=True, temperature=0.0)
+
+
+def test_recon_is_deterministic_and_handles_a_single_view(tiny):
+    """Two runs on the same input are bit-identical (no atomics / split-K on the recon path), and one view works
+    (the global-points decoder then cross-attends the view to itself)."""
+    sd, model = tiny
+    v = schema.synthetic_views(1, 56, 84, seed=21)
+    a = model.recon(StubTokenizer(), dict(TOKENS), None, v)
+    a = {k: a[k].clone() for k in ("points", "local_points", "global_points", "camera_poses")}
+    b = model.recon(StubTokenizer(), dict(TOKENS), None, v)
+    for k in a:
+        assert torch.equal(a[k], b[k]), k
+        assert torch.isfinite(a[k]).all(), k
+    assert a["camera_poses"].shape[-3:] == (1, 4, 4)     # [B=1, N=1, 4, 4] like the reference
