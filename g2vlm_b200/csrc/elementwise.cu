@@ -47,6 +47,10 @@ __device__ __forceinline__ void store4(void* out, bool bf16, long long off, floa
   }
 }
 
+// out_mode bit 1: the module itself is bf16 (training forward, reference Qwen2RMSNorm with a bf16 input): the normalised
+// value is cast to bf16 before the weight multiply (modeling_qwen2_vl.py:501 `weight * hidden.to(input_dtype)`)
+__device__ __forceinline__ float rn_(float x, int out_mode) { return (out_mode & 2) ? bf16_round(x) : x; }
+
 __global__ void rmsnorm_routed_kernel(const float* __restrict__ x, long long ldx, void* __restrict__ out,
                                       long long ldo, int out_bf16, const float* __restrict__ w_a,
                                       const float* __restrict__ w_b, long long rows, long long n_first,
@@ -67,7 +71,8 @@ __global__ void rmsnorm_routed_kernel(const float* __restrict__ x, long long ldx
   for (int i = lane; i < n4; i += 32) {
     const float4 v = xr[i];  // second pass hits L1
     const float4 g = __ldg(w + i);
-    store4(out, out_bf16, row * ldo + 4LL * i, g.x * (v.x * r), g.y * (v.y * r), g.z * (v.z * r), g.w * (v.w * r));
+    store4(out, out_bf16 & 1, row * ldo + 4LL * i, g.x * rn_(v.x * r, out_bf16), g.y * rn_(v.y * r, out_bf16),
+           g.z * rn_(v.z * r, out_bf16), g.w * rn_(v.w * r, out_bf16));
   }
 }
 
@@ -95,8 +100,8 @@ rmsnorm_routed_reg_kernel(const float* __restrict__ x, long long ldx, void* __re
   for (int u = 0; u < NV; ++u) {
     const int i = lane + 32 * u;
     const float4 g = __ldg(w + i);
-    store4(out, out_bf16, row * ldo + 4LL * i, g.x * (v[u].x * r), g.y * (v[u].y * r), g.z * (v[u].z * r),
-           g.w * (v[u].w * r));
+    store4(out, out_bf16 & 1, row * ldo + 4LL * i, g.x * rn_(v[u].x * r, out_bf16), g.y * rn_(v[u].y * r, out_bf16),
+           g.z * rn_(v[u].z * r, out_bf16), g.w * rn_(v[u].w * r, out_bf16));
   }
 }
 
@@ -129,8 +134,8 @@ rmsnorm_routed_block_kernel(const float* __restrict__ x, long long ldx, void* __
     const int i = threadIdx.x + 256 * u;
     if (i < n4) {
       const float4 g = __ldg(w + i);
-      store4(out, out_bf16, row * ldo + 4LL * i, g.x * (v[u].x * r), g.y * (v[u].y * r), g.z * (v[u].z * r),
-             g.w * (v[u].w * r));
+      store4(out, out_bf16 & 1, row * ldo + 4LL * i, g.x * rn_(v[u].x * r, out_bf16), g.y * rn_(v[u].y * r, out_bf16),
+             g.z * rn_(v[u].z * r, out_bf16), g.w * rn_(v[u].w * r, out_bf16));
     }
   }
 }
@@ -272,10 +277,12 @@ __global__ void qknorm_mrope_kernel(__nv_bfloat16* __restrict__ qkv, long long l
     float n = v[e] * r;
     if (round_normed) n = bf16_round(n);
     n = gw[e] * n;
+    if (round_normed == 2) n = bf16_round(n);
     const float partner = __shfl_xor_sync(0xffffffffu, n, 16);
     // rotate_half: first half gets -x2, second half gets +x1
     const float rot = lane < 16 ? -partner : partner;
-    o[e] = n * cs[e] + rot * sn[e];
+    o[e] = round_normed == 2 ? bf16_round(n * bf16_round(cs[e])) + bf16_round(rot * bf16_round(sn[e]))
+                             : n * cs[e] + rot * sn[e];
   }
   *reinterpret_cast<uint2*>(p) = make_uint2(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]));
 }
@@ -334,9 +341,11 @@ qknorm_mrope_row_kernel(__nv_bfloat16* __restrict__ qkv, long long ld, long long
       float n = v[e] * r;
       if (round_normed) n = bf16_round(n);
       n = (is_q ? wq[e] : wk[e]) * n;
+      if (round_normed == 2) n = bf16_round(n);
       const float partner = __shfl_xor_sync(0xffffffffu, n, 8);
       const float rot = k < 8 ? -partner : partner;  // rotate_half: first half gets -x2, second half gets +x1
-      o8[e] = n * cs[e] + rot * sn[e];
+      o8[e] = round_normed == 2 ? bf16_round(n * bf16_round(cs[e])) + bf16_round(rot * bf16_round(sn[e]))
+                                : n * cs[e] + rot * sn[e];
     }
     p[32 * u] = make_uint4(pack_bf16x2(o8[0], o8[1]), pack_bf16x2(o8[2], o8[3]), pack_bf16x2(o8[4], o8[5]),
                            pack_bf16x2(o8[6], o8[7]));

@@ -465,18 +465,23 @@ class G2VLMFast:
     # MoT language model
     # ------------------------------------------------------------------------------------------
     def _mot_layer(self, L, x, T, n_geo, qkv, attn, act, hbuf, cos, sin, work, kv_rows, causal, round_normed,
-                   kv_exchange=None, kv_len_dev=None, prompt_rows=0):
+                   kv_exchange=None, kv_len_dev=None, prompt_rows=0, train=None):
         # prompt_rows: the LAST prompt_rows of the T rows are the causal text prefill riding along with the geo
         # step (fused recon path); they take the und branch's rounding of the normed q/k (round_normed=True)
         cfg = self.cfg
         H, I = cfg.hidden_size, cfg.intermediate_size
         nq, nkv, hd = cfg.num_heads, cfg.num_kv_heads, cfg.head_dim
         groups = [(0, n_geo), (n_geo, T - n_geo)]
-        ops.rmsnorm_routed(x, hbuf, L["input_layernorm_geo"], L["input_layernorm_und"], n_geo, cfg.rms_norm_eps, rows=T)
+        # train = dict(perm, qkv_packed, attn_packed): the bf16-module numerics of forward_train (extra bf16 rounding in
+        # the norms / rotary, bf16 residual stream) and attention in PACKED row order (its masks depend on positions)
+        rn = train is not None
+        resid_flags = ops.GEMM_ROUND_AFTER_SCALE | (ops.GEMM_ROUND_SUM if rn else 0)
+        ops.rmsnorm_routed(x, hbuf, L["input_layernorm_geo"], L["input_layernorm_und"], n_geo, cfg.rms_norm_eps, rows=T,
+                           round_normed=rn)
         ops.gemm(hbuf[:T], L["wqkv"], qkv, epilogue=ops.EPI_STORE_BF16, groups=groups, bias=L["bqkv"])
         Tm = T - prompt_rows
         ops.qknorm_mrope(qkv, Tm, n_geo, nq, nkv, hd, L["q_norm_geo"], L["k_norm_geo"], L["q_norm_und"],
-                         L["k_norm_und"], cos, sin, cfg.rms_norm_eps, round_normed=round_normed)
+                         L["k_norm_und"], cos, sin, cfg.rms_norm_eps, round_normed=2 if rn else round_normed)
         if prompt_rows:
             ops.qknorm_mrope(qkv[Tm:], prompt_rows, 0, nq, nkv, hd, L["q_norm_geo"], L["k_norm_geo"], L["q_norm_und"],
                              L["k_norm_und"], cos[Tm:], sin[Tm:], cfg.rms_norm_eps, round_normed=True)
@@ -484,7 +489,13 @@ class G2VLMFast:
             k_all, v_all = qkv[:kv_rows, nq * hd:(nq + nkv) * hd], qkv[:kv_rows, (nq + nkv) * hd:]
         else:  # view-sharded: all ranks' K/V rows (+ prefix) gathered over NVLink
             k_all, v_all = kv_exchange(qkv)
-        if T == 1 and nq // nkv <= 8:
+        if rn:
+            qp, ap = train["qkv_packed"], train["attn_packed"]
+            ops.gather_rows(qkv[:T], qp, train["perm"], T, scatter=True)          # internal -> packed row order
+            ops.attention(qp[:, : nq * hd], qp[:, nq * hd:(nq + nkv) * hd], qp[:, (nq + nkv) * hd:], ap, work,
+                          num_q_heads=nq, num_kv_heads=nkv, head_dim=hd, scale=1.0 / math.sqrt(hd))
+            ops.gather_rows(ap, attn, train["perm"], T)                            # packed -> internal
+        elif T == 1 and nq // nkv <= 8:
             # decode step: one query row sees every cached key -> flash-decoding split over the keys
             ws = self.buf.get("und.dec_ws", (ops.attention_decode_workspace_floats(k_all.shape[0], nq),), torch.float32)
             ops.attention_decode(qkv[0, : nq * hd], k_all, v_all, attn[0], ws, num_q_heads=nq, num_kv_heads=nkv,
@@ -493,12 +504,12 @@ class G2VLMFast:
             ops.attention(qkv[:T, : nq * hd], k_all, v_all, attn, work, num_q_heads=nq, num_kv_heads=nkv, head_dim=hd,
                           scale=1.0 / math.sqrt(hd), causal=causal)
         ops.gemm(attn[:T], L["wo"], x, epilogue=ops.EPI_RESID_F32, groups=groups, scale=L["ls1"], scale_groups=1,
-                 flags=ops.GEMM_ROUND_AFTER_SCALE)
+                 flags=resid_flags)
         ops.rmsnorm_routed(x, hbuf, L["post_attention_layernorm_geo"], L["post_attention_layernorm_und"], n_geo,
-                           cfg.rms_norm_eps, rows=T)
+                           cfg.rms_norm_eps, rows=T, round_normed=rn)
         ops.gemm(hbuf[:T], L["wgu"], act, epilogue=ops.EPI_SWIGLU_BF16, groups=groups)
         ops.gemm(act[:T], L["wdown"], x, epilogue=ops.EPI_RESID_F32, groups=groups, scale=L["ls2"], scale_groups=1,
-                 flags=ops.GEMM_ROUND_AFTER_SCALE)
+                 flags=resid_flags)
 
     def _mot_buffers(self, rows_q: int, rows_kv: int):
         cfg = self.cfg
@@ -690,6 +701,59 @@ class G2VLMFast:
         out = [tokens[i:i + 1] for i in range(n_done)]
         ids = torch.stack(out, dim=0)
         return (ids, all_logits) if return_logits else ids
+
+    @torch.no_grad()
+    def language_model_forward_train(self, packed_sequence, sample_lens, split_lens, attn_modes, packed_position_ids,
+                                     packed_und_token_indexes, packed_geo_token_indexes):
+        """FORWARD of Qwen2VLModel.forward_train (reference g2vlm/qwen2vl.py:1200-1266, layers :783-840 / :445-553)
+        for a packed batch of samples, with the numerics of the bf16 module the training path requires (bf16 residual
+        stream, bf16 arithmetic in RMSNorm / rotary; pass bf16-representable weights, as FSDP mixed precision holds).
+        split_lens / attn_modes: one list per sample ('causal' text splits, 'full' image splits — data_utils.py:10-37:
+        a token sees every earlier split of its sample and its own split causally / fully); 'noise' splits are not
+        supported.  Each split is one attention segment with its own causal flag; the rows keep the expert-permuted
+        order for the grouped GEMMs and are put back in packed order around the attention, whose masks depend on
+        position.  Returns the routed final norm, fp32 [T, H] (bf16 values).  No backward: parity of the forward only."""
+        cfg, dev = self.cfg, self.device
+        nq, nkv, hd, H = cfg.num_heads, cfg.num_kv_heads, cfg.head_dim, cfg.hidden_size
+        T = int(sum(sample_lens))
+        geo_i, und_i = packed_geo_token_indexes.long().cpu(), packed_und_token_indexes.long().cpu()
+        n_geo = int(geo_i.numel())
+        perm = self._idx("train.perm", torch.cat([geo_i, und_i]))
+        if int(perm.numel()) != T or packed_sequence.shape[0] != T:
+            raise ValueError("geo + und indexes must cover every packed row exactly once")
+        items, off = [], 0
+        for n, lens, modes in zip(sample_lens, split_lens, attn_modes):
+            if sum(lens) != n:
+                raise ValueError("split_lens must add up to sample_lens")
+            c = off
+            for ln, mode in zip(lens, modes):
+                if mode not in ("causal", "full"):
+                    raise NotImplementedError(f"attention mode {mode!r} is not supported")
+                items += [[t0, c, c + ln, off, c + ln, int(mode == "causal"), 0, 0]
+                          for t0 in range(c, c + ln, ops.ATTN_ROWS_PER_ITEM)]
+                c += ln
+            off += n
+        work = self._idx("train.work", torch.tensor(items, dtype=torch.int32).reshape(-1, 8), torch.int32)
+        x = self.buf.get("train.x", (T, H), torch.float32)
+        ops.gather_rows(packed_sequence.to(dev, torch.float32).contiguous(), x, perm, T)
+        cos_p = self.buf.get("train.cos_p", (T, hd // 2), torch.float32)
+        sin_p = self.buf.get("train.sin_p", (T, hd // 2), torch.float32)
+        ops.mrope_table(self._idx("train.pos", packed_position_ids.contiguous()), self.inv_freq, cos_p, sin_p,
+                        cfg.mrope_section)
+        cos = self.buf.get("train.cos", (T, hd // 2), torch.float32)
+        sin = self.buf.get("train.sin", (T, hd // 2), torch.float32)
+        ops.gather_rows(cos_p, cos, perm, T)
+        ops.gather_rows(sin_p, sin, perm, T)
+        qkv, attn, act, hbuf = self._mot_buffers(T, T)
+        train = dict(perm=perm, qkv_packed=self.buf.get("train.qkv_p", tuple(qkv.shape), torch.bfloat16),
+                     attn_packed=self.buf.get("train.attn_p", tuple(attn.shape), torch.bfloat16))
+        for L in self.layers:
+            self._mot_layer(L, x, T, n_geo, qkv, attn, act, hbuf, cos, sin, work, T, False, False, train=train)
+        yb = self.buf.get("train.yb", (T, H), torch.bfloat16)
+        ops.rmsnorm_routed(x, yb, self.norm_geo, self.norm_und, n_geo, cfg.rms_norm_eps, rows=T, round_normed=True)
+        y = torch.empty(T, H, dtype=torch.bfloat16, device=dev)
+        ops.gather_rows(yb, y, perm, T, scatter=True)
+        return y.float()
 
     @torch.no_grad()
     def language_model_forward_geo(self, packed_sequence, packed_position_ids, packed_geo_token_indexes,

@@ -199,11 +199,11 @@ def gather_rows(src: torch.Tensor, dst: torch.Tensor, idx: Optional[torch.Tensor
     return dst
 
 
-def rmsnorm_routed(x, out, w_a, w_b, n_first: int, eps: float, rows: Optional[int] = None):
+def rmsnorm_routed(x, out, w_a, w_b, n_first: int, eps: float, rows: Optional[int] = None, round_normed: bool = False):
     _req(x, torch.float32, "x")
     rows = x.shape[0] if rows is None else rows
     _call("g2vlm_rmsnorm_routed", _vp(x.data_ptr()), _i64(x.stride(0)), _vp(out.data_ptr()),
-          _i64(out.stride(0)), _i32(int(out.dtype == torch.bfloat16)), _vp(w_a.data_ptr()),
+          _i64(out.stride(0)), _i32(int(out.dtype == torch.bfloat16) | (2 if round_normed else 0)), _vp(w_a.data_ptr()),
           _vp(w_b.data_ptr()), _i64(rows), _i64(n_first), _i32(x.shape[1]), _f32(eps))
     return out
 

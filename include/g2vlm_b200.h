@@ -161,7 +161,9 @@ int g2vlm_gather_rows(const void* src, int64_t src_pitch_bytes, void* dst, int64
 
 /* Qwen2RMSNorm (modeling/qwen2vl/modeling_qwen2_vl.py:496-501), routed (g2vlm/qwen2vl.py:862-865,
  * 897-898, 1326-1328): out = w * (x * rsqrt(mean(x^2) + eps)), x fp32 [rows, dim].
- * out_bf16 != 0: out is bf16 (the `.to(torch.bfloat16)` that follows the norm), else fp32. */
+ * out_bf16 bit 0: out is bf16 (the `.to(torch.bfloat16)` that follows the norm), else fp32;
+ * bit 1 (training forward, bf16 module): the normalised value is rounded to bf16 before the weight multiply
+ * (`self.weight * hidden_states.to(input_dtype)` with a bf16 input, :501). */
 int g2vlm_rmsnorm_routed(const float* x, int64_t ldx, void* out, int64_t ldo, int32_t out_bf16,
                          const float* w_a, const float* w_b, int64_t rows, int64_t n_first,
                          int32_t dim, float eps, void* stream);
@@ -185,7 +187,9 @@ int g2vlm_mrope_table(const int64_t* position_ids, int64_t ld_pos, const float* 
 /* Per-head RMSNorm + M-RoPE, in place on a fused bf16 QKV buffer [rows, ld] whose columns are
  * [q heads | k heads | v heads] x head_dim (=128): routed q_norm/k_norm weights, fp32 math, bf16
  * result (g2vlm/qwen2vl.py:600-619; rotate_half modeling_qwen2_vl.py:170-174, 229-231).
- * round_normed != 0 reproduces the `und` branch where the norm runs on a bf16 tensor (:575-576). */
+ * round_normed = 1 reproduces the `und` branch where the norm runs on a bf16 tensor (:575-576);
+ * round_normed = 2 is the bf16 MODULE of the training forward (:493-512): additionally the weight multiply, cos/sin
+ * (`cos.to(x.dtype)`) and both rotation products are rounded to bf16, as bf16 tensor arithmetic does. */
 int g2vlm_qknorm_mrope(void* qkv, int64_t ld, int64_t rows, int64_t n_first, int32_t n_q_heads,
                        int32_t n_kv_heads, int32_t head_dim, const float* qw_a, const float* kw_a,
                        const float* qw_b, const float* kw_b, const float* cos_tab,

@@ -5,6 +5,7 @@ harness (oracle/ref_harness.py).  Run in the build container only (needs /root/r
 
 Fixtures (all produced by the reference's own classes, tiny random-init model, seeded inputs):
   state_dict_keys.json      name -> shape of G2VLM(...).state_dict() for the tiny and the full dims
+  train_tiny.pt             Qwen2VLModel.forward_train output (bf16 module, two packed samples, nested masks)
   recon_tiny_{a,b}.pt       routing/permutation/position index tensors from the reference's
                             prepare_prompts_addbos / prepare_dino_images_pi3 (exact-match targets),
                             camera poses, strided samples of the point maps and of last_hidden.
@@ -169,6 +170,11 @@ def main():
     chatv = run_chat_vit_case()
     torch.save(chatv, os.path.join(GOLDEN, "chat_vit_tiny.pt"))
     print("wrote chat+vit", chatv["tokens"].tolist(), chatv["cache_len_before_decode"], repr(chatv["text"]))
+    # training forward of the MoT stack (row f.4 groundwork): LAST, because it converts the language model to bf16
+    x, pos, geo, und = rh.train_case_inputs(schema.TINY.hidden_size)
+    y = rh.run_reference_lm_forward_train(model, x, pos, geo, und)
+    torch.save(dict(case=rh.TRAIN_CASE, y=y.clone()), os.path.join(GOLDEN, "train_tiny.pt"))
+    print("wrote train_tiny", tuple(y.shape), float(y.float().abs().max()))
     keys["tiny_chat"] = {k: list(v.shape) for k, v in rh.build_reference_model(rh.TINY, visual_und=True).state_dict().items()}
     # full-size key schema: build on the meta device (no 18 GB allocation)
     with torch.device("meta"):

@@ -190,3 +190,50 @@ def run_reference_recon(model, images):
     install_shims()
     with torch.no_grad():
         return model.recon(StubTokenizer(), dict(NEW_TOKEN_IDS), None, images)
+
+
+TRAIN_CASE = dict(samples=[([5, 20, 4], ["causal", "full", "causal"]), ([12, 7], ["full", "causal"])], seed=0)
+
+
+def train_case_inputs(hidden_size: int, case=TRAIN_CASE):
+    """Packed two-sample training batch for the MoT stack: 'full' splits are image blocks (first/last token und =
+    <soi>/<eoi>, the rest geo), 'causal' splits are text (und).  Returns x (bf16), position ids, geo / und indexes."""
+    g = torch.Generator().manual_seed(case["seed"])
+    samples = case["samples"]
+    T = sum(sum(s) for s, _ in samples)
+    x = (torch.randn(T, hidden_size, generator=g) * 0.5).to(torch.bfloat16)
+    geo, und, off = [], [], 0
+    for lens, modes in samples:
+        for L, mode in zip(lens, modes):
+            if mode == "full":
+                und += [off, off + L - 1]
+                geo += list(range(off + 1, off + L - 1))
+            else:
+                und += list(range(off, off + L))
+            off += L
+    pos = torch.arange(T)[None].expand(3, -1).contiguous()
+    return x, pos, torch.tensor(geo), torch.tensor(sorted(und))
+
+
+def run_reference_lm_forward_train(model, x, pos, geo, und, case=TRAIN_CASE):
+    """Qwen2VLModel.forward_train of the UNMODIFIED reference (qwen2vl.py:1200-1266) on CPU with the nested dense
+    masks of data/data_utils.py:205-239.  The training path needs a bf16 module (it index-puts bf16 Linear outputs
+    into `new_zeros` of the packed sequence) — that is what FSDP mixed precision gives it — and its
+    `sdpa_kernel(EFFICIENT_ATTENTION)` context has no CPU backend, so that one context manager is replaced by a null
+    context (the SDPA call itself is the reference's).  NOTE: converts model.language_model to bf16 in place."""
+    import contextlib
+
+    install_shims()
+    import modeling.g2vlm.qwen2vl as q
+    from data.data_utils import prepare_attention_mask_per_sample
+    q.sdpa_kernel = lambda *a, **k: contextlib.nullcontext()
+    lm = model.language_model.model
+    lm.train()
+    lm.to(torch.bfloat16)
+    masks = [prepare_attention_mask_per_sample(s, m) for s, m in case["samples"]]
+    with torch.no_grad():
+        out = lm.forward_train(packed_sequence=x, sample_lens=[sum(s) for s, _ in case["samples"]],
+                               attention_mask=masks, packed_position_ids=pos, packed_und_token_indexes=und,
+                               packed_geo_token_indexes=geo)
+    lm.eval()
+    return out.packed_query_sequence

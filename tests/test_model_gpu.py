@@ -431,3 +431,26 @@ def test_recon_is_deterministic_and_handles_a_single_view(tiny):
         assert torch.equal(a[k], b[k]), k
         assert torch.isfinite(a[k]).all(), k
     assert a["camera_poses"].shape[-3:] == (1, 4, 4)     # [B=1, N=1, 4, 4] like the reference
+
+
+def test_training_forward_matches_reference_and_oracle():
+    """Row f.4: forward of Qwen2VLModel.forward_train on the CUDA path (bf16-module numerics, packed two-sample batch,
+    causal text splits + full image splits as per-item-causal attention segments) against the unmodified reference's
+    output (tests/golden/train_tiny.pt) and against the restatement."""
+    from g2vlm_b200.model import G2VLMFast
+    from oracle import ref_harness, restate
+    cfg = schema.TINY
+    g = torch.load(os.path.join(GOLDEN, "train_tiny.pt"))
+    case = g["case"]
+    x, pos, geo, und = ref_harness.train_case_inputs(cfg.hidden_size, case)
+    sd = {k: v.to(torch.bfloat16).float() for k, v in schema.init_synthetic(cfg, seed=0).items()}
+    model = G2VLMFast(cfg, {k: v.cuda() for k, v in sd.items()})
+    samples = case["samples"]
+    sample_lens, split_lens, modes = [sum(s) for s, _ in samples], [s for s, _ in samples], [m for _, m in samples]
+    y = model.language_model_forward_train(x.float(), sample_lens, split_lens, modes, pos, und, geo).cpu()
+    ref = g["y"].float()
+    orc = restate.lm_forward_train(sd, cfg, x.float(), pos, geo, und, sample_lens, split_lens, modes)
+    assert _maxrel(y, ref) < TOL and _maxrel(y, orc) < TOL
+    with pytest.raises(NotImplementedError):
+        model.language_model_forward_train(x.float(), sample_lens, split_lens, [["noise", "full", "causal"], modes[1]],
+                                           pos, und, geo)

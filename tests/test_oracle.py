@@ -164,3 +164,23 @@ def test_schema_with_vit_matches_reference_keys():
     ours = {k: list(v) for k, v in schema.state_dict_schema(schema.TINY_CHAT).items()}
     ref = {k: v for k, v in keys["tiny_chat"].items() if k != "dino_model.embeddings.mask_token"}
     assert ours == ref
+
+
+def test_training_forward_restatement_matches_reference(tiny_sd):
+    """Row f.4 groundwork: restate.lm_forward_train (MoT stack in training layout: two packed samples, causal text
+    splits and full image splits, bf16 module as under FSDP mixed precision) against the output of the unmodified
+    Qwen2VLModel.forward_train (tests/golden/train_tiny.pt): within one bf16 ulp of the largest activation."""
+    g = torch.load(os.path.join(GOLDEN, "train_tiny.pt"))
+    case = g["case"]
+    x, pos, geo, und = ref_harness.train_case_inputs(schema.TINY.hidden_size, case)
+    sd = {k: v.to(torch.bfloat16).float() for k, v in tiny_sd.items()}     # the reference module is cast to bf16
+    samples = case["samples"]
+    y = restate.lm_forward_train(sd, schema.TINY, x.float(), pos, geo, und, [sum(s) for s, _ in samples],
+                                 [s for s, _ in samples], [m for _, m in samples])
+    ref = g["y"].float()
+    assert ((y - ref).abs().max() / ref.abs().max()).item() < 8e-3
+    # mask semantics (data/data_utils.py:205-239)
+    m = restate.train_attention_mask([2, 3, 2], ["causal", "full", "noise"])
+    assert m[:2, :2].tolist() == [[True, False], [True, True]]
+    assert bool(m[2:5, :5].all()) and not bool(m[2:5, 5:].any())
+    assert not bool(m[:5, 5:].any()) and bool(m[5:, 5:].all()) and bool(m[5:, :5].any()) is True
