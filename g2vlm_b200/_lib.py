@@ -21,9 +21,10 @@ HEADER = REPO_ROOT / "include" / "g2vlm_b200.h"
 LIB_PATH = Path(os.environ.get("G2VLM_B200_LIB", PKG_DIR / "libg2vlm_b200.so"))
 
 NVCC_FLAGS = [
-    "-shared", "-Xcompiler", "-fPIC", "-gencode", "arch=compute_100a,code=sm_100a",
+    "-Xcompiler", "-fPIC", "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",
 ]
+OBJ_DIR = PKG_DIR / "build"
 
 
 def sources():
@@ -38,20 +39,45 @@ def _stale() -> bool:
     return any(d.stat().st_mtime > t for d in deps)
 
 
+def _header_abi_version() -> int:
+    m = re.search(r"#define\s+G2VLM_ABI_VERSION\s+(\d+)", HEADER.read_text())
+    if not m:
+        raise RuntimeError(f"G2VLM_ABI_VERSION not found in {HEADER}")
+    return int(m.group(1))
+
+
 def build(force: bool = False, verbose: bool = False) -> Path:
-    """Compile every CUDA source of the package for sm_100a into ``libg2vlm_b200.so``."""
+    """Compile every CUDA source of the package for sm_100a into ``libg2vlm_b200.so``: one object per source
+    (only the out-of-date ones, in parallel), then one link."""
     if not force and not _stale():
         return LIB_PATH
+    from concurrent.futures import ThreadPoolExecutor
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc, *NVCC_FLAGS, "-o", str(LIB_PATH), *map(str, sources())]
+    OBJ_DIR.mkdir(exist_ok=True)
+    headers = list(CSRC.glob("*.cuh")) + [HEADER]
+    hdr_t = max(h.stat().st_mtime for h in headers)
+
+    def compile_one(src: Path):
+        obj = OBJ_DIR / (src.stem + ".o")
+        if not force and obj.exists() and obj.stat().st_mtime > max(src.stat().st_mtime, hdr_t):
+            return obj, ""
+        cmd = [nvcc, *NVCC_FLAGS, "-c", "-o", str(obj), str(src)]
+        if verbose:
+            cmd[1:1] = ["-Xptxas", "-v"]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
+        return obj, res.stderr
+
+    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
+        results = list(ex.map(compile_one, sources()))
     if verbose:
-        cmd.insert(1, "-Xptxas")
-        cmd.insert(2, "-v")
+        print("".join(log for _, log in results))
+    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(LIB_PATH),
+           *[str(o) for o, _ in results]]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
-    if verbose:
-        print(res.stderr)
+        raise RuntimeError("link failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
     return LIB_PATH
 
 
@@ -80,5 +106,11 @@ def load() -> ctypes.CDLL:
         raise RuntimeError(f"{LIB_PATH} does not export {missing}; rebuild it")
     lib.g2vlm_last_error.restype = ctypes.c_char_p
     lib.g2vlm_abi_version.restype = ctypes.c_int
+    have, want = lib.g2vlm_abi_version(), _header_abi_version()
+    if have != want:   # a left-over library would silently misread the argument structs
+        raise RuntimeError(f"{LIB_PATH} implements ABI v{have} but include/g2vlm_b200.h declares v{want}; rebuild it")
+    if "G2VLM_B200_LIB" not in os.environ and _stale():
+        import warnings
+        warnings.warn(f"{LIB_PATH} is older than its sources; run __graft_entry__.build()")
     _lib = lib
     return lib

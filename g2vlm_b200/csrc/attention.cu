@@ -566,12 +566,7 @@ attention_tcgen05_kernel(const __grid_constant__ AttnKParams p) {
 
 template <int D>
 static int launch_attention(const AttnKParams& kp, cudaStream_t stream) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    G2_CUDA_OK(cudaFuncSetAttribute(attention_tcgen05_kernel<D>,
-                                    cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg<D>::kSmem));
-    attr_set = true;
-  }
+  if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(attention_tcgen05_kernel<D>), AttnCfg<D>::kSmem)) return rc;
   const long long units = (long long)kp.n_items * kp.n_heads;
   const unsigned grid = (unsigned)(units < num_sms() ? units : num_sms());  // one persistent CTA per SM
   attention_tcgen05_kernel<D><<<grid, ATT_THREADS, AttnCfg<D>::kSmem, stream>>>(kp);

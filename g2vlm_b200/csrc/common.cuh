@@ -44,6 +44,9 @@ int make_tmap_2d_bf16(CUtensorMap* map, const void* base, uint64_t rows, uint64_
                       uint64_t row_pitch_bytes, uint32_t box_rows, uint32_t box_cols);
 
 int num_sms();
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per DEVICE: remember per (kernel, device) that it was set, so a
+// process driving several GPUs configures every kernel on every device it launches on.
+int ensure_dyn_smem(const void* func, int bytes);
 
 // decode.cu: bandwidth-bound GEMV path of g2vlm_gemm_bf16 for calls with <= 8 rows in one group
 int launch_gemv(const g2vlm_gemm_args* a, int group, cudaStream_t stream);

@@ -506,11 +506,7 @@ extern "C" int g2vlm_attention_decode(const void* q, const void* k, int64_t ldk,
   // kv_len then only sizes the split grid, so one captured launch serves a growing cache
   const int L = static_cast<int>(kv_len);
   const int n_splits = (L + DEC_CHUNK - 1) / DEC_CHUNK;
-  static bool attr_set = false;
-  if (!attr_set) {
-    G2_CUDA_OK(cudaFuncSetAttribute(attn_decode_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DEC_SMEM));
-    attr_set = true;
-  }
+  if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(attn_decode_split_kernel), DEC_SMEM)) return rc;
   G2_REQUIRE((long long)n_splits * num_q_heads * 130 <= workspace_floats, "attention_decode: workspace too small");
   cudaStream_t st = (cudaStream_t)stream;
   attn_decode_split_kernel<<<dim3(n_splits, num_kv_heads), DEC_THREADS, DEC_SMEM, st>>>(

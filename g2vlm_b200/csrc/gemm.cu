@@ -610,12 +610,7 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ GemmKParams p) {
 
 template <int EPI>
 static int launch_gemm_pair(const GemmKParams& kp, cudaStream_t stream) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    G2_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_tcgen05_pair_kernel<EPI>,
-                                    cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM));
-    attr_set = true;
-  }
+  if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(gemm_bf16_tcgen05_pair_kernel<EPI>), PAIR_SMEM)) return rc;
   const int pairs = min(kp.num_pair_tiles, num_sms() / 2);
   gemm_bf16_tcgen05_pair_kernel<EPI><<<2 * pairs, GEMM_THREADS, PAIR_SMEM, stream>>>(kp);
   G2_CUDA_OK(cudaGetLastError());
@@ -624,12 +619,7 @@ static int launch_gemm_pair(const GemmKParams& kp, cudaStream_t stream) {
 
 template <int EPI>
 static int launch_gemm(const GemmKParams& kp, cudaStream_t stream) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    G2_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<EPI>,
-                                    cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
-    attr_set = true;
-  }
+  if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(gemm_bf16_tcgen05_kernel<EPI>), GEMM_SMEM)) return rc;
   const int grid = kp.num_tiles < num_sms() ? kp.num_tiles : num_sms();
   gemm_bf16_tcgen05_kernel<EPI><<<grid, GEMM_THREADS, GEMM_SMEM, stream>>>(kp);
   G2_CUDA_OK(cudaGetLastError());
@@ -714,7 +704,8 @@ extern "C" int g2vlm_gemm_bf16(const g2vlm_gemm_args* a, void* stream_) {
   if (rc) return rc;
 
   // Large problems run on CTA pairs (256 x 256 tiles, cta_group::2); small ones keep one CTA per 128 x 256 tile,
-  // which gives twice as many independent tiles to spread over the SMs.  G2VLM_GEMM_PAIR=0/1 forces either (A/B runs).
+  // which gives twice as many independent tiles to spread over the SMs.  The G2VLM_GEMM_FORCE_PAIR / _FORCE_SINGLE
+  // flags choose per call (tests run both kernels on the same shapes; A/B timing).
   int mp = 0;
   for (int g = 0; g < a->n_groups; ++g) {
     kp.grp_mpair0[g] = mp;
@@ -732,11 +723,12 @@ extern "C" int g2vlm_gemm_bf16(const g2vlm_gemm_args* a, void* stream_) {
     long long ph = (24LL << 20) / per_pair_bytes;
     kp.pair_panel = (int)(ph < 4 ? 4 : (ph > 32 ? 32 : ph));
   }
-  static const int force_pair = [] {
-    const char* e = getenv("G2VLM_GEMM_PAIR");
-    return e == nullptr ? -1 : atoi(e);
-  }();
-  const bool use_pair = force_pair >= 0 ? force_pair != 0 : kp.num_pair_tiles >= num_sms();
+  G2_REQUIRE((a->flags & (G2VLM_GEMM_FORCE_PAIR | G2VLM_GEMM_FORCE_SINGLE)) !=
+                 (G2VLM_GEMM_FORCE_PAIR | G2VLM_GEMM_FORCE_SINGLE),
+             "gemm: FORCE_PAIR and FORCE_SINGLE are mutually exclusive");
+  const bool use_pair = (a->flags & G2VLM_GEMM_FORCE_PAIR)     ? true
+                        : (a->flags & G2VLM_GEMM_FORCE_SINGLE) ? false
+                                                               : kp.num_pair_tiles >= num_sms();
   if (use_pair) {
     rc = make_tmap_2d_bf16(&kp.tmBh, a->B, (uint64_t)a->n_groups * a->N, (uint64_t)a->K, (uint64_t)a->ldb * 2, BN / 2,
                            BK);

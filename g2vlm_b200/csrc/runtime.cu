@@ -68,14 +68,40 @@ int make_tmap_2d_bf16(CUtensorMap* map, const void* base, uint64_t rows, uint64_
   return G2VLM_OK;
 }
 
+static constexpr int kMaxDevices = 64;
+
 int num_sms() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
-    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) n = 148;
+  static int n[kMaxDevices] = {0};   // per device (a process may drive several GPUs)
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return 148;
+  if (n[dev] == 0) {
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+    n[dev] = v;
   }
-  return n;
+  return n[dev];
+}
+
+int ensure_dyn_smem(const void* func, int bytes) {
+  struct Entry { const void* func; unsigned long long devices; };
+  static Entry table[64];
+  static int n_entries = 0;
+  static std::mutex mu;
+  int dev = 0;
+  G2_CUDA_OK(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= kMaxDevices) {
+    G2_CUDA_OK(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    return G2VLM_OK;
+  }
+  std::lock_guard<std::mutex> lock(mu);
+  Entry* e = nullptr;
+  for (int i = 0; i < n_entries; ++i)
+    if (table[i].func == func) { e = &table[i]; break; }
+  if (e == nullptr && n_entries < 64) { e = &table[n_entries++]; e->func = func; e->devices = 0; }
+  if (e != nullptr && (e->devices >> dev) & 1ull) return G2VLM_OK;
+  G2_CUDA_OK(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  if (e != nullptr) e->devices |= 1ull << dev;
+  return G2VLM_OK;
 }
 
 }  // namespace g2

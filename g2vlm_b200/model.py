@@ -162,6 +162,20 @@ def _split_hi_lo_hi(w: torch.Tensor) -> torch.Tensor:
     return torch.cat([hi, lo, hi], dim=1)
 
 
+def _on_device(fn):
+    """Public entry points run with the model's GPU as the current device (ops launch on the current device's stream),
+    so a process may hold models on several GPUs."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(self, *a, **k):
+        if torch.cuda.current_device() == self.device.index:
+            return fn(self, *a, **k)
+        with torch.cuda.device(self.device):
+            return fn(self, *a, **k)
+    return wrapped
+
+
 class _Buffers:
     """Shape-keyed cache of device workspaces (allocated once, reused across calls)."""
 
@@ -187,6 +201,8 @@ class G2VLMFast:
             raise ValueError("LLM head_dim must be 128 (mrope_section is hard-coded to [16,24,24])")
         self.cfg = cfg
         self.device = torch.device(device)
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
         self.buf = _Buffers(self.device)
         self._stage: Dict[str, dict] = {}
         self.device_resize = True   # recon(): LANCZOS resize of path / PIL inputs on the device (host_prep)
@@ -210,6 +226,30 @@ class G2VLMFast:
     @classmethod
     def from_state_dict(cls, cfg: G2Config, state_dict, device="cuda") -> "G2VLMFast":
         return cls(cfg, state_dict, device)
+
+    RECON_STAGES = ("forward_cache_update_text", "forward_cache_update_dino", "reconstruct")
+
+    @classmethod
+    def attach(cls, ref_model, device=None, stages=RECON_STAGES) -> "G2VLMFast":
+        """INTEGRATION.md §2 as code: build the CUDA path from a live reference `G2VLM` instance (its `config` and
+        `state_dict()`, key names unchanged) and replace the recon stages of THAT object — signatures identical to
+        g2vlm.py:701-711, 968-983, 1143-1154 — so `ref_model.recon(...)` (g2vlm.py:1240-1303), its host-side
+        `prepare_*` code and every caller (`inference_recon.py:36-43`) keep working unchanged.  The reference's
+        `NaiveCache` objects are adopted transparently (KVCache.adopt).  Duck-typed: nothing of the reference is
+        imported here.  Returns the G2VLMFast (also stored as `ref_model._g2vlm_b200`)."""
+        c = ref_model.config
+        vit = c.vit_config if getattr(ref_model, "vit_model", None) is not None else None
+        cfg = G2Config.from_reference(c.llm_config, c.dino_config, vit,
+                                      train_conf_pi3=bool(getattr(c, "train_conf_pi3", False)))
+        if device is None:
+            device = next(ref_model.parameters()).device
+            if device.type != "cuda":
+                device = torch.device("cuda", torch.cuda.current_device())
+        fast = cls(cfg, ref_model.state_dict(), device)
+        for name in stages:
+            setattr(ref_model, name, getattr(fast, name))
+        ref_model._g2vlm_b200 = fast
+        return fast
 
     # ------------------------------------------------------------------------------------------
     # weight packing (one-time; reference key names in, kernel-friendly layouts out)
@@ -565,6 +605,7 @@ class G2VLMFast:
             cache.len = L + T
         return y
 
+    @_on_device
     @torch.no_grad()
     def forward_cache_update_text(self, past_key_values: NaiveCache, packed_text_ids, packed_text_position_ids,
                                   text_token_lens, packed_text_indexes, packed_key_value_indexes, key_values_lens):
@@ -624,6 +665,7 @@ class G2VLMFast:
         a.attn_ws_floats = bufs["attn_ws"].numel()
         return a, (kv, bufs)
 
+    @_on_device
     @torch.no_grad()
     def generate_text(self, past_key_values, packed_key_value_indexes, key_values_lens, packed_start_tokens,
                       packed_query_position_ids, max_length: int, do_sample: bool = False, temperature: float = 1.0,
@@ -702,6 +744,7 @@ class G2VLMFast:
         ids = torch.stack(out, dim=0)
         return (ids, all_logits) if return_logits else ids
 
+    @_on_device
     @torch.no_grad()
     def language_model_forward_train(self, packed_sequence, sample_lens, split_lens, attn_modes, packed_position_ids,
                                      packed_und_token_indexes, packed_geo_token_indexes):
@@ -755,6 +798,7 @@ class G2VLMFast:
         ops.gather_rows(yb, y, perm, T, scatter=True)
         return y.float()
 
+    @_on_device
     @torch.no_grad()
     def language_model_forward_geo(self, packed_sequence, packed_position_ids, packed_geo_token_indexes,
                                    packed_text_indexes, past_key_values: NaiveCache,
@@ -905,6 +949,7 @@ class G2VLMFast:
             if collect is not None:
                 collect.append(x.clone())
 
+    @_on_device
     @torch.no_grad()
     def dino_forward(self, packed_pixel_values, dino_token_seqlens, collect: Optional[list] = None):
         """Dinov2WithRegistersModel.forward with the caller's cu_seqlens (reference
@@ -927,6 +972,7 @@ class G2VLMFast:
         ops.layernorm(x, tokens, self.dino_lnw, self.dino_lnb, cfg.dino_ln_eps, seg_in=S, seg_skip=1 + cfg.dino_registers)
         return tokens
 
+    @_on_device
     @torch.no_grad()
     def dino_forward_sharded(self, packed_pixel_values_all, shard, group):
         """View-sharded DINO (sharding.ViewShard): this rank runs the encoder on the flattened rows of ITS
@@ -966,6 +1012,7 @@ class G2VLMFast:
         ops.gather_rows(normed, tokens, idx.to(dev), shard.n_local * P)
         return tokens
 
+    @_on_device
     @torch.no_grad()
     def forward_cache_update_dino(self, past_key_values: NaiveCache, packed_text_ids, packed_text_indexes,
                                   packed_dino_token_indexes, dino_token_seqlens, packed_position_ids, packed_seqlens,
@@ -1083,6 +1130,7 @@ class G2VLMFast:
         ops.gemm(xs, w3, out, epilogue=ops.EPI_STORE_F32, bias=b, flags=ops.GEMM_RELU if relu else 0, residual=residual)
         return out
 
+    @_on_device
     @torch.no_grad()
     def reconstruct(self, past_key_values=None, packed_key_value_indexes=None, key_values_lens=None,
                     selected_hidden_states=None, packed_dino_token_indexes=None, packed_dino_images=None,
@@ -1176,6 +1224,7 @@ class G2VLMFast:
         return dict(points=points[None], local_points=local_points[None], conf=conf, camera_poses=poses[None],
                     global_points=global_points[None], images=original_images)
 
+    @_on_device
     @torch.no_grad()
     def recon_view_sharded(self, tokenizer, new_token_ids, images, group=None):
         """ONE long scene split by view over the ranks of `group` (sequence parallelism; no reference
@@ -1234,6 +1283,7 @@ class G2VLMFast:
             self._rope2d_cache[key] = t
         return t
 
+    @_on_device
     @torch.no_grad()
     def vit_forward(self, pixel_values, grid_thw, out=None):
         """Qwen2VisionTransformerPretrainedModel.forward (modeling_qwen2_vl.py:1050-1072): flattened patches
@@ -1314,6 +1364,7 @@ class G2VLMFast:
         }
         return gi, [kvlen + n + 2], [rope + delta + 3]
 
+    @_on_device
     @torch.no_grad()
     def forward_cache_update_vit(self, past_key_values, packed_text_ids, packed_text_indexes, packed_vit_images,
                                  packed_image_grid_thw, packed_vit_token_indexes, vit_token_seqlens, packed_position_ids,
@@ -1363,6 +1414,7 @@ class G2VLMFast:
             "packed_key_value_indexes": torch.arange(kvlen),
         }
 
+    @_on_device
     @torch.no_grad()
     def chat_with_recon(self, tokenizer, new_token_ids, image_transform, dino_image_transform, images, prompt,
                         max_length: int, do_sample: bool = False, temperature: float = 1.0, return_ids: bool = False):
@@ -1401,6 +1453,7 @@ class G2VLMFast:
         return host_prep.prepare_dino_images_pi3(curr_kvlens, curr_rope, images, new_token_ids, self.cfg.dino_patch,
                                                  normalize_on_host=normalize_on_host)
 
+    @_on_device
     @torch.no_grad()
     def recon(self, tokenizer, new_token_ids, dino_image_transform, images, prompt="Reconstruct the 3D scene.",
               collect: Optional[dict] = None):

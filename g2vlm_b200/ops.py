@@ -16,6 +16,7 @@ from . import _lib
 EPI_STORE_BF16, EPI_SWIGLU_BF16, EPI_RESID_F32, EPI_STORE_F32 = 0, 1, 2, 3
 GEMM_GELU, GEMM_ROUND_AFTER_SCALE, GEMM_RELU, GEMM_ACCUMULATE, GEMM_ROUND_BF16 = 1, 2, 4, 8, 16
 GEMM_QUICK_GELU, GEMM_ROUND_SUM = 32, 64
+GEMM_FORCE_PAIR, GEMM_FORCE_SINGLE = 128, 256   # choose the CTA-pair / 1-CTA kernel per call (tests, A/B timing)
 
 
 class G2Error(RuntimeError):
@@ -44,6 +45,10 @@ def _ptr(t: Optional[torch.Tensor]) -> ctypes.c_void_p:
 def _req(t: torch.Tensor, dtype, name: str) -> None:
     if not t.is_cuda:
         raise G2Error(f"{name} must be a CUDA tensor (there is no CPU fallback)")
+    if t.device.index != torch.cuda.current_device():
+        # the launch goes to the CURRENT device's stream: a tensor of another GPU would be a wild pointer there
+        raise G2Error(f"{name} lives on cuda:{t.device.index} but the current device is cuda:{torch.cuda.current_device()}"
+                      "; call inside `with torch.cuda.device(tensor.device):` (G2VLMFast's public methods do)")
     if t.dtype != dtype:
         raise G2Error(f"{name} must be {dtype}, got {t.dtype}")
     if t.dim() >= 2 and t.stride(-1) != 1:

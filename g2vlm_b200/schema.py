@@ -52,6 +52,25 @@ class G2Config:
     vit_merge: int = 2
     vit_temporal: int = 2
 
+    @classmethod
+    def from_reference(cls, llm_config, dino_config, vit_config=None, **overrides) -> "G2Config":
+        """Dimensions from the reference's own config objects (`Qwen2VLConfig`, `Dinov2WithRegistersConfig`,
+        optionally `Qwen2VLVisionConfig`, as built in g2vlm_utils.py:32-41) — duck-typed, nothing is imported."""
+        kw = dict(hidden_size=llm_config.hidden_size, num_layers=llm_config.num_hidden_layers,
+                  num_heads=llm_config.num_attention_heads, num_kv_heads=llm_config.num_key_value_heads,
+                  intermediate_size=llm_config.intermediate_size, vocab_size=llm_config.vocab_size,
+                  rms_norm_eps=llm_config.rms_norm_eps, rope_theta=llm_config.rope_theta,
+                  dino_hidden=dino_config.hidden_size, dino_layers=dino_config.num_hidden_layers,
+                  dino_heads=dino_config.num_attention_heads, dino_mlp_ratio=dino_config.mlp_ratio,
+                  dino_image_size=dino_config.image_size, dino_patch=dino_config.patch_size,
+                  dino_registers=dino_config.num_register_tokens, dino_ln_eps=dino_config.layer_norm_eps)
+        if vit_config is not None:
+            kw.update(vit_depth=vit_config.depth, vit_embed_dim=vit_config.embed_dim, vit_heads=vit_config.num_heads,
+                      vit_mlp_ratio=int(vit_config.mlp_ratio), vit_patch=vit_config.patch_size,
+                      vit_merge=vit_config.spatial_merge_size, vit_temporal=vit_config.temporal_patch_size)
+        kw.update(overrides)
+        return cls(**kw)
+
     @property
     def head_dim(self) -> int:
         return self.hidden_size // self.num_heads

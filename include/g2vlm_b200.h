@@ -66,6 +66,8 @@ const char* g2vlm_last_error(void);
 #define G2VLM_GEMM_ROUND_BF16 16u       /* STORE_F32: round (acc+bias) to bf16 before storing */
 #define G2VLM_GEMM_QUICK_GELU 32u       /* STORE_BF16: x*sigmoid(1.702x) on the bf16-rounded value (Qwen2-VL ViT MLP) */
 #define G2VLM_GEMM_ROUND_SUM 64u        /* RESID_F32: round the updated stream value to bf16 (bf16 residual stream) */
+#define G2VLM_GEMM_FORCE_PAIR 128u      /* run the CTA-pair kernel (256x256 tiles) whatever the problem size */
+#define G2VLM_GEMM_FORCE_SINGLE 256u    /* run the 1-CTA kernel (128x256 tiles) whatever the problem size */
 
 typedef struct g2vlm_gemm_args {
   const void* A; /* bf16 [a_rows, K], leading dimension lda */

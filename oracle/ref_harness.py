@@ -1,11 +1,14 @@
-"""TEST INFRASTRUCTURE — harness that runs the UNMODIFIED reference (`/root/reference`) on CPU.
+"""TEST INFRASTRUCTURE — harness that runs the UNMODIFIED reference classes: on the host cores (SDPA stand-in for
+flash-attn), or on a GPU with the reference's own flash-attn calls (`build_reference_model(device="cuda")`).
 
 Only `tests/`, `oracle/make_golden.py`, `__graft_entry__.smoke()` and `bench.py`'s cpu_baseline /
 `--impl reference` legs may import this module; the product package `g2vlm_b200` never does.
-`/root/reference` exists only in the build container, so everything here is used to (a) pin the
-restatement in `oracle/restate.py` against the real reference classes and (b) generate the golden
-fixtures under `tests/golden/` (script: `oracle/make_golden.py`).  On the GPU box this module is
-unusable and `available()` returns False.
+`/root/reference` exists only in the build container; `oracle/stage_ref.py` (run by `__graft_entry__.build()`)
+places a byte-identical, git-ignored copy under `oracle/_ref/`, which travels to the GPU box with the snapshot.
+Uses: (a) pin the restatement in `oracle/restate.py` against the real reference classes, (b) generate the golden
+fixtures under `tests/golden/` (script: `oracle/make_golden.py`), (c) on the B200: bf16 parity of the CUDA path
+against the real classes with real flash-attn and the PyTorch+FA2 speed baseline (`bench.py` `gpu_reference`),
+(d) `bench.py --impl reference`: the real classes timed on the host cores.
 
 The reference cannot run unmodified on CPU (hard bf16 casts + flash-attn + `.cuda()` + HF-hub
 downloads + transformers-4.49 symbols); the shims below are in-process only and
@@ -28,11 +31,37 @@ import types
 
 import torch
 
-REFERENCE_ROOT = os.environ.get("G2VLM_REFERENCE_ROOT", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _find_root() -> str:
+    """/root/reference in the build container; on the GPU box the byte-identical copy staged under oracle/_ref by
+    `oracle/stage_ref.py` (git-ignored, travels with the gpurun snapshot)."""
+    cands = [os.environ.get("G2VLM_REFERENCE_ROOT"), "/root/reference", os.path.join(_HERE, "_ref")]
+    for c in cands:
+        if c and os.path.isdir(os.path.join(c, "modeling", "g2vlm")):
+            return c
+    return cands[1]
+
+
+REFERENCE_ROOT = _find_root()
+# autocast('cuda') is redirected to 'cpu' only while the reference runs on the host (set by build_reference_model)
+_REDIRECT_AUTOCAST = True
 
 
 def available() -> bool:
     return os.path.isdir(os.path.join(REFERENCE_ROOT, "modeling", "g2vlm"))
+
+
+def gpu_available() -> bool:
+    """The reference can run on the GPU with its own flash-attn calls (needs the flash_attn wheel + a CUDA device)."""
+    if not (available() and torch.cuda.is_available()):
+        return False
+    try:
+        import flash_attn  # noqa: F401
+        return True
+    except Exception:
+        return False
 
 
 # ---- shim 3: flash_attn_varlen_func stand-in ----------------------------------------------------
@@ -117,12 +146,12 @@ def install_shims() -> None:
 
     class _ac(_orig_autocast):
         def __init__(self, device_type="cuda", *a, **k):
-            super().__init__("cpu" if device_type == "cuda" else device_type, *a, **k)
+            super().__init__("cpu" if (device_type == "cuda" and _REDIRECT_AUTOCAST) else device_type, *a, **k)
 
     torch.amp.autocast = _ac
     torch.amp.autocast_mode.autocast = _ac
     torch.autocast = _ac
-    torch.cuda.amp.autocast = lambda *a, **k: _ac("cpu", *a, **k)
+    torch.cuda.amp.autocast = lambda *a, **k: _ac("cuda", *a, **k)
     _installed = True
 
 
@@ -154,9 +183,28 @@ FULL = dict(
 )
 
 
-def build_reference_model(dims=TINY, visual_und=True):
-    """Constructs the reference G2VLM from its own classes (mirrors g2vlm_utils.py:31-55)."""
+def flash_attn_zero_fill(real):
+    """GPU runs use the reference's own flash-attn calls.  For PARITY runs the DINO call is wrapped so that query
+    rows beyond cu_seqlens[-1] — which flash-attn never writes (`out = torch.empty_like(q)`; quirk Q1,
+    g2vlm.py:988-990 vs dinov2_model.py:338-339) — hold zeros instead of whatever the caching allocator handed out.
+    That is the only deviation from the stock call; speed runs use the unwrapped function."""
+    def wrapped(q, k, v, cu_seqlens_q, cu_seqlens_k, *a, **kw):
+        out = real(q, k, v, cu_seqlens_q, cu_seqlens_k, *a, **kw)
+        n = int(cu_seqlens_q[-1])
+        if n < q.shape[0]:
+            out[n:] = 0
+        return out
+    return wrapped
+
+
+def build_reference_model(dims=TINY, visual_und=True, device="cpu", zero_fill_uncovered=True):
+    """Constructs the reference G2VLM from its own classes (mirrors g2vlm_utils.py:31-55).
+    device="cpu": flash-attn replaced by the SDPA stand-in, autocast('cuda') redirected to 'cpu'.
+    device="cuda": the reference's own flash-attn calls and CUDA autocast regions run unmodified (module parameters
+    are created directly on the GPU); `zero_fill_uncovered` wraps the DINO flash-attn call (see flash_attn_zero_fill)."""
+    global _REDIRECT_AUTOCAST
     install_shims()
+    _REDIRECT_AUTOCAST = device == "cpu"
     from modeling.dinov2_with_registers.configuration_dinov2_with_registers import Dinov2WithRegistersConfig
     from modeling.g2vlm.dinov2_model import Dinov2WithRegistersModel
     from modeling.g2vlm.g2vlm import G2VLM, G2VLMConfig
@@ -166,10 +214,16 @@ def build_reference_model(dims=TINY, visual_und=True):
     import modeling.g2vlm.dinov2_model as _dm
     import modeling.g2vlm.qwen2vl as _qm
 
-    _qm.flash_attn_varlen_func = varlen_sdpa
-    _dm.flash_attn_varlen_func = varlen_sdpa
     import modeling.qwen2vl.modeling_qwen2_vl as _vm
-    _vm.flash_attn_varlen_func = varlen_sdpa   # VisionFlashAttention2 (ViT of the chat path)
+    if device == "cpu":
+        _qm.flash_attn_varlen_func = varlen_sdpa
+        _dm.flash_attn_varlen_func = varlen_sdpa
+        _vm.flash_attn_varlen_func = varlen_sdpa   # VisionFlashAttention2 (ViT of the chat path)
+    else:
+        from flash_attn import flash_attn_varlen_func as _real
+        _qm.flash_attn_varlen_func = _real
+        _vm.flash_attn_varlen_func = _real
+        _dm.flash_attn_varlen_func = flash_attn_zero_fill(_real) if zero_fill_uncovered else _real
 
     llm = Qwen2VLConfig(pad_token_id=None, rope_scaling={"type": "mrope", "mrope_section": [16, 24, 24]},
                         qk_norm=True, layer_module="Qwen2VLMoTDecoderLayer", tie_word_embeddings=False,
@@ -178,11 +232,26 @@ def build_reference_model(dims=TINY, visual_und=True):
     vit = Qwen2VLVisionConfig(**dims["vit"])
     cfg = G2VLMConfig(visual_und=visual_und, visual_recon=True, llm_config=llm, vit_config=vit,
                       dino_config=dino, vit_max_num_patch_per_side=36)
-    lm = Qwen2VLForCausalLM(llm)
-    vm = Qwen2VisionTransformerPretrainedModel(vit) if visual_und else None
-    dm = Dinov2WithRegistersModel(dino)
-    model = G2VLM(lm, vm, dm, cfg).eval()
+    with torch.device(device):
+        lm = Qwen2VLForCausalLM(llm)
+        vm = Qwen2VisionTransformerPretrainedModel(vit) if visual_und else None
+        dm = Dinov2WithRegistersModel(dino)
+        model = G2VLM(lm, vm, dm, cfg).eval()
     return model
+
+
+def dims_from_cfg(cfg, vocab_size=None):
+    """ref_harness dims dict for a g2vlm_b200.schema.G2Config (so tests build the reference at the product's dims)."""
+    return dict(
+        llm=dict(hidden_size=cfg.hidden_size, num_hidden_layers=cfg.num_layers, num_attention_heads=cfg.num_heads,
+                 num_key_value_heads=cfg.num_kv_heads, intermediate_size=cfg.intermediate_size,
+                 vocab_size=vocab_size or cfg.vocab_size, rms_norm_eps=cfg.rms_norm_eps, rope_theta=cfg.rope_theta,
+                 max_position_embeddings=32768),
+        dino=dict(hidden_size=cfg.dino_hidden, num_hidden_layers=cfg.dino_layers, num_attention_heads=cfg.dino_heads,
+                  mlp_ratio=cfg.dino_mlp_ratio, image_size=cfg.dino_grid * cfg.dino_patch, patch_size=cfg.dino_patch,
+                  num_register_tokens=cfg.dino_registers, layer_norm_eps=cfg.dino_ln_eps),
+        vit=dict(depth=1, embed_dim=64, hidden_size=cfg.hidden_size, num_heads=2, mlp_ratio=2, patch_size=14),
+    )
 
 
 def run_reference_recon(model, images):

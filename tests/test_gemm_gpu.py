@@ -193,3 +193,116 @@ def test_store_bf16_column_regroup():
     assert bool((got[:, :, 96:] == 3.0).all())
     with pytest.raises(Exception):
         ops.gemm(a, w, out, epilogue=ops.EPI_STORE_BF16, out_col_group=48, out_col_stride=128)
+
+
+# ------------------------------------------------------------------------------------------------------
+# Both tile schedulers on the SAME shapes: the CTA-pair kernel (256x256, cta_group::2) is
+# what o_proj / down / DINO dense+fc2 / Pi3 proj+fc2 run in the benchmark; FORCE_PAIR / FORCE_SINGLE pick it per call.
+# ------------------------------------------------------------------------------------------------------
+_KERNELS = ["pair", "single"]
+
+
+def _force(kernel):
+    from g2vlm_b200 import ops
+    return ops.GEMM_FORCE_PAIR if kernel == "pair" else ops.GEMM_FORCE_SINGLE
+
+
+@pytest.mark.parametrize("kernel", _KERNELS)
+@pytest.mark.parametrize("rows,K,N,groups", [
+    (900, 512, 512, [(0, 850), (850, 50)]),          # few tiles, odd number of M tiles per group (pair padding)
+    (6500, 1024, 1536, [(0, 6400), (6400, 100)]),    # >= 148 pair tiles at N = 1536 (the automatic pair regime)
+    (130, 4096, 1024, None),                         # long K (DINO fc2 shape), second CTA of the pair nearly empty
+])
+def test_resid_f32_both_kernels(kernel, rows, K, N, groups):
+    from g2vlm_b200 import ops
+    ng = 1 if groups is None else len(groups)
+    a, w, bias = _mk(rows, K, N, ng, seed=21)
+    groups_ = groups or [(0, rows)]
+    gamma = (torch.rand(N) + 0.5).cuda()
+    x0 = torch.randn(rows, N, device="cuda")
+    for flags, rounded in ((ops.GEMM_ROUND_AFTER_SCALE, True), (0, False), (ops.GEMM_ROUND_SUM, False)):
+        x = x0.clone()
+        ops.gemm(a, w, x, epilogue=ops.EPI_RESID_F32, groups=groups, bias=bias, scale=gamma, scale_groups=1,
+                 flags=flags | _force(kernel))
+        y = _ref_linear(a, w, bias, groups_, N).to(torch.bfloat16).float()
+        n0 = groups_[0][1]
+        y[:n0] = y[:n0] * gamma                        # scale_groups = 1: LayerScale on group 0 only
+        if rounded:
+            y[:n0] = y[:n0].to(torch.bfloat16).float()
+        ref = x0 + y
+        if flags & ops.GEMM_ROUND_SUM:
+            ref = ref.to(torch.bfloat16).float()
+            assert _relerr(x, ref) < 1e-2
+        else:
+            assert _relerr(x, ref) < 5e-3, (kernel, flags)
+
+
+@pytest.mark.parametrize("kernel", _KERNELS)
+def test_store_f32_both_kernels(kernel):
+    from g2vlm_b200 import ops
+    rows, K, N = 6500, 512, 1536
+    a, w, bias = _mk(rows, K, N, 1, seed=22)
+    res = torch.randn(rows, N, device="cuda")
+    out = torch.full((rows, N), float("nan"), device="cuda")
+    ops.gemm(a, w, out, epilogue=ops.EPI_STORE_F32, bias=bias, flags=ops.GEMM_RELU | _force(kernel), residual=res)
+    ref = torch.relu(_ref_linear(a, w, bias, [(0, rows)], N)) + res
+    assert _relerr(out, ref) < 1e-4
+    out2 = out.clone()
+    ops.gemm(a, w, out2, epilogue=ops.EPI_STORE_F32, flags=ops.GEMM_ACCUMULATE | _force(kernel))
+    assert _relerr(out2, ref + _ref_linear(a, w, None, [(0, rows)], N)) < 1e-4
+    out3 = torch.empty(rows, N, device="cuda")
+    ops.gemm(a, w, out3, epilogue=ops.EPI_STORE_F32, bias=bias, flags=ops.GEMM_ROUND_BF16 | _force(kernel))
+    ref3 = _ref_linear(a, w, bias, [(0, rows)], N).to(torch.bfloat16).float()
+    assert ((out3 - ref3).abs() > 0).float().mean() < 0.05
+
+
+@pytest.mark.parametrize("kernel", _KERNELS)
+@pytest.mark.parametrize("act", ["gelu", "quick_gelu"])
+def test_gelu_both_kernels(kernel, act):
+    from g2vlm_b200 import ops
+    rows, K, N = 3000, 1024, 4096
+    a, w, bias = _mk(rows, K, N, 1, seed=23)
+    out = torch.empty(rows, N, device="cuda", dtype=torch.bfloat16)
+    flag = ops.GEMM_GELU if act == "gelu" else ops.GEMM_QUICK_GELU
+    ops.gemm(a, w, out, epilogue=ops.EPI_STORE_BF16, bias=bias, flags=flag | _force(kernel))
+    y = _ref_linear(a, w, bias, [(0, rows)], N).to(torch.bfloat16).float()
+    ref = torch.nn.functional.gelu(y) if act == "gelu" else y * torch.sigmoid(1.702 * y)
+    assert _relerr(out, ref) < 1e-2
+    # the activation of the bf16-rounded pre-activation, rounded once: at most 1 bf16 ulp from the reference
+    ulp = (out.float() - ref.to(torch.bfloat16).float()).abs() / ref.abs().clamp_min(1e-3)
+    assert ulp.max() < 2.0 ** -6
+
+
+@pytest.mark.parametrize("kernel", _KERNELS)
+def test_swiglu_both_kernels(kernel):
+    from g2vlm_b200 import ops
+    rows, K, I = 2100, 512, 1024
+    g = torch.Generator().manual_seed(24)
+    a = (torch.randn(rows, K, generator=g) * 0.5).to(torch.bfloat16).cuda()
+    wg = (torch.randn(2, I, K, generator=g) * 0.08).to(torch.bfloat16).cuda()
+    wu = (torch.randn(2, I, K, generator=g) * 0.08).to(torch.bfloat16).cuda()
+    w = torch.stack([wg.view(2, I // 128, 128, K), wu.view(2, I // 128, 128, K)], dim=2).reshape(2 * 2 * I, K).contiguous()
+    groups = [(0, 2000), (2000, 100)]
+    out = torch.empty(rows, I, device="cuda", dtype=torch.bfloat16)
+    ops.gemm(a, w, out, epilogue=ops.EPI_SWIGLU_BF16, groups=groups, flags=_force(kernel))
+    ref = torch.empty(rows, I, device="cuda")
+    for e, (r0, n) in enumerate(groups):
+        x = a[r0:r0 + n].float()
+        gt = (x @ wg[e].float().T).to(torch.bfloat16)
+        up = (x @ wu[e].float().T).to(torch.bfloat16)
+        ref[r0:r0 + n] = (torch.nn.functional.silu(gt.float()).to(torch.bfloat16).float() * up.float())
+    assert _relerr(out, ref) < 1.5e-2
+
+
+def test_pair_and_single_kernels_agree_bitwise_on_store_bf16():
+    """Same K order, same epilogue arithmetic: the two schedulers must produce identical bf16 outputs."""
+    from g2vlm_b200 import ops
+    rows, K, N = 1500, 768, 1024
+    a, w, bias = _mk(rows, K, N, 1, seed=25)
+    o1 = torch.empty(rows, N, device="cuda", dtype=torch.bfloat16)
+    o2 = torch.empty_like(o1)
+    ops.gemm(a, w, o1, epilogue=ops.EPI_STORE_BF16, bias=bias, flags=ops.GEMM_FORCE_PAIR)
+    ops.gemm(a, w, o2, epilogue=ops.EPI_STORE_BF16, bias=bias, flags=ops.GEMM_FORCE_SINGLE)
+    assert torch.equal(o1, o2)
+    with pytest.raises(Exception):
+        ops.gemm(a, w, o1, epilogue=ops.EPI_STORE_BF16, flags=ops.GEMM_FORCE_PAIR | ops.GEMM_FORCE_SINGLE)

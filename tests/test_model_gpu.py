@@ -139,6 +139,40 @@ def test_full_width_reduced_depth():
     torch.cuda.empty_cache()
 
 
+def test_config2_scene_full_width_depth1_vs_oracle():
+    """The BENCHMARKED configuration (BASELINE configs[1]: 16 views of 518x518, T = 21 936; 86 query tiles x 12 heads,
+    CTA-pair kernels on every GEMM, the prompt rows fused into the geo step) at full width on a depth-1 model,
+    stage by stage against the oracle.  The restatement runs on GPU tensors here (same code, `torch.device('cuda')`
+    places its factories): one layer at T = 21 936 is ~11 TFLOP of fp32 matmuls."""
+    from dataclasses import replace
+
+    from g2vlm_b200.model import G2VLMFast
+    from oracle import restate
+    cfg = replace(schema.FULL, num_layers=1, dino_layers=1, dec_depth=1)
+    sd = schema.init_synthetic(cfg, seed=5, embed_rows=32, device="cuda")
+    model = G2VLMFast(cfg, sd)
+    assert model.fuse_prompt
+    v = _views(dict(n=16, h=518, w=518, seed=6))
+    c_ref, c_out = {}, {}
+    out = model.recon(StubTokenizer(), dict(TOKENS), None, v, collect=c_out)
+    with torch.device("cuda"):
+        ref = restate.recon(sd, cfg, v.cuda(), mode="bf16", collect=c_ref)
+    gi_ref, _, _ = restate.prepare_dino_images(v, 7, 7, 3, 4)
+    for k in ("packed_text_indexes", "packed_dino_token_indexes", "packed_position_ids", "packed_indexes"):
+        assert torch.equal(c_out["generation_input"][k].cpu(), gi_ref[k]), k
+    errs = {"dino_tokens": _maxrel(c_out["dino_tokens"].view_as(c_ref["dino_tokens"]), c_ref["dino_tokens"]),
+            "mot0": _maxrel(c_out["mot_layers"][0], c_ref["mot_layers"][0]),
+            "last_hidden": _maxrel(c_out["last_hidden"], c_ref["last_hidden"])}
+    for k in ("point_hidden", "camera_hidden", "global_hidden"):
+        errs[k] = _maxrel(c_out[k], c_ref[k])
+    for k in ("local_points", "points", "global_points", "camera_poses"):
+        errs[k] = _maxrel(out[k], ref[k])
+    print("\n" + "\n".join(f"  {k:18s} {e:.3e}" for k, e in errs.items()))
+    assert all(e < TOL for e in errs.values()), errs
+    del model
+    torch.cuda.empty_cache()
+
+
 def test_full_depth_full_width_reference_layerscale_regime():
     """FULL model (28 MoT + 24 DINO layers, 5 blocks per decoder, full widths), one 518x518 view, LayerScale
     gammas at the reference's init value 0.01 (g2vlm/qwen2vl.py:765-766): every output within 2e-2 of the

@@ -1,0 +1,217 @@
+"""The CUDA path against the UNMODIFIED reference classes running on the same B200.
+
+`oracle/stage_ref.py` stages a byte-identical copy of the reference under the git-ignored `oracle/_ref/`, which travels
+to the GPU box; `oracle/ref_harness.build_reference_model(device="cuda")` builds the reference's own `G2VLM` there with
+its own flash-attn calls (g2vlm/qwen2vl.py:643-652, dinov2_model.py:49-58) and CUDA autocast regions.  The only
+deviation from the stock path is the zero-fill of the DINO attention rows flash-attn never writes (quirk Q1), which
+`test_flash_attn_leaves_uncovered_rows_unwritten` demonstrates on the real kernel.
+
+Tolerance: BASELINE.json — max|a-b| / max|ref| <= 2e-2 in bf16 mode.
+"""
+import contextlib
+import io
+import os
+
+import pytest
+import torch
+
+from g2vlm_b200 import schema
+
+pytestmark = pytest.mark.gpu
+TOL = 2e-2
+KEYS = ("points", "local_points", "global_points", "camera_poses")
+
+
+def _rh():
+    from oracle import ref_harness as rh
+    if not rh.gpu_available():
+        pytest.skip("reference tree (oracle/_ref) or flash_attn not available on this box")
+    return rh
+
+
+def _rel(a, b):
+    a, b = a.float(), b.float().to(a.device)
+    return ((a - b).abs().max() / b.abs().max()).item()
+
+
+def _pil(u8):
+    from PIL import Image
+    return [Image.fromarray(u8[i].permute(1, 2, 0).numpy()) for i in range(u8.shape[0])]
+
+
+def _views_u8(n, h, w, seed):
+    return (schema.synthetic_views(n, h, w, seed=seed) * 255).round().to(torch.uint8)
+
+
+def _quiet(fn, *a, **k):
+    with contextlib.redirect_stdout(io.StringIO()):   # the reference prints progress lines
+        return fn(*a, **k)
+
+
+def test_staged_reference_is_unmodified():
+    from oracle import stage_ref
+    if not os.path.exists(os.path.join(stage_ref.DST, "MANIFEST.json")):
+        pytest.skip("oracle/_ref not staged")
+    assert stage_ref.verify() > 50
+
+
+def test_flash_attn_leaves_uncovered_rows_unwritten():
+    """Quirk Q1 (g2vlm.py:988-990 vs dinov2_model.py:338-339): cu_seqlens built from PATCH counts cover only the first
+    N*P of the N*(P+5) DINO rows; flash-attn allocates `out = empty_like(q)` and never writes the rest.  Shown on
+    the real kernel: the allocator block that becomes `out` is poisoned first and the poison survives in the tail."""
+    _rh()
+    from flash_attn import flash_attn_varlen_func
+    q = torch.randn(300, 4, 64, device="cuda", dtype=torch.bfloat16)
+    cu = torch.tensor([0, 128, 256], dtype=torch.int32, device="cuda")
+    hits = 0
+    for _ in range(4):
+        poison = torch.full_like(q, 777.0)
+        del poison                                    # the caching allocator hands this block to flash-attn's `out`
+        o = flash_attn_varlen_func(q, q, q, cu, cu, 128, 128, causal=False)
+        assert torch.isfinite(o[:256].float()).all()
+        hits += int(bool((o[256:] == 777.0).all()))
+    assert hits > 0, "rows beyond cu_seqlens[-1] were written: the zero-fill definition of Q1 needs revisiting"
+
+
+# ----------------------------------------------------------------------------------------------------------
+# full-width, full-depth parity on BASELINE configs[0] (8 x 294x518) and configs[1] (16 x 518x518)
+# ----------------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def full_pair():
+    """(reference G2VLM on the GPU, G2VLMFast attached to the same weights); LayerScale gammas at the reference's
+    init value 0.01 (g2vlm/qwen2vl.py:765-766) — the regime a trained checkpoint is in."""
+    rh = _rh()
+    from g2vlm_b200.model import G2VLMFast
+    cfg = schema.FULL
+    sd = schema.init_synthetic(cfg, seed=0, embed_rows=32, device="cuda")
+    for k in sd:
+        if k.endswith("ls1.gamma") or k.endswith("ls2.gamma") or k.endswith(".lambda1"):
+            sd[k].fill_(0.01)
+    ref = rh.build_reference_model(rh.dims_from_cfg(cfg, vocab_size=32), visual_und=False, device="cuda")
+    msg = ref.load_state_dict(sd, strict=False)
+    assert not msg.unexpected_keys, msg.unexpected_keys[:5]
+    assert all("lm_head" in k or "vit_model" in k or "inv_freq" in k for k in msg.missing_keys), msg.missing_keys[:5]
+    fast = G2VLMFast(cfg, sd)
+    del sd
+    yield rh, ref, fast
+    del ref, fast
+    torch.cuda.empty_cache()
+
+
+@pytest.mark.parametrize("name,n,h,w", [("configs[0] 8x294x518", 8, 294, 518), ("configs[1] 16x518x518", 16, 518, 518)])
+def test_full_model_matches_reference_on_gpu(full_pair, name, n, h, w):
+    rh, ref, fast = full_pair
+    u8 = _views_u8(n, h, w, seed=1)
+    want = _quiet(rh.run_reference_recon, ref, _pil(u8))
+    got = fast.recon(rh.StubTokenizer(), dict(rh.NEW_TOKEN_IDS), None, u8.float() / 255.0)
+    torch.cuda.synchronize()
+    errs = {k: _rel(got[k], want[k]) for k in KEYS}
+    print(f"\n  {name}: " + "  ".join(f"{k} {e:.2e}" for k, e in errs.items()))
+    for k in KEYS:
+        assert got[k].shape == want[k].shape
+    assert torch.equal(got["images"].cpu(), want["images"].cpu())
+    assert all(e < TOL for e in errs.values()), errs
+
+
+def test_full_model_synthetic_layerscale_vs_reference_and_fp32(full_pair):
+    """The benchmark's own weights (LayerScale ~ U(0.5,1.5)) at full depth: a random network that
+    amplifies bf16 rounding through exp(z).  Reported against the real reference; asserted relative to how far the
+    REFERENCE's own bf16 result is from fp32 ground truth (restatement fp32 on GPU tensors): the CUDA path may not
+    be further from the truth than 1.5x the reference is."""
+    rh, ref, _ = full_pair
+    from g2vlm_b200.model import G2VLMFast
+    from oracle import restate
+    cfg = schema.FULL
+    sd = schema.init_synthetic(cfg, seed=0, embed_rows=32, device="cuda")
+    ref.load_state_dict(sd, strict=False)
+    fast = G2VLMFast(cfg, sd)
+    u8 = _views_u8(4, 518, 518, seed=1)
+    views = u8.float() / 255.0
+    want = _quiet(rh.run_reference_recon, ref, _pil(u8))
+    got = fast.recon(rh.StubTokenizer(), dict(rh.NEW_TOKEN_IDS), None, views)
+    with torch.device("cuda"):
+        truth = restate.recon(sd, cfg, views.cuda(), mode="fp32")
+    e_ours = {k: _rel(got[k], truth[k]) for k in KEYS}
+    e_ref = {k: _rel(want[k], truth[k]) for k in KEYS}
+    e_pair = {k: _rel(got[k], want[k]) for k in KEYS}
+    print("\n  ours vs fp32 : " + "  ".join(f"{k} {e:.2e}" for k, e in e_ours.items()))
+    print("  ref  vs fp32 : " + "  ".join(f"{k} {e:.2e}" for k, e in e_ref.items()))
+    print("  ours vs ref  : " + "  ".join(f"{k} {e:.2e}" for k, e in e_pair.items()))
+    for k in KEYS:
+        assert e_ours[k] < max(1.5 * e_ref[k], TOL), (k, e_ours[k], e_ref[k])
+    del fast
+    torch.cuda.empty_cache()
+
+
+# ----------------------------------------------------------------------------------------------------------
+# drop-in against the real object
+# ----------------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def tiny_ref():
+    rh = _rh()
+    cfg = schema.TINY
+    sd = schema.init_synthetic(cfg, seed=0, device="cuda")
+    ref = rh.build_reference_model(rh.dims_from_cfg(cfg), visual_und=False, device="cuda")
+    ref.load_state_dict(sd, strict=False)
+    return rh, ref, sd
+
+
+def _example_frames(rh):
+    d = os.path.join(rh.REFERENCE_ROOT, "examples", "dl3dv")
+    if not os.path.isdir(d):
+        pytest.skip("examples/dl3dv not staged")
+    return [os.path.join(d, f) for f in sorted(os.listdir(d))[:4]]
+
+
+def test_attach_patches_a_live_reference_object(tiny_ref):
+    """the three recon stages of a live reference `G2VLM` are replaced; the reference's OWN
+    `recon()` driver and host-side prepare_* code then run on top of the CUDA path, from image PATHS
+    (examples/dl3dv frames, 960x540 -> 294x518 through the reference's PIL LANCZOS loader)."""
+    rh, ref, sd = tiny_ref
+    from g2vlm_b200.model import G2VLMFast
+    paths = _example_frames(rh)
+    want = _quiet(rh.run_reference_recon, ref, paths)
+    saved = {n: getattr(ref, n) for n in G2VLMFast.RECON_STAGES}
+    try:
+        fast = G2VLMFast.attach(ref)
+        assert fast.cfg == schema.TINY
+        got = _quiet(rh.run_reference_recon, ref, paths)          # reference driver, CUDA stages
+    finally:
+        for n, f in saved.items():
+            setattr(ref, n, f)
+    assert got["points"].shape == want["points"].shape == (1, 4, 294, 518, 3)
+    errs = {k: _rel(got[k], want[k]) for k in KEYS}
+    print("\n  attach: " + "  ".join(f"{k} {e:.2e}" for k, e in errs.items()))
+    assert all(e < TOL for e in errs.values()), errs
+    # the swapped-in object called like inference_recon.py:36-43 does (device-side LANCZOS resize)
+    got2 = fast.recon(rh.StubTokenizer(), dict(rh.NEW_TOKEN_IDS), None, paths)
+    assert torch.equal(got2["images"].cpu(), want["images"].cpu())    # bit-identical preprocessing from the files
+    assert all(_rel(got2[k], want[k]) < TOL for k in KEYS)
+
+
+def test_adopts_a_reference_filled_naive_cache(tiny_ref):
+    """The reference runs its own text prefill (real flash-attn) and hands its `NaiveCache`
+    (g2vlm/qwen2vl.py:237-251) to the CUDA geo step; the merged cache that comes back keeps the reference contract."""
+    rh, ref, sd = tiny_ref
+    from g2vlm_b200.model import G2VLMFast
+    from modeling.g2vlm.qwen2vl import NaiveCache as RefCache
+    fast = G2VLMFast(schema.TINY, sd)
+    tok, ids = rh.StubTokenizer(), dict(rh.NEW_TOKEN_IDS)
+    u8 = _views_u8(3, 70, 518, seed=5)
+    with torch.no_grad(), torch.amp.autocast("cuda", dtype=torch.bfloat16):
+        gi, newlens, new_rope = ref.prepare_prompts_addbos([0], [0], ["Reconstruct the 3D scene."], tok, ids)
+        gi = {k: v.cuda() if torch.is_tensor(v) else v for k, v in gi.items()}
+        past_ref = ref.forward_cache_update_text(RefCache(schema.TINY.num_layers), **gi)
+        assert type(past_ref).__module__.startswith("modeling.")
+        gi2, _, _ = _quiet(ref.prepare_dino_images_pi3, newlens, new_rope, _pil(u8), None, ids)
+        gi2 = {k: v.cuda() if torch.is_tensor(v) else v for k, v in gi2.items()}
+        want_past, want_last = ref.forward_cache_update_dino(past_ref, **gi2)
+        want = ref.reconstruct(past_key_values=want_past, selected_hidden_states=want_last, **gi2)
+    got_past, got_last = fast.forward_cache_update_dino(past_ref, **gi2)
+    got = fast.reconstruct(past_key_values=got_past, selected_hidden_states=got_last, **gi2)
+    assert _rel(got_last, want_last) < TOL
+    for layer in range(schema.TINY.num_layers):
+        assert got_past.key_cache[layer].shape == want_past.key_cache[layer].shape
+        assert _rel(got_past.key_cache[layer], want_past.key_cache[layer]) < TOL
+        assert _rel(got_past.value_cache[layer], want_past.value_cache[layer]) < TOL
+    assert all(_rel(got[k], want[k]) < TOL for k in KEYS)
