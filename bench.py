@@ -16,8 +16,15 @@ units -> weak scaling, no data-path collective).  Rank 0 prints ONE JSON line.
   roofline  the dominant kernel (MoT shared attention, tcgen05): algorithmic FLOPs per launch
             4*T*(T+K0)*heads*head_dim / its mean launch duration measured with CUDA events on the
             launching stream inside the timed region, against MEASURED_PEAKS.json (sustained bf16)
-  cpu_baseline  the oracle port (oracle/restate.py = CPU restatement of the reference algorithm) timed
-            on the host cores on a bounded sample (rank 0, N = 1 only)
+  cpu_baseline  the reference's OWN classes (oracle/_ref = the unmodified tree staged by oracle/stage_ref.py, run
+            under oracle/ref_harness.py) on the host cores: full-width, full-depth model, a bounded sample of the
+            scene's views (rank 0, N = 1 only).  `--impl reference` times ONE OR MORE FULL steps of the same
+            16-view scene with those classes (capped by a time budget, never by shrinking the model).
+  gpu_reference the same classes on the same B200 with their own flash-attn calls (PyTorch + FA2): views/s on the
+            same weights and views — the number to beat — and max-rel error of our outputs against it
+  view_sharded  (N > 1 only) ONE long scene split by view over the N GPUs (BASELINE configs[3]): 64- and 256-view
+            scenes, strong-scaling efficiency against the single-GPU time of the same scene, exposed K/V exchange
+            time per layer, and `sp_parity_max_rel` = sharded result vs this rank's own single-GPU result
 
 Synthetic data: seeded random-init weights of the full architecture (no checkpoint / network) and
 blurred-noise views (g2vlm_b200.schema).  Inputs per step (5 GB of bf16 weights + activations) are far
@@ -120,12 +127,80 @@ def algorithmic_flops(cfg, n_views, P, K0=7):
 
 
 # --------------------------------------------------------------------------------------------------
-# reference arm / cpu baseline: the oracle port on host cores, bounded sample
+# reference legs (test infrastructure: the only places where bench.py touches oracle/)
 # --------------------------------------------------------------------------------------------------
-def cpu_sample(n_views: int, size: int, steps: int, warmup: int, threads: int, layer_frac: int = 1):
-    """Times oracle/restate.recon (CPU restatement of the reference algorithm, bf16 mode) on a bounded
-    sample: the FULL-width G2VLM-2B-MoT architecture at 1/`layer_frac` of every stack's depth, `n_views`
-    views of `size` px.  Returns (views/s extrapolated to full depth, description)."""
+DATA = "synthetic (seeded random-init weights: N(0,0.02^2) Linear/bias, U(0.5,1.5) norm weights, LayerScale {ls}; blurred-noise views rounded to 8 bit)"
+
+
+def bench_weights(cfg, device, layerscale):
+    """The benchmark's weights; LayerScale (ls1/ls2 gamma, DINO lambda1) either at the reference's
+    init value 0.01 — the regime a trained checkpoint lives in, default — or 'synthetic' ~U(0.5,1.5)."""
+    from g2vlm_b200 import schema
+    sd = schema.init_synthetic(cfg, seed=0, embed_rows=32, device=device)
+    if layerscale != "synthetic":
+        for k in sd:
+            if k.endswith("ls1.gamma") or k.endswith("ls2.gamma") or k.endswith(".lambda1"):
+                sd[k].fill_(float(layerscale))
+    return sd
+
+
+def bench_views_u8(n_views, size, seed):
+    from g2vlm_b200 import schema
+    return (schema.synthetic_views(n_views, size, size, seed=seed) * 255).round().to(torch.uint8)
+
+
+def to_pil(u8):
+    from PIL import Image
+    return [Image.fromarray(u8[i].permute(1, 2, 0).numpy()) for i in range(u8.shape[0])]
+
+
+def build_reference(cfg, device, layerscale):
+    """The reference's own G2VLM (oracle/_ref or /root/reference) with the benchmark's weights loaded."""
+    from oracle import ref_harness as rh
+    gen_dev = "cuda" if torch.cuda.is_available() else "cpu"   # same generator stream as our arm whenever a GPU exists
+    sd = bench_weights(cfg, gen_dev, layerscale)
+    ref = rh.build_reference_model(rh.dims_from_cfg(cfg, vocab_size=32), visual_und=False, device=device,
+                                   zero_fill_uncovered=False, skip_init=True)   # stock flash-attn call for timing
+    msg = ref.load_state_dict(sd, strict=False)
+    params = dict(ref.named_parameters())
+    with torch.no_grad():
+        for k in msg.missing_keys:                     # nothing recon reads; left uninitialised by skip_init
+            if k in params:
+                params[k].zero_()
+    del sd
+    return rh, ref
+
+
+def quiet(fn, *a, **k):
+    import contextlib
+    import io
+    with contextlib.redirect_stdout(io.StringIO()):    # the reference prints progress lines
+        return fn(*a, **k)
+
+
+def cpu_reference_steps(cfg, n_views, size, layerscale, threads, budget_s, max_steps, warm_views=1):
+    """Times the reference's own classes on the host cores (bf16 CPU autocast -> oneDNN/AMX; SDPA stand-in for
+    flash-attn): one untimed `warm_views`-view step (pages in oneDNN primitives), then full `n_views`-view steps
+    until `budget_s` is spent (at least one).  Returns (seconds per step, steps run, build seconds)."""
+    torch.set_num_threads(threads)
+    t0 = time.perf_counter()
+    rh, ref = build_reference(cfg, "cpu", layerscale)
+    build_s = time.perf_counter() - t0
+    if warm_views:
+        quiet(rh.run_reference_recon, ref, to_pil(bench_views_u8(warm_views, size, seed=7)))
+    pil = to_pil(bench_views_u8(n_views, size, seed=1))
+    times = []
+    t_start = time.perf_counter()
+    while len(times) < max_steps and (not times or time.perf_counter() - t_start + times[-1] < budget_s):
+        t0 = time.perf_counter()
+        quiet(rh.run_reference_recon, ref, pil)
+        times.append(time.perf_counter() - t0)
+    return sum(times) / len(times), len(times), build_s
+
+
+def cpu_port_sample(n_views: int, size: int, threads: int, layer_frac: int = 4):
+    """Fallback when no reference tree is reachable: the oracle port on a bounded sample (full-width model at
+    1/layer_frac depth), scaled to full depth.  Returns (views/s, description)."""
     from dataclasses import replace
 
     from g2vlm_b200 import schema
@@ -137,61 +212,179 @@ def cpu_sample(n_views: int, size: int, steps: int, warmup: int, threads: int, l
                   dino_layers=max(1, full.dino_layers // layer_frac), dec_depth=max(1, full.dec_depth // layer_frac))
     sd = schema.init_synthetic(cfg, seed=0, embed_rows=32)
     views = schema.synthetic_views(n_views, size, size, seed=1)
-    times = []
-    for i in range(warmup + steps):
-        t0 = time.perf_counter()
-        restate.recon(sd, cfg, views, mode="bf16")
-        dt = time.perf_counter() - t0
-        if i >= warmup:
-            times.append(dt)
-    per_step = sum(times) / len(times)
-    # depth scaling: every stack's cost is linear in its depth; the non-layer work (embeddings, heads'
-    # final linears, epilogue) is < 1% and is counted at its measured value
+    t0 = time.perf_counter()
+    restate.recon(sd, cfg, views, mode="bf16")
+    per_step = time.perf_counter() - t0
     scale = full.num_layers / cfg.num_layers
-    est_full = per_step * scale
-    desc = (f"oracle port (oracle/restate.py, torch CPU fp32 math with bf16 rounding points), full-width "
-            f"G2VLM-2B-MoT at 1/{layer_frac} depth ({cfg.num_layers} MoT + {cfg.dino_layers} DINO layers, "
-            f"{cfg.dec_depth} blocks per decoder), {n_views} view(s) of {size}x{size}, {threads} threads; "
-            f"{per_step:.2f} s per sample step, scaled x{scale:.0f} to full depth")
-    return n_views / est_full, desc, per_step
+    desc = (f"oracle PORT (oracle/restate.py; no reference tree on this box), full-width model at 1/{layer_frac} depth, "
+            f"{n_views} view(s) of {size}px, {threads} threads; {per_step:.2f} s per sample step, scaled x{scale:.0f}")
+    return n_views / (per_step * scale), desc
+
+
+def workload_string(n_views, size):
+    return (f"G2VLM-2B-MoT recon bf16, {n_views} views {size}px, single B200 (BASELINE configs[1]); one scene per GPU"
+            if (n_views, size) == (16, 518) else f"G2VLM-2B-MoT recon bf16, {n_views} views {size}px; one scene per GPU")
 
 
 def run_reference_arm(args):
+    """`--impl reference`: the UNMODIFIED reference classes on the box's host cores, on OUR arm's config (full
+    G2VLM-2B-MoT, `--views` views of `--size` px, bf16 autocast), every step one full scene."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    from g2vlm_b200 import schema
+    from oracle import ref_harness as rh
     threads = os.cpu_count() or 1
-    v, desc, per_step = cpu_sample(args.cpu_views, 518, max(1, args.steps), min(args.warmup, 1), threads,
-                                   layer_frac=args.cpu_layer_frac)
     P = (args.size // 14) ** 2
+    cfg = schema.TINY if args.tiny else schema.FULL
+    if rh.available():
+        per_step, n_steps, build_s = cpu_reference_steps(cfg, args.views, args.size, args.layerscale, threads,
+                                                         args.ref_budget_s, max(1, args.steps))
+        v = args.views / per_step
+        kind = "reference"
+        sample = (f"reference classes (oracle/_ref, unmodified; CPU bf16 autocast, SDPA stand-in for flash-attn), full-width "
+                  f"full-depth model, FULL scene of {args.views} views {args.size}px per step, {threads} threads; "
+                  f"{n_steps} timed step(s) of {per_step:.1f} s after one untimed 1-view step (time budget {args.ref_budget_s:.0f} s, "
+                  f"requested steps {args.steps}); model build {build_s:.0f} s untimed")
+    else:
+        v, sample = cpu_port_sample(1, args.size, threads)
+        per_step, n_steps, kind = args.views / v, 1, "port"
     line = dict(metric=METRIC, value=v, unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
-                ms_per_step=per_step * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16",
-                data="synthetic (seeded random-init weights, blurred-noise views)", impl="reference",
-                # same workload as our arm; every step is a BOUNDED SAMPLE of it (cpu_baseline.sample): the
-                # 1-view sample under-counts the quadratic attention of the 16-view scene, i.e. it favours the CPU
-                config=dict(workload="G2VLM-2B-MoT recon bf16, 16 views 518px, single B200 (BASELINE configs[1]); one scene per GPU",
+                steps_run=n_steps, ms_per_step=per_step * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None,
+                dtype="bf16", data=DATA.format(ls=args.layerscale), impl="reference",
+                config=dict(workload=workload_string(args.views, args.size) if not args.tiny else "TINY DEBUG MODEL (invalid as a benchmark)",
                             views_per_scene=args.views, image_size=args.size, tokens=args.views * (P + 2),
-                            scenes_per_step=1, parallelism="host cores (reference algorithm, CPU)"),
-                cpu_baseline=dict(value=v, unit=UNIT, cores=threads, kind="port", sample=desc),
+                            scenes_per_step=1, parallelism="host cores (reference classes, CPU)"),
+                cpu_baseline=dict(value=v, unit=UNIT, cores=threads, kind=kind, sample=sample),
                 e2e=dict(value=v, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
     print(json.dumps(line))
+
+
+def gpu_reference_leg(cfg, layerscale, u8, ours_pred, steps=3):
+    """The reference's own classes on THIS GPU (PyTorch + flash-attn 2, CUDA autocast), same weights and views:
+    views/s (CUDA events, 1 warm-up) and max-rel error of our outputs against it."""
+    try:
+        from oracle import ref_harness as rh
+        if not rh.gpu_available():
+            return dict(unavailable="no reference tree (oracle/_ref) or no flash_attn wheel on this box")
+        rh, ref = build_reference(cfg, "cuda", layerscale)
+        pil = to_pil(u8)
+        pred = quiet(rh.run_reference_recon, ref, pil)        # warm-up + parity sample
+        torch.cuda.synchronize()
+        max_rel = {}
+        for k in ("points", "local_points", "global_points", "camera_poses"):
+            a, b = ours_pred[k].float(), pred[k].float()
+            max_rel[k] = ((a - b).abs().max() / b.abs().max()).item()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            quiet(rh.run_reference_recon, ref, pil)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        import flash_attn
+        out = dict(value=u8.shape[0] / ms * 1e3, unit=UNIT, ms_per_step=ms, steps=steps,
+                   impl=f"reference classes (oracle/_ref, unmodified) on this GPU: PyTorch {torch.__version__} + flash_attn "
+                        f"{flash_attn.__version__}, bf16 autocast, input = the same 8-bit views as PIL images",
+                   max_rel_ours_vs_reference=max_rel,
+                   note="uncovered DINO rows (quirk Q1) are NOT zero-filled in this leg (stock flash-attn call)")
+        del ref, pred
+        torch.cuda.empty_cache()
+        return out
+    except Exception as e:  # a baseline must never take the measurement down with it
+        return dict(unavailable=f"{type(e).__name__}: {e}")
 
 
 # --------------------------------------------------------------------------------------------------
 # view-sharded long scene (BASELINE configs[3]): sequence parallel over the ranks
 # --------------------------------------------------------------------------------------------------
+def view_sharded_scene(model, dist, rank, world, n_views, size, steps, warmup, compare_single):
+    """ONE scene of n_views views split by view over the ranks (sequence parallel).  Returns a dict with the max-over-
+    ranks time per scene, the exposed K/V-exchange time per layer and, if `compare_single`, the single-GPU time of
+    the same scene on this rank plus sp_parity_max_rel (sharded result vs this rank's own single-GPU result)."""
+    tok = StubTokenizer()
+    views = bench_views_u8(n_views, size, seed=11).float() / 255.0
+
+    def allmax(x):
+        t = torch.tensor([float(x)], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def timed(fn, n):
+        dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            out = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return allmax(e0.elapsed_time(e1) / n), out
+
+    res = dict(views=n_views, tokens=n_views * ((size // 14) ** 2 + 2), mode=model.sp_mode, sm_margin=model.sp_sm_margin)
+    for _ in range(warmup):
+        model.recon_view_sharded(tok, dict(TOKENS), views)
+    model.sp_events = []
+    ms, pred = timed(lambda: model.recon_view_sharded(tok, dict(TOKENS), views), steps)
+    ev, model.sp_events = model.sp_events, None
+    exposed = [a.elapsed_time(b) for a, b in ev if b is not None]
+    res.update(ms_per_scene=ms, views_per_s=n_views / ms * 1e3,
+               exposed_exchange_ms_per_layer=allmax(sum(exposed) / max(1, len(exposed))),
+               mot_layer_ms=None)
+    if compare_single:
+        for _ in range(warmup):
+            model.recon(tok, dict(TOKENS), None, views)
+        ms1, full = timed(lambda: model.recon(tok, dict(TOKENS), None, views), steps)
+        v0, v1 = pred["view_range"]
+        worst = 0.0
+        for k in ("points", "local_points", "global_points", "camera_poses"):
+            a, b = pred[k].float(), full[k][:, v0:v1].float()
+            worst = max(worst, ((a - b).abs().max() / full[k].float().abs().max()).item())
+        worst = max(worst, ((pred["camera_poses_all"] - full["camera_poses"]).abs().max()
+                            / full["camera_poses"].abs().max()).item())
+        res.update(single_gpu_ms_per_scene=ms1, strong_scaling_efficiency=ms1 / (ms * world),
+                   sp_parity_max_rel=allmax(worst))
+    return res
+
+
+def view_sharded_block(model, cfg, dist, rank, world, args):
+    """`view_sharded` block of the N > 1 bench line (BASELINE configs[3])."""
+    out = dict(note="ONE scene split by view over the N GPUs: DINO by attention segment + neighbour exchange, per MoT "
+                    "layer a point-to-point K|V exchange (NCCL over NVLink) hidden behind the attention over the local "
+                    "keys + log-sum-exp merge, context broadcast; times are max over ranks, CUDA events",
+               scenes=[])
+    try:
+        P = (args.size // 14) ** 2
+        for n_views, cmp_single in ((64, True), (256, False)):
+            r = view_sharded_scene(model, dist, rank, world, n_views, args.size, steps=1, warmup=1, compare_single=cmp_single)
+            fl = algorithmic_flops(cfg, n_views, P)
+            r["achieved_tflops_per_gpu"] = fl["total"] / 1e12 / (r["ms_per_scene"] / 1e3) / world
+            r["mot_layer_algorithmic_ms_at_peak_per_gpu"] = fl["mot_layer"] / 1e12 / peaks()["tflops"] / world * 1e3
+            out["scenes"].append(r)
+            if n_views == 64:
+                out["sp_parity_max_rel"] = r["sp_parity_max_rel"]
+        # A/B of the exchange on the 64-view scene: v1 blocking all-gather
+        model.sp_mode = "allgather"
+        r = view_sharded_scene(model, dist, rank, world, 64, args.size, steps=1, warmup=1, compare_single=False)
+        model.sp_mode = "overlap"
+        out["allgather_v1_64views"] = dict(ms_per_scene=r["ms_per_scene"],
+                                           exposed_exchange_ms_per_layer=r["exposed_exchange_ms_per_layer"])
+    except Exception as e:   # must not take the scene-DP line down with it
+        out["error"] = f"{type(e).__name__}: {e}"
+    return out
+
+
 def run_view_sharded(args, cfg, dist, rank, world, local_rank):
-    from g2vlm_b200 import ops, schema
+    """`--workload views`: the standalone long-scene run (one JSON line, strong scaling)."""
+    from g2vlm_b200 import ops
     from g2vlm_b200.model import G2VLMFast
 
     n_views, size = args.views, args.size
     P = (size // 14) ** 2
-    sd = schema.init_synthetic(cfg, seed=0, embed_rows=32, device="cuda")
-    model = G2VLMFast(cfg, sd)
-    model.fuse_prompt = not args.no_fuse_prompt
-    del sd
+    model = G2VLMFast(cfg, bench_weights(cfg, "cuda", args.layerscale))
+    model.sp_mode, model.sp_sm_margin = args.sp_mode, args.sp_sm_margin
     torch.cuda.empty_cache()
-    views_host = schema.synthetic_views(n_views, size, size, seed=1)
+    views_host = bench_views_u8(n_views, size, seed=1).float() / 255.0
     tok = StubTokenizer()
 
     def step():
@@ -210,16 +403,20 @@ def run_view_sharded(args, cfg, dist, rank, world, local_rank):
     sampler = ClockSampler(local_rank)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     l0 = ops.LAUNCHES
+    model.sp_events = []
     e0.record()
     for _ in range(args.steps):
         step()
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
+    exposed = [a.elapsed_time(b) for a, b in model.sp_events if b is not None]
+    model.sp_events = None
+    exposed_ms = sum(exposed) / max(1, len(exposed))
     if dist is not None:
-        t = torch.tensor([ms], device="cuda")
+        t = torch.tensor([ms, exposed_ms], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+        ms, exposed_ms = float(t[0].item()), float(t[1].item())
     clocks = sampler.stop()
     barrier()
     if rank == 0:
@@ -229,12 +426,12 @@ def run_view_sharded(args, cfg, dist, rank, world, local_rank):
         print(json.dumps(dict(
             metric=METRIC, value=n_views / (per / 1e3), unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
             ms_per_step=per, higher_is_better=True, scaling="strong", vs_baseline=None, dtype="bf16",
-            data="synthetic (seeded random-init weights, blurred-noise views)",
+            data=DATA.format(ls=args.layerscale),
             config=dict(workload=f"G2VLM-2B-MoT long-sequence recon, ONE scene of {n_views} views {size}px, view-sharded "
-                                 f"over {world} GPU(s): DINO by segment + neighbour exchange, per-layer K/V all-gather "
-                                 f"(NCCL/NVLink), context broadcast", views_per_scene=n_views, image_size=size,
-                        tokens=n_views * (P + 2), parallelism=f"view-sp{world}"),
-            clocks=clocks, gpu_launches=ops.LAUNCHES - l0,
+                                 f"over {world} GPU(s): DINO by segment + neighbour exchange, per-layer K/V exchange "
+                                 f"({args.sp_mode}, NCCL/NVLink), context broadcast", views_per_scene=n_views, image_size=size,
+                        tokens=n_views * (P + 2), parallelism=f"view-sp{world}", sp_mode=args.sp_mode, sp_sm_margin=args.sp_sm_margin),
+            clocks=clocks, gpu_launches=ops.LAUNCHES - l0, exposed_exchange_ms_per_layer=exposed_ms,
             e2e=dict(value=n_views / (per / 1e3), unit=UNIT, h2d_bytes_per_step=views_host.numel() * 4 // world,
                      d2h_bytes_per_step=0, note="timed through recon_view_sharded from host views; outputs stay on the GPUs"),
             whole_step=dict(algorithmic_tflop=fl["total"] / 1e12,
@@ -255,9 +452,18 @@ def main():
     ap.add_argument("--impl", default="g2vlm_b200", choices=["g2vlm_b200", "reference"])
     ap.add_argument("--views", type=int, default=16)
     ap.add_argument("--size", type=int, default=518)
-    ap.add_argument("--cpu-views", type=int, default=1)
-    ap.add_argument("--cpu-layer-frac", type=int, default=4)
+    ap.add_argument("--cpu-views", type=int, default=2,
+                    help="views of the cpu_baseline sample (reference classes, full depth) inside our arm's run")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-reference", action="store_true")
+    ap.add_argument("--no-view-sharded", action="store_true", help="N > 1: skip the view_sharded block")
+    ap.add_argument("--layerscale", default="0.01",
+                    help="LayerScale value of the synthetic weights: 0.01 = the reference's init (g2vlm/qwen2vl.py:765-766), "
+                         "the regime of a trained checkpoint; 'synthetic' = U(0.5,1.5)")
+    ap.add_argument("--ref-budget-s", type=float, default=200.0,
+                    help="--impl reference: stop adding full-scene steps once this much time is spent (>= 1 step)")
+    ap.add_argument("--sp-mode", default="overlap", choices=["overlap", "allgather"])
+    ap.add_argument("--sp-sm-margin", type=int, default=8)
     ap.add_argument("--no-fuse-prompt", action="store_true",
                     help="run the 7-token prompt prefill as a separate und pass (reference order) instead of fused into the geo step")
     ap.add_argument("--profile", action="store_true",
@@ -293,12 +499,12 @@ def main():
         return
     n_views, size = args.views, args.size
     P = (size // 14) ** 2
-    sd = schema.init_synthetic(cfg, seed=0, embed_rows=32, device="cuda")
-    model = G2VLMFast(cfg, sd)
+    model = G2VLMFast(cfg, bench_weights(cfg, "cuda", args.layerscale))
     model.fuse_prompt = not args.no_fuse_prompt
-    del sd
+    model.sp_mode, model.sp_sm_margin = args.sp_mode, args.sp_sm_margin
     torch.cuda.empty_cache()
-    views_host = schema.synthetic_views(n_views, size, size, seed=1 + rank).pin_memory()
+    views_u8 = bench_views_u8(n_views, size, seed=1 + rank)          # 8-bit views: the reference legs read the same pixels
+    views_host = (views_u8.float() / 255.0).pin_memory()
     tok = StubTokenizer()
 
     # ---- device-resident arm ("value") ---------------------------------------------------------
@@ -413,6 +619,10 @@ def main():
         ms_single, _ = timed(step_single_call, 2)
         ms_single /= 2
 
+    view_sharded = None
+    if dist is not None and not args.no_view_sharded and not args.profile and not args.tiny:
+        view_sharded = view_sharded_block(model, cfg, dist, rank, world, args)
+
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -439,9 +649,8 @@ def main():
     line = dict(
         metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
         ms_per_step=ms_per_step, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16",
-        data="synthetic (seeded random-init weights, blurred-noise views)",
-        config=dict(workload="G2VLM-2B-MoT recon bf16, 16 views 518px, single B200 (BASELINE configs[1]); one scene per GPU"
-                    if not args.tiny else "TINY DEBUG MODEL (invalid as a benchmark)",
+        data=DATA.format(ls=args.layerscale),
+        config=dict(workload=workload_string(n_views, size) if not args.tiny else "TINY DEBUG MODEL (invalid as a benchmark)",
                     views_per_scene=n_views, image_size=size, tokens=T, scenes_per_step=world, parallelism=f"scene-dp{world}",
                     l2="inputs larger than L2 (5 GB of weights streamed per step); no flush"),
         clocks=clocks,
@@ -458,13 +667,36 @@ def main():
         whole_step=dict(algorithmic_tflop=fl["total"] / 1e12, achieved_tflops=fl["total"] / 1e12 / (ms_per_step / 1e3),
                         frac_of_peak=fl["total"] / 1e12 / (ms_per_step / 1e3) / pk["tflops"]),
     )
-    if world == 1 and not args.no_cpu_baseline and not args.tiny:
-        try:
-            v, desc, _ = cpu_sample(args.cpu_views, 518, 1, 0, os.cpu_count() or 1, layer_frac=args.cpu_layer_frac)
-            line["cpu_baseline"] = dict(value=v, unit=UNIT, cores=os.cpu_count() or 1, kind="port", sample=desc)
-        except Exception as e:  # the baseline must never take the GPU number down with it
-            line["cpu_baseline"] = dict(value=None, unit=UNIT, cores=os.cpu_count() or 1, kind="port",
-                                        sample=f"failed: {type(e).__name__}: {e}")
+    if view_sharded is not None:
+        line["view_sharded"] = view_sharded
+        if "sp_parity_max_rel" in view_sharded:
+            line["sp_parity_max_rel"] = view_sharded["sp_parity_max_rel"]
+    if world == 1 and not args.profile and not args.tiny:
+        if not args.no_gpu_reference:
+            # the number to beat: the reference's own classes on this GPU (PyTorch + flash-attn 2), same weights / views
+            ours = model.recon(tok, dict(TOKENS), None, views_host)
+            line["gpu_reference"] = gpu_reference_leg(cfg, args.layerscale, views_u8, ours)
+            if "value" in line["gpu_reference"]:
+                line["gpu_reference"]["speedup_e2e_vs_gpu_reference"] = e2e_value / line["gpu_reference"]["value"]
+        if not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            try:
+                from oracle import ref_harness as rh
+                if rh.available():
+                    per_step, n_steps, build_s = cpu_reference_steps(cfg, args.cpu_views, size, args.layerscale, cores,
+                                                                     budget_s=20.0, max_steps=2, warm_views=1)
+                    line["cpu_baseline"] = dict(
+                        value=args.cpu_views / per_step, unit=UNIT, cores=cores, kind="reference",
+                        sample=f"reference classes (oracle/_ref, unmodified; CPU bf16 autocast), full-width full-depth model, "
+                               f"bounded sample: {args.cpu_views} of the scene's {n_views} views ({size}px) per step, {n_steps} timed "
+                               f"step(s) of {per_step:.1f} s after one 1-view warm-up; under-counts the quadratic attention of "
+                               f"the full scene, i.e. favours the CPU (`--impl reference` times the full {n_views}-view scene)")
+                else:
+                    v, desc = cpu_port_sample(1, size, cores)
+                    line["cpu_baseline"] = dict(value=v, unit=UNIT, cores=cores, kind="port", sample=desc)
+            except Exception as e:  # the baseline must never take the GPU number down with it
+                line["cpu_baseline"] = dict(value=None, unit=UNIT, cores=cores, kind="reference",
+                                            sample=f"failed: {type(e).__name__}: {e}")
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()

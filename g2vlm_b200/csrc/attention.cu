@@ -40,6 +40,7 @@ struct AttnKParams {
   float scale_log2;
   int n_items, n_heads;
   int out_head_cols;  // columns of each head written to `out` (= head stride in `out`); D unless compacted
+  float* lse;         // optional [rows][n_heads]: ln(sum exp(scaled scores)) per row, for merging partial results
 };
 
 template <int D>
@@ -419,6 +420,7 @@ attention_tcgen05_kernel(const __grid_constant__ AttnKParams p) {
 #pragma unroll
           for (int q = 0; q < D / 8; ++q)
             if (q * 8 < p.out_head_cols) dst[q] = make_uint4(0, 0, 0, 0);
+          if (p.lse != nullptr) p.lse[(long long)row * p.n_heads + a.head] = -INFINITY;
         }
         continue;
       }
@@ -541,6 +543,10 @@ attention_tcgen05_kernel(const __grid_constant__ AttnKParams p) {
       __syncwarp();
       if (lane == 0) mbar_arrive(&o_free[t]);
       if (row_ok) {
+        // O and l are sums of 2^(s - m_used) terms, so m_used (however stale) + log2(l) is the exact log-sum-exp
+        if (p.lse != nullptr)
+          p.lse[(long long)row * p.n_heads + a.head] =
+              l_run > 0.f ? (m_used + log2f(l_run)) * 0.69314718055994531f : -INFINITY;
         const float inv_l = l_run > 0.f ? 1.0f / l_run : 0.f;
         uint4* dst = reinterpret_cast<uint4*>(p.out + (long long)row * p.ldo + a.head * p.out_head_cols);
 #pragma unroll
@@ -564,11 +570,53 @@ attention_tcgen05_kernel(const __grid_constant__ AttnKParams p) {
   }
 }
 
+// out = softmax-weighted combination of two partial attention results over disjoint key sets.
+// One thread per 8 output columns (16-byte loads/stores); memory-bound: 3 x rows x heads x cols x 2 B.
+__global__ void attention_merge_kernel(const __nv_bfloat16* __restrict__ oa, long long lda, const float* __restrict__ lse_a,
+                                       const __nv_bfloat16* __restrict__ ob, long long ldb, const float* __restrict__ lse_b,
+                                       __nv_bfloat16* __restrict__ out, long long ldo, long long rows, int heads,
+                                       int head_cols) {
+  const int vec_per_head = head_cols / 8;
+  const long long total = rows * heads * vec_per_head;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(i % vec_per_head);
+    const long long rh = i / vec_per_head;
+    const int h = (int)(rh % heads);
+    const long long r = rh / heads;
+    const float la = lse_a[r * heads + h], lb = lse_b[r * heads + h];
+    const float m = fmaxf(la, lb);
+    float wa = 0.f, wb = 0.f;
+    if (m > -INFINITY) {
+      const float ea = __expf(la - m), eb = __expf(lb - m);
+      const float inv = 1.0f / (ea + eb);
+      wa = ea * inv;
+      wb = eb * inv;
+    }
+    const long long col = (long long)h * head_cols + v * 8;
+    const uint4 a4 = *reinterpret_cast<const uint4*>(oa + r * lda + col);
+    const uint4 b4 = *reinterpret_cast<const uint4*>(ob + r * ldb + col);
+    const uint32_t aw[4] = {a4.x, a4.y, a4.z, a4.w}, bw[4] = {b4.x, b4.y, b4.z, b4.w};
+    uint32_t ow[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float a0 = __uint_as_float(aw[j] << 16), a1 = __uint_as_float(aw[j] & 0xffff0000u);
+      const float b0 = __uint_as_float(bw[j] << 16), b1 = __uint_as_float(bw[j] & 0xffff0000u);
+      // a weight of exactly 0 must not turn an uninitialised / inf partial into NaN
+      const float o0 = (wa > 0.f ? wa * a0 : 0.f) + (wb > 0.f ? wb * b0 : 0.f);
+      const float o1 = (wa > 0.f ? wa * a1 : 0.f) + (wb > 0.f ? wb * b1 : 0.f);
+      ow[j] = pack_bf16x2(o0, o1);
+    }
+    *reinterpret_cast<uint4*>(out + r * ldo + col) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+  }
+}
+
 template <int D>
-static int launch_attention(const AttnKParams& kp, cudaStream_t stream) {
+static int launch_attention(const AttnKParams& kp, int max_ctas, cudaStream_t stream) {
   if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(attention_tcgen05_kernel<D>), AttnCfg<D>::kSmem)) return rc;
   const long long units = (long long)kp.n_items * kp.n_heads;
-  const unsigned grid = (unsigned)(units < num_sms() ? units : num_sms());  // one persistent CTA per SM
+  long long cap = num_sms();                                                   // one persistent CTA per SM
+  if (max_ctas > 0 && max_ctas < cap) cap = max_ctas;
+  const unsigned grid = (unsigned)(units < cap ? units : cap);
   attention_tcgen05_kernel<D><<<grid, ATT_THREADS, AttnCfg<D>::kSmem, stream>>>(kp);
   G2_CUDA_OK(cudaGetLastError());
   return G2VLM_OK;
@@ -615,6 +663,30 @@ extern "C" int g2vlm_attention(const g2vlm_attn_args* a, void* stream_) {
   G2_REQUIRE(a->out_head_cols >= 0 && a->out_head_cols <= D && a->out_head_cols % 8 == 0,
              "attention: out_head_cols must be 0 or a multiple of 8 not above head_dim");
   kp.out_head_cols = a->out_head_cols ? a->out_head_cols : D;
-  if (D == 128) return launch_attention<128>(kp, stream);
-  return launch_attention<64>(kp, stream);
+  kp.lse = a->lse_out;
+  G2_REQUIRE(a->max_ctas >= 0, "attention: negative max_ctas");
+  if (D == 128) return launch_attention<128>(kp, a->max_ctas, stream);
+  return launch_attention<64>(kp, a->max_ctas, stream);
+}
+
+extern "C" int g2vlm_attention_merge(const void* o_a, int64_t lda, const float* lse_a, const void* o_b, int64_t ldb,
+                                     const float* lse_b, void* out, int64_t ldo, int64_t rows, int32_t heads,
+                                     int32_t head_cols, void* stream_) {
+  using namespace g2;
+  G2_REQUIRE(o_a && o_b && lse_a && lse_b && out, "attention_merge: null tensor");
+  G2_REQUIRE(rows >= 0 && heads > 0 && head_cols > 0 && head_cols % 8 == 0, "attention_merge: head_cols must be a multiple of 8");
+  G2_REQUIRE(lda % 8 == 0 && ldb % 8 == 0 && ldo % 8 == 0, "attention_merge: leading dimensions must be multiples of 8");
+  G2_REQUIRE(((reinterpret_cast<uintptr_t>(o_a) | reinterpret_cast<uintptr_t>(o_b) | reinterpret_cast<uintptr_t>(out)) & 15) == 0,
+             "attention_merge: tensors must be 16-byte aligned");
+  if (rows == 0) return G2VLM_OK;
+  const long long total = rows * heads * (head_cols / 8);
+  const int threads = 256;
+  long long blocks = (total + threads - 1) / threads;
+  const long long cap = (long long)num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  attention_merge_kernel<<<(unsigned)blocks, threads, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(o_a), lda, lse_a, reinterpret_cast<const __nv_bfloat16*>(o_b), ldb, lse_b,
+      reinterpret_cast<__nv_bfloat16*>(out), ldo, rows, heads, head_cols);
+  G2_CUDA_OK(cudaGetLastError());
+  return G2VLM_OK;
 }

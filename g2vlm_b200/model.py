@@ -24,6 +24,7 @@ import torch
 
 from . import _lib, host_prep, ops
 from .schema import G2Config, state_dict_schema
+from .sharding import view_ranges
 
 
 class NaiveCache:
@@ -215,6 +216,11 @@ class G2VLMFast:
         self._pos_cache: Dict[tuple, torch.Tensor] = {}
         self._work_cache: Dict[tuple, torch.Tensor] = {}
         self.stage_events: Optional[list] = None  # bench.py: [(name, cuda event)] at stage boundaries
+        # view-sharded K/V exchange: "overlap" (v2: point-to-point exchange hidden behind the local-key attention +
+        # LSE merge) or "allgather" (v1: one blocking all-gather per layer); SMs left to the NCCL kernel meanwhile
+        self.sp_mode = "overlap"
+        self.sp_sm_margin = 8
+        self.sp_events: Optional[list] = None     # bench.py: CUDA event pairs around every exchange wait
         self._raw_images = False  # True while recon() feeds un-normalised views (normalised on device)
 
     def _mark(self, name: str) -> None:
@@ -222,6 +228,16 @@ class G2VLMFast:
             ev = torch.cuda.Event(enable_timing=True)
             ev.record()
             self.stage_events.append((name, ev))
+
+    def _sp_mark(self, which: int) -> None:
+        """Event pair around the point where the compute stream waits for the K/V exchange (exposed time)."""
+        if self.sp_events is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            if which == 0:
+                self.sp_events.append([ev, None])
+            else:
+                self.sp_events[-1][1] = ev
 
     @classmethod
     def from_state_dict(cls, cfg: G2Config, state_dict, device="cuda") -> "G2VLMFast":
@@ -505,7 +521,7 @@ class G2VLMFast:
     # MoT language model
     # ------------------------------------------------------------------------------------------
     def _mot_layer(self, L, x, T, n_geo, qkv, attn, act, hbuf, cos, sin, work, kv_rows, causal, round_normed,
-                   kv_exchange=None, kv_len_dev=None, prompt_rows=0, train=None):
+                   kv_exchange=None, kv_len_dev=None, prompt_rows=0, train=None, attn_override=None):
         # prompt_rows: the LAST prompt_rows of the T rows are the causal text prefill riding along with the geo
         # step (fused recon path); they take the und branch's rounding of the normed q/k (round_normed=True)
         cfg = self.cfg
@@ -525,11 +541,15 @@ class G2VLMFast:
         if prompt_rows:
             ops.qknorm_mrope(qkv[Tm:], prompt_rows, 0, nq, nkv, hd, L["q_norm_geo"], L["k_norm_geo"], L["q_norm_und"],
                              L["k_norm_und"], cos[Tm:], sin[Tm:], cfg.rms_norm_eps, round_normed=True)
-        if kv_exchange is None:
+        if attn_override is not None:
+            pass  # view-sharded overlap mode: the callback runs the exchange and the split attention itself
+        elif kv_exchange is None:
             k_all, v_all = qkv[:kv_rows, nq * hd:(nq + nkv) * hd], qkv[:kv_rows, (nq + nkv) * hd:]
-        else:  # view-sharded: all ranks' K/V rows (+ prefix) gathered over NVLink
+        else:  # append-style cache / view-sharded all-gather: K/V rows come from the callback
             k_all, v_all = kv_exchange(qkv)
-        if rn:
+        if attn_override is not None:
+            attn_override(qkv, attn)
+        elif rn:
             qp, ap = train["qkv_packed"], train["attn_packed"]
             ops.gather_rows(qkv[:T], qp, train["perm"], T, scatter=True)          # internal -> packed row order
             ops.attention(qp[:, : nq * hd], qp[:, nq * hd:(nq + nkv) * hd], qp[:, (nq + nkv) * hd:], ap, work,
@@ -803,7 +823,7 @@ class G2VLMFast:
     def language_model_forward_geo(self, packed_sequence, packed_position_ids, packed_geo_token_indexes,
                                    packed_text_indexes, past_key_values: NaiveCache,
                                    update_past_key_values: bool = True, collect: Optional[list] = None,
-                                   group=None, prompt: Optional[dict] = None):
+                                   group=None, prompt: Optional[dict] = None, rank_rows: Optional[Sequence[int]] = None):
         """Qwen2VLModel.forward_inference(mode='geo', is_causal=False) incl. the routed final norm
         (reference g2vlm/qwen2vl.py:1267-1337).  packed_sequence: fp32 [T, H] in packed order.
 
@@ -851,22 +871,72 @@ class G2VLMFast:
         if update_past_key_values:
             past_key_values.reserve(K0 + T)
         kv_exchange = None
+        attn_override = None
         if group is not None:
-            # view-sharded sequence parallelism: this rank holds T of world*T rows (equal shards); per layer
-            # one all-gather of its K|V rows; keys = [rank 0 rows | ... | rank R-1 rows | K0 prefix rows]
+            # view-sharded sequence parallelism: this rank holds T of the scene's rows (rank_rows: every rank's count).
             import torch.distributed as dist
-            world = dist.get_world_size(group)
-            T_all = world * T
+            world, me = dist.get_world_size(group), dist.get_rank(group)
+            rank_rows = [T] * world if rank_rows is None else [int(r) for r in rank_rows]
+            if rank_rows[me] != T:
+                raise ValueError("rank_rows does not match this rank's packed rows")
+            T_all = sum(rank_rows)
             if update_past_key_values:
                 raise NotImplementedError("the merged NaiveCache is not materialised in view-sharded mode")
             kv_send = self.buf.get("mot.kv_send", (T, kvw), torch.bfloat16)
-            kv_all = self.buf.get("mot.kv_all", (T_all + K0, kvw), torch.bfloat16)
-            work = self._work([0, T], [0, T_all + K0], "geo_sp")
+            mode = self.sp_mode if len(set(rank_rows)) == 1 else "overlap"   # the all-gather needs equal shards
+            if mode == "allgather":
+                # v1: one blocking all-gather of the rank's K|V rows per layer on the compute stream;
+                # keys = [rank 0 rows | ... | rank R-1 rows | K0 prefix rows]
+                kv_all = self.buf.get("mot.kv_all", (T_all + K0, kvw), torch.bfloat16)
+                work = self._work([0, T], [0, T_all + K0], "geo_sp")
 
-            def kv_exchange(qkv_):
-                ops.gather_rows(qkv_[:T, nq * hd:], kv_send, None, T)
-                dist.all_gather_into_tensor(kv_all[:T_all], kv_send, group=group)
-                return kv_all[:, : nkv * hd], kv_all[:, nkv * hd:]
+                def kv_exchange(qkv_):
+                    ops.gather_rows(qkv_[:T, nq * hd:], kv_send, None, T)
+                    self._sp_mark(0)
+                    dist.all_gather_into_tensor(kv_all[:T_all], kv_send, group=group)
+                    self._sp_mark(1)
+                    return kv_all[:, : nkv * hd], kv_all[:, nkv * hd:]
+            else:
+                # v2: the remote K|V rows travel (one NCCL group of point-to-point sends/receives per layer, straight
+                # into their slot of kv_remote) WHILE the tensor cores run attention over the keys that are already
+                # here — this rank's own rows and the replicated prefix; then attention over the remote keys and an
+                # exact log-sum-exp merge of the two partials (the combination flash-attn does across key blocks).
+                others = [j for j in range(world) if j != me]
+                offs, o = {}, 0
+                for j in others:
+                    offs[j] = o
+                    o += rank_rows[j]
+                T_rem = o
+                kv_remote = self.buf.get("mot.kv_remote", (max(T_rem, 1), kvw), torch.bfloat16)
+                attn_b = self.buf.get("mot.attn_b", (T, nq * hd), torch.bfloat16)
+                lse_a = self.buf.get("mot.lse_a", (T, nq), torch.float32)
+                lse_b = self.buf.get("mot.lse_b", (T, nq), torch.float32)
+                work = None
+                work_local = self._work([0, T], [0, T + K0], "geo")       # own rows + prefix rows [T, T+K0) of qkv
+                work_remote = self._work([0, T], [0, T_rem], "geo_rem")
+                peers = {j: dist.get_global_rank(group, j) for j in others}
+                local_ctas = max(1, ops.num_sms() - self.sp_sm_margin)
+                scale = 1.0 / math.sqrt(hd)
+
+                def attn_override(qkv_, attn_):
+                    ops.gather_rows(qkv_[:T, nq * hd:], kv_send, None, T)          # contiguous send buffer
+                    reqs = []
+                    for j in others:
+                        reqs.append(dist.P2POp(dist.isend, kv_send, peers[j], group))
+                        reqs.append(dist.P2POp(dist.irecv, kv_remote[offs[j]:offs[j] + rank_rows[j]], peers[j], group))
+                    works = dist.batch_isend_irecv(reqs) if reqs else []
+                    ops.attention(qkv_[:T, : nq * hd], qkv_[:T + K0, nq * hd:(nq + nkv) * hd],
+                                  qkv_[:T + K0, (nq + nkv) * hd:], attn_, work_local, num_q_heads=nq, num_kv_heads=nkv,
+                                  head_dim=hd, scale=scale, lse=lse_a, max_ctas=local_ctas)
+                    self._sp_mark(0)
+                    for w_ in works:
+                        w_.wait()          # stream-side wait only: the host keeps enqueueing
+                    self._sp_mark(1)
+                    if T_rem:
+                        ops.attention(qkv_[:T, : nq * hd], kv_remote[:T_rem, : nkv * hd], kv_remote[:T_rem, nkv * hd:],
+                                      attn_b, work_remote, num_q_heads=nq, num_kv_heads=nkv, head_dim=hd, scale=scale,
+                                      lse=lse_b)
+                        ops.attention_merge(attn_, lse_a, attn_b, lse_b, attn_, nq, hd, rows=T)
         elif Kp:
             key = ("geo_fused", T, Kp)
             work = self._work_cache.get(key)
@@ -879,12 +949,12 @@ class G2VLMFast:
         for i, L in enumerate(self.layers):
             if K0:
                 # cached K|V rows (text prefill) become key rows [T, T+K0) (KV merge, qwen2vl.py:621-638)
-                if group is None:
+                if kv_exchange is None:
                     ops.gather_rows(past_key_values.buf[i], qkv[T:, nq * hd:], None, K0)
                 else:
                     ops.gather_rows(past_key_values.buf[i], kv_all[T_all:], None, K0)
             self._mot_layer(L, x, T + Kp, n_geo, qkv, attn, act, hbuf, cos, sin, work, T + K0 + Kp, False, False,
-                            kv_exchange=kv_exchange, prompt_rows=Kp)
+                            kv_exchange=kv_exchange, prompt_rows=Kp, attn_override=attn_override)
             if update_past_key_values:
                 # append in the reference's merged order: cached rows, then the PACKED query rows
                 ops.gather_rows(qkv[:T, nq * hd:], past_key_values.buf[i][K0:], perm, T, scatter=True)
@@ -1007,9 +1077,12 @@ class G2VLMFast:
         if reqs:
             for w in dist.batch_isend_irecv(reqs):
                 w.wait()
-        idx = torch.tensor(shard.token_row_index(), dtype=torch.long) - g0
+        key = ("dino_sp.idx", shard)
+        idx = self._work_cache.get(key)
+        if idx is None:   # built once per shard geometry, not per call
+            idx = self._work_cache[key] = (torch.tensor(shard.token_row_index(), dtype=torch.long) - g0).to(dev)
         tokens = self.buf.get("dino_sp.tokens", (shard.n_local * P, D), torch.bfloat16)
-        ops.gather_rows(normed, tokens, idx.to(dev), shard.n_local * P)
+        ops.gather_rows(normed, tokens, idx, shard.n_local * P)
         return tokens
 
     @_on_device
@@ -1060,7 +1133,8 @@ class G2VLMFast:
         last, past_key_values = self.language_model_forward_geo(
             packed, packed_position_ids, packed_dino_token_indexes, packed_text_indexes, past_key_values,
             update_past_key_values=update_past_key_values,
-            collect=None if collect is None else collect.setdefault("mot_layers", []), group=group, prompt=prompt)
+            collect=None if collect is None else collect.setdefault("mot_layers", []), group=group, prompt=prompt,
+            rank_rows=None if shard is None else [(b - a) * (shard.P + 2) for a, b in view_ranges(shard.n_views, shard.world)])
         self._mark("mot_end")
         return past_key_values, last
 
@@ -1253,9 +1327,13 @@ class G2VLMFast:
         finally:
             self._raw_images = False
         pred = self.reconstruct(selected_hidden_states=last, shard=shard, group=group, **gi)
-        poses_all = torch.empty(world, shard.n_local, 4, 4, dtype=torch.float32, device=dev)
-        dist.all_gather_into_tensor(poses_all, pred["camera_poses"][0].contiguous(), group=group)
-        pred["camera_poses_all"] = poses_all.view(1, N, 4, 4)
+        ranges = view_ranges(N, world)
+        n_max = max(b - a for a, b in ranges)
+        mine = torch.zeros(n_max, 4, 4, dtype=torch.float32, device=dev)
+        mine[: shard.n_local] = pred["camera_poses"][0]
+        poses_all = torch.empty(world, n_max, 4, 4, dtype=torch.float32, device=dev)
+        dist.all_gather_into_tensor(poses_all, mine, group=group)
+        pred["camera_poses_all"] = torch.cat([poses_all[r, : b - a] for r, (a, b) in enumerate(ranges)])[None]
         pred["view_range"] = (shard.v0, shard.v1)
         return pred
 

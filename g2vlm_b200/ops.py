@@ -34,6 +34,11 @@ def _check(rc: int) -> None:
         raise G2Error(f"g2vlm_b200 C ABI call failed (code {rc}): {msg}")
 
 
+def num_sms() -> int:
+    """SM count of the current device (persistent kernels launch one CTA per SM)."""
+    return torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
+
+
 def _stream() -> ctypes.c_void_p:
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -134,6 +139,7 @@ class AttnArgs(ctypes.Structure):
         ("softmax_scale", ctypes.c_float), ("n_items", ctypes.c_int32),
         ("work_items", ctypes.c_void_p),
         ("out_head_cols", ctypes.c_int32),
+        ("lse_out", ctypes.c_void_p), ("max_ctas", ctypes.c_int32),
     ]
 
 
@@ -156,10 +162,13 @@ def attention_work_table(cu_seqlens_q: Sequence[int], cu_seqlens_k: Sequence[int
 
 def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tensor, work: torch.Tensor,
               *, num_q_heads: int, num_kv_heads: int, head_dim: int, scale: float,
-              causal: bool = False, out_head_cols: int = 0) -> torch.Tensor:
+              causal: bool = False, out_head_cols: int = 0, lse: Optional[torch.Tensor] = None,
+              max_ctas: int = 0) -> torch.Tensor:
     """out[rows covered by `work`] = softmax(scale * q k^T) v, per segment; q/k/v/out are 2-D bf16
     views [rows, heads*head_dim] (they may be column slices of one fused QKV buffer).  out_head_cols: write only
-    that many columns per head, heads packed at that stride (96-wide heads computed in 128-wide slots)."""
+    that many columns per head, heads packed at that stride (96-wide heads computed in 128-wide slots).
+    lse: optional fp32 [q_rows, heads] receiving the log-sum-exp of every covered row (see attention_merge);
+    max_ctas: bound on the persistent grid (leaves SMs to a concurrent communication kernel)."""
     for t, n in ((q, "q"), (k, "k"), (v, "v"), (out, "out")):
         _req(t, torch.bfloat16, n)
     _req(work, torch.int32, "work")
@@ -176,7 +185,33 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tens
     args.causal, args.softmax_scale = int(causal), float(scale)
     args.n_items, args.work_items = work.shape[0], work.data_ptr()
     args.out_head_cols = int(out_head_cols)
+    if lse is not None:
+        _req(lse, torch.float32, "lse")
+        if not lse.is_contiguous() or lse.shape[0] < q.shape[0] or lse.shape[1] != num_q_heads:
+            raise G2Error("attention: lse must be a contiguous fp32 [q_rows, num_q_heads] tensor")
+        args.lse_out = lse.data_ptr()
+    args.max_ctas = int(max_ctas)
     _check(_lib.load().g2vlm_attention(ctypes.byref(args), _stream()))
+    return out
+
+
+def attention_merge(o_a: torch.Tensor, lse_a: torch.Tensor, o_b: torch.Tensor, lse_b: torch.Tensor, out: torch.Tensor,
+                    heads: int, head_cols: int, rows: Optional[int] = None) -> torch.Tensor:
+    """Combine two attention partials over disjoint key sets (see g2vlm_attention_merge); out may alias o_a."""
+    for t, n in ((o_a, "o_a"), (o_b, "o_b"), (out, "out")):
+        _req(t, torch.bfloat16, n)
+    for t, n in ((lse_a, "lse_a"), (lse_b, "lse_b")):
+        _req(t, torch.float32, n)
+        if not t.is_contiguous() or t.shape[1] != heads:
+            raise G2Error(f"attention_merge: {n} must be contiguous [rows, heads]")
+    rows = out.shape[0] if rows is None else rows
+    if min(o_a.shape[0], o_b.shape[0], out.shape[0], lse_a.shape[0], lse_b.shape[0]) < rows:
+        raise G2Error("attention_merge: a tensor has fewer rows than requested")
+    if min(o_a.shape[1], o_b.shape[1], out.shape[1]) < heads * head_cols:
+        raise G2Error("attention_merge: a tensor has fewer than heads*head_cols columns")
+    _call("g2vlm_attention_merge", _vp(o_a.data_ptr()), _i64(o_a.stride(0)), _vp(lse_a.data_ptr()), _vp(o_b.data_ptr()),
+          _i64(o_b.stride(0)), _vp(lse_b.data_ptr()), _vp(out.data_ptr()), _i64(out.stride(0)), _i64(rows), _i32(heads),
+          _i32(head_cols))
     return out
 
 

@@ -100,12 +100,24 @@ class ViewShard:
         return self.v0 * (self.P + 2), self.v1 * (self.P + 2)
 
 
+def view_ranges(n_views: int, world: int) -> List[Tuple[int, int]]:
+    """Contiguous view range of every rank; the first n_views % world ranks own one view more."""
+    if n_views < world:
+        raise ValueError(f"view-sharding needs at least one view per rank ({n_views} views, {world} ranks)")
+    base, rem = divmod(n_views, world)
+    out, v = [], 0
+    for r in range(world):
+        n = base + (1 if r < rem else 0)
+        out.append((v, v + n))
+        v += n
+    return out
+
+
 def shard_views(n_views: int, P: int, rank: int, world: int, n_reg: int = 5) -> ViewShard:
-    if n_views % world != 0:
-        raise ValueError(f"view-sharding needs n_views ({n_views}) divisible by the number of ranks ({world})")
-    n_loc = n_views // world
-    sh = ViewShard(rank=rank, world=world, n_views=n_views, P=P, n_reg=n_reg, v0=rank * n_loc, v1=(rank + 1) * n_loc)
-    # the neighbour exchange only reaches rank+1 if the shifted rows fit inside its block
-    if rank < world - 1 and n_reg * sh.v1 > n_loc * P:
+    ranges = view_ranges(n_views, world)
+    v0, v1 = ranges[rank]
+    sh = ViewShard(rank=rank, world=world, n_views=n_views, P=P, n_reg=n_reg, v0=v0, v1=v1)
+    # the neighbour exchange only reaches rank+1 if the shifted rows fit inside ITS block
+    if rank < world - 1 and n_reg * sh.v1 > (ranges[rank + 1][1] - ranges[rank + 1][0]) * P:
         raise ValueError("too many ranks for this scene: DINO row shift exceeds one rank's block")
     return sh

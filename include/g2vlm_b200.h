@@ -25,7 +25,8 @@ extern "C" {
 #define G2VLM_ERR_INVALID 1 /* bad argument / unsupported shape */
 #define G2VLM_ERR_CUDA 2    /* a CUDA runtime / driver call failed */
 
-#define G2VLM_ABI_VERSION 2 /* 2: gemm out_col_group/out_col_stride, attention item_causal + out_head_cols */
+#define G2VLM_ABI_VERSION 3 /* 2: gemm out_col_group/out_col_stride, attention item_causal + out_head_cols;
+                               3: gemm FORCE_PAIR/FORCE_SINGLE flags, attention lse_out + max_ctas, g2vlm_attention_merge */
 
 /* Version of this ABI (G2VLM_ABI_VERSION of the built library). */
 int g2vlm_abi_version(void);
@@ -143,9 +144,24 @@ typedef struct g2vlm_attn_args {
   /* 0, or the number of columns of each head that are written to `out`, heads packed at that stride
    * (multiple of 8, <= head_dim): a 96-wide head computed in a 128-wide slot leaves as [q_rows, heads*96]. */
   int32_t out_head_cols;
+  /* ABI v3.  lse_out: NULL, or fp32 [q_rows, num_q_heads] receiving ln(sum_k exp(scale * q.k)) of every covered row
+   * (-inf for a row without visible keys) so that partial results over disjoint key sets can be merged
+   * (g2vlm_attention_merge) — the view-sharded path runs the local keys while the remote K/V are in flight.
+   * max_ctas: 0, or an upper bound on the persistent grid (leaves SMs to a concurrent communication kernel). */
+  float* lse_out;
+  int32_t max_ctas;
 } g2vlm_attn_args;
 
 int g2vlm_attention(const g2vlm_attn_args* args, void* stream);
+
+/* Merge of two attention partials over disjoint key sets (same queries): out = (w_a o_a + w_b o_b) with
+ * w_x = exp(lse_x) / (exp(lse_a) + exp(lse_b)), fp32 math on the bf16 partials; rows whose two lse are -inf get
+ * zeros.  o_a / o_b / out: bf16 [rows, heads*head_cols] (row strides ld*, in elements; out may alias o_a);
+ * lse_a / lse_b: fp32 [rows, heads].  No reference counterpart (the reference has one device): this is the
+ * online-softmax combination flash-attn performs internally across key blocks (g2vlm/qwen2vl.py:643-652). */
+int g2vlm_attention_merge(const void* o_a, int64_t lda, const float* lse_a, const void* o_b, int64_t ldb,
+                          const float* lse_b, void* out, int64_t ldo, int64_t rows, int32_t heads,
+                          int32_t head_cols, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Memory-bound kernels (vectorised, coalesced, warp-shuffle reductions). "Routed" kernels take the

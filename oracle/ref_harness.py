@@ -197,11 +197,36 @@ def flash_attn_zero_fill(real):
     return wrapped
 
 
-def build_reference_model(dims=TINY, visual_und=True, device="cpu", zero_fill_uncovered=True):
+import contextlib
+
+
+@contextlib.contextmanager
+def _skip_random_init():
+    """Parameters are about to be overwritten by load_state_dict: skip the random initialisers (74 s of single-threaded
+    RNG for the 4.5 B-parameter model on the host).  Buffers (rotary inv_freq, ...) are still computed normally."""
+    import transformers
+    saved = []
+    for cls in (torch.nn.Linear, torch.nn.Embedding, torch.nn.Conv2d, torch.nn.Conv3d):
+        saved.append((cls, "reset_parameters", cls.reset_parameters))
+        cls.reset_parameters = lambda self: None
+    pm = transformers.PreTrainedModel
+    for name in ("init_weights", "_init_weights", "initialize_weights"):
+        if hasattr(pm, name):
+            saved.append((pm, name, getattr(pm, name)))
+            setattr(pm, name, lambda self, *a, **k: None)
+    try:
+        yield
+    finally:
+        for cls, name, fn in saved:
+            setattr(cls, name, fn)
+
+
+def build_reference_model(dims=TINY, visual_und=True, device="cpu", zero_fill_uncovered=True, skip_init=False):
     """Constructs the reference G2VLM from its own classes (mirrors g2vlm_utils.py:31-55).
     device="cpu": flash-attn replaced by the SDPA stand-in, autocast('cuda') redirected to 'cpu'.
     device="cuda": the reference's own flash-attn calls and CUDA autocast regions run unmodified (module parameters
-    are created directly on the GPU); `zero_fill_uncovered` wraps the DINO flash-attn call (see flash_attn_zero_fill)."""
+    are created directly on the GPU); `zero_fill_uncovered` wraps the DINO flash-attn call (see flash_attn_zero_fill).
+    skip_init: leave the parameters uninitialised (the caller loads a state_dict right away)."""
     global _REDIRECT_AUTOCAST
     install_shims()
     _REDIRECT_AUTOCAST = device == "cpu"
@@ -232,7 +257,7 @@ def build_reference_model(dims=TINY, visual_und=True, device="cpu", zero_fill_un
     vit = Qwen2VLVisionConfig(**dims["vit"])
     cfg = G2VLMConfig(visual_und=visual_und, visual_recon=True, llm_config=llm, vit_config=vit,
                       dino_config=dino, vit_max_num_patch_per_side=36)
-    with torch.device(device):
+    with torch.device(device), (_skip_random_init() if skip_init else contextlib.nullcontext()):
         lm = Qwen2VLForCausalLM(llm)
         vm = Qwen2VisionTransformerPretrainedModel(vit) if visual_und else None
         dm = Dinov2WithRegistersModel(dino)

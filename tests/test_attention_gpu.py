@@ -229,3 +229,62 @@ def test_causal_units_without_any_visible_key(d):
     assert bool((out[: lq - lk] == 0).all())
     ref = _ref_attention(q[lq - lk:], k, v, [0, lk], [0, lk], hq, hq, d, scale, True)
     assert (out[lq - lk:].float() - ref).abs().max() < 2e-2
+
+
+@pytest.mark.parametrize("d,hq,hk,lq,k_split,max_ctas", [
+    (128, 12, 2, 700, (391, 1400), 0),       # MoT head layout, ragged split, full grid
+    (128, 12, 2, 300, (7, 2048), 100),       # tiny local key set (the 7 prefix rows), capped persistent grid
+    (64, 4, 4, 520, (520, 777), 37),
+])
+def test_lse_output_and_two_way_merge_equal_one_pass(d, hq, hk, lq, k_split, max_ctas):
+    """View-sharded v2 path: attention over two disjoint key sets + g2vlm_attention_merge == one pass over all keys;
+    the lse output is ln(sum exp(scale q.k)) of the fp32 reference."""
+    from g2vlm_b200 import ops
+    g = torch.Generator().manual_seed(9)
+    ka, kb = k_split
+    q = torch.randn(lq, hq * d, generator=g).to(torch.bfloat16).cuda()
+    k = torch.randn(ka + kb, hk * d, generator=g).to(torch.bfloat16).cuda()
+    v = torch.randn(ka + kb, hk * d, generator=g).to(torch.bfloat16).cuda()
+    scale = 1.0 / math.sqrt(d)
+    o_a = torch.empty(lq, hq * d, device="cuda", dtype=torch.bfloat16)
+    o_b, o_all = torch.empty_like(o_a), torch.empty_like(o_a)
+    lse_a = torch.full((lq, hq), float("nan"), device="cuda")
+    lse_b, lse_all = lse_a.clone(), lse_a.clone()
+    kw = dict(num_q_heads=hq, num_kv_heads=hk, head_dim=d, scale=scale)
+    ops.attention(q, k[:ka], v[:ka], o_a, ops.attention_work_table([0, lq], [0, ka]).cuda(), lse=lse_a, max_ctas=max_ctas, **kw)
+    ops.attention(q, k[ka:], v[ka:], o_b, ops.attention_work_table([0, lq], [0, kb]).cuda(), lse=lse_b, **kw)
+    ops.attention(q, k, v, o_all, ops.attention_work_table([0, lq], [0, ka + kb]).cuda(), lse=lse_all, **kw)
+    merged = torch.empty_like(o_a)
+    ops.attention_merge(o_a, lse_a, o_b, lse_b, merged, hq, d)
+    inplace = o_a.clone()
+    ops.attention_merge(inplace, lse_a, o_b, lse_b, inplace, hq, d)      # out may alias o_a
+    torch.cuda.synchronize()
+    assert torch.equal(merged, inplace)
+    ref = _ref_attention(q, k, v, [0, lq], [0, ka + kb], hq, hk, d, scale, False)
+    mag = ref.abs().max().item()
+    assert (o_all.float() - ref).abs().max().item() < 2e-2 * max(mag, 1.0)
+    assert (merged.float() - ref).abs().max().item() < 2e-2 * max(mag, 1.0)
+    assert (merged.float() - o_all.float()).abs().max().item() < 1.5e-2 * max(mag, 1.0)   # two extra bf16 roundings
+    # log-sum-exp against fp32
+    qs = q.float().view(lq, hq, d).transpose(0, 1)
+    ks = k.float().view(-1, hk, d).transpose(0, 1).repeat_interleave(hq // hk, 0)
+    want = torch.logsumexp((qs @ ks.transpose(1, 2)) * scale, dim=-1).transpose(0, 1)
+    assert (lse_all - want).abs().max().item() < 2e-3
+    want_a = torch.logsumexp((qs @ ks[:, :ka].transpose(1, 2)) * scale, dim=-1).transpose(0, 1)
+    assert (lse_a - want_a).abs().max().item() < 2e-3
+
+
+def test_merge_ignores_an_empty_partial():
+    """A causal row that sees no key in one partial (lse = -inf, zeros) must take the other partial unchanged."""
+    from g2vlm_b200 import ops
+    hq, d, rows = 2, 128, 64
+    o_a = torch.randn(rows, hq * d, device="cuda").to(torch.bfloat16)
+    o_b = torch.full_like(o_a, float("nan"))                          # never read with weight > 0
+    lse_a = torch.randn(rows, hq, device="cuda")
+    lse_b = torch.full((rows, hq), float("-inf"), device="cuda")
+    out = torch.empty_like(o_a)
+    ops.attention_merge(o_a, lse_a, o_b, lse_b, out, hq, d)
+    assert torch.equal(out, o_a)
+    lse_a.fill_(float("-inf"))
+    ops.attention_merge(o_a, lse_a, o_b, lse_b, out, hq, d)
+    assert bool((out == 0).all())

@@ -29,7 +29,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, ret):
+def _worker(rank, world, port, ret, n_views=4):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
@@ -37,28 +37,36 @@ def _worker(rank, world, port, ret):
     cfg = schema.TINY
     sd = schema.init_synthetic(cfg, seed=0)
     model = G2VLMFast(cfg, sd, device=f"cuda:{rank}")
-    v = schema.synthetic_views(4, 42, 518, seed=6)
-    pred = model.recon_view_sharded(Tok(), dict(IDS), v)
-    v0, v1 = pred["view_range"]
+    v = schema.synthetic_views(n_views, 42, 518, seed=6)
     full = model.recon(Tok(), dict(IDS), None, v)          # every rank also runs the whole scene alone
-    torch.cuda.synchronize()
+    full = {k: full[k].clone() for k in ("points", "local_points", "global_points", "camera_poses")}
     errs = {}
-    for k in ("points", "local_points", "global_points", "camera_poses"):
-        a, b = pred[k].float().cpu(), full[k][:, v0:v1].float().cpu()
-        errs[k] = ((a - b).abs().max() / full[k].float().abs().max().cpu()).item()
-    errs["poses_all"] = ((pred["camera_poses_all"] - full["camera_poses"]).abs().max() / full["camera_poses"].abs().max()).item()
+    modes = ["overlap"] + (["allgather"] if n_views % world == 0 else [])   # the all-gather needs equal shards
+    for mode in modes:
+        model.sp_mode = mode
+        pred = model.recon_view_sharded(Tok(), dict(IDS), v)
+        v0, v1 = pred["view_range"]
+        torch.cuda.synchronize()
+        for k in ("points", "local_points", "global_points", "camera_poses"):
+            a, b = pred[k].float().cpu(), full[k][:, v0:v1].float().cpu()
+            errs[f"{mode}.{k}"] = ((a - b).abs().max() / full[k].float().abs().max().cpu()).item()
+        errs[f"{mode}.poses_all"] = ((pred["camera_poses_all"] - full["camera_poses"]).abs().max()
+                                     / full["camera_poses"].abs().max()).item()
     ret[rank] = (v0, v1, errs)
     dist.barrier()
     dist.destroy_process_group()
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-def test_view_sharded_recon_matches_single_gpu():
+@pytest.mark.parametrize("n_views,ranges", [(4, [(0, 2), (2, 4)]), (5, [(0, 3), (3, 5)])])
+def test_view_sharded_recon_matches_single_gpu(n_views, ranges):
     world = 2
     mgr = mp.Manager()
     ret = mgr.dict()
-    mp.spawn(_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
-    assert sorted((ret[r][0], ret[r][1]) for r in range(world)) == [(0, 2), (2, 4)]
+    mp.spawn(_worker, args=(world, _free_port(), ret, n_views), nprocs=world, join=True)
+    assert sorted((ret[r][0], ret[r][1]) for r in range(world)) == ranges
     for r in range(world):
         for k, e in ret[r][2].items():
-            assert e < 5e-3, (r, k, e)   # same kernels; only the key order inside attention differs
+            # same kernels; the key order inside attention differs (all-gather) / the two partials are rounded to
+            # bf16 before the log-sum-exp merge (overlap)
+            assert e < (5e-3 if k.startswith("allgather") else 1e-2), (r, k, e)

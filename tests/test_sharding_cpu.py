@@ -1,5 +1,6 @@
-"""N > 1 partitioning logic on CPU: ViewShard invariants and a world_size-2 gloo run that shards the
-DINO rows by attention segment + one neighbour exchange, and the MoT rows by view + K/V all-gather, using
+"""N > 1 partitioning logic on CPU: ViewShard invariants (even and uneven splits) and a world_size-2 gloo run that
+shards the DINO rows by attention segment + one neighbour exchange, and the MoT rows by view with the product's v2 K/V
+exchange (point-to-point rows of uneven size, local-key attention first, remote keys second, log-sum-exp merge), using
 the ORACLE functions as the arithmetic: the sharded result must equal the unsharded oracle."""
 import math
 import os
@@ -11,7 +12,7 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from g2vlm_b200 import schema
-from g2vlm_b200.sharding import scenes_for_rank, shard_views
+from g2vlm_b200.sharding import scenes_for_rank, shard_views, view_ranges
 
 
 def test_scene_round_robin_covers_all_scenes_once():
@@ -20,7 +21,8 @@ def test_scene_round_robin_covers_all_scenes_once():
         assert seen == list(range(n))
 
 
-@pytest.mark.parametrize("n_views,P,world", [(256, 1369, 8), (256, 1369, 2), (16, 1369, 4), (4, 185, 2), (6, 185, 3)])
+@pytest.mark.parametrize("n_views,P,world", [(256, 1369, 8), (256, 1369, 2), (16, 1369, 4), (4, 185, 2), (6, 185, 3),
+                                             (5, 185, 2), (7, 185, 3), (65, 1369, 8), (9, 1369, 8)])   # uneven splits
 def test_view_shard_invariants(n_views, P, world):
     S = P + 5
     shards = [shard_views(n_views, P, r, world) for r in range(world)]
@@ -44,12 +46,16 @@ def test_view_shard_invariants(n_views, P, world):
         ia, ib = s.dino_images
         assert ia * S <= s.dino_rows[0] and ib * S >= s.dino_rows[1]
     # MoT packed rows partition [0, N*(P+2))
-    assert [s.packed_rows for s in shards] == [(r * (n_views // world) * (P + 2), (r + 1) * (n_views // world) * (P + 2)) for r in range(world)]
+    ranges = view_ranges(n_views, world)
+    assert ranges[0][0] == 0 and ranges[-1][1] == n_views and all(ranges[i][1] == ranges[i + 1][0] for i in range(world - 1))
+    sizes = [b - a for a, b in ranges]
+    assert max(sizes) - min(sizes) <= 1 and sizes == sorted(sizes, reverse=True)
+    assert [s.packed_rows for s in shards] == [(a * (P + 2), b * (P + 2)) for a, b in ranges]
 
 
 def test_view_shard_rejects_bad_splits():
     with pytest.raises(ValueError):
-        shard_views(5, 185, 0, 2)            # not divisible
+        shard_views(3, 185, 0, 4)            # fewer views than ranks
     with pytest.raises(ValueError):
         shard_views(64, 37, 40, 64)          # row shift 5*v1 exceeds one rank's block
 
@@ -69,7 +75,7 @@ def _worker(rank, world, port, ret):
     from oracle import restate
     cfg = schema.TINY
     sd = schema.init_synthetic(cfg, seed=0)
-    N, Hh, Ww = 4, 28, 518
+    N, Hh, Ww = 5, 28, 518     # uneven split: rank 0 owns 3 views, rank 1 owns 2
     v = schema.synthetic_views(N, Hh, Ww, seed=5)
     gi, _, _ = restate.prepare_dino_images(v, 7, 7, 3, 4)
     P = (Hh // 14) * (Ww // 14)
@@ -133,16 +139,40 @@ def _worker(rank, world, port, ret):
 
     orig_attn = restate.attention_segments
 
+    rows = [(b - a) * (P + 2) for a, b in view_ranges(N, world)]
+    rb = lambda t: t.to(torch.bfloat16).float()
+
+    def partial(q, K, V, scale):
+        """attention over ONE key set with its log-sum-exp: (bf16-rounded output, lse [rows, heads])"""
+        hq, hk = q.shape[1], K.shape[1]
+        qs = rb(q).transpose(0, 1)
+        ks = rb(K).transpose(0, 1).repeat_interleave(hq // hk, dim=0)
+        vs = rb(V).transpose(0, 1).repeat_interleave(hq // hk, dim=0)
+        sc = (qs @ ks.transpose(1, 2)) * scale
+        lse = torch.logsumexp(sc, dim=-1)
+        return rb(torch.softmax(sc, dim=-1) @ vs).transpose(0, 1), lse.transpose(0, 1)
+
     def sharded_attn(q, K, V, cu_q, cu_k, scale, causal, mode):
-        # K, V = [prefix | my rows]; gather every rank's rows, keep ONE copy of the prefix
+        # the product's v2 exchange (model.py language_model_forward_geo): K, V = [prefix | my rows]; the other ranks'
+        # rows travel point to point (uneven sizes) while the LOCAL keys (prefix + mine) are attended to; then the
+        # remote keys, and an exact log-sum-exp merge of the two bf16 partials
         k0 = K.shape[0] - q.shape[0]
-        mine_k, mine_v = K[k0:].contiguous(), V[k0:].contiguous()
-        ks = [torch.empty_like(mine_k) for _ in range(world)]
-        vs = [torch.empty_like(mine_v) for _ in range(world)]
-        dist.all_gather(ks, mine_k)
-        dist.all_gather(vs, mine_v)
-        Ka, Va = torch.cat([K[:k0]] + ks), torch.cat([V[:k0]] + vs)
-        return orig_attn(q, Ka, Va, [0, q.shape[0]], [0, Ka.shape[0]], scale, causal, mode)
+        mine = torch.cat([K[k0:], V[k0:]], dim=-1).contiguous()
+        reqs, recv = [], {}
+        for j in range(world):
+            if j != rank:
+                recv[j] = torch.empty(rows[j], *mine.shape[1:])
+                reqs += [dist.P2POp(dist.isend, mine, j), dist.P2POp(dist.irecv, recv[j], j)]
+        works = dist.batch_isend_irecv(reqs)
+        o_a, lse_a = partial(q, K, V, scale)
+        for w in works:
+            w.wait()
+        rem = torch.cat([recv[j] for j in sorted(recv)])
+        hdim = K.shape[-1]
+        o_b, lse_b = partial(q, rem[..., :hdim], rem[..., hdim:], scale)
+        m = torch.maximum(lse_a, lse_b)
+        wa, wb = torch.exp(lse_a - m), torch.exp(lse_b - m)
+        return rb((o_a * wa[..., None] + o_b * wb[..., None]) / (wa + wb)[..., None])
 
     restate.attention_segments = sharded_attn
     try:
@@ -169,4 +199,5 @@ def test_view_sharding_equals_unsharded_oracle_gloo_world2():
     for r in range(world):
         err_dino, err_mot = ret[r]
         assert err_dino < 1e-5, (r, err_dino)      # identical arithmetic on a row subset (blocking noise only)
-        assert err_mot < 2e-3, (r, err_mot)        # key order differs -> fp32 summation order + bf16 rounding flips
+        # the two bf16 partials are rounded before the merge (one extra bf16 rounding per layer vs the one-pass result)
+        assert err_mot < 6e-3, (r, err_mot)
