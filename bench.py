@@ -471,7 +471,7 @@ def main():
     ap.add_argument("--ref-budget-s", type=float, default=120.0,
                     help="--impl reference: stop adding full-scene steps once this much time is spent (>= 1 step)")
     ap.add_argument("--sp-mode", default="overlap", choices=["overlap", "allgather"])
-    ap.add_argument("--sp-sm-margin", type=int, default=8)
+    ap.add_argument("--sp-sm-margin", type=int, default=4)
     ap.add_argument("--no-fuse-prompt", action="store_true",
                     help="run the 7-token prompt prefill as a separate und pass (reference order) instead of fused into the geo step")
     ap.add_argument("--profile", action="store_true",
@@ -496,6 +496,10 @@ def main():
     torch.cuda.set_device(local_rank)
     dist = None
     if world > 1:
+        # the view-sharded K/V exchange runs UNDER the local-key attention (a persistent kernel that leaves
+        # --sp-sm-margin SMs free): a few NCCL channels move the 45-180 MB per layer far faster than the attention
+        # it hides behind, and every channel is an SM taken from that attention
+        os.environ.setdefault("NCCL_MAX_NCHANNELS", str(max(1, args.sp_sm_margin)))
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     if args.warmup < 3 and not args.profile:

@@ -289,6 +289,15 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, const TileCo
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = bf16_round(f[j]);
         }
+        if (p.flags & G2VLM_GEMM_GELU) {   // fp32 mode: exact-erf GELU on the unrounded fp32 value
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
+        }
+        if (use_scale) {                   // fp32 mode: LayerScale without rounding, then `+ residual` below
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (j < cols_ok) f[j] *= __ldg(p.scale + col0 + j);
+        }
         const bool accum = (p.flags & G2VLM_GEMM_ACCUMULATE) != 0;
         const bool relu = (p.flags & G2VLM_GEMM_RELU) != 0;
         float* outp = reinterpret_cast<float*>(p.out) + (row_base + (lane >> 3)) * p.ldo + col0 + c4;

@@ -194,7 +194,20 @@ class _Buffers:
 
 
 class G2VLMFast:
-    def __init__(self, cfg: G2Config, state_dict: Dict[str, torch.Tensor], device="cuda"):
+    mode = "bf16"
+
+    def __new__(cls, cfg=None, state_dict=None, device="cuda", mode: str = "bf16"):
+        if cls is G2VLMFast and mode == "fp32":
+            from .model_fp32 import G2VLMFastFP32
+            return super().__new__(G2VLMFastFP32)
+        if mode not in ("bf16", "fp32"):
+            raise ValueError(f"mode must be 'bf16' or 'fp32', got {mode!r}")
+        return super().__new__(cls)
+
+    def __init__(self, cfg: G2Config, state_dict: Dict[str, torch.Tensor], device="cuda", mode: str = "bf16"):
+        """mode="bf16": the reference's autocast arithmetic (rounding points reproduced, tolerance 2e-2);
+        mode="fp32": no bf16 rounding anywhere (g2vlm_b200/model_fp32.py; <= 1e-4 against oracle/restate.py
+        mode="fp32"; recon only)."""
         if not torch.cuda.is_available():
             raise RuntimeError("G2VLMFast needs a CUDA device (sm_100a); there is no CPU fallback")
         _lib.load()  # fail loudly if the kernel library is missing
@@ -219,7 +232,7 @@ class G2VLMFast:
         # view-sharded K/V exchange: "overlap" (v2: point-to-point exchange hidden behind the local-key attention +
         # LSE merge) or "allgather" (v1: one blocking all-gather per layer); SMs left to the NCCL kernel meanwhile
         self.sp_mode = "overlap"
-        self.sp_sm_margin = 8
+        self.sp_sm_margin = 4    # = NCCL_MAX_NCHANNELS the launcher sets (bench.py); 2-GPU sweep: profiles/r02_sp_sweep_n2.txt
         self.sp_events: Optional[list] = None     # bench.py: CUDA event pairs around every exchange wait
         self._raw_images = False  # True while recon() feeds un-normalised views (normalised on device)
 
@@ -240,8 +253,8 @@ class G2VLMFast:
                 self.sp_events[-1][1] = ev
 
     @classmethod
-    def from_state_dict(cls, cfg: G2Config, state_dict, device="cuda") -> "G2VLMFast":
-        return cls(cfg, state_dict, device)
+    def from_state_dict(cls, cfg: G2Config, state_dict, device="cuda", mode: str = "bf16") -> "G2VLMFast":
+        return cls(cfg, state_dict, device, mode=mode)
 
     RECON_STAGES = ("forward_cache_update_text", "forward_cache_update_dino", "reconstruct")
 
@@ -1195,6 +1208,32 @@ class G2VLMFast:
             ops.gemm(h, dec["wout"], out, epilogue=ops.EPI_STORE_F32, bias=dec["bout"], flags=ops.GEMM_ROUND_BF16)
         return out
 
+    def _camera_head(self, camera_hidden, N, P):
+        """Pi3CameraHead.forward (camera_head.py:48-72), all fp32 (autocast disabled in the reference): split-bf16
+        Linears + mean pool + fc_t / fc_rot / SVD orthogonalisation.  camera_hidden fp32 [N*P, camera_dim]."""
+        cfg, dev = self.cfg, self.device
+        rows = N * P
+        C = cfg.camera_dim
+        feat = camera_hidden
+        t1 = self.buf.get("cam.t1", (rows, C), torch.float32)
+        t2 = self.buf.get("cam.t2", (rows, C), torch.float32)
+        f2 = self.buf.get("cam.f2", (rows, C), torch.float32)
+        f3 = self.buf.get("cam.f3", (rows, C), torch.float32)
+        for i, dst in ((0, f2), (1, f3)):
+            self._linear_fp32(feat, self.cam[f"r{i}1w"], self.cam[f"r{i}1b"], t1, relu=True)
+            self._linear_fp32(t1, self.cam[f"r{i}2w"], self.cam[f"r{i}2b"], t2, relu=True)
+            self._linear_fp32(t2, self.cam[f"r{i}3w"], self.cam[f"r{i}3b"], dst, relu=True, residual=feat)
+            feat = dst
+        pooled = self.buf.get("cam.pooled", (N, C), torch.float32)
+        ops.mean_pool(feat, pooled, N, P)
+        m1 = self.buf.get("cam.m1", (N, C), torch.float32)
+        m2 = self.buf.get("cam.m2", (N, C), torch.float32)
+        self._linear_fp32(pooled, self.cam["m0w"], self.cam["m0b"], m1, relu=True)
+        self._linear_fp32(m1, self.cam["m2w"], self.cam["m2b"], m2, relu=True)
+        poses = torch.empty(N, 4, 4, dtype=torch.float32, device=dev)
+        ops.camera_pose(m2, self.cam["fc_tw"], self.cam["fc_tb"], self.cam["fc_rotw"], self.cam["fc_rotb"], poses)
+        return poses
+
     def _linear_fp32(self, x, w3, b, out, relu=False, residual=None):
         """True-fp32 nn.Linear (autocast disabled in the reference) on the bf16 tensor cores:
         x = hi + lo, w = hi + lo, x.w ~ hi.hi + hi.lo + lo.hi as ONE GEMM over the concatenated K."""
@@ -1246,26 +1285,7 @@ class G2VLMFast:
                            camera_hidden=camera_hidden.view(N, P, -1).clone(),
                            global_hidden=global_hidden.float().view(N, P, -1).clone())
 
-        # camera head: fp32 (camera_head.py:48-72)
-        C = cfg.camera_dim
-        feat = camera_hidden
-        t1 = self.buf.get("cam.t1", (rows, C), torch.float32)
-        t2 = self.buf.get("cam.t2", (rows, C), torch.float32)
-        f2 = self.buf.get("cam.f2", (rows, C), torch.float32)
-        f3 = self.buf.get("cam.f3", (rows, C), torch.float32)
-        for i, dst in ((0, f2), (1, f3)):
-            self._linear_fp32(feat, self.cam[f"r{i}1w"], self.cam[f"r{i}1b"], t1, relu=True)
-            self._linear_fp32(t1, self.cam[f"r{i}2w"], self.cam[f"r{i}2b"], t2, relu=True)
-            self._linear_fp32(t2, self.cam[f"r{i}3w"], self.cam[f"r{i}3b"], dst, relu=True, residual=feat)
-            feat = dst
-        pooled = self.buf.get("cam.pooled", (N, C), torch.float32)
-        ops.mean_pool(feat, pooled, N, P)
-        m1 = self.buf.get("cam.m1", (N, C), torch.float32)
-        m2 = self.buf.get("cam.m2", (N, C), torch.float32)
-        self._linear_fp32(pooled, self.cam["m0w"], self.cam["m0b"], m1, relu=True)
-        self._linear_fp32(m1, self.cam["m2w"], self.cam["m2b"], m2, relu=True)
-        poses = torch.empty(N, 4, 4, dtype=torch.float32, device=dev)
-        ops.camera_pose(m2, self.cam["fc_tw"], self.cam["fc_tb"], self.cam["fc_rotw"], self.cam["fc_rotb"], poses)
+        poses = self._camera_head(camera_hidden, N, P)
 
         # point heads: fp32 Linear on bf16-exact activations = two bf16 GEMMs (W = hi + lo)
         nf = 3 * p * p

@@ -456,3 +456,74 @@ def resize_lanczos_u8(src: torch.Tensor, htab, vtab, out_h: int, out_w: int, out
           _i32(hc.shape[1] if hc is not None else 0), _ptr(vb), _ptr(vc), _i32(vc.shape[1] if vc is not None else 0),
           _ptr(tmp), _i32(out_h), _i32(out_w), _ptr(out_u8), _ptr(out_f32))
     return out_f32 if out_f32 is not None else out_u8
+
+
+# ---------------------------------------------------------------------------------------------------
+# fp32 mode (see include/g2vlm_b200.h): fp32 operands, no bf16 rounding point
+# ---------------------------------------------------------------------------------------------------
+def attention_f32(q, k, v, out, work, *, num_q_heads: int, num_kv_heads: int, head_dim: int, scale: float,
+                  causal: bool = False) -> torch.Tensor:
+    """fp32 counterpart of `attention` (same segment / work-table semantics), head_dim in {16,32,64,96,128}."""
+    for t, n in ((q, "q"), (k, "k"), (v, "v"), (out, "out")):
+        _req(t, torch.float32, n)
+    _req(work, torch.int32, "work")
+    if work.dim() != 2 or work.shape[1] != 8 or not work.is_contiguous():
+        raise G2Error("attention_f32: work table must be a contiguous int32 [n, 8] tensor")
+    args = AttnArgs()
+    args.q, args.ldq, args.q_rows = q.data_ptr(), q.stride(0), q.shape[0]
+    args.k, args.ldk = k.data_ptr(), k.stride(0)
+    args.v, args.ldv, args.kv_rows = v.data_ptr(), v.stride(0), k.shape[0]
+    args.out, args.ldo = out.data_ptr(), out.stride(0)
+    args.num_q_heads, args.num_kv_heads, args.head_dim = num_q_heads, num_kv_heads, head_dim
+    args.causal, args.softmax_scale = int(causal), float(scale)
+    args.n_items, args.work_items = work.shape[0], work.data_ptr()
+    _check(_lib.load().g2vlm_attention_f32(ctypes.byref(args), _stream()))
+    return out
+
+
+def im2col_patches_f32(images, out, patch: int, mean=None, std=None):
+    _req(images, torch.float32, "images")
+    _req(out, torch.float32, "out")
+    n, _, H, W = images.shape
+    if not images.is_contiguous() or not out.is_contiguous():
+        raise G2Error("im2col_f32: contiguous tensors required")
+    m3 = (ctypes.c_float * 3)(*mean) if mean is not None else None
+    s3 = (ctypes.c_float * 3)(*std) if std is not None else None
+    _call("g2vlm_im2col_patches_f32", _vp(images.data_ptr()), _vp(out.data_ptr()), _i32(n), _i32(H), _i32(W),
+          _i32(patch), _i32(out.shape[1]), m3, s3)
+    return out
+
+
+def dino_embed_f32(patch_emb, cls, reg, pos, out, n: int, P: int, n_reg: int):
+    _req(patch_emb, torch.float32, "patch_emb")
+    _req(out, torch.float32, "out")
+    _call("g2vlm_dino_embed_f32", _vp(patch_emb.data_ptr()), _i64(patch_emb.stride(0)), _vp(cls.data_ptr()),
+          _vp(reg.data_ptr()), _vp(pos.data_ptr()), _vp(out.data_ptr()), _i32(n), _i32(P), _i32(n_reg),
+          _i32(out.shape[1]))
+    return out
+
+
+def qknorm_mrope_f32(qkv, rows, n_first, n_q, n_kv, head_dim, qw_a, kw_a, qw_b, kw_b, cos, sin, eps):
+    _req(qkv, torch.float32, "qkv")
+    _call("g2vlm_qknorm_mrope_f32", _vp(qkv.data_ptr()), _i64(qkv.stride(0)), _i64(rows), _i64(n_first),
+          _i32(n_q), _i32(n_kv), _i32(head_dim), _vp(qw_a.data_ptr()), _vp(kw_a.data_ptr()),
+          _vp(qw_b.data_ptr()), _vp(kw_b.data_ptr()), _vp(cos.data_ptr()), _vp(sin.data_ptr()), _f32(eps))
+
+
+def rope2d_f32(buf, rows, n_heads_total, head_stride, head_dim, tokens_per_view, grid_w, cos, sin):
+    _req(buf, torch.float32, "buf")
+    _call("g2vlm_rope2d_f32", _vp(buf.data_ptr()), _i64(buf.stride(0)), _i64(rows), _i32(n_heads_total),
+          _i32(head_stride), _i32(head_dim), _i32(tokens_per_view), _i32(grid_w), _vp(cos.data_ptr()),
+          _vp(sin.data_ptr()))
+
+
+def swiglu_f32(gate_up, out, rows: Optional[int] = None):
+    """out[r, c] = silu(gate_up[r, c]) * gate_up[r, I + c], I = out.shape[1]."""
+    _req(gate_up, torch.float32, "gate_up")
+    _req(out, torch.float32, "out")
+    rows = out.shape[0] if rows is None else rows
+    if gate_up.shape[1] != 2 * out.shape[1]:
+        raise G2Error("swiglu_f32: gate_up must have 2 * out.shape[1] columns")
+    _call("g2vlm_swiglu_f32", _vp(gate_up.data_ptr()), _i64(gate_up.stride(0)), _vp(out.data_ptr()), _i64(out.stride(0)),
+          _i64(rows), _i32(out.shape[1]))
+    return out

@@ -58,9 +58,9 @@ const char* g2vlm_last_error(void);
 #define G2VLM_EPI_STORE_BF16 0  /* out_bf16 = bf16(acc + bias) [; gelu] */
 #define G2VLM_EPI_SWIGLU_BF16 1 /* B rows interleave gate/up in blocks of 128; out[:, N/2] */
 #define G2VLM_EPI_RESID_F32 2   /* out_f32 += [bf16](scale * bf16(acc + bias)) */
-#define G2VLM_EPI_STORE_F32 3   /* out_f32 = [resid +] [relu] [bf16] (acc + bias) [+ out_f32] */
+#define G2VLM_EPI_STORE_F32 3   /* out_f32 = [resid +] [relu] [scale *] [gelu] [bf16] (acc + bias) [+ out_f32] */
 
-#define G2VLM_GEMM_GELU 1u              /* STORE_BF16: exact-erf GELU on the bf16-rounded value */
+#define G2VLM_GEMM_GELU 1u              /* STORE_BF16: exact-erf GELU on the bf16-rounded value; STORE_F32 (fp32 mode): on the fp32 value */
 #define G2VLM_GEMM_ROUND_AFTER_SCALE 2u /* RESID_F32: round scale*x to bf16 (MoT ls1/ls2) */
 #define G2VLM_GEMM_RELU 4u              /* STORE_F32 */
 #define G2VLM_GEMM_ACCUMULATE 8u        /* STORE_F32: out += value (second pass of split-bf16) */
@@ -153,6 +153,11 @@ typedef struct g2vlm_attn_args {
 } g2vlm_attn_args;
 
 int g2vlm_attention(const g2vlm_attn_args* args, void* stream);
+
+/* fp32 MODE (north_star "fp32 mode <= 1e-4"; ground truth = oracle/restate.py mode="fp32"): the same call with
+ * fp32 q / k / v / out (leading dimensions in floats, multiples of 4), head_dim in {16, 32, 64, 96, 128} (no padding of
+ * the 96-wide Pi3 heads), FP32-pipe dot products and exp2f softmax.  lse_out / max_ctas / out_head_cols unsupported. */
+int g2vlm_attention_f32(const g2vlm_attn_args* args, void* stream);
 
 /* Merge of two attention partials over disjoint key sets (same queries): out = (w_a o_a + w_b o_b) with
  * w_x = exp(lse_x) / (exp(lse_a) + exp(lse_b)), fp32 math on the bf16 partials; rows whose two lse are -inf get
@@ -296,6 +301,31 @@ int g2vlm_attention_decode(const void* q, const void* k, int64_t ldk, const void
 int g2vlm_kv_append(const void* src, int64_t src_pitch_bytes, void* dst, int64_t dst_pitch_bytes,
                     const int32_t* len_dev, int64_t static_row, int64_t rows, int64_t row_bytes,
                     void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * fp32-mode elementwise kernels (no bf16 rounding anywhere; every Linear of that mode is a split-bf16 GEMM
+ * [hi|hi|lo] x [hi|lo|hi] through g2vlm_split3_f32 + g2vlm_gemm_bf16 with the STORE_F32 epilogue).
+ * ---------------------------------------------------------------------------------------------- */
+/* g2vlm_im2col_patches with an fp32 output [n*gh*gw, k_pad]. */
+int g2vlm_im2col_patches_f32(const float* images, float* out, int32_t n, int32_t H, int32_t W, int32_t patch,
+                             int32_t k_pad, const float* mean3, const float* std3, void* stream);
+/* g2vlm_dino_embed with an fp32 patch embedding [n*P, dim] (ld_patch in floats). */
+int g2vlm_dino_embed_f32(const float* patch_emb, int64_t ld_patch, const float* cls, const float* reg,
+                         const float* pos, float* out, int32_t n, int32_t P, int32_t n_reg, int32_t dim,
+                         void* stream);
+/* g2vlm_qknorm_mrope on an fp32 fused QKV buffer (head_dim 128): per-head RMSNorm with the routed weights, then
+ * x*cos + rotate_half(x)*sin, all fp32 (g2vlm/qwen2vl.py:600-619 without the bf16 casts). */
+int g2vlm_qknorm_mrope_f32(float* qkv, int64_t ld, int64_t rows, int64_t n_first, int32_t n_q_heads,
+                           int32_t n_kv_heads, int32_t head_dim, const float* qw_a, const float* kw_a,
+                           const float* qw_b, const float* kw_b, const float* cos_tab, const float* sin_tab,
+                           float eps, void* stream);
+/* g2vlm_rope2d on an fp32 buffer; tables fp32 [n_pos, head_dim/4] of EXACT fp32 angles (pos_embed.py:120-128). */
+int g2vlm_rope2d_f32(float* buf, int64_t ld, int64_t rows, int32_t n_heads_total, int32_t head_stride,
+                     int32_t head_dim, int32_t tokens_per_view, int32_t grid_w, const float* cos_tab,
+                     const float* sin_tab, void* stream);
+/* Qwen2MLP gate (modeling_qwen2_vl.py:519-521) in fp32: out[r, c] = silu(gu[r, c]) * gu[r, inter + c]. */
+int g2vlm_swiglu_f32(const float* gate_up, int64_t ld_gu, float* out, int64_t ldo, int64_t rows, int32_t inter,
+                     void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * One greedy decode step of generate_text (g2vlm.py:1086-1131), `und` expert, batch 1, enqueued as ONE call:
