@@ -134,6 +134,30 @@ __global__ void rope2d_f32_kernel(float* __restrict__ buf, long long ld, long lo
   }
 }
 
+// fp32 [rows, k] -> bf16 [rows, 6k] = [m | l | h | m | h | h], x = h + m + l EXACTLY (3 x 8 significand bits); pairs with
+// weights stored as [m | h | l | h | m | h]: the six products mm + lh + hl + mh + hm + hh (smallest first) drop only
+// terms <= 2^-24.
+__global__ void split6_kernel(const float* __restrict__ x, long long ldx, __nv_bfloat16* __restrict__ out, long long ldo,
+                              long long rows, int k) {
+  const long long total = rows * k;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / k;
+    const int c = static_cast<int>(i - r * k);
+    const float v = x[r * ldx + c];
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    const float r1 = v - __bfloat162float(h);
+    const __nv_bfloat16 m = __float2bfloat16_rn(r1);
+    const __nv_bfloat16 l = __float2bfloat16_rn(r1 - __bfloat162float(m));
+    __nv_bfloat16* o = out + r * ldo + c;
+    o[0] = m;
+    o[k] = l;
+    o[2 * k] = h;
+    o[3 * k] = m;
+    o[4 * k] = h;
+    o[5 * k] = h;
+  }
+}
+
 __global__ void swiglu_f32_kernel(const float* __restrict__ gu, long long ld_gu, float* __restrict__ out, long long ldo,
                                   long long rows, int inter) {
   const int c4n = inter >> 2;
@@ -218,6 +242,16 @@ extern "C" int g2vlm_rope2d_f32(float* buf, int64_t ld, int64_t rows, int32_t n_
   const long long total = rows * n_heads_total * (head_dim / 2);
   rope2d_f32_kernel<<<f32_blocks(total, F32_THREADS * 4), F32_THREADS, 0, (cudaStream_t)stream>>>(
       buf, ld, rows, n_heads_total, head_stride, head_dim, tokens_per_view, grid_w, cos_tab, sin_tab);
+  G2_CUDA_OK(cudaGetLastError());
+  return G2VLM_OK;
+}
+
+extern "C" int g2vlm_split6_f32(const float* x, int64_t ldx, void* out, int64_t ldo, int64_t rows, int32_t k, void* stream) {
+  using namespace g2;
+  G2_REQUIRE(x && out && k > 0 && ldo >= 6LL * k, "split6: bad arguments");
+  if (rows <= 0) return G2VLM_OK;
+  split6_kernel<<<f32_blocks(rows * k, F32_THREADS * 4), F32_THREADS, 0, (cudaStream_t)stream>>>(
+      x, ldx, reinterpret_cast<__nv_bfloat16*>(out), ldo, rows, k);
   G2_CUDA_OK(cudaGetLastError());
   return G2VLM_OK;
 }

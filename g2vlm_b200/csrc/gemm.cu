@@ -54,6 +54,7 @@ struct GemmKParams {
   int grp_mpair0[3];
   int num_pair_tiles;
   int pair_panel;   // rasterisation: pair_panel M pairs x all N tiles per panel
+  int k_chunk_kb;   // > 0 (fp32 mode, STORE_F32): k-blocks per accumulator chunk, chunks summed in fp32 RN by the epilogue
 };
 
 struct TileCoord {
@@ -133,9 +134,13 @@ __device__ __forceinline__ float4 stage_read_f32(const uint8_t* stg, int lane, i
   return *reinterpret_cast<const float4*>(stg + row * 128 + ((lane & 7) ^ (row & 7)) * 16);
 }
 
+// chunk_first / chunk_last (STORE_F32 with k_chunk_kb > 0, fp32 mode): the accumulator of ONE K chunk — bias only with
+// the first chunk, `out +=` for every later one (fp32 round-to-nearest on the CUDA cores), activation / scale / residual
+// only with the last.
 template <int EPI>
 __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, const TileCoord& t, uint32_t taddr,
-                                              int sub, int half, int lane, uint8_t* stg) {
+                                              int sub, int half, int lane, uint8_t* stg, bool chunk_first = true,
+                                              bool chunk_last = true) {
   const int rows_ok = t.rows_valid - sub * 32;  // rows of this warp's 32-row slab that are real
   const long long row_base = t.row0 + sub * 32;
   const int n0 = t.n_tile * BN;
@@ -167,7 +172,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, const TileCo
     }
     return;
   } else {
-    const float* bias = p.bias ? p.bias + (long long)t.g * p.N : nullptr;
+    const float* bias = (p.bias && chunk_first) ? p.bias + (long long)t.g * p.N : nullptr;
     const bool use_scale = p.scale != nullptr && ((p.scale_groups >> t.g) & 1u);
 #pragma unroll 1
     for (int c = half * 4; c < half * 4 + 4; ++c) {
@@ -289,20 +294,21 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, const TileCo
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = bf16_round(f[j]);
         }
-        if (p.flags & G2VLM_GEMM_GELU) {   // fp32 mode: exact-erf GELU on the unrounded fp32 value
-#pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
-        }
-        if (use_scale) {                   // fp32 mode: LayerScale without rounding, then `+ residual` below
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (j < cols_ok) f[j] *= __ldg(p.scale + col0 + j);
-        }
-        const bool accum = (p.flags & G2VLM_GEMM_ACCUMULATE) != 0;
-        const bool relu = (p.flags & G2VLM_GEMM_RELU) != 0;
+        // order: v = acc [+ bias] [+ out] ; [gelu] ; [* scale] ; [relu] ; [+ residual]   (the last four only with
+        // the final K chunk)
+        const bool accum = (p.flags & G2VLM_GEMM_ACCUMULATE) != 0 || !chunk_first;
+        const bool relu = chunk_last && (p.flags & G2VLM_GEMM_RELU) != 0;
+        const bool gelu = chunk_last && (p.flags & G2VLM_GEMM_GELU) != 0;   // fp32 mode: exact erf on the fp32 value
+        const bool scl = chunk_last && use_scale;                           // fp32 mode: LayerScale without rounding
         float* outp = reinterpret_cast<float*>(p.out) + (row_base + (lane >> 3)) * p.ldo + col0 + c4;
-        const float* resp = p.residual ? p.residual + (row_base + (lane >> 3)) * p.ldr + col0 + c4 : nullptr;
+        const float* resp = (p.residual && chunk_last) ? p.residual + (row_base + (lane >> 3)) * p.ldr + col0 + c4 : nullptr;
         stage_write_f32(stg, lane, f);
+        float sc[4] = {1.f, 1.f, 1.f, 1.f};
+        if (scl) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (c4 + j < cols_ok) sc[j] = __ldg(p.scale + col0 + c4 + j);
+        }
         float4 po[8], pr[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {  // batch the loads (accumulate / residual operands)
@@ -318,6 +324,14 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, const TileCo
           if (row < rows_ok) {
             if (c4 + 4 <= cols_ok) {
               float xv[4] = {a.x + po[i].x, a.y + po[i].y, a.z + po[i].z, a.w + po[i].w};
+              if (gelu) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) xv[j] = gelu_erf(xv[j]);
+              }
+              if (scl) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) xv[j] *= sc[j];
+              }
               if (relu) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) xv[j] = fmaxf(xv[j], 0.f);
@@ -329,6 +343,8 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, const TileCo
                 if (c4 + j < cols_ok) {
                   float x = av[j];
                   if (accum) x += d[j];
+                  if (gelu) x = gelu_erf(x);
+                  if (scl) x *= sc[j];
                   if (relu) x = fmaxf(x, 0.f);
                   if (resp) x += resp[(long long)i * 4 * p.ldr + j];
                   d[j] = x;
@@ -410,26 +426,34 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ GemmKParams p) {
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
+      // k_chunk_kb > 0 (fp32 mode): the accumulator leaves the tensor core every k_chunk_kb k-blocks and the chunks
+      // are summed by the epilogue warps in fp32 round-to-nearest.  The tensor core adds into its fp32 accumulator
+      // with truncation, so a K of tens of thousands (6 x 8960 in the split form) loses ~1e-5 relative when it is
+      // accumulated in one go (measured: 3e-5 per MoT layer); 16 MMA steps per chunk keep that below 1e-6.
+      const int chunk = p.k_chunk_kb > 0 ? p.k_chunk_kb : p.num_kb;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int kb = 0; kb < p.num_kb; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
+        for (int kb0 = 0; kb0 < p.num_kb; kb0 += chunk) {
+          mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem + stage * STAGE_BYTES);
-          const uint32_t b_addr = a_addr + A_BYTES;
+          const uint32_t d_tmem = tmem_base + acc * BN;
+          const int kb1 = min(p.num_kb, kb0 + chunk);
+          for (int kb = kb0; kb < kb1; ++kb) {
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after();
+            const uint32_t a_addr = smem_u32(smem + stage * STAGE_BYTES);
+            const uint32_t b_addr = a_addr + A_BYTES;
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            umma_ss(d_tmem, umma_desc_kmajor(a_addr + k * 32), umma_desc_kmajor(b_addr + k * 32),
-                    idesc, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < BK / 16; ++k) {
+              umma_ss(d_tmem, umma_desc_kmajor(a_addr + k * 32), umma_desc_kmajor(b_addr + k * 32),
+                      idesc, ((kb - kb0) | k) != 0 ? 1u : 0u);
+            }
+            umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
-          umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          umma_commit(&tmem_full_bar[acc]);  // accumulator (chunk) complete -> epilogue
+          acc ^= 1;
+          if (acc == 0) acc_phase ^= 1;
         }
-        umma_commit(&tmem_full_bar[acc]);  // accumulator complete -> epilogue
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1;
       }
     }
   } else {
@@ -439,16 +463,19 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ GemmKParams p) {
     uint8_t* stg = staging + (warp - 2) * 4096;
     int acc = 0;
     uint32_t acc_phase = 0;
+    const int chunk = p.k_chunk_kb > 0 ? p.k_chunk_kb : p.num_kb;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       const TileCoord t = decode_tile(p, tile);
-      mbar_wait(&tmem_full_bar[acc], acc_phase);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(sub * 32) << 16) + acc * BN;
-      epilogue_tile<EPI>(p, t, taddr, sub, half, lane, stg);
-      tc_fence_before();
-      mbar_arrive(&tmem_empty_bar[acc]);
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1;
+      for (int kb0 = 0; kb0 < p.num_kb; kb0 += chunk) {
+        mbar_wait(&tmem_full_bar[acc], acc_phase);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(sub * 32) << 16) + acc * BN;
+        epilogue_tile<EPI>(p, t, taddr, sub, half, lane, stg, kb0 == 0, kb0 + chunk >= p.num_kb);
+        tc_fence_before();
+        mbar_arrive(&tmem_empty_bar[acc]);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
     }
   }
 
@@ -706,6 +733,13 @@ extern "C" int g2vlm_gemm_bf16(const g2vlm_gemm_args* a, void* stream_) {
   kp.ldr = a->ldr;
   kp.out_col_group = a->out_col_group;
   kp.out_col_stride = a->out_col_stride;
+  G2_REQUIRE(a->k_chunk_blocks >= 0, "gemm: negative k_chunk_blocks");
+  G2_REQUIRE(a->k_chunk_blocks == 0 || (a->epilogue == G2VLM_EPI_STORE_F32 && !(a->flags & G2VLM_GEMM_ROUND_BF16)),
+             "gemm: k_chunk_blocks needs the STORE_F32 epilogue without ROUND_BF16");
+  // the chunks accumulate IN `out`, so the residual operand (added with the last chunk) must live elsewhere
+  G2_REQUIRE(a->k_chunk_blocks == 0 || a->residual == nullptr || a->residual != a->out,
+             "gemm: with k_chunk_blocks the residual must not alias out");
+  kp.k_chunk_kb = a->k_chunk_blocks;
 
   int rc = make_tmap_2d_bf16(&kp.tmA, a->A, (uint64_t)a->a_rows, (uint64_t)a->K, (uint64_t)a->lda * 2, BM, BK);
   if (rc) return rc;
@@ -735,7 +769,9 @@ extern "C" int g2vlm_gemm_bf16(const g2vlm_gemm_args* a, void* stream_) {
   G2_REQUIRE((a->flags & (G2VLM_GEMM_FORCE_PAIR | G2VLM_GEMM_FORCE_SINGLE)) !=
                  (G2VLM_GEMM_FORCE_PAIR | G2VLM_GEMM_FORCE_SINGLE),
              "gemm: FORCE_PAIR and FORCE_SINGLE are mutually exclusive");
-  const bool use_pair = (a->flags & G2VLM_GEMM_FORCE_PAIR)     ? true
+  G2_REQUIRE(!(a->k_chunk_blocks > 0 && (a->flags & G2VLM_GEMM_FORCE_PAIR)), "gemm: k_chunk_blocks runs on the 1-CTA kernel");
+  const bool use_pair = a->k_chunk_blocks > 0                  ? false
+                        : (a->flags & G2VLM_GEMM_FORCE_PAIR)   ? true
                         : (a->flags & G2VLM_GEMM_FORCE_SINGLE) ? false
                                                                : kp.num_pair_tiles >= num_sms();
   if (use_pair) {

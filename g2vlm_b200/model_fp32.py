@@ -6,10 +6,14 @@ modeling/g2vlm/qwen2vl.py:579, 617-619; dinov2_model.py:50-52), so the ground tr
 `oracle/restate.py` with mode="fp32" — the same algorithm with every bf16 rounding point removed.
 
 Arithmetic: no bf16 rounding of any activation.
-* every nn.Linear is a split-bf16 GEMM on the tcgen05 tensor cores: x = hi + lo, w = hi + lo,
-  x.w ~= hi.hi + hi.lo + lo.hi as ONE bf16 GEMM over the concatenated K ([hi|hi|lo] x [hi|lo|hi]^T, fp32 accumulation
-  in TMEM), i.e. the kernel of §3.3 of DESIGN.md for every layer; 2^-16 relative per product, ~1e-5 end to end
-  (emulated against fp64 before building: oracle-level check in tests/test_fp32_mode_gpu.py);
+* every nn.Linear is a split-bf16 GEMM on the tcgen05 tensor cores: x = h + m + l and w = h + m + l EXACTLY (three
+  bf16 pieces hold all 24 significand bits), x.w = mm + lh + hl + mh + hm + hh (+ terms <= 2^-24) as ONE bf16 GEMM over
+  the concatenated K ([m|l|h|m|h|h] x [m|h|l|h|m|h]^T, smallest products first).  The tensor core adds into its fp32
+  accumulator with truncation, so the accumulator leaves TMEM every 256 K elements and the chunks are summed in fp32
+  round-to-nearest by the epilogue warps (`k_chunk_blocks`).  Measured on the way here at full width, depth 1
+  (8 x 294x518): two pieces / one accumulation 1.04e-4 on local_points (on the tolerance: exp(z) turns the absolute
+  error of z into a relative one); three pieces / one accumulation still 3e-5 per MoT layer (the truncation, not the
+  split, was the limit);
 * attention: `g2vlm_attention_f32` (FP32-pipe dot products, exp2f softmax), no head padding (Pi3 heads are 96 wide);
 * norms / rotary / SwiGLU / GELU / LayerScale / residuals: fp32 kernels or fp32 GEMM epilogues (STORE_F32 with the
   GELU / scale / residual options).
@@ -29,8 +33,18 @@ from .model import G2VLMFast, KVCache, NaiveCache, _f32, _on_device, _split_hi_l
 
 
 def _w3(w: torch.Tensor, dev) -> torch.Tensor:
-    """fp32 weight [N, K] -> bf16 [N, 3K] = [hi | lo | hi] on the device."""
-    return _split_hi_lo_hi(w.float()).contiguous().to(dev)
+    """fp32 weight [N, K] -> bf16 [N, 6K] = [m | h | l | h | m | h] on the device, w = h + m + l exactly; pairs with
+    activations split as [m | l | h | m | h | h] by g2vlm_split6_f32: the six products mm, lh, hl, mh, hm, hh are
+    accumulated smallest first."""
+    w = w.float()
+    h = w.to(torch.bfloat16)
+    r1 = w - h.float()
+    m = r1.to(torch.bfloat16)
+    l = (r1 - m.float()).to(torch.bfloat16)
+    return torch.cat([m, h, l, h, m, h], dim=1).contiguous().to(dev)
+
+
+K_CHUNK_BLOCKS = 4   # the accumulator leaves the tensor core every 4 x 64 K elements (see g2vlm_gemm_args.k_chunk_blocks)
 
 
 class G2VLMFastFP32(G2VLMFast):
@@ -41,7 +55,7 @@ class G2VLMFastFP32(G2VLMFast):
     # ------------------------------------------------------------------------------------------
     def _pack(self, sd):
         cfg, dev = self.cfg, self.device
-        self._split_rows = {}
+        self._split_rows, self._tmp_rows = {}, {}
         g = lambda k: sd[k].detach().float()
         lm = "language_model.model."
         self.embed = _f32(g(lm + "embed_tokens.weight"), dev)
@@ -161,12 +175,24 @@ class G2VLMFastFP32(G2VLMFast):
         """out = [residual +] [scale *] [gelu|relu] (x @ w.T + bias), fp32 in / out; x [rows, K] fp32."""
         rows = x.shape[0] if rows is None else rows
         k = x.shape[1]
-        xs = self.buf.get(f"f32.split.{k}", (max(rows, self._split_rows.get(k, 0)), 3 * k), torch.bfloat16)
+        xs = self.buf.get(f"f32.split.{k}", (max(rows, self._split_rows.get(k, 0)), 6 * k), torch.bfloat16)
         self._split_rows[k] = xs.shape[0]
-        ops.split3(x, xs, rows)
-        ops.gemm(xs[:rows], w3, out, epilogue=ops.EPI_STORE_F32, groups=groups, bias=bias, flags=flags, scale=scale,
-                 scale_groups=scale_groups, residual=residual)
+        ops.split6(x, xs, rows)
+        dst = out
+        if residual is not None and residual.data_ptr() == out.data_ptr():
+            # x = x + f(x): the K chunks accumulate in the output buffer, so the residual operand must live elsewhere
+            n = out.shape[1]
+            dst = self.buf.get(f"f32.lin_tmp.{n}", (max(rows, self._tmp_rows.get(n, 0)), n), torch.float32)
+            self._tmp_rows[n] = dst.shape[0]
+        ops.gemm(xs[:rows], w3, dst, epilogue=ops.EPI_STORE_F32, groups=groups, bias=bias, flags=flags, scale=scale,
+                 scale_groups=scale_groups, residual=residual, k_chunk_blocks=K_CHUNK_BLOCKS)
+        if dst is not out:
+            ops.gather_rows(dst, out, None, rows)
         return out
+
+    def _linear_fp32(self, x, w3, b, out, relu=False, residual=None):
+        """The camera head (shared driver `_camera_head`) with this mode's three-piece split."""
+        return self._lin(x, w3, b, out, flags=ops.GEMM_RELU if relu else 0, residual=residual)
 
     def _rope2d_tables_f32(self, gh: int, gw: int):
         """RoPE2D tables of EXACT fp32 angles (pos_embed.py:120-128 without the bf16 cast of the bf16 path)."""

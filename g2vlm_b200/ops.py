@@ -71,13 +71,15 @@ class GemmArgs(ctypes.Structure):
         ("bias", ctypes.c_void_p), ("scale", ctypes.c_void_p), ("scale_groups", ctypes.c_uint32),
         ("residual", ctypes.c_void_p), ("ldr", ctypes.c_int64),
         ("out_col_group", ctypes.c_int32), ("out_col_stride", ctypes.c_int32),
+        ("k_chunk_blocks", ctypes.c_int32),
     ]
 
 
 def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, epilogue: int,
          groups: Optional[Sequence[tuple]] = None, bias: Optional[torch.Tensor] = None,
          scale: Optional[torch.Tensor] = None, scale_groups: int = 0, flags: int = 0,
-         residual: Optional[torch.Tensor] = None, out_col_group: int = 0, out_col_stride: int = 0) -> torch.Tensor:
+         residual: Optional[torch.Tensor] = None, out_col_group: int = 0, out_col_stride: int = 0,
+         k_chunk_blocks: int = 0) -> torch.Tensor:
     """out <- epilogue(a @ w_g.T) per token group; see g2vlm_gemm_bf16 in include/g2vlm_b200.h.
     out_col_group / out_col_stride (STORE_BF16): output column c lands at (c // group) * stride + c % group.
 
@@ -124,6 +126,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, epilogue: int,
     if residual is not None:
         _req(residual, torch.float32, "residual")
         args.residual, args.ldr = residual.data_ptr(), residual.stride(0)
+    args.k_chunk_blocks = int(k_chunk_blocks)
     _check(_lib.load().g2vlm_gemm_bf16(ctypes.byref(args), _stream()))
     return out
 
@@ -526,4 +529,14 @@ def swiglu_f32(gate_up, out, rows: Optional[int] = None):
         raise G2Error("swiglu_f32: gate_up must have 2 * out.shape[1] columns")
     _call("g2vlm_swiglu_f32", _vp(gate_up.data_ptr()), _i64(gate_up.stride(0)), _vp(out.data_ptr()), _i64(out.stride(0)),
           _i64(rows), _i32(out.shape[1]))
+    return out
+
+
+def split6(x, out, rows: Optional[int] = None):
+    """fp32 [rows, k] -> bf16 [rows, 6k] = [h|h|m|h|l|m] (see g2vlm_split6_f32)."""
+    _req(x, torch.float32, "x")
+    _req(out, torch.bfloat16, "out")
+    rows = x.shape[0] if rows is None else rows
+    _call("g2vlm_split6_f32", _vp(x.data_ptr()), _i64(x.stride(0)), _vp(out.data_ptr()), _i64(out.stride(0)),
+          _i64(rows), _i32(x.shape[1]))
     return out

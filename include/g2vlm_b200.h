@@ -96,6 +96,11 @@ typedef struct g2vlm_gemm_args {
    * (Pi3 decoders: modeling/pi3/models/layers/attention.py:353-357). The pad columns are not written. */
   int32_t out_col_group;
   int32_t out_col_stride;
+  /* ABI v3, STORE_F32 only (fp32 mode): 0, or the number of 64-element k-blocks after which the accumulator leaves
+   * the tensor core; the chunks are then summed in fp32 round-to-nearest by the epilogue (bias with the first chunk,
+   * gelu / scale / relu / residual with the last).  The tensor core accumulates with truncation: a split-form K of
+   * tens of thousands loses ~1e-5 relative in one go, 4 k-blocks (16 MMA steps) per chunk keep it below 1e-6. */
+  int32_t k_chunk_blocks;
 } g2vlm_gemm_args;
 
 int g2vlm_gemm_bf16(const g2vlm_gemm_args* args, void* stream);
@@ -323,6 +328,11 @@ int g2vlm_qknorm_mrope_f32(float* qkv, int64_t ld, int64_t rows, int64_t n_first
 int g2vlm_rope2d_f32(float* buf, int64_t ld, int64_t rows, int32_t n_heads_total, int32_t head_stride,
                      int32_t head_dim, int32_t tokens_per_view, int32_t grid_w, const float* cos_tab,
                      const float* sin_tab, void* stream);
+/* fp32 [rows, k] -> bf16 [rows, 6k] = [m | l | h | m | h | h] with x = h + m + l exactly (three bf16 pieces hold all
+ * 24 significand bits); weights are stored as [m | h | l | h | m | h], so ONE bf16 GEMM over 6k sums the six products
+ * mm + lh + hl + mh + hm + hh, smallest first (dropped terms <= 2^-24 relative): fp32-accurate Linear layers on the
+ * tensor cores when combined with g2vlm_gemm_args.k_chunk_blocks. */
+int g2vlm_split6_f32(const float* x, int64_t ldx, void* out, int64_t ldo, int64_t rows, int32_t k, void* stream);
 /* Qwen2MLP gate (modeling_qwen2_vl.py:519-521) in fp32: out[r, c] = silu(gu[r, c]) * gu[r, inter + c]. */
 int g2vlm_swiglu_f32(const float* gate_up, int64_t ld_gu, float* out, int64_t ldo, int64_t rows, int32_t inter,
                      void* stream);

@@ -93,6 +93,22 @@ def test_split_bf16_gemm_with_fp32_epilogue_options():
         y = torch.nn.functional.gelu(a[r0:r0 + n].double().cpu() @ w[e * N:(e + 1) * N].double().cpu().T + b[e * N:(e + 1) * N].double().cpu())
         ref[r0:r0 + n] = x0[r0:r0 + n].double().cpu() + (y * gamma.double().cpu() if e == 0 else y)
     assert _rel(x, ref) < 2e-5
+    # three-piece split (what fp32 mode uses): x = h + m + l exactly, six products -> fp32-level accuracy
+    from g2vlm_b200.model_fp32 import _w3
+    a6 = torch.empty(rows, 6 * K, device="cuda", dtype=torch.bfloat16)
+    ops.split6(a, a6)
+    pieces = a6.float().view(rows, 6, K)
+    assert torch.equal(pieces[:, 2] + pieces[:, 0] + pieces[:, 1], a)            # h + m + l == x, bit for bit
+    errs = {}
+    for chunk in (0, 4):   # 0: one accumulation in the tensor core (truncating adds); 4: chunks summed in fp32 RN
+        x = torch.full_like(x0, float("nan"))
+        ops.gemm(a6, _w3(w, "cuda"), x, epilogue=ops.EPI_STORE_F32, groups=groups, bias=b, flags=ops.GEMM_GELU, scale=gamma,
+                 scale_groups=1, residual=x0, k_chunk_blocks=chunk)
+        errs[chunk] = _rel(x, ref)
+    with pytest.raises(Exception):   # the chunks accumulate in `out`: an aliased residual is rejected
+        ops.gemm(a6, _w3(w, "cuda"), x, epilogue=ops.EPI_STORE_F32, groups=groups, residual=x, k_chunk_blocks=4)
+    print("\n  three-piece split vs fp64:", errs)
+    assert errs[4] < 1e-6 and errs[4] <= errs[0]
 
 
 def test_fp32_elementwise_kernels():
@@ -219,10 +235,15 @@ def test_fp32_full_width_configs0_shape(depth):
             sd[k].fill_(0.01)
     model = G2VLMFast(cfg, sd, mode="fp32")
     v = _views(8, 294, 518, 1)
-    out = model.recon(Tok(), dict(IDS), None, v)
+    c_ref, c_out = {}, {}
+    out = model.recon(Tok(), dict(IDS), None, v, collect=c_out)
     with torch.device("cuda"):
-        ref = restate.recon(sd, cfg, v.cuda(), mode="fp32")
-    errs = {k: _rel(out[k], ref[k]) for k in ("local_points", "points", "global_points", "camera_poses")}
+        ref = restate.recon(sd, cfg, v.cuda(), mode="fp32", collect=c_ref)
+    errs = {"dino_tokens": _rel(c_out["dino_tokens"].view_as(c_ref["dino_tokens"]), c_ref["dino_tokens"]),
+            "last_hidden": _rel(c_out["last_hidden"], c_ref["last_hidden"])}
+    for k in ("point_hidden", "camera_hidden", "global_hidden"):
+        errs[k] = _rel(c_out[k], c_ref[k])
+    errs.update({k: _rel(out[k], ref[k]) for k in ("local_points", "points", "global_points", "camera_poses")})
     print(f"\n  depth {depth or 'full'}: " + "  ".join(f"{k} {e:.2e}" for k, e in errs.items()))
     assert all(e < TOL for e in errs.values()), errs
     del model
