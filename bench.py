@@ -410,7 +410,7 @@ def run_view_sharded(args, cfg, dist, rank, world, local_rank):
     barrier()
     sampler = ClockSampler(local_rank)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    l0 = ops.LAUNCHES
+    l0 = ops.launches()
     model.sp_events = []
     e0.record()
     for _ in range(args.steps):
@@ -439,7 +439,7 @@ def run_view_sharded(args, cfg, dist, rank, world, local_rank):
                                  f"over {world} GPU(s): DINO by segment + neighbour exchange, per-layer K/V exchange "
                                  f"({args.sp_mode}, NCCL/NVLink), context broadcast", views_per_scene=n_views, image_size=size,
                         tokens=n_views * (P + 2), parallelism=f"view-sp{world}", sp_mode=args.sp_mode, sp_sm_margin=args.sp_sm_margin),
-            clocks=clocks, gpu_launches=ops.LAUNCHES - l0, exposed_exchange_ms_per_layer=exposed_ms,
+            clocks=clocks, gpu_launches=ops.launches() - l0, exposed_exchange_ms_per_layer=exposed_ms,
             e2e=dict(value=n_views / (per / 1e3), unit=UNIT, h2d_bytes_per_step=views_host.numel() * 4 // world,
                      d2h_bytes_per_step=0, note="timed through recon_view_sharded from host views; outputs stay on the GPUs"),
             whole_step=dict(algorithmic_tflop=fl["total"] / 1e12,
@@ -472,6 +472,8 @@ def main():
                     help="--impl reference: stop adding full-scene steps once this much time is spent (>= 1 step)")
     ap.add_argument("--sp-mode", default="overlap", choices=["overlap", "allgather"])
     ap.add_argument("--sp-sm-margin", type=int, default=4)
+    ap.add_argument("--no-native", action="store_true",
+                    help="per-op calls from Python (~630 per step) instead of the three native stage calls (bit-identical results)")
     ap.add_argument("--no-fuse-prompt", action="store_true",
                     help="run the 7-token prompt prefill as a separate und pass (reference order) instead of fused into the geo step")
     ap.add_argument("--profile", action="store_true",
@@ -513,6 +515,7 @@ def main():
     P = (size // 14) ** 2
     model = G2VLMFast(cfg, bench_weights(cfg, "cuda", args.layerscale))
     model.fuse_prompt = not args.no_fuse_prompt
+    model.native = not args.no_native
     model.sp_mode, model.sp_sm_margin = args.sp_mode, args.sp_sm_margin
     torch.cuda.empty_cache()
     views_u8 = bench_views_u8(n_views, size, seed=1 + rank)          # 8-bit views: the reference legs read the same pixels
@@ -527,20 +530,8 @@ def main():
     gi, _, _ = model.prepare_dino_images_pi3(newlens, new_rope, views_host, None, TOKENS)
     gi = {k: (v if k in HOST_META else v.cuda()) for k, v in gi.items()}
 
-    att_events = []
-    orig_attention = ops.attention
     T = n_views * (P + 2)
     K_PROMPT = int(gi_text["packed_text_ids"].numel())   # prompt rows ride along in the fused path
-
-    def timed_attention(q, *a, **k):
-        if q.shape[0] in (T, T + K_PROMPT) and k.get("num_kv_heads") == cfg.num_kv_heads and not k.get("causal", False):
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            r = orig_attention(q, *a, **k)
-            e1.record()
-            att_events.append((e0, e1))
-            return r
-        return orig_attention(q, *a, **k)
 
     def step_resident():
         # same sequence as G2VLMFast.recon(): the 7-token prompt prefill rides along with the geo step
@@ -579,7 +570,7 @@ def main():
     def timed(fn, steps, finish=None):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        launches0 = ops.LAUNCHES
+        launches0 = ops.launches()
         e0.record()
         for _ in range(steps):
             fn()
@@ -593,10 +584,25 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
         barrier()
-        return ms, ops.LAUNCHES - launches0
+        return ms, ops.launches() - launches0
 
     for _ in range(args.warmup):
         step_resident()
+    # CUDA events around every MoT shared-attention launch, recorded on the launching stream by the native stage
+    # driver (g2vlm_mot_forward_geo's attention_events) or, on the per-op path, by a wrapper around ops.attention
+    model.attn_events = []
+    orig_attention = ops.attention
+
+    def timed_attention(q, *a, **k):
+        if q.shape[0] in (T, T + K_PROMPT) and k.get("num_kv_heads") == cfg.num_kv_heads and not k.get("causal", False):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            r = orig_attention(q, *a, **k)
+            e1.record()
+            model.attn_events.append((e0, e1))
+            return r
+        return orig_attention(q, *a, **k)
+
     ops.attention = timed_attention
     model.stage_events = []
     sampler = ClockSampler(local_rank)
@@ -604,6 +610,7 @@ def main():
     clocks = sampler.stop()
     ops.attention = orig_attention
     stage_events, model.stage_events = model.stage_events, None
+    att_events, model.attn_events = model.attn_events, None
 
     att_ms = [a.elapsed_time(b) for a, b in att_events]
     att_mean_ms = sum(att_ms) / max(1, len(att_ms))

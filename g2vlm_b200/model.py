@@ -234,6 +234,13 @@ class G2VLMFast:
         self.sp_mode = "overlap"
         self.sp_sm_margin = 4    # = NCCL_MAX_NCHANNELS the launcher sets (bench.py); 2-GPU sweep: profiles/r02_sp_sweep_n2.txt
         self.sp_events: Optional[list] = None     # bench.py: CUDA event pairs around every exchange wait
+        # stack-level C ABI (g2vlm_dino_forward / g2vlm_mot_forward_geo / g2vlm_recon_heads): the fused recon path is
+        # THREE native calls instead of ~630 per-op calls from Python; False keeps the per-op path (bit-identical)
+        self.native = self.mode == "bf16"
+        self._nctx = None
+        self._nws: Dict[tuple, torch.Tensor] = {}
+        self._nplan: Optional[tuple] = None
+        self.attn_events: Optional[list] = None   # bench.py: (start, end) CUDA events of every MoT attention launch
         self._raw_images = False  # True while recon() feeds un-normalised views (normalised on device)
 
     def _mark(self, name: str) -> None:
@@ -529,6 +536,119 @@ class G2VLMFast:
             t = (freqs.cos().float().contiguous().to(self.device), freqs.sin().float().contiguous().to(self.device))
             self._rope2d_cache[key] = t
         return t
+
+    # ------------------------------------------------------------------------------------------
+    # stack-level C ABI: opaque context, caller-owned workspace, one call per stage
+    # ------------------------------------------------------------------------------------------
+    def _native_ctx(self):
+        if self._nctx is None:
+            c = ops.NativeContext(self.cfg)
+            reg = c.load
+            reg("embed", self.embed); reg("inv_freq", self.inv_freq)
+            reg("norm_geo", self.norm_geo); reg("norm_und", self.norm_und)
+            reg("dino2llm.w", self.w_dino2llm); reg("dino2llm.b", self.b_dino2llm)
+            for i, L in enumerate(self.layers):
+                for k, t in L.items():
+                    reg(f"mot.{i}.{k}", t)
+            reg("dino.wpatch", self.dino_wpatch); reg("dino.bpatch", self.dino_bpatch)
+            reg("dino.cls", self.dino_cls); reg("dino.reg", self.dino_reg)
+            reg("dino.lnw", self.dino_lnw); reg("dino.lnb", self.dino_lnb)
+            for i, L in enumerate(self.dino_layers):
+                for k, t in L.items():
+                    reg(f"dino.{i}.{k}", t)
+            for name, dec in self.decoders.items():
+                for b, B in enumerate(dec["blocks"]):
+                    for k, t in B.items():
+                        reg(f"dec.{name}.{b}.{k}", t)
+                reg(f"dec.{name}.wout", dec["wout"]); reg(f"dec.{name}.bout", dec["bout"])
+            for hname in ["point_head", "global_point_head"] + (["conf_head"] if self.cfg.train_conf_pi3 else []):
+                for sfx in ("whi", "wlo", "b"):
+                    reg(f"head.{hname}.{sfx}", getattr(self, f"{hname}_{sfx}"))
+            for k, t in self.cam.items():
+                reg(f"cam.{k}", t)
+            self._nctx = c
+        return self._nctx
+
+    def _native_plan(self, N: int, Hh: int, Ww: int, Kp: int, seqlens) -> torch.Tensor:
+        """Workspace of one geometry (cached) with its tables in place (g2vlm_recon_plan, once per geometry switch)."""
+        ctx = self._native_ctx()
+        seq = tuple(int(n) for n in seqlens)
+        key = (N, Hh, Ww, Kp, seq)
+        ws = self._nws.get(key[:4])
+        if ws is None:
+            ws = self._nws[key[:4]] = torch.empty(ctx.workspace_bytes(N, Hh, Ww, Kp), dtype=torch.uint8, device=self.device)
+        if self._nplan != key:
+            import ctypes
+            arr = (ctypes.c_int32 * N)(*seq)
+            ctx.call("g2vlm_recon_plan", ops._i32(N), ops._i32(Hh), ops._i32(Ww), ops._i32(Kp), arr, ops._vp(ws.data_ptr()),
+                     ops._i64(ws.numel()), ops._stream())
+            self._nplan = key
+        return ws
+
+    def _native_dino_mot(self, packed_text_ids, packed_text_indexes, packed_dino_token_indexes, dino_token_seqlens,
+                         packed_position_ids, packed_dino_images, prompt):
+        """Encoder + dino2llm + the MoT stack as TWO native calls (same kernels as the per-op path)."""
+        import ctypes
+        cfg, dev = self.cfg, self.device
+        img = packed_dino_images.to(dev, torch.float32).contiguous()
+        N, _, Hh, Ww = img.shape
+        p = cfg.dino_patch
+        gh, gw = Hh // p, Ww // p
+        P = gh * gw
+        T = N * (P + 2)
+        if int(packed_text_ids.numel()) != 2 * N or int(packed_dino_token_indexes.numel()) != N * P:
+            raise ValueError("index tensors do not match the image geometry")
+        Kp = int(prompt["packed_text_ids"].numel())
+        ws = self._native_plan(N, Hh, Ww, Kp, dino_token_seqlens.tolist())
+        ctx, st = self._native_ctx(), ops._stream()
+        tokens = ctypes.c_void_p()
+        self._mark("dino_begin")
+        ctx.call("g2vlm_dino_forward", ops._vp(img.data_ptr()), ops._i32(N), ops._i32(Hh), ops._i32(Ww),
+                 ops._i32(int(self._raw_images)), ops._vp(self._dino_pos(gh, gw, Hh == Ww).data_ptr()), ops._vp(ws.data_ptr()),
+                 ctypes.byref(tokens), st)
+        self._mark("dino_end")
+        ids = self._idx("dino.txt_ids", packed_text_ids)
+        tidx = self._idx("dino.txt_idx", packed_text_indexes)
+        gidx = self._idx("dino.geo_idx", packed_dino_token_indexes)
+        pos = self._idx("mot.pos", packed_position_ids.contiguous())
+        pids = self._idx("mot.prompt_ids", prompt["packed_text_ids"])
+        ppos = self._idx("mot.prompt_pos", prompt["packed_text_position_ids"].contiguous())
+        last = torch.empty(T, cfg.hidden_size, dtype=torch.float32, device=dev)
+        events = None
+        if self.attn_events is not None:
+            evs = [torch.cuda.Event(enable_timing=True) for _ in range(2 * cfg.num_layers)]
+            for e in evs:
+                e.record()                      # creates the underlying cudaEvent_t; re-recorded by the driver
+            events = (ctypes.c_void_p * len(evs))(*[e.cuda_event for e in evs])
+            self.attn_events += [(evs[2 * i], evs[2 * i + 1]) for i in range(cfg.num_layers)]
+        ctx.call("g2vlm_mot_forward_geo", tokens, ops._vp(ids.data_ptr()), ops._vp(tidx.data_ptr()), ops._vp(gidx.data_ptr()),
+                 ops._vp(pos.data_ptr()), ops._vp(pids.data_ptr()), ops._vp(ppos.data_ptr()), ops._vp(ws.data_ptr()),
+                 ops._vp(last.data_ptr()), events, st)
+        self._mark("mot_end")
+        return last
+
+    def _native_heads(self, selected_hidden_states, packed_dino_token_indexes, N, Hh, Ww):
+        cfg, dev = self.cfg, self.device
+        p = cfg.dino_patch
+        gh, gw = Hh // p, Ww // p
+        P = gh * gw
+        if self._nplan is None or self._nplan[:3] != (N, Hh, Ww):
+            self._native_plan(N, Hh, Ww, 0, [P] * N)
+        ws = self._nws[self._nplan[:4]]
+        geo = self._idx("recon.geo_idx", packed_dino_token_indexes)
+        cos, sin = self._rope2d_tables(gh, gw)
+        out = {k: torch.empty(N, Hh, Ww, 3, dtype=torch.float32, device=dev) for k in ("points", "local_points", "global_points")}
+        poses = torch.empty(N, 4, 4, dtype=torch.float32, device=dev)
+        conf = torch.empty(N, Hh, Ww, 1, dtype=torch.float32, device=dev) if cfg.train_conf_pi3 else None
+        hid = selected_hidden_states
+        if hid.dtype != torch.float32 or not hid.is_contiguous() or hid.device != dev:
+            hid = hid.to(dev, torch.float32).contiguous()
+        self._native_ctx().call("g2vlm_recon_heads", ops._vp(hid.data_ptr()), ops._vp(geo.data_ptr()), ops._vp(cos.data_ptr()),
+                                ops._vp(sin.data_ptr()), ops._vp(ws.data_ptr()), ops._vp(out["points"].data_ptr()),
+                                ops._vp(out["local_points"].data_ptr()), ops._vp(out["global_points"].data_ptr()),
+                                ops._vp(poses.data_ptr()), ops._ptr(conf), ops._stream())
+        self._mark("heads_end")
+        return out, poses, conf
 
     # ------------------------------------------------------------------------------------------
     # MoT language model
@@ -1114,6 +1234,11 @@ class G2VLMFast:
         T, H = int(sum(packed_seqlens.tolist())), cfg.hidden_size
         if packed_dino_images.shape[0] < 1:
             raise ValueError("at least one view is required")
+        if (self.native and prompt is not None and collect is None and shard is None and group is None
+                and not update_past_key_values and KVCache.adopt(past_key_values, cfg, dev).len == 0):
+            last = self._native_dino_mot(packed_text_ids, packed_text_indexes, packed_dino_token_indexes, dino_token_seqlens,
+                                         packed_position_ids, packed_dino_images, prompt)
+            return past_key_values, last
         self._mark("dino_begin")
         if shard is None:
             tokens = self.dino_forward(packed_dino_images, dino_token_seqlens,
@@ -1256,6 +1381,13 @@ class G2VLMFast:
         p = cfg.dino_patch
         gh, gw = Hh // p, Ww // p
         P, H = gh * gw, cfg.hidden_size
+        if self.native and collect is None and shard is None:
+            out, poses, conf = self._native_heads(selected_hidden_states, packed_dino_token_indexes, N, Hh, Ww)
+            if original_images is not None and original_images.dim() == 4:
+                original_images = original_images.unsqueeze(0)
+            return dict(points=out["points"][None], local_points=out["local_points"][None],
+                        conf=None if conf is None else conf[None], camera_poses=poses[None],
+                        global_points=out["global_points"][None], images=original_images)
         geo = self._idx("recon.geo_idx", packed_dino_token_indexes)
         if shard is not None:
             p0, p1 = shard.packed_rows

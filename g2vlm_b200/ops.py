@@ -26,6 +26,14 @@ class G2Error(RuntimeError):
 LAUNCHES = 0  # number of C-ABI kernel launches issued by this process (bench.py reads it)
 
 
+def launches() -> int:
+    """Kernels launched so far by this process through the C ABI: per-op calls from Python (LAUNCHES) plus the
+    launches issued inside the native stage drivers (g2vlm_dino_forward / g2vlm_mot_forward_geo / g2vlm_recon_heads)."""
+    lib = _lib.load()
+    lib.g2vlm_driver_launches.restype = ctypes.c_int64
+    return LAUNCHES + int(lib.g2vlm_driver_launches())
+
+
 def _check(rc: int) -> None:
     global LAUNCHES
     LAUNCHES += 1
@@ -540,3 +548,63 @@ def split6(x, out, rows: Optional[int] = None):
     _call("g2vlm_split6_f32", _vp(x.data_ptr()), _i64(x.stride(0)), _vp(out.data_ptr()), _i64(out.stride(0)),
           _i64(rows), _i32(x.shape[1]))
     return out
+
+
+# ---------------------------------------------------------------------------------------------------
+# stack-level entry points (opaque context + one call per stage; see include/g2vlm_b200.h)
+# ---------------------------------------------------------------------------------------------------
+class Dims(ctypes.Structure):
+    _fields_ = [
+        ("hidden", ctypes.c_int32), ("layers", ctypes.c_int32), ("heads", ctypes.c_int32), ("kv_heads", ctypes.c_int32),
+        ("intermediate", ctypes.c_int32), ("rms_eps", ctypes.c_float), ("mrope_s0", ctypes.c_int32), ("mrope_s1", ctypes.c_int32),
+        ("dino_hidden", ctypes.c_int32), ("dino_layers", ctypes.c_int32), ("dino_heads", ctypes.c_int32),
+        ("dino_mlp_ratio", ctypes.c_int32), ("dino_patch", ctypes.c_int32), ("dino_registers", ctypes.c_int32),
+        ("dino_ln_eps", ctypes.c_float),
+        ("dec_depth", ctypes.c_int32), ("dec_heads", ctypes.c_int32), ("dec_mlp_ratio", ctypes.c_int32),
+        ("point_dim", ctypes.c_int32), ("camera_dim", ctypes.c_int32), ("train_conf", ctypes.c_int32),
+    ]
+
+
+class NativeContext:
+    """Owner of one `g2vlm_ctx` (destroyed with the object); thin ctypes plumbing only."""
+
+    def __init__(self, cfg):
+        lib = _lib.load()
+        lib.g2vlm_workspace_bytes.restype = ctypes.c_int64
+        d = Dims(hidden=cfg.hidden_size, layers=cfg.num_layers, heads=cfg.num_heads, kv_heads=cfg.num_kv_heads,
+                 intermediate=cfg.intermediate_size, rms_eps=cfg.rms_norm_eps, mrope_s0=cfg.mrope_section[0],
+                 mrope_s1=cfg.mrope_section[1], dino_hidden=cfg.dino_hidden, dino_layers=cfg.dino_layers,
+                 dino_heads=cfg.dino_heads, dino_mlp_ratio=cfg.dino_mlp_ratio, dino_patch=cfg.dino_patch,
+                 dino_registers=cfg.dino_registers, dino_ln_eps=cfg.dino_ln_eps, dec_depth=cfg.dec_depth,
+                 dec_heads=cfg.dec_heads, dec_mlp_ratio=cfg.dec_mlp_ratio, point_dim=cfg.point_dim,
+                 camera_dim=cfg.camera_dim, train_conf=int(cfg.train_conf_pi3))
+        self._h = ctypes.c_void_p()
+        self._lib = lib
+        self._keep = []          # registered tensors must outlive the context
+        rc = lib.g2vlm_ctx_create(ctypes.byref(d), ctypes.byref(self._h))
+        if rc != 0:
+            raise G2Error(f"g2vlm_ctx_create failed (code {rc}): {lib.g2vlm_last_error().decode()}")
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            self._lib.g2vlm_ctx_destroy(h)
+
+    def call(self, name: str, *args) -> None:
+        rc = getattr(self._lib, name)(self._h, *args)
+        if rc != 0:
+            raise G2Error(f"{name} failed (code {rc}): {self._lib.g2vlm_last_error().decode()}")
+
+    def load(self, name: str, t: torch.Tensor) -> None:
+        if t.dtype not in (torch.float32, torch.bfloat16) or not t.is_cuda or not t.is_contiguous():
+            raise G2Error(f"weight {name}: contiguous CUDA fp32 / bf16 tensor required")
+        rows = t.shape[0] if t.dim() > 1 else 1
+        self._keep.append(t)
+        self.call("g2vlm_load_weights", name.encode(), _vp(t.data_ptr()), _i32(int(t.dtype == torch.bfloat16)), _i64(rows),
+                  _i64(t.numel() // max(rows, 1)))
+
+    def workspace_bytes(self, n_views: int, H: int, W: int, n_prompt: int) -> int:
+        n = int(self._lib.g2vlm_workspace_bytes(self._h, _i32(n_views), _i32(H), _i32(W), _i32(n_prompt)))
+        if n < 0:
+            raise G2Error(f"g2vlm_workspace_bytes: {self._lib.g2vlm_last_error().decode()}")
+        return n

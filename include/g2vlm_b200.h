@@ -389,6 +389,93 @@ int g2vlm_argmax_bf16(const void* logits, int64_t ld, int64_t rows, int32_t voca
                       void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Stack-level entry points: an opaque per-model context and ONE call per stage of G2VLM.recon.
+ * The host mirror (`G2VLMFast`) packs the reference's state_dict tensors into the layouts below and registers them;
+ * every stage call then enqueues its whole kernel sequence from native code through the per-op entry points above
+ * (same kernels, order and rounding points as the per-op path: bit-identical results).  Ownership: the context owns no
+ * device memory — weights and the workspace belong to the caller.  Threading: a context may be used by one host thread
+ * at a time; distinct contexts are independent.  After g2vlm_recon_plan the stage calls only launch kernels (no
+ * allocation, no host<->device copy, no synchronisation): CUDA-graph capturable.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct g2vlm_dims {
+  /* Qwen2-VL MoT language model (modeling/g2vlm/qwen2vl.py:50-234) */
+  int32_t hidden, layers, heads, kv_heads, intermediate;
+  float rms_eps;
+  int32_t mrope_s0, mrope_s1; /* mrope_section[0..1] (16, 24; hard-coded in the reference, modeling_qwen2_vl.py:562-566) */
+  /* DINOv2-with-registers encoder */
+  int32_t dino_hidden, dino_layers, dino_heads, dino_mlp_ratio, dino_patch, dino_registers;
+  float dino_ln_eps;
+  /* Pi3 decoders / heads (g2vlm.py:162-226) */
+  int32_t dec_depth, dec_heads, dec_mlp_ratio, point_dim, camera_dim;
+  int32_t train_conf; /* 1: conf_decoder + conf_head exist (train_conf_pi3) */
+} g2vlm_dims;
+
+typedef struct g2vlm_ctx g2vlm_ctx;
+
+#define G2VLM_DTYPE_F32 0
+#define G2VLM_DTYPE_BF16 1
+
+int g2vlm_ctx_create(const g2vlm_dims* dims, g2vlm_ctx** ctx);
+int g2vlm_ctx_destroy(g2vlm_ctx* ctx);
+
+/* Registers ONE packed weight tensor (device pointer, 16-byte aligned, row-major [rows, cols]) under its slot name.
+ * Slots (geo expert first wherever two experts are stacked; "bias" tensors hold bf16-rounded values as fp32):
+ *   embed f32 [vocab_rows,H] | inv_freq f32 [64] | norm_geo, norm_und f32 [H] | dino2llm.w bf16 [H,D] | dino2llm.b f32 [H]
+ *   mot.{i}.wqkv bf16 [2*(nq+2nkv)*128, H]   mot.{i}.bqkv f32   mot.{i}.wo bf16 [2H, nq*128]
+ *   mot.{i}.wgu bf16 [2*2I, H] (gate/up interleaved in blocks of 128 rows)   mot.{i}.wdown bf16 [2H, I]
+ *   mot.{i}.{input_layernorm,post_attention_layernorm,q_norm,k_norm}_{geo,und} f32   mot.{i}.ls1, ls2 f32 [H]
+ *   dino.wpatch bf16 [D, kpad] | dino.bpatch | dino.cls f32 [D] | dino.reg f32 [n_reg, D] | dino.lnw, dino.lnb
+ *   dino.{i}.wqkv bf16 [3*heads*hp, D] (heads zero-padded to hp = 64 | 128)  bqkv  wdense bf16 [D, heads*hp]  bdense
+ *   dino.{i}.wfc1, bfc1, wfc2, bfc2, norm1w, norm1b, norm2w, norm2b, ls1, ls2
+ *   dec.{point_decoder|camera_decoder|global_points_decoder|conf_decoder}.{b}.{wqkv,bqkv,wproj,bproj,wfc1,bfc1,wfc2,
+ *        bfc2,norm1w,norm1b,norm2w,norm2b} (+ norm3w, norm3b, norm_yw, norm_yb, wcq, bcq, wckv, bckv, wcproj, bcproj for the
+ *        cross-attention decoder)   dec.{name}.wout, bout
+ *   head.{point_head|global_point_head|conf_head}.whi, wlo bf16 [3*14*14 | 14*14, point_dim] (w = hi + lo), .b f32
+ *   cam.r{0,1}{1,2,3}w, cam.m{0,2}w bf16 [C, 3C] = [hi|lo|hi]; cam.*b f32; cam.fc_tw f32 [3,C], fc_tb, fc_rotw [9,C], fc_rotb
+ * A missing slot makes the stage call that needs it fail with G2VLM_ERR_INVALID and a message naming it. */
+int g2vlm_load_weights(g2vlm_ctx* ctx, const char* name, const void* ptr, int32_t dtype, int64_t rows, int64_t cols);
+
+/* Bytes of caller-owned workspace the three stages need for one scene geometry (-1: bad arguments). */
+int64_t g2vlm_workspace_bytes(const g2vlm_ctx* ctx, int32_t n_views, int32_t H, int32_t W, int32_t n_prompt);
+
+/* Once per geometry (NOT capturable: host->device copies): writes the attention work tables into the workspace and
+ * clears the regions that must be zero where no kernel writes.  dino_seqlens: HOST int32 [n_views], the caller's
+ * cu_seqlens lengths (the reference passes patch counts, quirk Q1 g2vlm.py:988-990).  n_prompt: rows of the und
+ * prompt prefill fused into the geo step (K0 = 7 in recon; 0 = none). */
+int g2vlm_recon_plan(g2vlm_ctx* ctx, int32_t n_views, int32_t H, int32_t W, int32_t n_prompt,
+                     const int32_t* dino_seqlens, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* Dinov2WithRegistersModel.forward (g2vlm/dinov2_model.py:301-356): images fp32 [n,3,H,W] (normalize != 0: raw [0,1]
+ * views, ImageNet-normalised on the fly) -> bf16 tokens [n*P, D] inside the workspace (*tokens_out).  pos_embed: fp32
+ * [1+P, D], the position table already resampled to this grid (interpolate_pos_encoding, :93-145). */
+int g2vlm_dino_forward(g2vlm_ctx* ctx, const float* images, int32_t n_views, int32_t H, int32_t W, int32_t normalize,
+                       const float* pos_embed, void* workspace, void** tokens_out, void* stream);
+
+/* forward_cache_update_dino after the encoder (g2vlm.py:984-1039) = dino2llm + scatter + Qwen2VLModel.forward_inference
+ * (mode="geo", g2vlm/qwen2vl.py:1267-1337) with the und prompt prefill (g2vlm.py:701-733) riding along as n_prompt extra
+ * rows.  All index tensors are DEVICE int64 built by the host exactly as the reference does (prepare_dino_images_pi3):
+ * packed_text_ids / packed_text_indexes [2n], packed_dino_token_indexes [n*P], packed_position_ids [3, T] contiguous,
+ * prompt_ids [n_prompt], prompt_position_ids [3, n_prompt] contiguous.  last_hidden: fp32 [T, H] (caller buffer).
+ * attention_events: NULL, or HOST array of 2*layers cudaEvent_t recorded before / after every shared-attention launch
+ * (bench.py's roofline timing). */
+int g2vlm_mot_forward_geo(g2vlm_ctx* ctx, const void* dino_tokens, const int64_t* packed_text_ids,
+                          const int64_t* packed_text_indexes, const int64_t* packed_dino_token_indexes,
+                          const int64_t* packed_position_ids, const int64_t* prompt_ids,
+                          const int64_t* prompt_position_ids, void* workspace, float* last_hidden,
+                          void* const* attention_events, void* stream);
+
+/* G2VLM.reconstruct (g2vlm.py:1143-1238): 3 (4 with conf) Pi3 decoders, camera head, point heads, epilogue.
+ * rope_cos / rope_sin: fp32 [max(gh,gw), head_dim/4] RoPE2D tables built like the reference's cache (pos_embed.py:118-128).
+ * Outputs (caller buffers): points, local_points, global_points fp32 [n,H,W,3]; camera_poses fp32 [n,4,4]; conf fp32
+ * [n,H,W,1] or NULL. */
+int g2vlm_recon_heads(g2vlm_ctx* ctx, const float* last_hidden, const int64_t* packed_dino_token_indexes,
+                      const float* rope_cos, const float* rope_sin, void* workspace, float* points, float* local_points,
+                      float* global_points, float* camera_poses, float* conf, void* stream);
+
+/* Kernels launched so far by the stage drivers of this process (bench.py's gpu_launches). */
+int64_t g2vlm_driver_launches(void);
+
+/* ------------------------------------------------------------------------------------------------
  * Output side of the path ("next" row f3): device-side replacement of the numpy stage of
  * save_ply_visualization (g2vlm_utils.py:84-149): drop points with a NaN/Inf coordinate (:126-143),
  * keep the original order, and pack binary-little-endian PLY vertex records
