@@ -144,9 +144,9 @@ def bench_weights(cfg, device, layerscale):
     return sd
 
 
-def bench_views_u8(n_views, size, seed):
+def bench_views_u8(n_views, size, seed, width=None):
     from g2vlm_b200 import schema
-    return (schema.synthetic_views(n_views, size, size, seed=seed) * 255).round().to(torch.uint8)
+    return (schema.synthetic_views(n_views, size, width or size, seed=seed) * 255).round().to(torch.uint8)
 
 
 def to_pil(u8):
@@ -450,6 +450,87 @@ def run_view_sharded(args, cfg, dist, rank, world, local_rank):
 
 
 # --------------------------------------------------------------------------------------------------
+# fp32 mode (north_star "fp32 mode <= 1e-4"; BASELINE configs[0] "8 views fp32")
+# --------------------------------------------------------------------------------------------------
+def run_fp32(args, cfg, local_rank):
+    """`--mode fp32`: the fp32-mode path (g2vlm_b200/model_fp32.py) on BASELINE configs[0]'s geometry by default
+    (8 views of 294x518 = examples/dl3dv frames after load_and_resize14).  One JSON line, dtype "fp32"; `value` and
+    `e2e` as in the bf16 line; `max_rel_vs_fp32_oracle` = outputs against oracle/restate.py mode="fp32" evaluated on GPU
+    tensors in this run (the checker; not timed)."""
+    from g2vlm_b200 import ops
+    from g2vlm_b200.model import G2VLMFast, NaiveCache
+    n_views, Hh, Ww = args.views, args.height, args.width
+    P = (Hh // 14) * (Ww // 14)
+    sd = bench_weights(cfg, "cuda", args.layerscale)
+    model = G2VLMFast(cfg, sd, mode="fp32")
+    views_u8 = bench_views_u8(n_views, Hh, seed=1, width=Ww)
+    views_host = (views_u8.float() / 255.0).pin_memory()
+    tok = StubTokenizer()
+    gi_text, newlens, new_rope = model.prepare_prompts_addbos([0], [0], ["x"], tok, TOKENS)
+    HOST_META = ("text_token_lens", "key_values_lens", "packed_seqlens", "dino_token_seqlens")
+    gi, _, _ = model.prepare_dino_images_pi3(newlens, new_rope, views_host, None, TOKENS)
+    gi = {k: (v if k in HOST_META else v.cuda()) for k, v in gi.items()}
+
+    def step_resident():
+        past, last = model.forward_cache_update_dino(NaiveCache(cfg.num_layers), prompt=gi_text, **gi)
+        return model.reconstruct(past_key_values=past, selected_hidden_states=last, **gi)
+
+    out_host = {}
+
+    def step_e2e():
+        pred = model.recon(tok, dict(TOKENS), None, views_host)
+        for k in ("points", "local_points", "global_points", "camera_poses"):
+            if k not in out_host:
+                out_host[k] = torch.empty(pred[k].shape, dtype=pred[k].dtype, pin_memory=True)
+            out_host[k].copy_(pred[k], non_blocking=True)
+        return pred
+
+    def timed(fn, steps):
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = ops.launches()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / steps, (ops.launches() - l0)
+
+    for _ in range(max(3, args.warmup)):
+        step_resident()
+    sampler = ClockSampler(local_rank)
+    ms, launches = timed(step_resident, args.steps)
+    clocks = sampler.stop()
+    step_e2e()
+    ms_e2e, _ = timed(step_e2e, max(1, min(args.steps, 3)))
+    pred = model.recon(tok, dict(TOKENS), None, views_host)
+    try:
+        from oracle import restate
+        with torch.device("cuda"):
+            ref = restate.recon(sd, cfg, views_host.cuda(), mode="fp32")
+        max_rel = {k: ((pred[k].double() - ref[k].double()).abs().max() / ref[k].double().abs().max()).item()
+                   for k in ("points", "local_points", "global_points", "camera_poses")}
+    except Exception as e:
+        max_rel = dict(error=f"{type(e).__name__}: {e}")
+    fl = algorithmic_flops(cfg, n_views, P)
+    d2h = sum(v.numel() * v.element_size() for v in out_host.values())
+    print(json.dumps(dict(
+        metric=METRIC, value=n_views / ms * 1e3, unit=UNIT, n_gpus=1, steps=args.steps, warmup=max(3, args.warmup),
+        ms_per_step=ms, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="fp32",
+        data=DATA.format(ls=args.layerscale),
+        config=dict(workload=f"G2VLM-2B-MoT recon fp32 mode, {n_views} views {Hh}x{Ww} (BASELINE configs[0] geometry: "
+                             f"examples/dl3dv frames after load_and_resize14), single B200", views_per_scene=n_views,
+                    image_height=Hh, image_width=Ww, tokens=n_views * (P + 2), parallelism="scene-dp1",
+                    arithmetic="every Linear = three-piece split-bf16 GEMM on tcgen05 (6 products, fp32 RN chunk sums); "
+                               "fp32 FFMA attention; fp32 elementwise", l2="inputs larger than L2; no flush"),
+        clocks=clocks, gpu_launches=launches,
+        e2e=dict(value=n_views / ms_e2e * 1e3, unit=UNIT, h2d_bytes_per_step=views_host.numel() * 4, d2h_bytes_per_step=d2h,
+                 ms_per_step=ms_e2e, note="one blocking recon() from pinned host views + download of all outputs per step"),
+        max_rel_vs_fp32_oracle=max_rel, tolerance=1e-4,
+        whole_step=dict(algorithmic_tflop=fl["total"] / 1e12, achieved_tflops=fl["total"] / 1e12 / (ms / 1e3)))))
+
+
+# --------------------------------------------------------------------------------------------------
 # our arm
 # --------------------------------------------------------------------------------------------------
 def main():
@@ -470,6 +551,10 @@ def main():
                          "the regime of a trained checkpoint; 'synthetic' = U(0.5,1.5)")
     ap.add_argument("--ref-budget-s", type=float, default=120.0,
                     help="--impl reference: stop adding full-scene steps once this much time is spent (>= 1 step)")
+    ap.add_argument("--mode", default="bf16", choices=["bf16", "fp32"],
+                    help="fp32: the fp32-mode path on BASELINE configs[0]'s geometry (--views 8 --height 294 --width 518 unless given)")
+    ap.add_argument("--height", type=int, default=None)
+    ap.add_argument("--width", type=int, default=None)
     ap.add_argument("--sp-mode", default="overlap", choices=["overlap", "allgather"])
     ap.add_argument("--sp-sm-margin", type=int, default=4)
     ap.add_argument("--no-native", action="store_true",
@@ -508,6 +593,15 @@ def main():
         args.warmup = 3  # timing rule: at least 3 warm-up steps
 
     cfg = schema.TINY if args.tiny else schema.FULL
+    if args.mode == "fp32":
+        if "--views" not in sys.argv:
+            args.views = 8
+        args.height, args.width = args.height or 294, args.width or 518
+        if rank == 0:
+            run_fp32(args, cfg, local_rank)
+        if dist is not None:
+            dist.destroy_process_group()
+        return
     if args.workload == "views":
         run_view_sharded(args, cfg, dist, rank, world, local_rank)
         return

@@ -26,7 +26,7 @@ extern "C" int g2vlm_und_decode_step(const g2vlm_decode_step_args* a, void* stre
   G2_REQUIRE(a->kv_bound > 0 && a->kv_bound <= a->kv_capacity, "decode_step: kv_bound exceeds the cache capacity");
   const int H = a->hidden, I = a->intermediate, nq = a->n_q_heads, nkv = a->n_kv_heads, hd = a->head_dim;
   const int qkv_w = (nq + 2 * nkv) * hd, kvw = 2 * nkv * hd;
-  const float scale = 1.0f / sqrtf(static_cast<float>(hd));
+  const float scale = static_cast<float>(1.0 / sqrt(static_cast<double>(hd)));  // same rounding as the host mirror (1/math.sqrt in double, then float)
   __nv_bfloat16* qkv = reinterpret_cast<__nv_bfloat16*>(a->qkv);
 
   // embedding row of the current token (device index) and the M-RoPE angles of the current position

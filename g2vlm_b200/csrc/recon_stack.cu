@@ -312,6 +312,15 @@ extern "C" int g2vlm_recon_plan(g2vlm_ctx* ctx, int32_t n_views, int32_t H, int3
   return G2VLM_OK;
 }
 
+extern "C" int g2vlm_workspace_region(const g2vlm_ctx* ctx, const char* name, int64_t* offset, int64_t* bytes) {
+  G2_REQUIRE(ctx && ctx->planned && name && offset && bytes, "workspace_region: needs a planned context");
+  auto it = ctx->plan.r.find(name);
+  G2_REQUIRE(it != ctx->plan.r.end(), "workspace_region: unknown region");
+  *offset = it->second.off;
+  *bytes = it->second.bytes;
+  return G2VLM_OK;
+}
+
 #define G2_PLAN_CHECK(nv, hh, ww)                                                                              \
   G2_REQUIRE(ctx && ctx->planned, "g2vlm_recon_plan must run before the stage calls");                         \
   G2_REQUIRE(ctx->plan.n_views == (nv) && ctx->plan.H == (hh) && ctx->plan.W == (ww), "geometry differs from the plan")
@@ -345,7 +354,7 @@ extern "C" int g2vlm_dino_forward(g2vlm_ctx* ctx, const float* images, int32_t n
                               normalize ? std3 : nullptr, stream));
   G2_TRY(Gemm(patches, kpad, (long long)N * P, wpatch, D, kpad, G2VLM_EPI_STORE_BF16, emb, D).bias(bpatch).run(stream));
   G2_TRY(g2vlm_dino_embed(emb, D, cls, reg, pos_embed, x, N, P, d.dino_registers, D, stream));
-  const float scale = 1.0f / sqrtf((float)(D / nh));
+  const float scale = (float)(1.0 / sqrt((double)(D / nh)));
   const int qw = nh * hp;
   for (int l = 0; l < d.dino_layers; ++l) {
     G2_W(n1w, float, key("dino.%d.%s", l, "norm1w")); G2_W(n1b, float, key("dino.%d.%s", l, "norm1b"));
@@ -427,7 +436,7 @@ extern "C" int g2vlm_mot_forward_geo(g2vlm_ctx* ctx, const void* dino_tokens, co
     G2_TRY(g2vlm_mrope_table(prompt_position_ids, Kp, inv_freq, cosb + (long long)T * half, sinb + (long long)T * half, Kp,
                              half, d.mrope_s0, d.mrope_s1, stream));
   }
-  const float scale = 1.0f / sqrtf((float)hd);
+  const float scale = (float)(1.0 / sqrt((double)hd));
   const int n_second = R - n_geo;
   for (int l = 0; l < d.layers; ++l) {
     G2_W(in_g, float, key("mot.%d.%s", l, "input_layernorm_geo")); G2_W(in_u, float, key("mot.%d.%s", l, "input_layernorm_und"));
@@ -480,7 +489,7 @@ static int run_decoder(g2vlm_ctx* ctx, const Ws& ws, const char* name, bool cros
   bf16* qc = ws.p<bf16>("dec.qc");
   const int32_t* work = ws.p<int32_t>("tab.dec_work");
   const int32_t* cwork = ws.p<int32_t>("tab.cross_work");
-  const float scale = 1.0f / sqrtf((float)ehd);
+  const float scale = (float)(1.0 / sqrt((double)ehd));
   const int qw = dh * hp;
   const std::string pre = std::string("dec.") + name + ".";
   G2_TRY(g2vlm_gather_rows(hidden, (int64_t)H * 4, x, (int64_t)H * 4, nullptr, rows, (int64_t)H * 4, 0, stream));

@@ -603,6 +603,13 @@ class NativeContext:
         self.call("g2vlm_load_weights", name.encode(), _vp(t.data_ptr()), _i32(int(t.dtype == torch.bfloat16)), _i64(rows),
                   _i64(t.numel() // max(rows, 1)))
 
+    def region(self, ws: torch.Tensor, name: str, dtype, cols: int) -> torch.Tensor:
+        """View of a named intermediate inside the planned workspace (see g2vlm_workspace_region)."""
+        off, nb = ctypes.c_int64(), ctypes.c_int64()
+        self.call("g2vlm_workspace_region", name.encode(), ctypes.byref(off), ctypes.byref(nb))
+        flat = ws[off.value: off.value + nb.value].view(dtype)
+        return flat.view(-1, cols)
+
     def workspace_bytes(self, n_views: int, H: int, W: int, n_prompt: int) -> int:
         n = int(self._lib.g2vlm_workspace_bytes(self._h, _i32(n_views), _i32(H), _i32(W), _i32(n_prompt)))
         if n < 0:

@@ -445,6 +445,11 @@ int64_t g2vlm_workspace_bytes(const g2vlm_ctx* ctx, int32_t n_views, int32_t H, 
 int g2vlm_recon_plan(g2vlm_ctx* ctx, int32_t n_views, int32_t H, int32_t W, int32_t n_prompt,
                      const int32_t* dino_seqlens, void* workspace, int64_t workspace_bytes, void* stream);
 
+/* Where a named intermediate of the planned geometry lives inside the workspace (debugging / stage-by-stage parity):
+ * e.g. "dino.tokens" bf16 [n*P, D], "mot.x" fp32 [T+n_prompt, H] (expert-permuted rows), "rec.point_hidden" bf16,
+ * "rec.camera_hidden" fp32, "rec.global_hidden" bf16, "dec.x" fp32 (residual stream of the last decoder run). */
+int g2vlm_workspace_region(const g2vlm_ctx* ctx, const char* name, int64_t* offset, int64_t* bytes);
+
 /* Dinov2WithRegistersModel.forward (g2vlm/dinov2_model.py:301-356): images fp32 [n,3,H,W] (normalize != 0: raw [0,1]
  * views, ImageNet-normalised on the fly) -> bf16 tokens [n*P, D] inside the workspace (*tokens_out).  pos_embed: fp32
  * [1+P, D], the position table already resampled to this grid (interpolate_pos_encoding, :93-145). */
