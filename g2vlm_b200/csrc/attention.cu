@@ -29,6 +29,7 @@ constexpr int ATT_BN = 128;       // keys per block
 constexpr int ATT_THREADS = 384;  // 12 warps
 constexpr float ATT_RESCALE_TAU = 8.0f;
 constexpr int ATT_PCHUNKS = 4;    // P_t reaches the MMA warp in 4 chunks of 32 keys (PV overlaps the exp tail)
+constexpr int ATT64_POLY = 0;     // head_dim 64: exp2 pairs (of every 8) on the FMA pipe instead of the MUFU — 0: measured slower (r02)
 
 struct AttnKParams {
   CUtensorMap tmQ, tmK, tmV;
@@ -83,7 +84,67 @@ struct AttnUnit {
   bool causal;
 };
 
-template <int D>
+// P = 2^(s*scale - m) of one 128-key block: packed to bf16 pairs, written to the P columns of TMEM and handed to the MMA
+// warp 32 keys at a time so PV starts while the rest of the row is still in exp2.
+// POLY (0..8): of every 8 score pairs, POLY take exp2 on the FMA pipe (round-to-nearest split x = n + f, degree-3 minimax
+// polynomial for 2^f on [-0.5, 0.5], max rel error 7.5e-5 — far below the bf16 rounding of P — and n added to the
+// exponent field) instead of MUFU.EX2.  At head_dim 64 a 128 x 128 tile needs 1024 MUFU clocks (16 exp2 / clk / SM,
+// measured: tools/micro/mufu_bench.cu) against 512 tensor clocks, so the kernel is MUFU-bound and the FMA pipe is idle.
+template <int POLY>
+__device__ __forceinline__ void softmax_block(const uint32_t (&sv)[128], float m_used, float scale_log2, uint64_t& sum2,
+                                              uint32_t tP_w, uint64_t* p_full_t, int lane) {
+  const uint64_t neg_m2 = pack2(-m_used, -m_used);
+  const uint64_t scale2 = pack2(scale_log2, scale_log2);
+  [[maybe_unused]] const uint64_t magic2 = pack2(12582912.f, 12582912.f), nmagic2 = pack2(-12582912.f, -12582912.f);
+  [[maybe_unused]] const uint64_t none2 = pack2(-1.f, -1.f);
+  [[maybe_unused]] const uint64_t c0 = pack2(0.99992806f, 0.99992806f), c1 = pack2(0.69326097f, 0.69326097f);
+  [[maybe_unused]] const uint64_t c2 = pack2(0.24261113f, 0.24261113f), c3 = pack2(0.05517167f, 0.05517167f);
+#pragma unroll
+  for (int c = 0; c < ATT_PCHUNKS; ++c) {
+    constexpr int CW = ATT_BN / ATT_PCHUNKS;  // keys per chunk
+    uint32_t pk[CW / 2];
+#pragma unroll
+    for (int i = 0; i < CW; i += 2) {
+      const uint64_t x2 = fma2(pack2(__uint_as_float(sv[c * CW + i]), __uint_as_float(sv[c * CW + i + 1])), scale2, neg_m2);
+      float x0, x1, p0, p1;
+      unpack2(x2, x0, x1);
+      if (((i >> 1) & 7) < POLY) {
+        const uint64_t xc = pack2(fmaxf(x0, -125.f), fmaxf(x1, -125.f));
+        const uint64_t t2 = add2(xc, magic2);           // integer part in the low mantissa bits
+        const uint64_t f2 = fma2(add2(t2, nmagic2), none2, xc);
+        uint64_t q2 = fma2(c3, f2, c2);
+        q2 = fma2(q2, f2, c1);
+        q2 = fma2(q2, f2, c0);
+        float q0, q1, t0, t1;
+        unpack2(q2, q0, q1);
+        unpack2(t2, t0, t1);
+        p0 = __int_as_float(__float_as_int(q0) + (__float_as_int(t0) << 23));
+        p1 = __int_as_float(__float_as_int(q1) + (__float_as_int(t1) << 23));
+      } else {
+        p0 = ex2_approx(x0);
+        p1 = ex2_approx(x1);
+      }
+      sum2 = add2(sum2, pack2(p0, p1));
+      pk[i >> 1] = pack_bf16x2(p0, p1);
+    }
+    // the store of chunk c-1 has had a whole chunk of exp2 to land: publishing it here keeps the
+    // tcgen05.wait::st latency off the critical path
+    if (c > 0) {
+      tmem_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full_t[c - 1]);
+    }
+    if constexpr (CW == 32) tmem_st16(tP_w + c * 16, pk);
+    else tmem_st32(tP_w + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&pk[0]));
+  }
+  tmem_wait_st();
+  tc_fence_before();
+  __syncwarp();
+  if (lane == 0) mbar_arrive(&p_full_t[ATT_PCHUNKS - 1]);
+}
+
+template <int D, int POLY>
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 attention_tcgen05_kernel(const __grid_constant__ AttnKParams p) {
   using Cfg = AttnCfg<D>;
@@ -494,38 +555,11 @@ attention_tcgen05_kernel(const __grid_constant__ AttnKParams p) {
           }
         }
         uint64_t sum2 = pack2(0.f, 0.f);
-        const uint64_t neg_m2 = pack2(-m_used, -m_used);
-        const uint64_t scale2 = pack2(p.scale_log2, p.scale_log2);
-#pragma unroll
-        for (int c = 0; c < ATT_PCHUNKS; ++c) {
-          constexpr int CW = ATT_BN / ATT_PCHUNKS;  // keys per chunk
-          uint32_t pk[CW / 2];
-#pragma unroll
-          for (int i = 0; i < CW; i += 2) {
-            const uint64_t x2 = fma2(pack2(__uint_as_float(sv[c * CW + i]), __uint_as_float(sv[c * CW + i + 1])),
-                                     scale2, neg_m2);
-            float x0, x1;
-            unpack2(x2, x0, x1);
-            const float p0 = ex2_approx(x0);
-            const float p1 = ex2_approx(x1);
-            sum2 = add2(sum2, pack2(p0, p1));
-            pk[i >> 1] = pack_bf16x2(p0, p1);
-          }
-          // the store of chunk c-1 has had a whole chunk of exp2 to land: publishing it here keeps the
-          // tcgen05.wait::st latency off the critical path
-          if (c > 0) {
-            tmem_wait_st();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&p_full[t * ATT_PCHUNKS + c - 1]);
-          }
-          if constexpr (CW == 32) tmem_st16(tP_w + c * 16, pk);
-          else tmem_st32(tP_w + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&pk[0]));
-        }
-        tmem_wait_st();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&p_full[t * ATT_PCHUNKS + ATT_PCHUNKS - 1]);
+        // fully unmasked block of a non-causal item: part of the exp2 may run on the FMA pipe (never for a block
+        // that holds a masked -inf score: the polynomial would turn it into 2^-125 instead of an exact 0)
+        const bool poly_ok = POLY > 0 && !a.causal && col_base + ATT_BN <= a.len_k;
+        if (poly_ok) softmax_block<POLY>(sv, m_used, p.scale_log2, sum2, tP_w, &p_full[t * ATT_PCHUNKS], lane);
+        else softmax_block<0>(sv, m_used, p.scale_log2, sum2, tP_w, &p_full[t * ATT_PCHUNKS], lane);
         float sum0, sum1;
         unpack2(sum2, sum0, sum1);
         l_run += sum0 + sum1;
@@ -610,14 +644,14 @@ __global__ void attention_merge_kernel(const __nv_bfloat16* __restrict__ oa, lon
   }
 }
 
-template <int D>
+template <int D, int POLY>
 static int launch_attention(const AttnKParams& kp, int max_ctas, cudaStream_t stream) {
-  if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(attention_tcgen05_kernel<D>), AttnCfg<D>::kSmem)) return rc;
+  if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(attention_tcgen05_kernel<D, POLY>), AttnCfg<D>::kSmem)) return rc;
   const long long units = (long long)kp.n_items * kp.n_heads;
   long long cap = num_sms();                                                   // one persistent CTA per SM
   if (max_ctas > 0 && max_ctas < cap) cap = max_ctas;
   const unsigned grid = (unsigned)(units < cap ? units : cap);
-  attention_tcgen05_kernel<D><<<grid, ATT_THREADS, AttnCfg<D>::kSmem, stream>>>(kp);
+  attention_tcgen05_kernel<D, POLY><<<grid, ATT_THREADS, AttnCfg<D>::kSmem, stream>>>(kp);
   G2_CUDA_OK(cudaGetLastError());
   return G2VLM_OK;
 }
@@ -665,8 +699,16 @@ extern "C" int g2vlm_attention(const g2vlm_attn_args* a, void* stream_) {
   kp.out_head_cols = a->out_head_cols ? a->out_head_cols : D;
   kp.lse = a->lse_out;
   G2_REQUIRE(a->max_ctas >= 0, "attention: negative max_ctas");
-  if (D == 128) return launch_attention<128>(kp, a->max_ctas, stream);
-  return launch_attention<64>(kp, a->max_ctas, stream);
+  if (D == 128) return launch_attention<128, 0>(kp, a->max_ctas, stream);
+  // head_dim 64 needs 1024 MUFU clocks per 128 x 128 tile against 512 tensor clocks, so part of the exp2 was moved to
+  // the FMA pipe (softmax_block<POLY>).  Measured on the DINO shape (profiles/r02_attention64_poly.txt): 224.6 us with
+  // 0/8, 247.7 / 239.3 / 247.6 / 312.6 us with 1..4 of 8 pairs offloaded — the softmax warps are bound by their own
+  // instruction stream and the per-tile QK -> softmax -> PV chain, not by MUFU throughput.  The default stays 0;
+  // G2VLM_ATTN_POLY=2 reproduces the measurement (tools/attn64_poly_ab.py).
+  int poly = ATT64_POLY;
+  if (const char* e = getenv("G2VLM_ATTN_POLY")) poly = atoi(e);
+  if (poly == 2) return launch_attention<64, 2>(kp, a->max_ctas, stream);
+  return launch_attention<64, 0>(kp, a->max_ctas, stream);
 }
 
 extern "C" int g2vlm_attention_merge(const void* o_a, int64_t lda, const float* lse_a, const void* o_b, int64_t ldb,

@@ -43,6 +43,10 @@ void set_last_error(const char* file, int line, const char* msg);
 int make_tmap_2d_bf16(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols,
                       uint64_t row_pitch_bytes, uint32_t box_rows, uint32_t box_cols);
 
+// 2-D row-major fp32 tensor map with 128-byte swizzle and a 32 x 32 box (the epilogue's per-warp staging tile): target of
+// the TMA reduce-add / store of the GEMM epilogues.
+int make_tmap_2d_f32_box32(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t row_pitch_bytes);
+
 int num_sms();
 // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per DEVICE: remember per (kernel, device) that it was set, so a
 // process driving several GPUs configures every kernel on every device it launches on.
@@ -132,6 +136,18 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 // ----------------------------------------------------------------------------------------------
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
+}
+// global[tile] += smem tile (fp32 add performed by the L2 reduction units; one bulk group per call)
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* m, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
+               :
+               : "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+// all bulk groups of this thread have finished READING their shared-memory source (it may be overwritten)
+__device__ __forceinline__ void tma_store_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m, uint64_t* bar,
                                             int c0, int c1) {

@@ -54,6 +54,8 @@ struct GemmKParams {
   int grp_mpair0[3];
   int num_pair_tiles;
   int pair_panel;   // rasterisation: pair_panel M pairs x all N tiles per panel
+  CUtensorMap tmOut;   // RESID_F32: fp32 output as a TMA target (32 x 32 boxes, 128-byte swizzle) when use_tma_out
+  int use_tma_out;
   int k_chunk_kb;   // > 0 (fp32 mode, STORE_F32): k-blocks per accumulator chunk, chunks summed in fp32 RN by the epilogue
 };
 
@@ -182,18 +184,28 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, const TileCo
       const int c4 = (lane & 7) * 4;  // this lane's 4 columns in the transposed (coalesced) domain
       [[maybe_unused]] float4 old[8];
       [[maybe_unused]] float* out_piece = nullptr;
+      // RESID_F32 through the TMA: the chunk goes to the (128-byte-swizzled) staging tile and ONE thread issues a bulk
+      // reduce-add of the 32 x 32 box — the fp32 add happens in the L2 reduction units (same single rounding as the
+      // SM-side add), the SM never reads the residual stream and never waits for it.  Only whole 32 x 32 chunks of a
+      // tile whose 32 rows all belong to this expert group; ragged slabs / column tails keep the read-modify-write.
+      [[maybe_unused]] bool tma_chunk = false;
+      if constexpr (EPI == G2VLM_EPI_RESID_F32) {
+        tma_chunk = p.use_tma_out && rows_ok >= 32 && cols_ok == 32;
+      }
       if constexpr (EPI == G2VLM_EPI_RESID_F32) {
         out_piece = reinterpret_cast<float*>(p.out) + (row_base + (lane >> 3)) * p.ldo + col0 + c4;
+        if (!tma_chunk) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          old[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (i * 4 + (lane >> 3) < rows_ok && c4 + 4 <= cols_ok)
-            old[i] = *reinterpret_cast<const float4*>(out_piece + (long long)i * 4 * p.ldo);
+          for (int i = 0; i < 8; ++i) {
+            old[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (i * 4 + (lane >> 3) < rows_ok && c4 + 4 <= cols_ok)
+              old[i] = *reinterpret_cast<const float4*>(out_piece + (long long)i * 4 * p.ldo);
+          }
         }
         // Pull the NEXT chunk's residual lines (32 rows x 128 B) into L2 now, without holding registers for them:
         // their loads one chunk later then cost an L2 hit instead of an HBM round trip (same-box A/B: DINO dense
         // 69 -> 63.5 us, the other residual GEMMs -1 %; prefetching a whole tile ahead instead was 5-8 % SLOWER).
-        if (c + 1 < half * 4 + 4 && col0 + 32 < p.N && (lane & 7) == 0) {
+        if (!tma_chunk && c + 1 < half * 4 + 4 && col0 + 32 < p.N && (lane & 7) == 0) {
 #pragma unroll
           for (int i = 0; i < 8; ++i)
             if (i * 4 + (lane >> 3) < rows_ok)
@@ -223,6 +235,10 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, const TileCo
 
       if constexpr (EPI == G2VLM_EPI_STORE_BF16) {
         if (p.flags & G2VLM_GEMM_GELU) {
+          // exact-erf GELU of the bf16-rounded pre-activation (bit-identical to torch's nn.GELU on a bf16 tensor on
+          // 100 % of 2 x 10^8 sampled outputs, tools/gemm_gelu_ab.py).  Measured and rejected (r02): tabulating the
+          // 3072 bf16 inputs with 2^-9 <= |x| < 8 in shared memory instead — also bit-identical, but 249 us against
+          // 184 us on DINO fc1 (divergent range checks + bank-conflicted 2-byte loads cost more than erff's ~25 FMAs).
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = gelu_erf(bf16_round(f[j]));
         } else if (p.flags & G2VLM_GEMM_QUICK_GELU) {
@@ -262,8 +278,21 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, const TileCo
             for (int j = 0; j < 32; ++j) f[j] = bf16_round(f[j]);
           }
         }
+        if (tma_chunk) {
+          if (lane == 0) tma_store_wait_read();   // the previous chunk's bulk read of this staging tile is done
+          __syncwarp();
+          stage_write_f32(stg, lane, f);          // ends with __syncwarp
+          fence_proxy_async_smem();               // generic-proxy writes -> visible to the async proxy
+          __syncwarp();
+          if (lane == 0) tma_reduce_add_2d(&p.tmOut, stg, col0, (int)row_base);
+          continue;
+        }
         // RMW of the fp32 residual stream in the transposed (coalesced) domain. The 8 old values were
         // loaded BEFORE the accumulator chunk was read (`old`, below), so their latency is hidden.
+        if (p.use_tma_out) {                      // a pending bulk read of the staging tile must finish first
+          if (lane == 0) tma_store_wait_read();
+          __syncwarp();
+        }
         stage_write_f32(stg, lane, f);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -477,6 +506,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ GemmKParams p) {
         if (acc == 0) acc_phase ^= 1;
       }
     }
+    if (lane == 0) tma_store_wait_read();   // outstanding bulk reduce-adds still read this warp's staging tile
   }
 
   tc_fence_before();
@@ -634,6 +664,7 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ GemmKParams p) {
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
+    if (lane == 0) tma_store_wait_read();   // outstanding bulk reduce-adds still read this warp's staging tile
   }
 
   tc_fence_before();
@@ -733,6 +764,14 @@ extern "C" int g2vlm_gemm_bf16(const g2vlm_gemm_args* a, void* stream_) {
   kp.ldr = a->ldr;
   kp.out_col_group = a->out_col_group;
   kp.out_col_stride = a->out_col_stride;
+  // RESID_F32: the residual stream is updated through TMA reduce-add (fp32 add in L2) unless the caller needs the
+  // rounded sum (bf16 residual stream of the ViT / training forward) or opts out for A/B timing
+  kp.use_tma_out = 0;
+  if (a->epilogue == G2VLM_EPI_RESID_F32 && !(a->flags & (G2VLM_GEMM_ROUND_SUM | G2VLM_GEMM_NO_TMA_OUT)) && max_row >= 32) {
+    if (int rc_out = make_tmap_2d_f32_box32(&kp.tmOut, a->out, (uint64_t)max_row, (uint64_t)a->N, (uint64_t)a->ldo * 4))
+      return rc_out;
+    kp.use_tma_out = 1;
+  }
   G2_REQUIRE(a->k_chunk_blocks >= 0, "gemm: negative k_chunk_blocks");
   G2_REQUIRE(a->k_chunk_blocks == 0 || (a->epilogue == G2VLM_EPI_STORE_F32 && !(a->flags & G2VLM_GEMM_ROUND_BF16)),
              "gemm: k_chunk_blocks needs the STORE_F32 epilogue without ROUND_BF16");

@@ -68,6 +68,32 @@ int make_tmap_2d_bf16(CUtensorMap* map, const void* base, uint64_t rows, uint64_
   return G2VLM_OK;
 }
 
+int make_tmap_2d_f32_box32(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t row_pitch_bytes) {
+  PFN_encodeTiled enc = get_encode_fn();
+  if (!enc) {
+    set_last_error(__FILE__, __LINE__, "cuTensorMapEncodeTiled driver entry point unavailable");
+    return G2VLM_ERR_CUDA;
+  }
+  if ((reinterpret_cast<uintptr_t>(base) & 15) || (row_pitch_bytes & 15) || rows == 0 || cols == 0) {
+    set_last_error(__FILE__, __LINE__, "tensor map (fp32): base/pitch must be 16-byte aligned");
+    return G2VLM_ERR_INVALID;
+  }
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {row_pitch_bytes};
+  cuuint32_t box[2] = {32, 32};   // 32 fp32 = 128 bytes: one swizzle row
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char msg[128];
+    snprintf(msg, sizeof(msg), "cuTensorMapEncodeTiled (fp32) failed with CUresult %d", (int)r);
+    set_last_error(__FILE__, __LINE__, msg);
+    return G2VLM_ERR_CUDA;
+  }
+  return G2VLM_OK;
+}
+
 static constexpr int kMaxDevices = 64;
 
 int num_sms() {

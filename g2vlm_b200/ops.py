@@ -16,6 +16,7 @@ from . import _lib
 EPI_STORE_BF16, EPI_SWIGLU_BF16, EPI_RESID_F32, EPI_STORE_F32 = 0, 1, 2, 3
 GEMM_GELU, GEMM_ROUND_AFTER_SCALE, GEMM_RELU, GEMM_ACCUMULATE, GEMM_ROUND_BF16 = 1, 2, 4, 8, 16
 GEMM_QUICK_GELU, GEMM_ROUND_SUM = 32, 64
+GEMM_NO_TMA_OUT = 512   # RESID_F32: SM-side read-modify-write instead of the TMA reduce-add
 GEMM_FORCE_PAIR, GEMM_FORCE_SINGLE = 128, 256   # choose the CTA-pair / 1-CTA kernel per call (tests, A/B timing)
 
 

@@ -69,6 +69,7 @@ const char* g2vlm_last_error(void);
 #define G2VLM_GEMM_ROUND_SUM 64u        /* RESID_F32: round the updated stream value to bf16 (bf16 residual stream) */
 #define G2VLM_GEMM_FORCE_PAIR 128u      /* run the CTA-pair kernel (256x256 tiles) whatever the problem size */
 #define G2VLM_GEMM_FORCE_SINGLE 256u    /* run the 1-CTA kernel (128x256 tiles) whatever the problem size */
+#define G2VLM_GEMM_NO_TMA_OUT 512u      /* RESID_F32: SM-side read-modify-write instead of the TMA reduce-add (A/B timing) */
 
 typedef struct g2vlm_gemm_args {
   const void* A; /* bf16 [a_rows, K], leading dimension lda */

@@ -235,6 +235,12 @@ def test_resid_f32_both_kernels(kernel, rows, K, N, groups):
             assert _relerr(x, ref) < 1e-2
         else:
             assert _relerr(x, ref) < 5e-3, (kernel, flags)
+            # the TMA reduce-add (fp32 add in the L2 reduction units) and the SM-side read-modify-write perform the
+            # same single fp32 addition per element: bit-identical residual streams
+            x2 = x0.clone()
+            ops.gemm(a, w, x2, epilogue=ops.EPI_RESID_F32, groups=groups, bias=bias, scale=gamma, scale_groups=1,
+                     flags=flags | _force(kernel) | ops.GEMM_NO_TMA_OUT)
+            assert torch.equal(x, x2), (kernel, flags)
 
 
 @pytest.mark.parametrize("kernel", _KERNELS)
