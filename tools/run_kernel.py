@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Stand-alone launcher of one hot kernel at its config-2 shape (for ncu --set full captures and
-quick timing).  usage: python tools/run_kernel.py {attention|gateup|down|qkv} [iters]"""
+quick timing).  usage: python tools/run_kernel.py {attention|attention64|gateup|down|qkv|oproj|dino_dense|dino_fc1} [iters]"""
 import math
 import os
 import sys
@@ -37,6 +37,36 @@ elif which == "down":
     fn = lambda: ops.gemm(a, w, out, epilogue=ops.EPI_RESID_F32, groups=groups, scale=sc, scale_groups=1,
                           flags=ops.GEMM_ROUND_AFTER_SCALE)
     flops = 2 * T * H * I
+elif which == "attention64":     # DINO encoder attention: 16 views x 1374 rows, segments of 1369 (quirk Q1), 16 heads x 64
+    N, P, S = 16, 1369, 1374
+    qkv = rnd(N * S, 3 * 1024).to(torch.bfloat16)
+    out = torch.zeros(N * S, 1024, device="cuda", dtype=torch.bfloat16)
+    cu = [i * P for i in range(N + 1)]
+    work = ops.attention_work_table(cu, cu).cuda()
+    fn = lambda: ops.attention(qkv[:, :1024], qkv[:, 1024:2048], qkv[:, 2048:], out, work, num_q_heads=16,
+                               num_kv_heads=16, head_dim=64, scale=1 / math.sqrt(64))
+    flops = 4 * N * P * P * 16 * 64
+elif which == "oproj":           # routed o_proj + LayerScale + residual (TMA reduce-add epilogue)
+    a = (rnd(T, H) * 0.5).to(torch.bfloat16); w = (rnd(2 * H, H) * 0.05).to(torch.bfloat16)
+    out = torch.zeros(T, H, device="cuda")
+    sc = torch.ones(H, device="cuda")
+    fn = lambda: ops.gemm(a, w, out, epilogue=ops.EPI_RESID_F32, groups=groups, scale=sc, scale_groups=1,
+                          flags=ops.GEMM_ROUND_AFTER_SCALE)
+    flops = 2 * T * H * H
+elif which == "dino_dense":      # DINO attention.output.dense + lambda1 + residual (K = N = 1024)
+    M = 16 * 1374
+    a = (rnd(M, 1024) * 0.5).to(torch.bfloat16); w = (rnd(1024, 1024) * 0.05).to(torch.bfloat16)
+    b, sc = rnd(1024), torch.ones(1024, device="cuda")
+    out = torch.zeros(M, 1024, device="cuda")
+    fn = lambda: ops.gemm(a, w, out, epilogue=ops.EPI_RESID_F32, bias=b, scale=sc, scale_groups=1)
+    flops = 2 * M * 1024 * 1024
+elif which == "dino_fc1":        # DINO mlp.fc1 + exact-erf GELU
+    M = 16 * 1374
+    a = (rnd(M, 1024) * 0.5).to(torch.bfloat16); w = (rnd(4096, 1024) * 0.05).to(torch.bfloat16)
+    b = rnd(4096)
+    out = torch.empty(M, 4096, device="cuda", dtype=torch.bfloat16)
+    fn = lambda: ops.gemm(a, w, out, epilogue=ops.EPI_STORE_BF16, bias=b, flags=ops.GEMM_GELU)
+    flops = 2 * M * 1024 * 4096
 else:
     a = (rnd(T, H) * 0.5).to(torch.bfloat16); w = (rnd(2 * 2048, H) * 0.05).to(torch.bfloat16)
     b = rnd(2 * 2048)
