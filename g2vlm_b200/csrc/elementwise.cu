@@ -709,63 +709,90 @@ __global__ void camera_pose_kernel(const float* __restrict__ feat, long long ldf
 // argmax over the vocabulary (greedy decode): one block per row, lowest index wins ties
 // ------------------------------------------------------------------------------------------------
 // blockIdx.y slices the vocabulary (ARGMAX_SLICES partial results per row, merged by the last slice to finish)
-constexpr int ARGMAX_SLICES = 64;
-__device__ float g_argmax_val[ARGMAX_SLICES * 64];
-__device__ int g_argmax_idx[ARGMAX_SLICES * 64];
-__device__ unsigned g_argmax_ticket[64];
+// torch.argmax semantics: the maximum, ties -> lowest index, NaN counts as the maximum (first NaN wins) so that a
+// numerical blow-up surfaces in the generated ids instead of being skipped.
+__device__ __forceinline__ bool argmax_better(float v, int i, float bv, int bi) {
+  const bool vn = v != v, bn = bv != bv;
+  if (vn != bn) return vn;
+  if (vn || v == bv) return i < bi;
+  return v > bv;
+}
 
-__global__ void argmax_bf16_kernel(const __nv_bfloat16* __restrict__ logits, long long ld, int vocab,
-                                   long long* __restrict__ out) {
+constexpr int ARGMAX_SLICES = 8;   // one thread-block cluster per row: the slices merge through distributed shared memory
+constexpr int ARGMAX_THREADS = 512;
+
+// grid (rows, SLICES) with cluster dims (1, SLICES, 1) for large vocabularies, grid (rows, 1) otherwise.  No global
+// scratch: concurrent launches on different streams (two generations, a graph replay next to an eager step) are
+// independent.  16-byte loads when the row is 16-byte aligned.
+template <int SLICES>
+__global__ void __launch_bounds__(ARGMAX_THREADS)
+argmax_bf16_kernel(const __nv_bfloat16* __restrict__ logits, long long ld, int vocab, long long* __restrict__ out) {
   const __nv_bfloat16* row = logits + blockIdx.x * ld;
   float best = -INFINITY;
   int idx = 0x7fffffff;
-  const int per = (vocab + gridDim.y - 1) / gridDim.y;
+  const int per = ((vocab + SLICES - 1) / SLICES + 7) & ~7;
   const int lo = blockIdx.y * per, hi = min(vocab, lo + per);
-  for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) {
-    const float v = __bfloat162float(row[i]);
-    if (v > best || (v == best && i < idx)) { best = v; idx = i; }
+  if ((reinterpret_cast<uintptr_t>(row) & 15) == 0) {
+    for (int i = lo + threadIdx.x * 8; i < hi; i += ARGMAX_THREADS * 8) {
+      if (i + 8 <= hi) {
+        const uint4 raw = *reinterpret_cast<const uint4*>(row + i);
+        const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float v0 = __uint_as_float(w[j] << 16), v1 = __uint_as_float(w[j] & 0xffff0000u);
+          if (argmax_better(v0, i + 2 * j, best, idx)) { best = v0; idx = i + 2 * j; }
+          if (argmax_better(v1, i + 2 * j + 1, best, idx)) { best = v1; idx = i + 2 * j + 1; }
+        }
+      } else {
+        for (int j = i; j < hi; ++j) {
+          const float v = __bfloat162float(row[j]);
+          if (argmax_better(v, j, best, idx)) { best = v; idx = j; }
+        }
+      }
+    }
+  } else {
+    for (int i = lo + threadIdx.x; i < hi; i += ARGMAX_THREADS) {
+      const float v = __bfloat162float(row[i]);
+      if (argmax_better(v, i, best, idx)) { best = v; idx = i; }
+    }
   }
   __shared__ float sb[32];
   __shared__ int si[32];
+  __shared__ float cb[SLICES];   // rank 0's copy receives every slice's winner
+  __shared__ int ci[SLICES];
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     const float ob = __shfl_xor_sync(0xffffffffu, best, o);
     const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
-    if (ob > best || (ob == best && oi < idx)) { best = ob; idx = oi; }
+    if (argmax_better(ob, oi, best, idx)) { best = ob; idx = oi; }
   }
   if ((threadIdx.x & 31) == 0) { sb[threadIdx.x >> 5] = best; si[threadIdx.x >> 5] = idx; }
   __syncthreads();
   if (threadIdx.x < 32) {
-    best = threadIdx.x < (blockDim.x >> 5) ? sb[threadIdx.x] : -INFINITY;
-    idx = threadIdx.x < (blockDim.x >> 5) ? si[threadIdx.x] : 0x7fffffff;
+    best = threadIdx.x < (ARGMAX_THREADS >> 5) ? sb[threadIdx.x] : -INFINITY;
+    idx = threadIdx.x < (ARGMAX_THREADS >> 5) ? si[threadIdx.x] : 0x7fffffff;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
       const float ob = __shfl_xor_sync(0xffffffffu, best, o);
       const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
-      if (ob > best || (ob == best && oi < idx)) { best = ob; idx = oi; }
+      if (argmax_better(ob, oi, best, idx)) { best = ob; idx = oi; }
     }
-    if (threadIdx.x == 0) {
-      if (gridDim.y == 1) {
-        out[blockIdx.x] = idx == 0x7fffffff ? 0 : idx;
-      } else {
-        const int slot = (blockIdx.x & 63) * ARGMAX_SLICES + blockIdx.y;
-        g_argmax_val[slot] = best;
-        g_argmax_idx[slot] = idx;
-        __threadfence();
-        const unsigned t = atomicAdd(&g_argmax_ticket[blockIdx.x & 63], 1u);
-        if (t == gridDim.y - 1) {  // last slice of this row: merge (ties -> lowest index)
-          __threadfence();
-          float b = -INFINITY;
-          int bi = 0x7fffffff;
-          for (int s2 = 0; s2 < (int)gridDim.y; ++s2) {
-            const float v = g_argmax_val[(blockIdx.x & 63) * ARGMAX_SLICES + s2];
-            const int ii = g_argmax_idx[(blockIdx.x & 63) * ARGMAX_SLICES + s2];
-            if (v > b || (v == b && ii < bi)) { b = v; bi = ii; }
-          }
-          out[blockIdx.x] = bi == 0x7fffffff ? 0 : bi;
-          g_argmax_ticket[blockIdx.x & 63] = 0;
-        }
-      }
+  }
+  if constexpr (SLICES == 1) {
+    if (threadIdx.x == 0) out[blockIdx.x] = idx == 0x7fffffff ? 0 : idx;
+  } else {
+    if (threadIdx.x == 0) {   // publish this slice's winner in rank 0's shared memory
+      const uint32_t rank = cluster_ctarank();
+      asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(mapa_shared(smem_u32(&cb[rank]), 0)), "f"(best) : "memory");
+      asm volatile("st.shared::cluster.s32 [%0], %1;" ::"r"(mapa_shared(smem_u32(&ci[rank]), 0)), "r"(idx) : "memory");
+    }
+    cluster_sync_all();
+    if (cluster_ctarank() == 0 && threadIdx.x == 0) {
+      float b = cb[0];
+      int bi = ci[0];
+      for (int s2 = 1; s2 < SLICES; ++s2)
+        if (argmax_better(cb[s2], ci[s2], b, bi)) { b = cb[s2]; bi = ci[s2]; }
+      out[blockIdx.x] = bi == 0x7fffffff ? 0 : bi;
     }
   }
 }
@@ -854,8 +881,10 @@ __global__ void ply_scatter_kernel(const float* __restrict__ pts, const float* _
   for (int k = 0; k < 3; ++k) {
     const double d = static_cast<double>(p[k]);
     memcpy(rec + 8 * k, &d, 8);  // records are 27 bytes: unaligned doubles
-    const double col = fmin(255.0, fmax(0.0, static_cast<double>(c[(long long)k * hw]) * 255.0));
-    rec[24 + k] = static_cast<uint8_t>(col);
+    // Open3D's PLY writer (the reference's output path, g2vlm_utils.py:146) converts with utility::ColorToUint8 =
+    // round(clamp(c, 0, 1) * 255): colours are float32 k/255, so c * 255 often lands at k - 1e-7 and must ROUND to k
+    const double col = fmin(1.0, fmax(0.0, static_cast<double>(c[(long long)k * hw]))) * 255.0;
+    rec[24 + k] = static_cast<uint8_t>(__double2int_rn(col));
   }
 }
 
@@ -1173,12 +1202,27 @@ extern "C" int g2vlm_argmax_bf16(const void* logits, int64_t ld, int64_t rows, i
                                  void* stream) {
   G2_REQUIRE(logits && out && vocab > 0, "argmax: bad arguments");
   if (rows <= 0) return G2VLM_OK;
-  // large vocabularies: slice the row over 64 blocks (a single block is latency-bound: 72 us for 151 936)
-  G2_REQUIRE(rows <= 64 || vocab < 16384, "argmax: at most 64 rows with a sliced vocabulary");
-  const unsigned slices = vocab >= 16384 ? ARGMAX_SLICES : 1;
-  argmax_bf16_kernel<<<dim3(static_cast<unsigned>(rows), slices), 256, 0, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)logits, ld, vocab, (long long*)out);
-  G2_LAUNCH_CHECK();
+  G2_REQUIRE(rows < (1LL << 31), "argmax: too many rows");
+  if (vocab >= 16384) {
+    // large vocabularies: one cluster of 8 CTAs per row (a single block is latency-bound: 72 us for 151 936)
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(static_cast<unsigned>(rows), ARGMAX_SLICES);
+    cfg.blockDim = dim3(ARGMAX_THREADS);
+    cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = 1;
+    attr.val.clusterDim.y = ARGMAX_SLICES;
+    attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = 1;
+    G2_CUDA_OK(cudaLaunchKernelEx(&cfg, argmax_bf16_kernel<ARGMAX_SLICES>, (const __nv_bfloat16*)logits, (long long)ld,
+                                  (int)vocab, (long long*)out));
+  } else {
+    argmax_bf16_kernel<1><<<dim3(static_cast<unsigned>(rows), 1), ARGMAX_THREADS, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)logits, ld, vocab, (long long*)out);
+    G2_LAUNCH_CHECK();
+  }
   return G2VLM_OK;
 }
 

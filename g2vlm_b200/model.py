@@ -228,6 +228,7 @@ class G2VLMFast:
         self._rope2d_cache: Dict[tuple, tuple] = {}
         self._pos_cache: Dict[tuple, torch.Tensor] = {}
         self._work_cache: Dict[tuple, torch.Tensor] = {}
+        self._dino_attn_cover: Dict[int, int] = {}   # zero-initialised DINO attention buffer -> rows covered last time
         self.stage_events: Optional[list] = None  # bench.py: [(name, cuda event)] at stage boundaries
         # view-sharded K/V exchange: "overlap" (v2: point-to-point exchange hidden behind the local-key attention +
         # LSE merge) or "allgather" (v1: one blocking all-gather per layer); SMs left to the NCCL kernel meanwhile
@@ -1137,6 +1138,9 @@ class G2VLMFast:
         # rows covered by no segment are never written by the attention kernel: they stay ZERO
         # (definition of the uninitialised flash-attn rows, quirk Q1)
         attn = self.buf.get("dino.attn", (rows, nh * hp), torch.bfloat16, zero=True)
+        if self._dino_attn_cover.get(attn.data_ptr()) not in (None, cu[-1]) :
+            attn.zero_()     # same buffer, different coverage than the previous call: stale rows must not leak in
+        self._dino_attn_cover[attn.data_ptr()] = cu[-1]
         mid = self.buf.get("dino.mid", (rows, D * cfg.dino_mlp_ratio), torch.bfloat16)
         scale = 1.0 / math.sqrt(cfg.dino_head_dim)
         x = x[:rows]

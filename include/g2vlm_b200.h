@@ -489,7 +489,7 @@ int64_t g2vlm_driver_launches(void);
  * points fp32 [n_views*H*W, 3] (= pred["points"]), images fp32 [n_views, 3, H, W] in [0,1]
  * (= pred["images"]; colour of point (v,y,x) is images[v,:,y,x], :121). out must hold n*27 bytes;
  * block_counts is an int32 workspace of ceil(n/1024)+1 entries; *n_valid (device int64) receives the
- * number of records written. colour byte = (uchar) min(255, max(0, c*255)) (truncation).
+ * number of records written. colour byte = round(clamp(c, 0, 1) * 255), Open3D's utility::ColorToUint8.
  * ---------------------------------------------------------------------------------------------- */
 int g2vlm_ply_pack(const float* points, const float* images, int32_t n_views, int32_t H, int32_t W,
                    void* out, int32_t* block_counts, int64_t* n_valid, void* stream);

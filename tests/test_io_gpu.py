@@ -31,8 +31,14 @@ def test_ply_pack_matches_numpy_filtering(tmp_path):
     got = np.stack([rec["x"], rec["y"], rec["z"]], 1)
     assert np.array_equal(got, p.astype(np.float64))      # order preserved, fp32 -> double exact
     col = np.stack([rec["red"], rec["green"], rec["blue"]], 1)
-    expect = np.minimum(255.0, np.maximum(0.0, c.astype(np.float64) * 255.0)).astype(np.uint8)
+    expect = np.rint(np.clip(c.astype(np.float64), 0.0, 1.0) * 255.0).astype(np.uint8)   # Open3D ColorToUint8
     assert np.array_equal(col, expect)
+    # colours are 8-bit pixel values k / 255 in float32: every one must come back as exactly k (a truncating
+    # conversion returns k - 1 for roughly half of them)
+    k = torch.arange(256, dtype=torch.float32)
+    assert np.array_equal(np.rint((k / 255.0).double().numpy() * 255.0), k.numpy())
+    src = (img.permute(0, 2, 3, 1).reshape(-1, 3)[torch.from_numpy(valid)] * 255.0).round().numpy().astype(np.uint8)
+    assert np.array_equal(col, src)
     head = open(path, "rb").read(200).decode("ascii", "ignore")
     assert head.startswith("ply\nformat binary_little_endian 1.0") and f"element vertex {n}" in head
 
