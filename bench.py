@@ -159,8 +159,8 @@ def build_reference(cfg, device, layerscale):
     from oracle import ref_harness as rh
     gen_dev = "cuda" if torch.cuda.is_available() else "cpu"   # same generator stream as our arm whenever a GPU exists
     sd = bench_weights(cfg, gen_dev, layerscale)
-    ref = rh.build_reference_model(rh.dims_from_cfg(cfg, vocab_size=32), visual_und=False, device=device,
-                                   zero_fill_uncovered=False, skip_init=True)   # stock flash-attn call for timing
+    ref = quiet(rh.build_reference_model, rh.dims_from_cfg(cfg, vocab_size=32), visual_und=False, device=device,
+                zero_fill_uncovered=False, skip_init=True)     # stock flash-attn call for timing
     msg = ref.load_state_dict(sd, strict=False)
     params = dict(ref.named_parameters())
     with torch.no_grad():
@@ -173,8 +173,7 @@ def build_reference(cfg, device, layerscale):
 
 def quiet(fn, *a, **k):
     import contextlib
-    import io
-    with contextlib.redirect_stdout(io.StringIO()):    # the reference prints progress lines
+    with contextlib.redirect_stdout(sys.stderr):       # the reference prints progress lines: stdout carries ONE JSON line
         return fn(*a, **k)
 
 
