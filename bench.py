@@ -555,7 +555,8 @@ def main():
     ap.add_argument("--height", type=int, default=None)
     ap.add_argument("--width", type=int, default=None)
     ap.add_argument("--sp-mode", default="overlap", choices=["overlap", "allgather"])
-    ap.add_argument("--sp-sm-margin", type=int, default=4)
+    ap.add_argument("--sp-sm-margin", type=int, default=-1,
+                    help="SMs the local-key attention leaves to the NCCL exchange kernel (= NCCL_MAX_NCHANNELS); -1: min(32, 4*N)")
     ap.add_argument("--no-native", action="store_true",
                     help="per-op calls from Python (~630 per step) instead of the three native stage calls (bit-identical results)")
     ap.add_argument("--no-fuse-prompt", action="store_true",
@@ -585,6 +586,9 @@ def main():
         # the view-sharded K/V exchange runs UNDER the local-key attention (a persistent kernel that leaves
         # --sp-sm-margin SMs free): a few NCCL channels move the 45-180 MB per layer far faster than the attention
         # it hides behind, and every channel is an SM taken from that attention
+        if args.sp_sm_margin < 0:
+            args.sp_sm_margin = min(32, 4 * world)   # more peers -> more P2P channels; the local-key attention they
+                                                     # take SMs from is only 1/world of the layer's attention
         os.environ.setdefault("NCCL_MAX_NCHANNELS", str(max(1, args.sp_sm_margin)))
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
