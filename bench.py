@@ -357,8 +357,9 @@ def view_sharded_scene(model, dist, rank, world, n_views, size, steps, warmup, c
 def view_sharded_block(model, cfg, dist, rank, world, args):
     """`view_sharded` block of the N > 1 bench line (BASELINE configs[3])."""
     out = dict(note="ONE scene split by view over the N GPUs: DINO by attention segment + neighbour exchange, per MoT "
-                    "layer a point-to-point K|V exchange (NCCL over NVLink) hidden behind the attention over the local "
-                    "keys + log-sum-exp merge, context broadcast; times are max over ranks, CUDA events",
+                    "layer the K|V rows are exchanged over NVLink (mode peer: symmetric memory + copy-engine pulls) behind "
+                    "the attention over the local keys, then remote keys + log-sum-exp merge; context broadcast; times are "
+                    "max over ranks, CUDA events",
                scenes=[])
     try:
         P = (args.size // 14) ** 2
@@ -370,12 +371,13 @@ def view_sharded_block(model, cfg, dist, rank, world, args):
             out["scenes"].append(r)
             if n_views == 64:
                 out["sp_parity_max_rel"] = r["sp_parity_max_rel"]
-        # A/B of the exchange on the 64-view scene: v1 blocking all-gather
-        model.sp_mode = "allgather"
-        r = view_sharded_scene(model, dist, rank, world, 64, args.size, steps=1, warmup=1, compare_single=False)
-        model.sp_mode = "overlap"
-        out["allgather_v1_64views"] = dict(ms_per_scene=r["ms_per_scene"],
-                                           exposed_exchange_ms_per_layer=r["exposed_exchange_ms_per_layer"])
+        # A/B of the exchange on the 64-view scene: v2 (NCCL point-to-point under the local attention), v1 (all-gather)
+        keep = model.sp_mode
+        for tag, mode in (("nccl_p2p_v2_64views", "overlap"), ("allgather_v1_64views", "allgather")):
+            model.sp_mode = mode
+            r = view_sharded_scene(model, dist, rank, world, 64, args.size, steps=1, warmup=1, compare_single=False)
+            out[tag] = dict(ms_per_scene=r["ms_per_scene"], exposed_exchange_ms_per_layer=r["exposed_exchange_ms_per_layer"])
+        model.sp_mode = keep
     except Exception as e:   # must not take the scene-DP line down with it
         out["error"] = f"{type(e).__name__}: {e}"
     return out
@@ -554,7 +556,7 @@ def main():
                     help="fp32: the fp32-mode path on BASELINE configs[0]'s geometry (--views 8 --height 294 --width 518 unless given)")
     ap.add_argument("--height", type=int, default=None)
     ap.add_argument("--width", type=int, default=None)
-    ap.add_argument("--sp-mode", default="overlap", choices=["overlap", "allgather"])
+    ap.add_argument("--sp-mode", default="peer", choices=["peer", "overlap", "allgather"])
     ap.add_argument("--sp-sm-margin", type=int, default=-1,
                     help="SMs the local-key attention leaves to the NCCL exchange kernel (= NCCL_MAX_NCHANNELS); -1: min(32, 4*N)")
     ap.add_argument("--no-native", action="store_true",

@@ -230,9 +230,11 @@ class G2VLMFast:
         self._work_cache: Dict[tuple, torch.Tensor] = {}
         self._dino_attn_cover: Dict[int, int] = {}   # zero-initialised DINO attention buffer -> rows covered last time
         self.stage_events: Optional[list] = None  # bench.py: [(name, cuda event)] at stage boundaries
-        # view-sharded K/V exchange: "overlap" (v2: point-to-point exchange hidden behind the local-key attention +
-        # LSE merge) or "allgather" (v1: one blocking all-gather per layer); SMs left to the NCCL kernel meanwhile
-        self.sp_mode = "overlap"
+        # view-sharded K/V exchange: "peer" (v3: symmetric memory + copy-engine pulls behind the local-key attention, no SM
+        # taken), "overlap" (v2: NCCL point-to-point exchange behind the local-key attention; sp_sm_margin SMs left to
+        # the NCCL kernel) or "allgather" (v1: one blocking all-gather per layer); all but v1 end in an LSE merge
+        self.sp_mode = "peer"
+        self._sp_sym: Dict[tuple, object] = {}
         self.sp_sm_margin = 4    # = NCCL_MAX_NCHANNELS the launcher sets (bench.py); 2-GPU sweep: profiles/r02_sp_sweep_n2.txt
         self.sp_events: Optional[list] = None     # bench.py: CUDA event pairs around every exchange wait
         # stack-level C ABI (g2vlm_dino_forward / g2vlm_mot_forward_geo / g2vlm_recon_heads): the fused recon path is
@@ -259,6 +261,28 @@ class G2VLMFast:
                 self.sp_events.append([ev, None])
             else:
                 self.sp_events[-1][1] = ev
+
+    def _sp_symmetric(self, group, t_max: int, kvw: int):
+        """(symmetric K|V send buffer bf16 [2, t_max, kvw], its rendezvous handle, side stream) for the view-sharded
+        exchange, or None when symmetric memory is unavailable on ANY rank (decided collectively).  Cached."""
+        import torch.distributed as dist
+        key = (id(group), t_max, kvw)
+        if key in self._sp_sym:
+            return self._sp_sym[key]
+        t, ok = None, 1
+        try:
+            import torch.distributed._symmetric_memory as symm
+            t = symm.empty((2, t_max, kvw), dtype=torch.bfloat16, device=self.device)
+        except Exception:
+            ok = 0
+        flag = torch.tensor([ok], dtype=torch.int32, device=self.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+        res = None
+        if int(flag.item()):
+            hdl = symm.rendezvous(t, group)
+            res = (t, hdl, torch.cuda.Stream(device=self.device))
+        self._sp_sym[key] = res
+        return res
 
     @classmethod
     def from_state_dict(cls, cfg: G2Config, state_dict, device="cuda", mode: str = "bf16") -> "G2VLMFast":
@@ -1017,7 +1041,12 @@ class G2VLMFast:
             if update_past_key_values:
                 raise NotImplementedError("the merged NaiveCache is not materialised in view-sharded mode")
             kv_send = self.buf.get("mot.kv_send", (T, kvw), torch.bfloat16)
-            mode = self.sp_mode if len(set(rank_rows)) == 1 else "overlap"   # the all-gather needs equal shards
+            mode = self.sp_mode
+            if mode == "allgather" and len(set(rank_rows)) != 1:
+                mode = "overlap"                                   # the all-gather needs equal shards
+            sym = self._sp_symmetric(group, max(rank_rows), kvw) if mode == "peer" else None
+            if mode == "peer" and sym is None:
+                mode = "overlap"                                   # no symmetric memory on this box: NCCL point-to-point
             if mode == "allgather":
                 # v1: one blocking all-gather of the rank's K|V rows per layer on the compute stream;
                 # keys = [rank 0 rows | ... | rank R-1 rows | K0 prefix rows]
@@ -1030,6 +1059,58 @@ class G2VLMFast:
                     dist.all_gather_into_tensor(kv_all[:T_all], kv_send, group=group)
                     self._sp_mark(1)
                     return kv_all[:, : nkv * hd], kv_all[:, nkv * hd:]
+            elif mode == "peer":
+                # v3: each rank writes its K|V rows into a SYMMETRIC buffer (peer-mapped over NVLink on every rank); after
+                # a device-side barrier on a side stream the COPY ENGINES pull the other ranks' rows straight into
+                # kv_remote — no SM is taken from the attention over the local keys that runs meanwhile on the full
+                # grid (the NCCL exchange of v2 needs 16-32 SMs at 8 ranks and still leaves 0.2 ms per layer exposed).
+                # Two send buffers alternate per layer: rank Y overwrites buffer b at layer i only after its remote
+                # attention of layer i-1, which waited for Y's pulls of layer i-1, which were queued behind barrier i-1,
+                # which every rank reaches only after ITS pulls of layer i-2 (the last readers of buffer b) completed.
+                sym_t, sym_h, side = sym
+                T_max = sym_t.shape[1]
+                others = [j for j in range(world) if j != me]
+                offs, o = {}, 0
+                for j in others:
+                    offs[j] = o
+                    o += rank_rows[j]
+                T_rem = o
+                kv_remote = self.buf.get("mot.kv_remote", (max(T_rem, 1), kvw), torch.bfloat16)
+                attn_b = self.buf.get("mot.attn_b", (T, nq * hd), torch.bfloat16)
+                lse_a = self.buf.get("mot.lse_a", (T, nq), torch.float32)
+                lse_b = self.buf.get("mot.lse_b", (T, nq), torch.float32)
+                work = None
+                work_local = self._work([0, T], [0, T + K0], "geo")
+                work_remote = self._work([0, T], [0, T_rem], "geo_rem")
+                peer_bufs = {(j, b): sym_h.get_buffer(j, (rank_rows[j], kvw), torch.bfloat16, b * T_max * kvw)
+                             for j in others for b in (0, 1)}
+                scale = 1.0 / math.sqrt(hd)
+                state = dict(layer=0)
+
+                def attn_override(qkv_, attn_):
+                    b = state["layer"] & 1
+                    state["layer"] += 1
+                    ops.gather_rows(qkv_[:T, nq * hd:], sym_t[b], None, T)         # my rows -> symmetric send buffer b
+                    written = torch.cuda.Event()
+                    written.record()
+                    done = torch.cuda.Event()
+                    with torch.cuda.stream(side):
+                        side.wait_event(written)
+                        sym_h.barrier(channel=0)                                    # every rank has written layer i
+                        for j in others:                                            # copy-engine pulls over NVLink
+                            kv_remote[offs[j]:offs[j] + rank_rows[j]].copy_(peer_bufs[(j, b)], non_blocking=True)
+                        done.record()
+                    ops.attention(qkv_[:T, : nq * hd], qkv_[:T + K0, nq * hd:(nq + nkv) * hd],
+                                  qkv_[:T + K0, (nq + nkv) * hd:], attn_, work_local, num_q_heads=nq, num_kv_heads=nkv,
+                                  head_dim=hd, scale=scale, lse=lse_a)
+                    self._sp_mark(0)
+                    torch.cuda.current_stream().wait_event(done)
+                    self._sp_mark(1)
+                    if T_rem:
+                        ops.attention(qkv_[:T, : nq * hd], kv_remote[:T_rem, : nkv * hd], kv_remote[:T_rem, nkv * hd:],
+                                      attn_b, work_remote, num_q_heads=nq, num_kv_heads=nkv, head_dim=hd, scale=scale,
+                                      lse=lse_b)
+                        ops.attention_merge(attn_, lse_a, attn_b, lse_b, attn_, nq, hd, rows=T)
             else:
                 # v2: the remote K|V rows travel (one NCCL group of point-to-point sends/receives per layer, straight
                 # into their slot of kv_remote) WHILE the tensor cores run attention over the keys that are already

@@ -41,10 +41,12 @@ def _worker(rank, world, port, ret, n_views=4):
     full = model.recon(Tok(), dict(IDS), None, v)          # every rank also runs the whole scene alone
     full = {k: full[k].clone() for k in ("points", "local_points", "global_points", "camera_poses")}
     errs = {}
-    modes = ["overlap"] + (["allgather"] if n_views % world == 0 else [])   # the all-gather needs equal shards
+    modes = ["peer", "overlap"] + (["allgather"] if n_views % world == 0 else [])   # the all-gather needs equal shards
     for mode in modes:
         model.sp_mode = mode
         pred = model.recon_view_sharded(Tok(), dict(IDS), v)
+        if mode == "peer":
+            errs["peer.symmetric_memory_available"] = 0.0 if any(x is not None for x in model._sp_sym.values()) else 1.0
         v0, v1 = pred["view_range"]
         torch.cuda.synchronize()
         for k in ("points", "local_points", "global_points", "camera_poses"):

@@ -8,6 +8,7 @@ for V in $VIEWS; do
     $T bench.py --gpus $N --workload views --views $V --steps 2 --warmup 1 --sp-mode overlap --sp-sm-margin $M 2>/dev/null | tail -1 > ${OUT}_n${N}_v${V}_overlap_m${M}.json
   done
   $T bench.py --gpus $N --workload views --views $V --steps 2 --warmup 1 --sp-mode allgather 2>/dev/null | tail -1 > ${OUT}_n${N}_v${V}_allgather.json
+  $T bench.py --gpus $N --workload views --views $V --steps 2 --warmup 1 --sp-mode peer 2>/dev/null | tail -1 > ${OUT}_n${N}_v${V}_peer.json
 done
 for f in ${OUT}_n${N}_*.json; do python - "$f" <<'PY'
 import json,sys
