@@ -1062,8 +1062,8 @@ class G2VLMFast:
             elif mode == "peer":
                 # v3: each rank writes its K|V rows into a SYMMETRIC buffer (peer-mapped over NVLink on every rank); after
                 # a device-side barrier on a side stream the COPY ENGINES pull the other ranks' rows straight into
-                # kv_remote — no SM is taken from the attention over the local keys that runs meanwhile on the full
-                # grid (the NCCL exchange of v2 needs 16-32 SMs at 8 ranks and still leaves 0.2 ms per layer exposed).
+                # kv_remote — the attention over the local keys that runs meanwhile gives up 2 SMs for the barrier kernel only
+                # (the NCCL exchange of v2 needs 16-32 SMs at 8 ranks and still leaves 0.2 ms per layer exposed).
                 # Two send buffers alternate per layer: rank Y overwrites buffer b at layer i only after its remote
                 # attention of layer i-1, which waited for Y's pulls of layer i-1, which were queued behind barrier i-1,
                 # which every rank reaches only after ITS pulls of layer i-2 (the last readers of buffer b) completed.
@@ -1100,9 +1100,11 @@ class G2VLMFast:
                         for j in others:                                            # copy-engine pulls over NVLink
                             kv_remote[offs[j]:offs[j] + rank_rows[j]].copy_(peer_bufs[(j, b)], non_blocking=True)
                         done.record()
+                    # two SMs stay free: the barrier is a one-CTA kernel and the persistent attention would otherwise
+                    # hold every SM until it ends (measured: 0.125 ms per layer exposed with the full grid)
                     ops.attention(qkv_[:T, : nq * hd], qkv_[:T + K0, nq * hd:(nq + nkv) * hd],
                                   qkv_[:T + K0, (nq + nkv) * hd:], attn_, work_local, num_q_heads=nq, num_kv_heads=nkv,
-                                  head_dim=hd, scale=scale, lse=lse_a)
+                                  head_dim=hd, scale=scale, lse=lse_a, max_ctas=max(1, ops.num_sms() - 2))
                     self._sp_mark(0)
                     torch.cuda.current_stream().wait_event(done)
                     self._sp_mark(1)
