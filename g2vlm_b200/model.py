@@ -234,6 +234,8 @@ class G2VLMFast:
         # taken), "overlap" (v2: NCCL point-to-point exchange behind the local-key attention; sp_sm_margin SMs left to
         # the NCCL kernel) or "allgather" (v1: one blocking all-gather per layer); all but v1 end in an LSE merge
         self.sp_mode = "peer"
+        self.sp_peer_margin = 2                   # SMs the local-key attention leaves to the barrier kernel in peer mode
+        self.sp_trace: Optional[list] = None      # tools/sp_peer_trace.py: per-layer events of the peer exchange
         self._sp_sym: Dict[tuple, object] = {}
         self.sp_sm_margin = 4    # = NCCL_MAX_NCHANNELS the launcher sets (bench.py); 2-GPU sweep: profiles/r02_sp_sweep_n2.txt
         self.sp_events: Optional[list] = None     # bench.py: CUDA event pairs around every exchange wait
@@ -1091,12 +1093,16 @@ class G2VLMFast:
                     b = state["layer"] & 1
                     state["layer"] += 1
                     ops.gather_rows(qkv_[:T, nq * hd:], sym_t[b], None, T)         # my rows -> symmetric send buffer b
-                    written = torch.cuda.Event()
+                    trace = self.sp_trace is not None
+                    written = torch.cuda.Event(enable_timing=trace)
                     written.record()
-                    done = torch.cuda.Event()
+                    done = torch.cuda.Event(enable_timing=trace)
                     with torch.cuda.stream(side):
                         side.wait_event(written)
                         sym_h.barrier(channel=0)                                    # every rank has written layer i
+                        if trace:
+                            bar = torch.cuda.Event(enable_timing=True)
+                            bar.record()
                         for j in others:                                            # copy-engine pulls over NVLink
                             kv_remote[offs[j]:offs[j] + rank_rows[j]].copy_(peer_bufs[(j, b)], non_blocking=True)
                         done.record()
@@ -1104,7 +1110,11 @@ class G2VLMFast:
                     # hold every SM until it ends (measured: 0.125 ms per layer exposed with the full grid)
                     ops.attention(qkv_[:T, : nq * hd], qkv_[:T + K0, nq * hd:(nq + nkv) * hd],
                                   qkv_[:T + K0, (nq + nkv) * hd:], attn_, work_local, num_q_heads=nq, num_kv_heads=nkv,
-                                  head_dim=hd, scale=scale, lse=lse_a, max_ctas=max(1, ops.num_sms() - 2))
+                                  head_dim=hd, scale=scale, lse=lse_a, max_ctas=max(1, ops.num_sms() - self.sp_peer_margin))
+                    if trace:
+                        local_end = torch.cuda.Event(enable_timing=True)
+                        local_end.record()
+                        self.sp_trace.append(dict(written=written, barrier=bar, done=done, local_end=local_end))
                     self._sp_mark(0)
                     torch.cuda.current_stream().wait_event(done)
                     self._sp_mark(1)
