@@ -806,9 +806,9 @@ __device__ __forceinline__ bool point_finite(const float* p) {
   return isfinite(p[0]) && isfinite(p[1]) && isfinite(p[2]);
 }
 
-__global__ void ply_count_kernel(const float* __restrict__ pts, long long n, int* __restrict__ block_counts) {
+__global__ void ply_count_kernel(const float* __restrict__ pts, long long n, int* __restrict__ block_counts, int keep_all) {
   const long long i = blockIdx.x * (long long)PLY_BLOCK + threadIdx.x;
-  const int ok = (i < n) && point_finite(pts + 3 * i);
+  const int ok = (i < n) && (keep_all || point_finite(pts + 3 * i));
   const int c = __syncthreads_count(ok);
   if (threadIdx.x == 0) block_counts[blockIdx.x] = c;
 }
@@ -853,10 +853,10 @@ __global__ void ply_scan_kernel(int* __restrict__ block_counts, int n_blocks, lo
 }
 
 __global__ void ply_scatter_kernel(const float* __restrict__ pts, const float* __restrict__ img, long long n,
-                                   int hw, const int* __restrict__ block_offsets, uint8_t* __restrict__ out) {
+                                   int hw, const int* __restrict__ block_offsets, uint8_t* __restrict__ out, int keep_all) {
   __shared__ int warp_cnt[32];
   const long long i = blockIdx.x * (long long)PLY_BLOCK + threadIdx.x;
-  const int ok = (i < n) && point_finite(pts + 3 * i);
+  const int ok = (i < n) && (keep_all || point_finite(pts + 3 * i));
   const unsigned ballot = __ballot_sync(0xffffffffu, ok);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (lane == 0) warp_cnt[warp] = __popc(ballot);
@@ -1178,21 +1178,22 @@ extern "C" int g2vlm_camera_pose(const float* feat, int64_t ldf, const float* w_
 }
 
 extern "C" int g2vlm_ply_pack(const float* points, const float* images, int32_t n_views, int32_t H, int32_t W,
-                              void* out, int32_t* block_counts, int64_t* n_valid, void* stream) {
+                              void* out, int32_t* block_counts, int64_t* n_valid, int32_t filter_nonfinite, void* stream) {
   G2_REQUIRE(points && images && out && block_counts && n_valid, "ply_pack: null tensor");
+  const int keep_all = filter_nonfinite ? 0 : 1;
   G2_REQUIRE(n_views >= 0 && H > 0 && W > 0, "ply_pack: bad geometry");
   const long long n = (long long)n_views * H * W;
   G2_REQUIRE(n < (1LL << 31), "ply_pack: too many points");
   cudaStream_t st = (cudaStream_t)stream;
   const int n_blocks = static_cast<int>((n + PLY_BLOCK - 1) / PLY_BLOCK);
   if (n_blocks > 0) {
-    ply_count_kernel<<<n_blocks, PLY_BLOCK, 0, st>>>(points, n, block_counts);
+    ply_count_kernel<<<n_blocks, PLY_BLOCK, 0, st>>>(points, n, block_counts, keep_all);
     G2_LAUNCH_CHECK();
   }
   ply_scan_kernel<<<1, 1024, 0, st>>>(block_counts, n_blocks, (long long*)n_valid);
   G2_LAUNCH_CHECK();
   if (n_blocks > 0) {
-    ply_scatter_kernel<<<n_blocks, PLY_BLOCK, 0, st>>>(points, images, n, H * W, block_counts, (uint8_t*)out);
+    ply_scatter_kernel<<<n_blocks, PLY_BLOCK, 0, st>>>(points, images, n, H * W, block_counts, (uint8_t*)out, keep_all);
     G2_LAUNCH_CHECK();
   }
   return G2VLM_OK;

@@ -29,13 +29,11 @@ def ply_header(n_vertices: int) -> bytes:
 def save_ply_visualization(pred_dict: Dict[str, torch.Tensor], save_path: str, filter_nan: bool = True,
                            verbose: bool = False) -> int:
     """Same call shape as the reference function; returns the number of vertices written."""
-    if not filter_nan:
-        raise NotImplementedError("filter_nan=False is not supported (non-finite vertices are always dropped)")
     points = pred_dict["points"][0].contiguous()            # (N, H, W, 3)
     images = pred_dict["images"][0].to(points.device).contiguous()   # (N, 3, H, W)
     if images.shape[-2:] != points.shape[1:3]:
         raise ValueError("points and images must have the same spatial size (recon guarantees it)")
-    records, n = ops.ply_pack(points, images)
+    records, n = ops.ply_pack(points, images, filter_nonfinite=filter_nan)
     host = records.cpu().numpy()
     d = os.path.dirname(save_path)
     if d:

@@ -248,7 +248,17 @@ class G2VLMFast:
         self.attn_events: Optional[list] = None   # bench.py: (start, end) CUDA events of every MoT attention launch
         self._raw_images = False  # True while recon() feeds un-normalised views (normalised on device)
 
+    _NVTX = {"dino_begin": (0, "g2vlm.dino_encoder"), "dino_end": (1, "g2vlm.mot_stack"), "mot_end": (1, None),
+             "heads_begin": (0, "g2vlm.pi3_heads"), "heads_end": (1, None)}
+
     def _mark(self, name: str) -> None:
+        """Stage boundary: NVTX range (nsys / ncu --nvtx see dino_encoder / mot_stack / pi3_heads) and, for bench.py,
+        a CUDA event."""
+        pop, push = self._NVTX.get(name, (0, None))
+        if pop:
+            torch.cuda.nvtx.range_pop()
+        if push:
+            torch.cuda.nvtx.range_push(push)
         if self.stage_events is not None:
             ev = torch.cuda.Event(enable_timing=True)
             ev.record()
@@ -1478,6 +1488,7 @@ class G2VLMFast:
         p = cfg.dino_patch
         gh, gw = Hh // p, Ww // p
         P, H = gh * gw, cfg.hidden_size
+        self._mark("heads_begin")
         if self.native and collect is None and shard is None:
             out, poses, conf = self._native_heads(selected_hidden_states, packed_dino_token_indexes, N, Hh, Ww)
             if original_images is not None and original_images.dim() == 4:

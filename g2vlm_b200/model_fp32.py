@@ -424,6 +424,7 @@ class G2VLMFastFP32(G2VLMFast):
         gh, gw = Hh // p, Ww // p
         P, H = gh * gw, cfg.hidden_size
         rows = N * P
+        self._mark("heads_begin")
         geo = self._idx("recon.geo_idx", packed_dino_token_indexes)
         hidden = self.buf.get("f32.rec.hidden", (rows, H), torch.float32)
         ops.gather_rows(selected_hidden_states, hidden, geo, rows)

@@ -355,9 +355,10 @@ def camera_pose(feat, w_t, b_t, w_r, b_r, poses):
     return poses
 
 
-def ply_pack(points: torch.Tensor, images: torch.Tensor):
+def ply_pack(points: torch.Tensor, images: torch.Tensor, filter_nonfinite: bool = True):
     """points fp32 [N,H,W,3], images fp32 [N,3,H,W] (device) -> (uint8 [n_valid*27] packed PLY vertex
-    records on the device, n_valid).  Order-preserving; points with a NaN/Inf coordinate are dropped."""
+    records on the device, n_valid).  Order-preserving; points with a NaN/Inf coordinate are dropped unless
+    filter_nonfinite is False (the reference's filter_nan=False)."""
     _req(points, torch.float32, "points")
     _req(images, torch.float32, "images")
     n, H, W, _ = points.shape
@@ -368,7 +369,7 @@ def ply_pack(points: torch.Tensor, images: torch.Tensor):
     counts = torch.empty((total + 1023) // 1024 + 1, dtype=torch.int32, device=points.device)
     n_valid = torch.zeros(1, dtype=torch.int64, device=points.device)
     _call("g2vlm_ply_pack", _vp(points.data_ptr()), _vp(images.data_ptr()), _i32(n), _i32(H), _i32(W),
-          _vp(out.data_ptr()), _vp(counts.data_ptr()), _vp(n_valid.data_ptr()))
+          _vp(out.data_ptr()), _vp(counts.data_ptr()), _vp(n_valid.data_ptr()), _i32(int(filter_nonfinite)))
     k = int(n_valid.item())
     return out[: k * 27], k
 

@@ -25,8 +25,9 @@ extern "C" {
 #define G2VLM_ERR_INVALID 1 /* bad argument / unsupported shape */
 #define G2VLM_ERR_CUDA 2    /* a CUDA runtime / driver call failed */
 
-#define G2VLM_ABI_VERSION 3 /* 2: gemm out_col_group/out_col_stride, attention item_causal + out_head_cols;
-                               3: gemm FORCE_PAIR/FORCE_SINGLE flags, attention lse_out + max_ctas, g2vlm_attention_merge */
+#define G2VLM_ABI_VERSION 4 /* 2: gemm out_col_group/out_col_stride, attention item_causal + out_head_cols;
+                               3: gemm FORCE_PAIR/FORCE_SINGLE flags, attention lse_out + max_ctas, g2vlm_attention_merge;
+                               4: g2vlm_ply_pack filter_nonfinite */
 
 /* Version of this ABI (G2VLM_ABI_VERSION of the built library). */
 int g2vlm_abi_version(void);
@@ -483,7 +484,8 @@ int64_t g2vlm_driver_launches(void);
 
 /* ------------------------------------------------------------------------------------------------
  * Output side of the path ("next" row f3): device-side replacement of the numpy stage of
- * save_ply_visualization (g2vlm_utils.py:84-149): drop points with a NaN/Inf coordinate (:126-143),
+ * save_ply_visualization (g2vlm_utils.py:84-149): drop points with a NaN/Inf coordinate (:126-143; filter_nonfinite = 0
+ * keeps every point, the reference's filter_nan=False),
  * keep the original order, and pack binary-little-endian PLY vertex records
  *   double x, y, z ; uchar red, green, blue          (27 bytes, the layout Open3D writes)
  * points fp32 [n_views*H*W, 3] (= pred["points"]), images fp32 [n_views, 3, H, W] in [0,1]
@@ -491,8 +493,8 @@ int64_t g2vlm_driver_launches(void);
  * block_counts is an int32 workspace of ceil(n/1024)+1 entries; *n_valid (device int64) receives the
  * number of records written. colour byte = round(clamp(c, 0, 1) * 255), Open3D's utility::ColorToUint8.
  * ---------------------------------------------------------------------------------------------- */
-int g2vlm_ply_pack(const float* points, const float* images, int32_t n_views, int32_t H, int32_t W,
-                   void* out, int32_t* block_counts, int64_t* n_valid, void* stream);
+int g2vlm_ply_pack(const float* points, const float* images, int32_t n_views, int32_t H, int32_t W, void* out,
+                   int32_t* block_counts, int64_t* n_valid, int32_t filter_nonfinite, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Input side of the path ("next" row f3): device-side replacement of the per-view

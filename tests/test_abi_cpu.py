@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol(lib):
     assert len(names) >= 17 and "g2vlm_gemm_bf16" in names and "g2vlm_attention" in names
     for n in names:
         assert hasattr(lib, n), n
-    assert lib.g2vlm_abi_version() == _lib._header_abi_version() == 3
+    assert lib.g2vlm_abi_version() == _lib._header_abi_version() == 4
 
 
 def test_invalid_arguments_are_rejected_without_launching(lib):

@@ -43,6 +43,20 @@ def test_ply_pack_matches_numpy_filtering(tmp_path):
     assert head.startswith("ply\nformat binary_little_endian 1.0") and f"element vertex {n}" in head
 
 
+def test_ply_filter_nan_false_keeps_every_point(tmp_path):
+    """The reference's filter_nan=False (g2vlm_utils.py:126): non-finite vertices are written as they are."""
+    from g2vlm_b200 import io
+    pts = torch.randn(1, 6, 7, 3)
+    pts[0, 2, 3] = torch.tensor([float("nan"), 1.0, float("inf")])
+    img = torch.rand(1, 3, 6, 7)
+    pred = dict(points=pts[None].cuda(), images=img[None].cuda())
+    path = str(tmp_path / "all.ply")
+    assert io.save_ply_visualization(pred, path, filter_nan=False) == 42
+    rec = io.read_ply(path)
+    assert len(rec) == 42 and np.isnan(rec["x"][2 * 7 + 3]) and np.isinf(rec["z"][2 * 7 + 3])
+    assert io.save_ply_visualization(pred, path, filter_nan=True) == 41
+
+
 def test_ply_pack_all_invalid_and_large():
     from g2vlm_b200 import ops
     pts = torch.full((1, 4, 5, 3), float("nan"), device="cuda")

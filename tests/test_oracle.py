@@ -184,3 +184,47 @@ def test_training_forward_restatement_matches_reference(tiny_sd):
     assert m[:2, :2].tolist() == [[True, False], [True, True]]
     assert bool(m[2:5, :5].all()) and not bool(m[2:5, 5:].any())
     assert not bool(m[:5, 5:].any()) and bool(m[5:, 5:].all()) and bool(m[5:, :5].any()) is True
+
+
+def test_chunked_attention_equals_one_piece():
+    """attention_segments processes the query rows in chunks (the 16-view scene's score matrix is 23 GB in one piece):
+    exact, including the bottom-right aligned causal mask and GQA."""
+    import math
+    from oracle import restate
+    g = torch.Generator().manual_seed(0)
+    q = torch.randn(37, 4, 16, generator=g)
+    k = torch.randn(50, 2, 16, generator=g)
+    v = torch.randn(50, 2, 16, generator=g)
+    for causal in (False, True):
+        whole = restate.attention_segments(q, k, v, [0, 20, 37], [0, 30, 50], 1 / math.sqrt(16), causal, "fp32")
+        keep = restate.ATTN_CHUNK_ELEMS
+        restate.ATTN_CHUNK_ELEMS = 4 * 30 * 3          # 3 query rows per chunk
+        try:
+            parts = restate.attention_segments(q, k, v, [0, 20, 37], [0, 30, 50], 1 / math.sqrt(16), causal, "fp32")
+        finally:
+            restate.ATTN_CHUNK_ELEMS = keep
+        assert torch.allclose(whole, parts, atol=1e-6)
+        # against torch SDPA with an explicit mask (segment 0)
+        qs, ks, vs = q[:20].transpose(0, 1), k[:30].transpose(0, 1).repeat_interleave(2, 0), v[:30].transpose(0, 1).repeat_interleave(2, 0)
+        mask = torch.ones(20, 30, dtype=torch.bool).tril(diagonal=10) if causal else None
+        ref = torch.nn.functional.scaled_dot_product_attention(qs[None], ks[None], vs[None], attn_mask=mask)[0].transpose(0, 1)
+        assert torch.allclose(whole[:20], ref, atol=1e-5)
+
+
+def test_reference_staging_recipe_and_config_bridge():
+    """oracle/stage_ref.py copies the reference byte for byte (sha256 manifest) and G2Config.from_reference reads the
+    reference's own config objects."""
+    from oracle import ref_harness as rh
+    from oracle import stage_ref
+    if not os.path.isdir(os.path.join(stage_ref.SRC, "modeling", "g2vlm")):
+        pytest.skip("no /root/reference in this environment")
+    dst = stage_ref.stage()
+    assert dst and stage_ref.verify() > 50
+    import hashlib
+    rel = "modeling/g2vlm/g2vlm.py"
+    assert hashlib.sha256(open(os.path.join(stage_ref.SRC, rel), "rb").read()).hexdigest() == \
+        hashlib.sha256(open(os.path.join(dst, rel), "rb").read()).hexdigest()
+    model = rh.build_reference_model(rh.TINY, visual_und=False, skip_init=True)
+    cfg = schema.G2Config.from_reference(model.config.llm_config, model.config.dino_config)
+    assert cfg == schema.TINY
+    assert rh.dims_from_cfg(schema.TINY)["llm"]["hidden_size"] == 256
