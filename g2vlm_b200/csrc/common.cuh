@@ -54,6 +54,8 @@ int ensure_dyn_smem(const void* func, int bytes);
 
 // decode.cu: bandwidth-bound GEMV path of g2vlm_gemm_bf16 for calls with <= 8 rows in one group
 int launch_gemv(const g2vlm_gemm_args* a, int group, cudaStream_t stream);
+// decode_fused.cu: the whole greedy decode step as one persistent cooperative kernel
+int launch_decode_fused(const g2vlm_decode_step_args* a, cudaStream_t stream);
 
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 

@@ -24,6 +24,7 @@ extern "C" int g2vlm_und_decode_step(const g2vlm_decode_step_args* a, void* stre
   G2_REQUIRE(a && a->layers && a->kv, "decode_step: null args");
   G2_REQUIRE(a->head_dim == 128 && a->num_layers > 0, "decode_step: head_dim must be 128");
   G2_REQUIRE(a->kv_bound > 0 && a->kv_bound <= a->kv_capacity, "decode_step: kv_bound exceeds the cache capacity");
+  if (a->fused_ws != nullptr) return launch_decode_fused(a, (cudaStream_t)stream);
   const int H = a->hidden, I = a->intermediate, nq = a->n_q_heads, nkv = a->n_kv_heads, hd = a->head_dim;
   const int qkv_w = (nq + 2 * nkv) * hd, kvw = 2 * nkv * hd;
   const float scale = static_cast<float>(1.0 / sqrt(static_cast<double>(hd)));  // same rounding as the host mirror (1/math.sqrt in double, then float)

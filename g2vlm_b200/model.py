@@ -18,6 +18,7 @@ permutation invariant, and the result is scattered back to the packed order at t
 from __future__ import annotations
 
 import math
+import os
 from typing import Dict, Optional, Sequence
 
 import torch
@@ -814,8 +815,9 @@ class G2VLMFast:
         self._und_forward(x, packed_text_position_ids, cache, causal=True)
         return cache
 
-    def _decode_args(self, cache: "KVCache", bound: int, cur, pos, len_dev):
-        """Plain-C argument block of g2vlm_und_decode_step for this generation (und-expert weight pointers)."""
+    def _decode_args(self, cache: "KVCache", bound: int, cur, pos, len_dev, fused: bool = True):
+        """Plain-C argument block of g2vlm_und_decode_step for this generation (und-expert weight pointers).
+        fused: run the step as one persistent kernel (csrc/decode_fused.cu) instead of ~280 launches."""
         import ctypes
         cfg = self.cfg
         H, I, nq, nkv, hd = cfg.hidden_size, cfg.intermediate_size, cfg.num_heads, cfg.num_kv_heads, cfg.head_dim
@@ -853,13 +855,18 @@ class G2VLMFast:
         for k, t in bufs.items():
             setattr(a, k, t.data_ptr())
         a.attn_ws_floats = bufs["attn_ws"].numel()
+        if fused:
+            # zeroed once (it carries the barrier counter from step to step), one generation at a time
+            ws = g("dec.fused_ws", (ops.und_decode_workspace_bytes(nq, nkv),), torch.uint8, zero=True)
+            a.fused_ws, a.fused_ws_bytes = ws.data_ptr(), ws.numel()
         return a, (kv, bufs)
 
     @_on_device
     @torch.no_grad()
     def generate_text(self, past_key_values, packed_key_value_indexes, key_values_lens, packed_start_tokens,
                       packed_query_position_ids, max_length: int, do_sample: bool = False, temperature: float = 1.0,
-                      end_token_id: Optional[int] = None, return_logits: bool = False, use_cuda_graph: bool = False):
+                      end_token_id: Optional[int] = None, return_logits: bool = False, use_cuda_graph: bool = False,
+                      fused_step: Optional[bool] = None):
         """Decode loop of the reference (g2vlm.py:1070-1141), batch 1: returns the generated ids [steps, 1]
         INCLUDING the start token, like the reference.  The KV cache is appended in place.  Greedy decoding runs
         the native one-call step; do_sample=True keeps the reference's sampling tail — softmax(logits /
@@ -898,9 +905,14 @@ class G2VLMFast:
             pos.add_(1)
             len_dev.add_(1)
 
+        fused_active = False
         if not return_logits and not do_sample:
-            # native driver: the whole step (~260 launches) is enqueued by ONE C-ABI call
-            args, keep = self._decode_args(cache, bound, cur, pos, len_dev)
+            # native driver: the whole step is enqueued by ONE C-ABI call — one persistent kernel (fused_step, default)
+            # or ~280 launches
+            if fused_step is None:
+                fused_step = os.environ.get("G2VLM_DECODE_FUSED", "1") != "0"
+            fused_active = bool(fused_step)
+            args, keep = self._decode_args(cache, bound, cur, pos, len_dev, fused=fused_active)
 
             def step():  # noqa: F811
                 ops.und_decode_step(args)
@@ -909,7 +921,8 @@ class G2VLMFast:
         check_every = 8
         while n_done < max_length:
             tokens[n_done].copy_(cur[0])
-            if use_cuda_graph and n_done == 1 and graph is None and not return_logits and not do_sample:
+            # (the one-kernel step is a single launch already: a graph around one cooperative kernel only adds replay cost)
+            if use_cuda_graph and n_done == 1 and graph is None and not return_logits and not do_sample and not fused_active:
                 torch.cuda.synchronize()
                 graph = torch.cuda.CUDAGraph()
                 # capture WITHOUT executing: the captured launches read token / position / length from device

@@ -431,12 +431,21 @@ class DecodeStepArgs(ctypes.Structure):
         ("x", ctypes.c_void_p), ("h", ctypes.c_void_p), ("qkv", ctypes.c_void_p), ("attn", ctypes.c_void_p),
         ("act", ctypes.c_void_p), ("y", ctypes.c_void_p), ("cos_sin", ctypes.c_void_p),
         ("attn_ws", ctypes.c_void_p), ("attn_ws_floats", ctypes.c_int64), ("logits", ctypes.c_void_p),
+        ("fused_ws", ctypes.c_void_p), ("fused_ws_bytes", ctypes.c_int64),
     ]
 
 
 def und_decode_step(args: DecodeStepArgs) -> None:
-    """One greedy decode step issued natively (see g2vlm_und_decode_step)."""
+    """One greedy decode step issued natively (see g2vlm_und_decode_step): one persistent kernel when args.fused_ws
+    is set, ~280 launches otherwise."""
     _check(_lib.load().g2vlm_und_decode_step(ctypes.byref(args), _stream()))
+
+
+def und_decode_workspace_bytes(n_q_heads: int, n_kv_heads: int) -> int:
+    """Bytes of the zero-initialised workspace of the one-kernel decode step (current device)."""
+    fn = _lib.load().g2vlm_und_decode_workspace_bytes
+    fn.restype = ctypes.c_int64
+    return int(fn(_i32(n_q_heads), _i32(n_kv_heads)))
 
 
 def rope_vision(buf, rows, n_heads_total, head_stride, head_dim, cos, sin):

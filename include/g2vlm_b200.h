@@ -27,7 +27,8 @@ extern "C" {
 
 #define G2VLM_ABI_VERSION 4 /* 2: gemm out_col_group/out_col_stride, attention item_causal + out_head_cols;
                                3: gemm FORCE_PAIR/FORCE_SINGLE flags, attention lse_out + max_ctas, g2vlm_attention_merge;
-                               4: g2vlm_ply_pack filter_nonfinite */
+                               4: g2vlm_ply_pack filter_nonfinite; decode_step fused_ws (one-kernel step),
+                                  g2vlm_und_decode_workspace_bytes */
 
 /* Version of this ABI (G2VLM_ABI_VERSION of the built library). */
 int g2vlm_abi_version(void);
@@ -381,9 +382,16 @@ typedef struct g2vlm_decode_step_args {
   float* cos_sin;  /* fp32 [head_dim] (cos | sin) */
   float* attn_ws;  int64_t attn_ws_floats;
   void* logits;    /* bf16 [round_up(vocab, 8)] */
+  /* ABI v4.  Non-null: the step runs as ONE persistent cooperative kernel (one CTA per SM, grid barriers between the
+   * phases of a layer, L2 prefetch of the next phases' weights across them; csrc/decode_fused.cu) instead of ~280
+   * launches.  Device buffer of >= g2vlm_und_decode_workspace_bytes() bytes, 16-byte aligned, ZEROED ONCE by the caller
+   * when it is allocated (it carries the barrier counter from step to step) and owned by ONE generation at a time. */
+  void* fused_ws;  int64_t fused_ws_bytes;
 } g2vlm_decode_step_args;
 
 int g2vlm_und_decode_step(const g2vlm_decode_step_args* args, void* stream);
+/* Size of `fused_ws` for this head geometry on the current device. */
+int64_t g2vlm_und_decode_workspace_bytes(int32_t n_q_heads, int32_t n_kv_heads);
 
 /* Greedy token selection of generate_text (g2vlm.py:1122-1126, `torch.argmax(pred_logits, dim=-1)`):
  * logits bf16 [rows, vocab] (leading dim ld) -> int64 [rows]; ties resolve to the lowest index. */

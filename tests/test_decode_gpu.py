@@ -138,3 +138,90 @@ def test_argmax_lowest_index_on_ties(rows, vocab):
         ops.argmax_bf16(logits.cuda(), out)
         assert out[0].item() == vocab // 3
         assert torch.equal(out.cpu()[1:], logits[1:].float().argmax(-1))
+
+
+_FUSED_CFGS = {
+    "tiny": dict(cfg=dict(hidden_size=256, num_layers=2, num_heads=2, num_kv_heads=1, intermediate_size=512, vocab_size=512,
+                          dino_hidden=64, dino_layers=1, dino_heads=2)),
+    # the full model's und-expert geometry (12 q / 2 kv heads, 1536 / 8960), 3 layers, a vocabulary with a ragged tail
+    "full-width": dict(cfg=dict(num_layers=3, vocab_size=20011, dino_hidden=64, dino_layers=1, dino_heads=2, dec_depth=1)),
+}
+
+
+@pytest.mark.parametrize("name,L0,steps", [("tiny", 5, 6), ("tiny", 700, 4), ("full-width", 37, 4), ("full-width", 3100, 5)])
+def test_fused_decode_step_matches_multi_launch(name, L0, steps):
+    """Row f1: the one-kernel decode step (csrc/decode_fused.cu; persistent cooperative kernel, grid barriers) against
+    the ~280-launch driver it replaces: same tokens, same logits up to the accumulation order of the attention
+    partials, same appended K|V rows, device-resident token / position / cache length advanced alike; eager and through
+    a captured CUDA graph."""
+    from g2vlm_b200 import schema
+    from g2vlm_b200.model import G2VLMFast, NaiveCache
+    cfg = schema.G2Config(**_FUSED_CFGS[name]["cfg"])
+    model = G2VLMFast(cfg, schema.init_synthetic(cfg, seed=3, device="cuda"))
+    V = cfg.vocab_size
+
+    def prefill():
+        ids = (torch.arange(L0) * 7 + 11) % V
+        return model.forward_cache_update_text(
+            NaiveCache(cfg.num_layers), text_token_lens=torch.tensor([L0], dtype=torch.int), packed_text_ids=ids,
+            packed_text_position_ids=torch.arange(L0).expand(3, -1), packed_text_indexes=torch.arange(L0),
+            packed_key_value_indexes=torch.arange(0), key_values_lens=torch.tensor([0], dtype=torch.int))
+
+    def run(fused, graph, n):
+        past = prefill()
+        ids = model.generate_text(past, None, None, torch.tensor([23]), torch.full((3, 1), L0), n, end_token_id=None,
+                                  use_cuda_graph=graph, fused_step=fused)
+        torch.cuda.synchronize()
+        logits = model.buf.get("dec.logits", ((V + 7) // 8 * 8,), torch.bfloat16)[:V].float().clone()
+        rows = [b[L0:L0 + n].float().clone() for b in past.buf]
+        return ids[:, 0].tolist(), logits, rows, past.seq_lens
+
+    def run_forced(fused, tokens):
+        """One step at a time from given start tokens (teacher forcing): the logits of every step."""
+        past = prefill()
+        outs = []
+        for i, tok in enumerate(tokens):
+            model.generate_text(past, None, None, torch.tensor([tok]), torch.full((3, 1), L0 + i), 1, end_token_id=None,
+                                fused_step=fused)
+            torch.cuda.synchronize()
+            outs.append(model.buf.get("dec.logits", ((V + 7) // 8 * 8,), torch.bfloat16)[:V].float().clone())
+        return outs, [b[L0:L0 + len(tokens)].float().clone() for b in past.buf], past.seq_lens
+
+    t_ref, _, rows_ref, len_ref = run(False, False, steps)
+    assert len_ref == L0 + steps and t_ref[0] == 23
+    # the same inputs step by step: logits agree to accumulation-order noise (one bf16 ulp of the largest logit), the
+    # argmax agrees unless the multi-launch path itself has a near tie there
+    lg_ref, rows_a, _ = run_forced(False, t_ref)
+    lg_fus, rows_b, len_b = run_forced(True, t_ref)
+    assert len_b == L0 + steps
+    for a, b in zip(lg_fus, lg_ref):
+        assert _relerr(a, b) < 1.6e-2          # bf16 logits: 3 ulps of the largest one
+        top2 = b.topk(2).values
+        if (top2[0] - top2[1]) > 2e-2 * b.abs().max():
+            assert int(a.argmax()) == int(b.argmax())
+    for a, b in zip(rows_b, rows_a):
+        assert _relerr(a, b) < 2e-2
+    # free-running generation: eager and graph replay of the one-kernel step are the same computation
+    t_e, lg_e, rows_e, len_e = run(True, False, steps)
+    t_g, lg_g, rows_g, len_g = run(True, True, steps)
+    assert t_e == t_g and len_e == len_g == L0 + steps and torch.equal(lg_e, lg_g)
+    for a, b in zip(rows_e, rows_g):
+        assert torch.equal(a, b)
+    if all((l.topk(2).values[0] - l.topk(2).values[1]) > 2e-2 * l.abs().max() for l in lg_ref[:-1]):
+        assert t_e == t_ref
+
+
+def test_fused_decode_step_rejects_small_workspace():
+    from g2vlm_b200 import ops
+    a = ops.DecodeStepArgs()
+    a.num_layers, a.hidden, a.intermediate, a.n_q_heads, a.n_kv_heads, a.head_dim, a.vocab = 1, 256, 512, 2, 1, 128, 512
+    ws = torch.zeros(64, dtype=torch.uint8, device="cuda")
+    a.fused_ws, a.fused_ws_bytes = ws.data_ptr(), ws.numel()
+    dummy = torch.zeros(8, device="cuda")
+    layers = (ops.UndLayerWeights * 1)()
+    import ctypes
+    kv = (ctypes.c_void_p * 1)(dummy.data_ptr())
+    a.layers, a.kv, a.kv_capacity, a.kv_bound = layers, kv, 8, 4
+    with pytest.raises(RuntimeError, match="workspace"):
+        ops.und_decode_step(a)
+    assert ops.und_decode_workspace_bytes(12, 2) > 74 * 12 * 128 * 4

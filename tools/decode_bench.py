@@ -27,7 +27,7 @@ def text_inputs(n, kvlen, rope):
                 packed_key_value_indexes=torch.arange(kvlen), key_values_lens=torch.tensor([kvlen], dtype=torch.int)), kvlen + n, rope + n
 
 
-def run(graph=True):
+def run(graph=True, fused=True):
     past = NaiveCache(cfg.num_layers)
     gi, kvlen, rope = text_inputs(20, 0, 0)
     past = model.forward_cache_update_text(past, **gi)
@@ -39,14 +39,18 @@ def run(graph=True):
     torch.cuda.synchronize(); t_prefill = time.perf_counter() - t0
     t0 = time.perf_counter()
     out = model.generate_text(past, None, None, torch.tensor([7]), torch.full((3, 1), rope), steps, end_token_id=None,
-                              use_cuda_graph=graph)
+                              use_cuda_graph=graph, fused_step=fused)
     torch.cuda.synchronize(); t_dec = time.perf_counter() - t0
     return t_prefill, t_dec, past.seq_lens, out
 
 
 run()
-tp, td, L, out = run(graph=False)
-print(f"eager launches: {td / steps * 1e3:.3f} ms/token")
-tp, td, L, out = run()
-print(f"cache length {L}; 60-token question prefill {tp * 1e3:.2f} ms; decode {steps} tokens in {td * 1e3:.1f} ms = "
-      f"{td / steps * 1e3:.3f} ms/token = {steps / td:.1f} tokens/s (batch 1, greedy, lm_head {cfg.vocab_size}-way)")
+for fused in (False, True):
+    name = "one persistent kernel per step" if fused else "~280 launches per step"
+    tp, td, L, out = run(graph=False, fused=fused)
+    print(f"[{name}] eager: {td / steps * 1e3:.3f} ms/token")
+    tp, td, L, out = run(fused=fused)
+    gb = 2.62 + 0.47 + L * 28 * 1024 / 1e9
+    print(f"[{name}] CUDA graph: cache length {L}; 60-token question prefill {tp * 1e3:.2f} ms; decode {steps} tokens in "
+          f"{td * 1e3:.1f} ms = {td / steps * 1e3:.3f} ms/token = {steps / td:.1f} tokens/s (batch 1, greedy, lm_head "
+          f"{cfg.vocab_size}-way); {gb:.2f} GB per token -> {gb / (td / steps) / 1e3:.2f} TB/s")
