@@ -46,6 +46,9 @@ constexpr int DF_KS_MAX = 1536;                  // columns per stage: whole row
 constexpr int DF_TILE = 8;                       // weight rows per stage
 constexpr int DF_STAGE_BYTES = DF_TILE * (2 * DF_KS_MAX + 64);   // pitch = 2 KS + 64 (conflict-free LDS.128)
 constexpr int DF_STAGE = 160;                    // keys per attention stage (K and V rows: 2 x 40 KB)
+constexpr int DF_NKV = 1;                        // K|V stage buffers.  (2 x 80 keys, the next stage loading under this one's
+                                                 //   softmax: measured 3 % slower — a stage costs ~1500 cycles of barriers and
+                                                 //   warp reductions whatever its size, and the load is mostly hidden anyway)
 constexpr int DF_SLD = DF_STAGE + 4;             // row pitch of the score matrix (bank-conflict-free C stores)
 constexpr int DF_ROUND = 32;                     // stages per round of a phase: the partial table (32 x 8 rows x 33 floats =
                                                  //   33 KB) lives in the K buffer
@@ -55,6 +58,8 @@ struct DecFusedParams {
   float eps, scale_log2;
   int s0, s1;
   int ks_h, ks_a, ks_i;            // columns per ring stage for K = H, nq*128, I
+  int opt;                         // experiment switches (G2VLM_DECODE_OPT): 1 = no explicit fences in the grid barrier,
+                                   //   2 = L2 prefetch of the next phase's rows by the producer
   g2vlm_und_layer_weights layers[DF_MAX_LAYERS];
   __nv_bfloat16* kv[DF_MAX_LAYERS];
   long long kv_capacity;
@@ -92,15 +97,15 @@ __device__ __forceinline__ void csync() {   // the 16 consumer warps
 // ---- grid barrier (consumer warps), split in two so that independent work sits between ----------------------------
 // Monotonic arrival counter; `target` advances by gridDim.x per barrier.  arrive: bar.sync + fence + release add by
 // thread 0 publish the CTA's writes; wait: thread 0 polls with acquire loads, the other threads wait at bar.sync.
-__device__ __forceinline__ void barrier_arrive(unsigned* ctr, unsigned& target) {
+__device__ __forceinline__ void barrier_arrive(unsigned* ctr, unsigned& target, bool fences = true) {
   csync();
   target += gridDim.x;
   if (threadIdx.x == 0) {
-    __threadfence();
+    if (fences) __threadfence();
     asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
   }
 }
-__device__ __forceinline__ void barrier_wait(unsigned* ctr, unsigned target) {
+__device__ __forceinline__ void barrier_wait(unsigned* ctr, unsigned target, bool fences = true) {
   if (threadIdx.x == 0) {
     unsigned v;
     long long t0 = 0;
@@ -116,7 +121,7 @@ __device__ __forceinline__ void barrier_wait(unsigned* ctr, unsigned target) {
         }
       }
     }
-    __threadfence();
+    if (fences) __threadfence();
   }
   csync();
 }
@@ -216,8 +221,8 @@ __device__ __forceinline__ long long df_row(const DfPhase& ph, int r) {
 
 struct DfSmem {
   uint8_t ring[DF_NS][DF_STAGE_BYTES];           // the weight stream
-  uint8_t kbuf[DF_STAGE * 256];                  // K rows of one KV head, 16-byte chunks XOR-swizzled by row & 7;
-  uint8_t vbuf[DF_STAGE * 256];                  //   outside the attention phase kbuf holds the partial table and vbuf
+  uint8_t kbuf[DF_NKV * DF_STAGE * 256];         // K rows of one KV head, 16-byte chunks XOR-swizzled by row & 7;
+  uint8_t vbuf[DF_NKV * DF_STAGE * 256];              //   outside the attention phase kbuf holds the partial table and vbuf
                                                  //   the fp32 input vector of the GEMV phase
   float score[8][DF_SLD];                        // scores, then probabilities (heads >= G stay zero)
   float red[2][8][128];                          // P.V halves; scratch of the merge
@@ -228,9 +233,24 @@ struct DfSmem {
   float best_v[DF_CWARPS];
   int best_i[DF_CWARPS];
   uint64_t full[DF_NS], empty[DF_NS];
-  long long t_acc[14], t_gu[5];                  // TIMING build only
+  long long t_acc[14], t_gu[5], t_at[6];         // TIMING build only
 };
 
+// the producer's wait for a free slot backs off between polls: a tight mbarrier.try_wait loop keeps the shared-memory /
+// SYNCS path of the SM busy and slows the consumers' LDS / STS / SHFL (measured: the softmax of the attention phase
+// took 4100 cycles per stage next to a spinning producer)
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  long long t0 = clock64();
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(128);
+    if ((++spins & 0x3ff) == 0 && clock64() - t0 > 4000000000LL) {
+      printf("g2vlm_b200: decode producer watchdog fired (block %d parity %u)\n", blockIdx.x, parity);
+      __trap();
+    }
+  }
+}
 // producer: one phase of the stream.  Lane i < 8 copies the KS-column piece of tile row i (>= 2.5 KB per copy: the TMA
 // unit of an SM retires a bulk copy every ~45 ns whatever its size — tools/micro/bulk_copy_bench.cu: 16 x 1.5 KB pieces
 // per stage stream at 5.4 TB/s over the chip, 8 x 3 KB at 7.4 TB/s).
@@ -243,7 +263,7 @@ __device__ __forceinline__ void df_produce(DfSmem& s, const DfPhase& ph, uint32_
     const __nv_bfloat16* src = ph.w + (row >= 0 ? row : 0) * ph.K;
     for (int slab = 0; slab < ph.n_slabs; ++slab, ++q) {
       const int slot = q % DF_NS;
-      if (q >= DF_NS) mbar_wait(&s.empty[slot], ((q / DF_NS) - 1) & 1);
+      if (q >= DF_NS) mbar_wait_backoff(&s.empty[slot], ((q / DF_NS) - 1) & 1);
       if (lane == 0) mbar_arrive_expect_tx(&s.full[slot], total);
       __syncwarp();
       if (row >= 0) bulk_g2s(s.ring[slot] + lane * pitch, src + (long long)slab * ph.KS, piece, &s.full[slot]);
@@ -388,14 +408,26 @@ __global__ void __launch_bounds__(DF_THREADS, 1) und_decode_fused_kernel(const _
   // ================= producer warp: the whole step's weights, in order ==========================================
   if (warp == DF_CWARPS) {
     uint32_t q = 0;
-    for (int l = 0; l < p.num_layers; ++l) {
-      const g2vlm_und_layer_weights& w = p.layers[l];
-      df_produce(s, df_phase(w.wqkv, qkv_w, H, p.ks_h, false), q, lane);
-      df_produce(s, df_phase(w.wo, H, nq * 128, p.ks_a, false), q, lane);
-      df_produce(s, df_phase(w.wgu, I, H, p.ks_h, true), q, lane);
-      df_produce(s, df_phase(w.wdown, H, I, p.ks_i, false), q, lane);
+    const int n_phases = 4 * p.num_layers + 1;
+    auto phase_at = [&](int idx) {
+      if (idx >= 4 * p.num_layers) return df_phase(p.lm_head, p.vocab, H, p.ks_h, false);
+      const g2vlm_und_layer_weights& w = p.layers[idx >> 2];
+      switch (idx & 3) {
+        case 0: return df_phase(w.wqkv, qkv_w, H, p.ks_h, false);
+        case 1: return df_phase(w.wo, H, nq * 128, p.ks_a, false);
+        case 2: return df_phase(w.wgu, I, H, p.ks_h, true);
+        default: return df_phase(w.wdown, H, I, p.ks_i, false);
+      }
+    };
+    for (int idx = 0; idx < n_phases; ++idx) {
+      if ((p.opt & 2) && idx + 1 < n_phases) {             // ask L2 for (the first 256 KB of) the next phase's rows
+        const DfPhase nx = phase_at(idx + 1);
+        const int rows = min(nx.count, (256 * 1024) / (2 * nx.K) + 1);
+        for (int r = lane; r < rows; r += 32)
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(nx.w + df_row(nx, r) * nx.K), "r"(2 * nx.K) : "memory");
+      }
+      df_produce(s, phase_at(idx), q, lane);
     }
-    df_produce(s, df_phase(p.lm_head, p.vocab, H, p.ks_h, false), q, lane);
     return;
   }
 
@@ -404,6 +436,7 @@ __global__ void __launch_bounds__(DF_THREADS, 1) und_decode_fused_kernel(const _
   float* ptab = reinterpret_cast<float*>(s.kbuf);
   uint4* xs = reinterpret_cast<uint4*>(s.vbuf);
   unsigned target = __ldcg(p.sync + 1);
+  const bool fences = (p.opt & 1) == 0;
   // TIMING (tools/decode_phase_trace.py): SM cycles CTA 0 and the last CTA spend in each phase / at each barrier
   long long t_prev = 0;
   long long* t_acc = s.t_acc;
@@ -413,6 +446,7 @@ __global__ void __launch_bounds__(DF_THREADS, 1) und_decode_fused_kernel(const _
     if (tid == 0) {
       for (int i = 0; i < 14; ++i) t_acc[i] = 0;
       for (int i = 0; i < 5; ++i) t_gu[i] = 0;
+      for (int i = 0; i < 6; ++i) s.t_at[i] = 0;
     }
     t_prev = clock64();
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns0));
@@ -422,6 +456,17 @@ __global__ void __launch_bounds__(DF_THREADS, 1) und_decode_fused_kernel(const _
       const long long t = clock64();
       if (tid == 0) t_acc[slot] += t - t_prev;
       t_prev = t;
+    }
+  };
+  long long t_at_prev = 0;
+  auto amark = [&](int slot) {                      // attention sub-phases (TIMING build)
+    if constexpr (TIMING) {
+      // (bar.sync does not block at issue: a load of barrier-protected state does, so the clock is read after one)
+      const float dummy = *reinterpret_cast<volatile float*>(&s.part[0]);
+      long long t = clock64();
+      if (dummy == 1.2345e-30f) t += 1;
+      if (tid == 0 && slot >= 0) s.t_at[slot] += t - t_at_prev;
+      t_at_prev = t;
     }
   };
   const int L = *p.cache_len;                       // keys already in the cache; this step's key is row L
@@ -453,7 +498,7 @@ __global__ void __launch_bounds__(DF_THREADS, 1) und_decode_fused_kernel(const _
       const int n_old = max(0, min(c1, L) - c0);
       for (int i = tid; i < n_old * 16; i += DF_CTHREADS) {
         const int r = i >> 4, c = i & 15;
-        const int off = r * 256 + ((c ^ (r & 7)) << 4);
+        const int off = (st % DF_NKV) * (DF_STAGE * 256) + r * 256 + ((c ^ (r & 7)) << 4);
         cp_async16_df(s.kbuf + off, kc + (long long)(c0 + r) * kvw + c * 8);
         cp_async16_df(s.vbuf + off, vc + (long long)(c0 + r) * kvw + c * 8);
       }
@@ -470,11 +515,13 @@ __global__ void __launch_bounds__(DF_THREADS, 1) und_decode_fused_kernel(const _
       });
     }
     mark(0);
-    barrier_arrive(p.sync, target);                    // (its bar.sync also ends the reads of the partial table)
+    barrier_arrive(p.sync, target, fences);                    // (its bar.sync also ends the reads of the partial table)
     if (nst > 0) load_stage(0);                        // the cache rows do not depend on this step: load across the barrier
-    barrier_wait(p.sync, target);
+    if (DF_NKV > 1 && nst > 1) load_stage(1);
+    barrier_wait(p.sync, target, fences);
     mark(1);
     // ================= phase 2: q/k-norm + M-RoPE, K|V append, attention partials over this CTA's key range =====
+    amark(-1);
     {
       // q heads of this KV head (warps 0..G-1), the new key (warp G of the owner), the new value (warp G+1)
       if (at_active && warp <= G) {
@@ -519,6 +566,7 @@ __global__ void __launch_bounds__(DF_THREADS, 1) und_decode_fused_kernel(const _
         reinterpret_cast<uint32_t*>(&s.q[G][0])[i] = 0u;
       if (tid < 8) { s.m_run[tid] = -INFINITY; s.l_run[tid] = 0.f; }
       csync();                                     // s.q / s.new_k / s.new_v / m_run are read below
+      amark(0);
       float o_acc[4] = {0.f, 0.f, 0.f, 0.f};              // O^T[d = 16 dt + g (+8)][head = 2 t (+1)] of this warp's key half
       const int g8 = lane >> 2, t4 = lane & 3;
       // P.V: warp = (d tile dt, key half khalf); d tile 7 has no second warp (15 consumer warps) and takes every key tile
@@ -527,18 +575,21 @@ __global__ void __launch_bounds__(DF_THREADS, 1) und_decode_fused_kernel(const _
         const int c0 = k0 + st * sub, c1 = min(k1, c0 + sub), nkc = c1 - c0;
         const int nkc16 = (nkc + 15) & ~15;
         const int n_old = max(0, min(c1, L) - c0);
-        if (st > 0) load_stage(st);                        // (single-buffered: a range longer than 160 keys serialises)
+        uint8_t* kst = s.kbuf + (st % DF_NKV) * (DF_STAGE * 256);
+        uint8_t* vst = s.vbuf + (st % DF_NKV) * (DF_STAGE * 256);
         // rows the cp.async round does not write: the new key (owner) and the zero rows that pad the last 16-key tile
         for (int idx = tid; idx < 32 * (nkc16 - n_old); idx += DF_CTHREADS) {
           const int r = n_old + (idx >> 5), c = (idx & 31) >> 1, hsel = idx & 1;   // 16 lanes x 16 B per row, K and V
           {
             uint4 val = make_uint4(0, 0, 0, 0);
             if (r < nkc) val = reinterpret_cast<const uint4*>(hsel ? s.new_v : s.new_k)[c];   // only the new key is >= n_old
-            *reinterpret_cast<uint4*>((hsel ? s.vbuf : s.kbuf) + r * 256 + ((c ^ (r & 7)) << 4)) = val;
+            *reinterpret_cast<uint4*>((hsel ? vst : kst) + r * 256 + ((c ^ (r & 7)) << 4)) = val;
           }
         }
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        if (DF_NKV > 1 && st + 1 < nst) asm volatile("cp.async.wait_group 1;" ::: "memory");   // stage st + 1 stays in flight
+        else asm volatile("cp.async.wait_group 0;" ::: "memory");
         csync();
+        amark(1);
         // scores S[key, head] = K . q^T on mma.sync m16n8k16: A = 16 keys x 16 dims (ldmatrix), B = q (registers)
         {
           uint32_t qf[8][2];
@@ -548,21 +599,32 @@ __global__ void __launch_bounds__(DF_THREADS, 1) und_decode_fused_kernel(const _
             qf[ks][1] = *reinterpret_cast<const uint32_t*>(&s.q[g8][16 * ks + 2 * t4 + 8]);
           }
           for (int mt = warp; mt * 16 < nkc; mt += DF_CWARPS) {
-            float c4[4] = {0.f, 0.f, 0.f, 0.f};
+            // four independent accumulators: the legacy MMA path of sm_100 has a latency of several hundred cycles, a
+            // chain of 8 dependent MMAs took ~4000 (measured)
+            float c4[4] = {0.f, 0.f, 0.f, 0.f}, c5[4] = {0.f, 0.f, 0.f, 0.f}, c6[4] = {0.f, 0.f, 0.f, 0.f},
+                  c7[4] = {0.f, 0.f, 0.f, 0.f};
             const int row = mt * 16 + (lane & 7) + 8 * ((lane >> 3) & 1);
-            const uint32_t rbase = smem_u32(s.kbuf) + row * 256;
+            const uint32_t rbase = smem_u32(kst) + row * 256;
+            uint32_t a[8][4];
 #pragma unroll
-            for (int ks = 0; ks < 8; ++ks) {
-              uint32_t a[4];
-              ldmatrix_x4(a, rbase + (((2 * ks + (lane >> 4)) ^ (row & 7)) << 4));
-              mma_16816(c4, a[0], a[1], a[2], a[3], qf[ks][0], qf[ks][1]);
-            }
+            for (int ks = 0; ks < 8; ++ks) ldmatrix_x4(a[ks], rbase + (((2 * ks + (lane >> 4)) ^ (row & 7)) << 4));
+            mma_16816(c4, a[0][0], a[0][1], a[0][2], a[0][3], qf[0][0], qf[0][1]);
+            mma_16816(c5, a[1][0], a[1][1], a[1][2], a[1][3], qf[1][0], qf[1][1]);
+            mma_16816(c6, a[2][0], a[2][1], a[2][2], a[2][3], qf[2][0], qf[2][1]);
+            mma_16816(c7, a[3][0], a[3][1], a[3][2], a[3][3], qf[3][0], qf[3][1]);
+            mma_16816(c4, a[4][0], a[4][1], a[4][2], a[4][3], qf[4][0], qf[4][1]);
+            mma_16816(c5, a[5][0], a[5][1], a[5][2], a[5][3], qf[5][0], qf[5][1]);
+            mma_16816(c6, a[6][0], a[6][1], a[6][2], a[6][3], qf[6][0], qf[6][1]);
+            mma_16816(c7, a[7][0], a[7][1], a[7][2], a[7][3], qf[7][0], qf[7][1]);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) c4[e] = (c4[e] + c5[e]) + (c6[e] + c7[e]);
             const int key = mt * 16 + g8;
             if (key < nkc) { s.score[2 * t4][key] = c4[0] * p.scale_log2; s.score[2 * t4 + 1][key] = c4[1] * p.scale_log2; }
             if (key + 8 < nkc) { s.score[2 * t4][key + 8] = c4[2] * p.scale_log2; s.score[2 * t4 + 1][key + 8] = c4[3] * p.scale_log2; }
           }
         }
         csync();
+        amark(2);
         // per head: stage max, running max, exp2, sums (one warp per head); rows >= G and keys >= nkc become 0
         if (warp < 8) {
           if (warp < G) {
@@ -590,20 +652,28 @@ __global__ void __launch_bounds__(DF_THREADS, 1) und_decode_fused_kernel(const _
           }
         }
         csync();
+        amark(3);
         // O^T[d, head] += V^T[d, key] . P^T[key, head]: A = V^T (ldmatrix.trans of the [key][d] rows), B = bf16 P
         {
           const float a0 = s.alpha[2 * t4], a1 = s.alpha[2 * t4 + 1];
           o_acc[0] *= a0; o_acc[1] *= a1; o_acc[2] *= a0; o_acc[3] *= a1;
-          for (int kt = khalf; kt * 16 < nkc; kt += kstep) {
+          float o_b[4] = {0.f, 0.f, 0.f, 0.f};              // second accumulator: two independent MMA chains
+          int par = 0;
+          for (int kt = khalf; kt * 16 < nkc; kt += kstep, par ^= 1) {
             const int row = kt * 16 + (lane & 7) + 8 * (lane >> 4);
             uint32_t a[4];
-            ldmatrix_x4_trans(a, smem_u32(s.vbuf) + row * 256 + (((2 * dt + ((lane >> 3) & 1)) ^ (row & 7)) << 4));
+            ldmatrix_x4_trans(a, smem_u32(vst) + row * 256 + (((2 * dt + ((lane >> 3) & 1)) ^ (row & 7)) << 4));
             const float2 p0 = *reinterpret_cast<const float2*>(&s.score[g8][kt * 16 + 2 * t4]);
             const float2 p1 = *reinterpret_cast<const float2*>(&s.score[g8][kt * 16 + 2 * t4 + 8]);
-            mma_16816(o_acc, a[0], a[1], a[2], a[3], pack_bf16x2(p0.x, p0.y), pack_bf16x2(p1.x, p1.y));
+            if (par == 0) mma_16816(o_acc, a[0], a[1], a[2], a[3], pack_bf16x2(p0.x, p0.y), pack_bf16x2(p1.x, p1.y));
+            else mma_16816(o_b, a[0], a[1], a[2], a[3], pack_bf16x2(p0.x, p0.y), pack_bf16x2(p1.x, p1.y));
           }
+#pragma unroll
+          for (int e = 0; e < 4; ++e) o_acc[e] += o_b[e];
         }
         csync();                                   // every read of this stage is done
+        amark(4);
+        if (st + DF_NKV < nst) load_stage(st + DF_NKV);
       }
       if (dt == 7) {                                       // no second warp for this d tile: its half stays zero
         s.red[1][2 * t4][112 + g8] = 0.f; s.red[1][2 * t4 + 1][112 + g8] = 0.f;
@@ -623,9 +693,10 @@ __global__ void __launch_bounds__(DF_THREADS, 1) und_decode_fused_kernel(const _
         }
       }
     }
+    amark(5);
     mark(2);
-    barrier_arrive(p.sync, target);
-    barrier_wait(p.sync, target);
+    barrier_arrive(p.sync, target, fences);
+    barrier_wait(p.sync, target, fences);
     mark(3);
 
     // ================= phase 3: merge of the partials, spread over the grid: CTA = (head, slice of d) ==========
@@ -671,8 +742,8 @@ __global__ void __launch_bounds__(DF_THREADS, 1) und_decode_fused_kernel(const _
       }
     }
     mark(4);
-    barrier_arrive(p.sync, target);
-    barrier_wait(p.sync, target);
+    barrier_arrive(p.sync, target, fences);
+    barrier_wait(p.sync, target, fences);
     mark(5);
 
     // ================= phase 4: o_proj GEMV, x += bf16(acc) ====================================================
@@ -685,8 +756,8 @@ __global__ void __launch_bounds__(DF_THREADS, 1) und_decode_fused_kernel(const _
       });
     }
     mark(6);
-    barrier_arrive(p.sync, target);
-    barrier_wait(p.sync, target);
+    barrier_arrive(p.sync, target, fences);
+    barrier_wait(p.sync, target, fences);
     mark(7);
 
     // ================= phase 5: RMSNorm + gate/up GEMV + SwiGLU ================================================
@@ -703,8 +774,8 @@ __global__ void __launch_bounds__(DF_THREADS, 1) und_decode_fused_kernel(const _
       }, (TIMING && tid == 0) ? t_gu : nullptr);
     }
     mark(8);
-    barrier_arrive(p.sync, target);
-    barrier_wait(p.sync, target);
+    barrier_arrive(p.sync, target, fences);
+    barrier_wait(p.sync, target, fences);
     mark(9);
 
     // ================= phase 6: down GEMV, x += bf16(acc) ======================================================
@@ -717,8 +788,8 @@ __global__ void __launch_bounds__(DF_THREADS, 1) und_decode_fused_kernel(const _
       });
     }
     mark(10);
-    barrier_arrive(p.sync, target);
-    barrier_wait(p.sync, target);
+    barrier_arrive(p.sync, target, fences);
+    barrier_wait(p.sync, target, fences);
     mark(11);
   }
 
@@ -751,8 +822,8 @@ __global__ void __launch_bounds__(DF_THREADS, 1) und_decode_fused_kernel(const _
     }
   }
   mark(12);
-  barrier_arrive(p.sync, target);
-  barrier_wait(p.sync, target);
+  barrier_arrive(p.sync, target, fences);
+  barrier_wait(p.sync, target, fences);
   mark(13);
   if constexpr (TIMING) {
     if (tid == 0 && (cta == 0 || cta == grid - 1)) {
@@ -761,6 +832,7 @@ __global__ void __launch_bounds__(DF_THREADS, 1) und_decode_fused_kernel(const _
       unsigned long long ns1;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns1));
       dst[14] = static_cast<long long>(ns1 - ns0);
+      if (cta == 0) { for (int i = 0; i < 6; ++i) (reinterpret_cast<long long*>(p.sync + 16) + 35)[i] = s.t_at[i]; }
       if (cta == 0) { long long* d2 = reinterpret_cast<long long*>(p.sync + 16) + 30; d2[0] = t_gu[0]; d2[1] = t_gu[1]; d2[2] = t_gu[2]; d2[3] = t_gu[3]; d2[4] = t_gu[4]; }
     }
   }
@@ -849,6 +921,8 @@ int launch_decode_fused(const g2vlm_decode_step_args* a, cudaStream_t stream) {
   q.cand = reinterpret_cast<float*>(ws + 512);
   q.part = reinterpret_cast<float*>(ws + 512 + (long long)grid * 8);
   const int smem = static_cast<int>(sizeof(DfSmem));
+  const char* opt = getenv("G2VLM_DECODE_OPT");
+  q.opt = opt ? atoi(opt) : 1;
   const char* trace = getenv("G2VLM_DECODE_TRACE");   // phase cycle counters at fused_ws + 64 (tools/decode_phase_trace.py)
   const bool timing = trace != nullptr && atoi(trace) != 0;
   if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(und_decode_fused_kernel<false>), smem)) return rc;

@@ -44,6 +44,10 @@ class ReconServer:
         cur = torch.cuda.current_stream()
         if self.dev_in[s] is None or self.dev_in[s].shape != views_host.shape:
             self.dev_in[s] = torch.empty(views_host.shape, dtype=views_host.dtype, device=self.model.device)
+            # a fresh block may be memory that kernels already enqueued on the compute stream still use (the caching
+            # allocator hands freed blocks back in stream order of the ALLOCATING stream): the first upload into it
+            # must not overtake them
+            self.up.wait_stream(cur)
         self.up.wait_event(self.compute_done[s])            # the slot's previous scene has consumed its views
         with torch.cuda.stream(self.up):
             self.dev_in[s].copy_(views_host, non_blocking=True)

@@ -45,6 +45,13 @@ def run(graph=True, fused=True):
 
 
 run()
+if os.environ.get("G2VLM_DECODE_OPT_SWEEP"):
+    for opt in os.environ["G2VLM_DECODE_OPT_SWEEP"].split(","):
+        os.environ["G2VLM_DECODE_OPT"] = opt
+        run(graph=False, fused=True)
+        tp, td, L, out = run(graph=False, fused=True)
+        print(f"G2VLM_DECODE_OPT={opt}: {td / steps * 1e3:.3f} ms/token")
+    sys.exit(0)
 for fused in (False, True):
     name = "one persistent kernel per step" if fused else "~280 launches per step"
     tp, td, L, out = run(graph=False, fused=fused)

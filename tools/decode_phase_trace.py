@@ -32,6 +32,9 @@ for mode in modes:
     n = max(gu[2], 1)
     print(f"  gate/up of CTA 0, warp 0: {gu[2]} stages; mean cycles per stage: wait {gu[0] / n:.0f}, multiply + release "
           f"{gu[1] / n:.0f}; cycles per layer: RMSNorm {gu[3] / cfg.num_layers:.0f}, all stages + sync {gu[4] / cfg.num_layers:.0f}")
+    at = ws[64 + 35 * 8:64 + 41 * 8].view(torch.int64).cpu().tolist()
+    print("  attention of CTA 0, cycles per layer: " + "  ".join(f"{n} {v / cfg.num_layers:.0f}" for n, v in zip(
+        ("q/k-norm + rope", "wait for K|V", "scores", "softmax", "P.V", "reduce + store"), at)))
     for c, who in enumerate(("CTA 0", "last CTA")):
         cyc, ns = t[c, :14], t[c, 14].item()
         mhz = cyc.sum().item() / ns * 1e3
