@@ -58,8 +58,8 @@ struct DecFusedParams {
   float eps, scale_log2;
   int s0, s1;
   int ks_h, ks_a, ks_i;            // columns per ring stage for K = H, nq*128, I
-  int opt;                         // experiment switches (G2VLM_DECODE_OPT): 1 = no explicit fences in the grid barrier,
-                                   //   2 = L2 prefetch of the next phase's rows by the producer
+  int opt;                         // G2VLM_DECODE_OPT, default 1: bit 0 = no explicit __threadfence around the grid barrier's
+                                   //   release-add / acquire-poll (0: with fences, +0.1 ms per token)
   g2vlm_und_layer_weights layers[DF_MAX_LAYERS];
   __nv_bfloat16* kv[DF_MAX_LAYERS];
   long long kv_capacity;
@@ -420,12 +420,6 @@ __global__ void __launch_bounds__(DF_THREADS, 1) und_decode_fused_kernel(const _
       }
     };
     for (int idx = 0; idx < n_phases; ++idx) {
-      if ((p.opt & 2) && idx + 1 < n_phases) {             // ask L2 for (the first 256 KB of) the next phase's rows
-        const DfPhase nx = phase_at(idx + 1);
-        const int rows = min(nx.count, (256 * 1024) / (2 * nx.K) + 1);
-        for (int r = lane; r < rows; r += 32)
-          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(nx.w + df_row(nx, r) * nx.K), "r"(2 * nx.K) : "memory");
-      }
       df_produce(s, phase_at(idx), q, lane);
     }
     return;
