@@ -2,26 +2,27 @@
 // generate_text, modeling/g2vlm/g2vlm.py:1086-1131, und expert of modeling/g2vlm/qwen2vl.py:555-664, 842-910).
 //
 // A decode step streams 3.7 GB through the GPU (2.6 GB of und-expert weights, 0.47 GB of lm_head, the K/V cache)
-// for ~6 GFLOP: it is HBM-bound, and as ~280 dependent launches of a few microseconds each it ran at 0.26 of the HBM
+// for ~6 GFLOP: it is HBM-bound, and as ~280 dependent launches of a few microseconds each it ran at 0.24 of the HBM
 // roofline — every launch drains the memory pipeline, waits for the grid to retire and ramps up again.  Here the
-// step is one cooperative launch of one CTA per SM:
-//   * warp 16 of every CTA is a PRODUCER: it walks the CTA's share of every weight matrix of the step, in order —
+// step is one cooperative launch of one CTA per SM, 16 warps:
+//   * warp 15 of every CTA is a PRODUCER: it walks the CTA's share of every weight matrix of the step, in order —
 //     qkv, o_proj, gate/up, down of every layer, then lm_head — and streams it with TMA bulk copies
-//     (cp.async.bulk.shared.global, one 1.3-1.5 KB piece of a weight row per lane) into a 4-stage shared-memory ring
-//     guarded by full / empty mbarriers.  It depends on nothing but free ring slots, so it runs ahead ACROSS the grid
-//     barriers and the latency-bound phases: HBM keeps streaming while the grid synchronises.
-//   * warps 0-15 are CONSUMERS.  The phases of a layer
+//     (cp.async.bulk.shared.global; one whole 3 KB weight row, or a 2.5 KB piece of a down-projection row, per copy)
+//     into a 4-stage shared-memory ring of 8-row tiles guarded by full / empty mbarriers.  It depends on nothing but free
+//     ring slots, so it runs ahead ACROSS the grid barriers and the latency-bound phases.
+//   * warps 0-14 are CONSUMERS.  The phases of a layer
 //         qkv GEMV | attention partials over a key range | merge | o_proj GEMV | gate/up GEMV + SwiGLU | down GEMV
-//     are separated by grid barriers (release-add + acquire-poll on a device counter).  A ring stage is 16 weight rows x
-//     <= 768 columns and is multiplied by ONE warp on mma.sync m16n8k16 (the 16 rows are the M side, the step's input
-//     vector is replicated over the 8 columns): 2 LDS.128 + 2 MMA per KB of weights instead of ~60 FMA-pipe
-//     instructions — the first version of this kernel, with register loads and FMA dot products, was bound by issue
-//     slots and by load/compute rounds in lockstep (gate/up at 2.9 TB/s), see profiles/r02_decode_fused.txt.
+//     are separated by grid barriers (release-add + acquire-poll on a device counter).  In a GEMV phase warp w < 8
+//     multiplies tile row w of every ring stage by the phase's input vector with packed fp32 FMAs (fma.rn.f32x2) and
+//     leaves its lanes' partial sums in a table that one thread per output row reduces at the end of the phase.
 //   * attention: each CTA owns a key range of one KV head; its K|V rows are pulled with cp.async (issued in front of
-//     the barrier wait: the cache rows do not depend on this step), scores and P.V run on mma.sync as well.
+//     the barrier wait: the cache rows do not depend on this step); scores and P.V are 16-key tiles on mma.sync.
 // Every vector a phase needs (normalised hidden state, attention output, SwiGLU activations) is rebuilt per CTA in
 // shared memory from the L2-resident fp32 / bf16 vectors; everything written during the kernel is read back with
 // ld.global.cg (L2 only — the other CTAs' updates).
+// Inside a GEMV phase the weight stream runs at the HBM rate (6.3 TB/s); the step as a whole reaches 0.40 of it because the
+// six grid-wide dependencies of a layer are latency.  Measurements, the earlier versions of this kernel and what was
+// tried and rejected: profiles/r02_decode_fused.txt.
 //
 // Rounding points are those of the multi-launch driver (csrc/decode_step.cu) kernel by kernel: fp32 RMSNorm -> bf16,
 // bf16 x bf16 products accumulated in fp32, q/k-norm on the bf16 tensor (normalised value rounded to bf16 before the
@@ -277,8 +278,8 @@ __device__ __forceinline__ void df_produce(DfSmem& s, const DfPhase& ph, uint32_
 // is a shift / a mask), and releases the slot as soon as its row is in registers: a stage is held ~300 cycles, so the
 // slots spend their time being filled.  The row sum of stage i goes to ptab[(i - i0) * 8 + w].  Warps 8-14 idle in these phases.
 // Measured on the way here (profiles/r02_decode_fused.txt): mma.sync m16n8k16 with the vector replicated over the 8
-// columns retires one MMA per ~10 cycles and SM on sm_100 (3.5 TB/s); `c < n ? smem[c] : 0` compiles to a branch per
-// LDS.128 (4400 cycles per stage), hence the clamped indices; a warp pair per slot holds a stage for 1700 cycles.
+// columns was no faster; `c < n ? smem[c] : 0` compiles to a branch per LDS.128 (4400 cycles per stage), hence the
+// clamped indices; a warp pair per slot holds a stage for 1700 cycles.
 __device__ __forceinline__ unsigned long long df_f2(uint32_t w) {   // bf16x2 -> f32x2
   unsigned long long r;
   asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(w << 16), "r"(w & 0xffff0000u));
@@ -593,8 +594,7 @@ __global__ void __launch_bounds__(DF_THREADS, 1) und_decode_fused_kernel(const _
             qf[ks][1] = *reinterpret_cast<const uint32_t*>(&s.q[g8][16 * ks + 2 * t4 + 8]);
           }
           for (int mt = warp; mt * 16 < nkc; mt += DF_CWARPS) {
-            // four independent accumulators: the legacy MMA path of sm_100 has a latency of several hundred cycles, a
-            // chain of 8 dependent MMAs took ~4000 (measured)
+            // four independent accumulators instead of a chain of 8 dependent MMAs
             float c4[4] = {0.f, 0.f, 0.f, 0.f}, c5[4] = {0.f, 0.f, 0.f, 0.f}, c6[4] = {0.f, 0.f, 0.f, 0.f},
                   c7[4] = {0.f, 0.f, 0.f, 0.f};
             const int row = mt * 16 + (lane & 7) + 8 * ((lane >> 3) & 1);
