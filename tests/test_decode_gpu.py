@@ -148,7 +148,8 @@ _FUSED_CFGS = {
 }
 
 
-@pytest.mark.parametrize("name,L0,steps", [("tiny", 5, 6), ("tiny", 700, 4), ("full-width", 37, 4), ("full-width", 3100, 5)])
+@pytest.mark.parametrize("name,L0,steps", [("tiny", 5, 6), ("tiny", 700, 4), ("full-width", 37, 4), ("full-width", 3100, 5),
+                                           ("full-width", 30011, 3)])   # 406 keys per CTA: three 160-key stages
 def test_fused_decode_step_matches_multi_launch(name, L0, steps):
     """Row f1: the one-kernel decode step (csrc/decode_fused.cu; persistent cooperative kernel, grid barriers) against
     the ~280-launch driver it replaces: same tokens, same logits up to the accumulation order of the attention
