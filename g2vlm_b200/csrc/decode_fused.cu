@@ -231,6 +231,7 @@ struct DfSmem {
   __nv_bfloat16 new_k[128], new_v[128];          // this step's K / V row of the CTA's KV head
   float m_run[8], l_run[8], alpha[8];
   float part[DF_CWARPS];
+  float rope_cs[64], rope_sn[64];                // M-RoPE angles of this step's position (the same for every layer)
   float best_v[DF_CWARPS];
   int best_i[DF_CWARPS];
   uint64_t full[DF_NS], empty[DF_NS];
@@ -467,6 +468,10 @@ __global__ void __launch_bounds__(DF_THREADS, 1) und_decode_fused_kernel(const _
   const int L = *p.cache_len;                       // keys already in the cache; this step's key is row L
   const long long token = *p.cur_token;
   const long long pos0 = p.position[0], pos1 = p.position[1], pos2 = p.position[2];
+  if (tid < 64) {                                   // mrope_table_kernel's arithmetic, once per step instead of per layer
+    const long long pos = tid < p.s0 ? pos0 : (tid < p.s0 + p.s1 ? pos1 : pos2);
+    sincosf(static_cast<float>(pos) * __ldg(p.inv_freq + tid), &s.rope_sn[tid], &s.rope_cs[tid]);
+  }
   const float* x_in = p.embed + token * H;          // layer 0 reads the embedding row; CTA 0 copies it into x
   if (cta == 0)
     for (int i = tid; i < H; i += DF_CTHREADS) p.x[i] = __ldg(x_in + i);
@@ -535,10 +540,7 @@ __global__ void __launch_bounds__(DF_THREADS, 1) und_decode_fused_kernel(const _
           float o[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            const int j = j0 + e;
-            const long long pos = j < p.s0 ? pos0 : (j < p.s0 + p.s1 ? pos1 : pos2);
-            float sn, cs;
-            sincosf(static_cast<float>(pos) * __ldg(p.inv_freq + j), &sn, &cs);
+            const float sn = s.rope_sn[j0 + e], cs = s.rope_cs[j0 + e];   // (written before the first grid barrier)
             const float nv = gw[e] * bf16_round(v[e] * r);
             const float partner = __shfl_xor_sync(0xffffffffu, nv, 16);
             const float rot = lane < 16 ? -partner : partner;
@@ -700,10 +702,23 @@ __global__ void __launch_bounds__(DF_THREADS, 1) und_decode_fused_kernel(const _
       const int dps = (128 + n_slices - 1) / n_slices;   // d per CTA (<= 16)
       const int head = cta / n_slices, slice = cta % n_slices;
       if (head < nq && slice * dps < 128) {
+        // every thread pulls its splits' (m, l, o[d]) in ONE round trip to L2, then the block agrees on the maximum
         const float* base = p.part + (long long)head * DF_PART;
         const long long stride = (long long)nq * DF_PART;
-        float M = -INFINITY;
-        for (int sp = tid; sp < S; sp += DF_CTHREADS) M = fmaxf(M, __ldcg(base + sp * stride + 128));
+        const int dl = tid & 15, sl = tid >> 4;
+        const int d = slice * dps + dl;
+        const bool d_ok = dl < dps && d < 128;
+        constexpr int MS = 4;                              // splits per thread held in registers (S <= 4 * DF_MSL = 120)
+        float pm[MS], pl[MS], po[MS];
+#pragma unroll
+        for (int k = 0; k < MS; ++k) {
+          const int sp = sl + k * DF_MSL;
+          const float* pp = base + min(sp, S - 1) * stride;
+          pm[k] = sp < S ? __ldcg(pp + 128) : -INFINITY;
+          pl[k] = sp < S ? __ldcg(pp + 129) : 0.f;
+          po[k] = (sp < S && d_ok) ? __ldcg(pp + d) : 0.f;
+        }
+        float M = fmaxf(fmaxf(pm[0], pm[1]), fmaxf(pm[2], pm[3]));
         M = warp_max(M);
         float* wmax = &s.red[0][0][0];                   // [16]
         float* racc = wmax + 32;                         // [DF_MSL][16]
@@ -713,11 +728,14 @@ __global__ void __launch_bounds__(DF_THREADS, 1) und_decode_fused_kernel(const _
         M = wmax[0];
 #pragma unroll
         for (int i = 1; i < DF_CWARPS; ++i) M = fmaxf(M, wmax[i]);
-        const int dl = tid & 15, sl = tid >> 4;
-        const int d = slice * dps + dl;
-        const bool d_ok = dl < dps && d < 128;
         float acc = 0.f, lt = 0.f;
-        for (int sp = sl; sp < S; sp += DF_MSL) {
+#pragma unroll
+        for (int k = 0; k < MS; ++k) {
+          const float wgt = pl[k] > 0.f ? exp2f(pm[k] - M) : 0.f;
+          acc = fmaf(wgt, po[k], acc);
+          lt = fmaf(wgt, pl[k], lt);
+        }
+        for (int sp = sl + MS * DF_MSL; sp < S; sp += DF_MSL) {   // (more than 120 splits per head: not on a 148-SM part)
           const float* pp = base + sp * stride;
           const float ps = __ldcg(pp + 129);
           const float wgt = ps > 0.f ? exp2f(__ldcg(pp + 128) - M) : 0.f;
