@@ -143,8 +143,11 @@ __device__ __forceinline__ void rmsnorm_to_smem(const float* src, const float* w
   const int n4 = dim >> 2;
   const float4* xr = reinterpret_cast<const float4*>(src);
   const int i0 = threadIdx.x;
-  float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (i0 < n4) v0 = __ldcg(xr + i0);
+  float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), g0 = v0;
+  if (i0 < n4) {
+    v0 = __ldcg(xr + i0);
+    g0 = __ldg(reinterpret_cast<const float4*>(w) + i0);   // (cold in HBM: in flight together with x, not after the reduction)
+  }
   float ss = v0.x * v0.x + v0.y * v0.y + v0.z * v0.z + v0.w * v0.w;
   for (int i = i0 + DF_CTHREADS; i < n4; i += DF_CTHREADS) {
     const float4 v = __ldcg(xr + i);
@@ -159,7 +162,7 @@ __device__ __forceinline__ void rmsnorm_to_smem(const float* src, const float* w
   const float r = rsqrtf(tot / dim + eps);
   for (int i = i0; i < n4; i += DF_CTHREADS) {
     const float4 v = i == i0 ? v0 : __ldcg(xr + i);
-    const float4 g = __ldg(reinterpret_cast<const float4*>(w) + i);
+    const float4 g = i == i0 ? g0 : __ldg(reinterpret_cast<const float4*>(w) + i);
     reinterpret_cast<uint2*>(xs)[i] = make_uint2(pack_bf16x2(g.x * (v.x * r), g.y * (v.y * r)),
                                                  pack_bf16x2(g.z * (v.z * r), g.w * (v.w * r)));
   }
@@ -508,10 +511,12 @@ __global__ void __launch_bounds__(DF_THREADS, 1) und_decode_fused_kernel(const _
     // ================= phase 1: RMSNorm + qkv GEMV (+bias) =====================================================
     {
       const DfPhase ph = df_phase(w.wqkv, qkv_w, H, p.ks_h, false);
+      // what the epilogue thread of row `tid` needs from global memory is requested now, not after the stream
+      const float bias_r = (w.bqkv && tid < ph.count) ? __ldg(w.bqkv + ph.first + tid) : 0.f;
       rmsnorm_to_smem(l == 0 ? x_in : p.x, w.input_norm, H, p.eps, xs, s.part);
       df_gemv(s, ph, q, ptab, warp, lane, [&](int r, float f, float) {
-        const int n = ph.first + r;
-        p.qkv[n] = __float2bfloat16_rn(f + (w.bqkv ? w.bqkv[n] : 0.f));
+        const float b = r == tid ? bias_r : (w.bqkv ? __ldg(w.bqkv + ph.first + r) : 0.f);
+        p.qkv[ph.first + r] = __float2bfloat16_rn(f + b);
       });
     }
     mark(0);
@@ -761,10 +766,11 @@ __global__ void __launch_bounds__(DF_THREADS, 1) und_decode_fused_kernel(const _
     // ================= phase 4: o_proj GEMV, x += bf16(acc) ====================================================
     {
       const DfPhase ph = df_phase(w.wo, H, nq * 128, p.ks_a, false);
+      const float x_r = tid < ph.count ? __ldcg(p.x + ph.first + tid) : 0.f;   // this CTA's rows: nobody else writes them
       vec_from_bf16(xs, p.attn, (nq * 128) >> 3);
       df_gemv(s, ph, q, ptab, warp, lane, [&](int r, float f, float) {
         const int n = ph.first + r;
-        p.x[n] = __ldcg(p.x + n) + bf16_round(f);
+        p.x[n] = (r == tid ? x_r : __ldcg(p.x + n)) + bf16_round(f);
       });
     }
     mark(6);
@@ -793,10 +799,11 @@ __global__ void __launch_bounds__(DF_THREADS, 1) und_decode_fused_kernel(const _
     // ================= phase 6: down GEMV, x += bf16(acc) ======================================================
     {
       const DfPhase ph = df_phase(w.wdown, H, I, p.ks_i, false);
+      const float x_r = tid < ph.count ? __ldcg(p.x + ph.first + tid) : 0.f;
       vec_from_bf16(xs, p.act, I >> 3);
       df_gemv(s, ph, q, ptab, warp, lane, [&](int r, float f, float) {
         const int n = ph.first + r;
-        p.x[n] = __ldcg(p.x + n) + bf16_round(f);
+        p.x[n] = (r == tid ? x_r : __ldcg(p.x + n)) + bf16_round(f);
       });
     }
     mark(10);
