@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Row f.1 next to the reference itself: greedy `generate_text` of the UNMODIFIED reference classes (oracle/_ref, real
 flash-attn, CUDA autocast, its per-step NaiveCache re-allocation) and of the CUDA path on the same B200, the same
-weights and the same KV cache.   python tools/decode_vs_reference.py [cache_rows] [tokens]
+weights and the same KV cache.   python tests/probes/decode_vs_reference.py [cache_rows] [tokens]
 Test infrastructure (uses oracle/)."""
 import contextlib
 import io
@@ -9,7 +9,7 @@ import os
 import sys
 import time
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 

@@ -1,14 +1,14 @@
 #!/usr/bin/env python
 """One-off check (too slow for the test suite): FULL-depth, FULL-width G2VLM-2B-MoT (28 MoT + 24 DINO layers,
 5 blocks per decoder) on N views of 518x518 — CUDA path vs the CPU oracle (bf16 mode), same weights.
-usage: python tools/full_depth_parity.py [n_views] [layerscale|-] [H W]   (N=1, 518x518: ~6 TFLOP on the CPU;
+usage: python tests/probes/full_depth_parity.py [n_views] [layerscale|-] [H W]   (N=1, 518x518: ~6 TFLOP on the CPU;
        8 294 518 = BASELINE configs[0], the reference's CPU-runnable shape)"""
 import json
 import os
 import sys
 import time
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 
 from g2vlm_b200 import schema

@@ -1,6 +1,6 @@
 """B200 probe: the UNMODIFIED reference classes (oracle/_ref, real flash-attn, CUDA autocast) next to the CUDA path.
 
-    python tools/gpu_reference.py [--views 16 --height 518 --width 518] [--ls 0.01|synthetic] [--depth full|N]
+    python tests/probes/gpu_reference.py [--views 16 --height 518 --width 518] [--ls 0.01|synthetic] [--depth full|N]
 
 Prints, for one scene: max-rel error of every output between {ours, reference-GPU, restatement bf16 (GPU tensors),
 restatement fp32 (GPU tensors)} and the reference's views/s (stock flash-attn call, CUDA events).  Test
@@ -14,7 +14,7 @@ import sys
 import time
 from dataclasses import replace
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 
 import torch  # noqa: E402
