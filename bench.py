@@ -305,6 +305,59 @@ def gpu_reference_leg(cfg, layerscale, u8, ours_pred, steps=3):
 # --------------------------------------------------------------------------------------------------
 # view-sharded long scene (BASELINE configs[3]): sequence parallel over the ranks
 # --------------------------------------------------------------------------------------------------
+def decode_leg(cfg, layerscale, views_host, tokens=64):
+    """Row f.1 next to the headline: greedy decode tokens/s behind this scene in the KV cache (20-token system prompt, the
+    16-view geo step with cache update, a 60-token question), full 151 936-row embedding / lm_head, batch 1.  Device-timed
+    (CUDA events around the token loop); `multi_launch` = the ~280-launch step of round 1 on the same cache, CUDA graph."""
+    from g2vlm_b200 import schema
+    from g2vlm_b200.model import G2VLMFast, NaiveCache
+    sd = schema.init_synthetic(cfg, seed=0, device="cuda")
+    if layerscale != "synthetic":
+        for k in sd:
+            if k.endswith("ls1.gamma") or k.endswith("ls2.gamma") or k.endswith(".lambda1"):
+                sd[k].fill_(float(layerscale))
+    model = G2VLMFast(cfg, sd)
+    del sd
+    torch.cuda.empty_cache()
+
+    def text(n, kvlen, rope):
+        return dict(text_token_lens=torch.tensor([n], dtype=torch.int), packed_text_ids=torch.arange(10, 10 + n),
+                    packed_text_position_ids=(rope + torch.arange(n)).expand(3, -1), packed_text_indexes=kvlen + torch.arange(n),
+                    packed_key_value_indexes=torch.arange(kvlen), key_values_lens=torch.tensor([kvlen], dtype=torch.int)), kvlen + n, rope + n
+
+    def run(n, fused):
+        gi, kvlen, rope = text(20, 0, 0)
+        past = model.forward_cache_update_text(NaiveCache(cfg.num_layers), **gi)
+        gi, nl, nr = model.prepare_dino_images_pi3([kvlen], [rope], views_host, None, TOKENS)
+        past, _ = model.forward_cache_update_dino(past, **gi)
+        gi, kvlen, rope = text(60, nl[0], nr[0])
+        past = model.forward_cache_update_text(past, **gi)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        model.generate_text(past, None, None, torch.tensor([7]), torch.full((3, 1), rope), n, end_token_id=None,
+                            use_cuda_graph=not fused, fused_step=fused)
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n, kvlen
+
+    run(8, True)
+    ms, rows = run(tokens, True)
+    run(8, False)
+    ms_multi, _ = run(max(16, tokens // 2), False)
+    H, I, nq, nkv, hd = cfg.hidden_size, cfg.intermediate_size, cfg.num_heads, cfg.num_kv_heads, cfg.head_dim
+    w_layer = 2 * ((nq + 2 * nkv) * hd * H + H * nq * hd + 3 * H * I)           # bf16 und-expert weights of a layer
+    nbytes = cfg.num_layers * (w_layer + 2 * 2 * nkv * hd * rows) + 2 * cfg.vocab_size * H
+    pk = peaks()
+    return dict(metric="greedy decode tokens/sec (batch 1)", value=1e3 / ms, unit="tokens/s", ms_per_token=ms, cached_rows=rows,
+                tokens_timed=tokens, bytes_per_token=nbytes,
+                roofline=dict(bound="hbm", achieved=nbytes / ms / 1e6, peak=pk["hbm"], unit="GB/s", frac=nbytes / ms / 1e6 / pk["hbm"],
+                              kernel="und_decode_fused_kernel (one persistent cooperative launch per token)"),
+                multi_launch_ms_per_token=ms_multi,
+                note="`next` row f.1 (chat path), not the headline metric; algorithmic bytes = und-expert weights + lm_head + "
+                     "the K|V rows of the cache, each read once per token")
+
+
 def view_sharded_scene(model, dist, rank, world, n_views, size, steps, warmup, compare_single):
     """ONE scene of n_views views split by view over the ranks (sequence parallel).  Returns a dict with the max-over-
     ranks time per scene, the exposed K/V-exchange time per layer and, if `compare_single`, the single-GPU time of
@@ -547,6 +600,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gpu-reference", action="store_true")
     ap.add_argument("--no-view-sharded", action="store_true", help="N > 1: skip the view_sharded block")
+    ap.add_argument("--no-decode", action="store_true", help="N = 1: skip the `decode` block (row f.1: tokens/s behind this scene)")
     ap.add_argument("--layerscale", default="0.01",
                     help="LayerScale value of the synthetic weights: 0.01 = the reference's init (g2vlm/qwen2vl.py:765-766), "
                          "the regime of a trained checkpoint; 'synthetic' = U(0.5,1.5)")
@@ -796,6 +850,13 @@ def main():
             line["gpu_reference"] = gpu_reference_leg(cfg, args.layerscale, views_u8, ours)
             if "value" in line["gpu_reference"]:
                 line["gpu_reference"]["speedup_e2e_vs_gpu_reference"] = e2e_value / line["gpu_reference"]["value"]
+        if not args.no_decode:
+            try:
+                del model, server
+                torch.cuda.empty_cache()
+                line["decode"] = decode_leg(cfg, args.layerscale, views_host)
+            except Exception as e:  # a `next`-row block must never take the headline number down with it
+                line["decode"] = dict(failed=f"{type(e).__name__}: {e}")
         if not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
             try:
