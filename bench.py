@@ -349,10 +349,15 @@ def decode_leg(cfg, layerscale, views_host, tokens=64):
     w_layer = 2 * ((nq + 2 * nkv) * hd * H + H * nq * hd + 3 * H * I)           # bf16 und-expert weights of a layer
     nbytes = cfg.num_layers * (w_layer + 2 * 2 * nkv * hd * rows) + 2 * cfg.vocab_size * H
     pk = peaks()
+    traffic = None
+    try:  # dram bytes of one step from the committed ncu capture (same cache length within 0.6 %)
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "kernel_traffic.json")))["und_decode_fused_kernel@L=22144"]["traffic_bytes"]
+    except Exception:
+        pass
     return dict(metric="greedy decode tokens/sec (batch 1)", value=1e3 / ms, unit="tokens/s", ms_per_token=ms, cached_rows=rows,
                 tokens_timed=tokens, bytes_per_token=nbytes,
                 roofline=dict(bound="hbm", achieved=nbytes / ms / 1e6, peak=pk["hbm"], unit="GB/s", frac=nbytes / ms / 1e6 / pk["hbm"],
-                              kernel="und_decode_fused_kernel (one persistent cooperative launch per token)"),
+                              traffic=traffic, kernel="und_decode_fused_kernel (one persistent cooperative launch per token)"),
                 multi_launch_ms_per_token=ms_multi,
                 note="`next` row f.1 (chat path), not the headline metric; algorithmic bytes = und-expert weights + lm_head + "
                      "the K|V rows of the cache, each read once per token")
