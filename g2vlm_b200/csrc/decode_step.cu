@@ -77,3 +77,54 @@ extern "C" int g2vlm_und_decode_step(const g2vlm_decode_step_args* a, void* stre
   G2_CUDA_OK(cudaGetLastError());
   return G2VLM_OK;
 }
+
+// Text prefill / ViT step of the und expert, T >= 2 rows: the per-op sequence of G2VLMFast._und_forward issued natively.
+extern "C" int g2vlm_und_prefill(const g2vlm_und_prefill_args* a, void* stream) {
+  using namespace g2;
+  G2_REQUIRE(a && a->layers && a->kv && a->x && a->y && a->h && a->qkv && a->attn && a->act && a->cos && a->sin &&
+                 a->position_ids && a->work, "und_prefill: null argument");
+  G2_REQUIRE(a->head_dim == 128 && a->num_layers > 0 && a->rows >= 2, "und_prefill: head_dim must be 128, rows >= 2");
+  G2_REQUIRE(a->cache_len >= 0 && a->cache_len + a->rows <= a->kv_capacity, "und_prefill: the rows do not fit the cache");
+  const int H = a->hidden, I = a->intermediate, nq = a->n_q_heads, nkv = a->n_kv_heads, hd = a->head_dim, T = a->rows;
+  const int qkv_w = (nq + 2 * nkv) * hd, kvw = 2 * nkv * hd;
+  const float scale = static_cast<float>(1.0 / sqrt(static_cast<double>(hd)));
+  __nv_bfloat16* qkv = reinterpret_cast<__nv_bfloat16*>(a->qkv);
+  G2_TRY(g2vlm_mrope_table(a->position_ids, T, a->inv_freq, a->cos, a->sin, T, hd / 2, a->mrope_s0, a->mrope_s1, stream));
+  g2vlm_gemm_args g;
+  auto gemm = [&](const void* x, int K, const void* w, int N, int epilogue, void* out, const float* bias) -> int {
+    memset(&g, 0, sizeof(g));
+    g.A = x; g.lda = K; g.a_rows = T;
+    g.B = w; g.ldb = K; g.N = N; g.K = K;
+    g.n_groups = 1; g.group_row0[0] = 0; g.group_rows[0] = T;
+    g.epilogue = epilogue;
+    g.flags = epilogue == G2VLM_EPI_RESID_F32 ? G2VLM_GEMM_ROUND_AFTER_SCALE : 0;
+    g.out = out; g.ldo = (epilogue == G2VLM_EPI_SWIGLU_BF16) ? N / 2 : N;
+    g.bias = bias;
+    return g2vlm_gemm_bf16(&g, stream);
+  };
+  for (int l = 0; l < a->num_layers; ++l) {
+    const g2vlm_und_layer_weights& w = a->layers[l];
+    __nv_bfloat16* kvbuf = reinterpret_cast<__nv_bfloat16*>(a->kv[l]);
+    G2_TRY(g2vlm_rmsnorm_routed(a->x, H, a->h, H, 1, w.input_norm, w.input_norm, T, 0, H, a->rms_eps, stream));
+    G2_TRY(gemm(a->h, H, w.wqkv, qkv_w, G2VLM_EPI_STORE_BF16, a->qkv, w.bqkv));
+    G2_TRY(g2vlm_qknorm_mrope(a->qkv, qkv_w, T, 0, nq, nkv, hd, w.q_norm, w.k_norm, w.q_norm, w.k_norm, a->cos, a->sin,
+                              a->rms_eps, 1, stream));
+    G2_TRY(g2vlm_kv_append(qkv + nq * hd, (int64_t)qkv_w * 2, kvbuf, (int64_t)kvw * 2, nullptr, a->cache_len, T,
+                           (int64_t)kvw * 2, stream));
+    g2vlm_attn_args at;
+    memset(&at, 0, sizeof(at));
+    at.q = a->qkv; at.ldq = qkv_w; at.q_rows = T;
+    at.k = kvbuf; at.ldk = kvw; at.v = kvbuf + nkv * hd; at.ldv = kvw; at.kv_rows = a->cache_len + T;
+    at.out = a->attn; at.ldo = nq * hd;
+    at.num_q_heads = nq; at.num_kv_heads = nkv; at.head_dim = hd;
+    at.causal = a->causal; at.softmax_scale = scale;
+    at.n_items = a->n_items; at.work_items = a->work;
+    G2_TRY(g2vlm_attention(&at, stream));
+    G2_TRY(gemm(a->attn, nq * hd, w.wo, H, G2VLM_EPI_RESID_F32, a->x, nullptr));
+    G2_TRY(g2vlm_rmsnorm_routed(a->x, H, a->h, H, 1, w.post_norm, w.post_norm, T, 0, H, a->rms_eps, stream));
+    G2_TRY(gemm(a->h, H, w.wgu, 2 * I, G2VLM_EPI_SWIGLU_BF16, a->act, nullptr));
+    G2_TRY(gemm(a->act, I, w.wdown, H, G2VLM_EPI_RESID_F32, a->x, nullptr));
+  }
+  G2_TRY(g2vlm_rmsnorm_routed(a->x, H, a->y, H, 0, a->final_norm, a->final_norm, T, 0, H, a->rms_eps, stream));
+  return G2VLM_OK;
+}

@@ -766,7 +766,9 @@ class G2VLMFast:
         pos = self._idx("und.pos", position_ids)
         cos = self.buf.get("und.cos", (T, hd // 2), torch.float32)
         sin = self.buf.get("und.sin", (T, hd // 2), torch.float32)
-        ops.mrope_table(pos, self.inv_freq, cos, sin, cfg.mrope_section)
+        use_native = self.native and T >= 2 and len_dev is None and hd == 128
+        if not use_native:
+            ops.mrope_table(pos, self.inv_freq, cos, sin, cfg.mrope_section)
         qkv, attn, act, hbuf = self._mot_buffers(T, T)
         if T == 1:
             work = None                   # single-token steps use the split-K decode attention
@@ -776,6 +778,26 @@ class G2VLMFast:
             work = self._work([0, T], [0, L + T], "und")
         xs = self.buf.get("und.x", (T, H), torch.float32)
         ops.gather_rows(x, xs, None, T)
+        y = self.buf.get("und.y", (T, H), torch.float32)   # reused workspace (valid until the next und step)
+        if use_native:
+            # the whole step as ONE C-ABI call (g2vlm_und_prefill): the same per-op entry points in the same order
+            import ctypes
+            a = ops.UndPrefillArgs()
+            a.num_layers, a.hidden, a.intermediate, a.n_q_heads, a.n_kv_heads, a.head_dim = \
+                cfg.num_layers, H, cfg.intermediate_size, nq, nkv, hd
+            a.rms_eps, a.mrope_s0, a.mrope_s1 = cfg.rms_norm_eps, cfg.mrope_section[0], cfg.mrope_section[1]
+            kvp = (ctypes.c_void_p * cfg.num_layers)(*[b.data_ptr() for b in cache.buf])
+            a.layers, a.kv, a.kv_capacity, a.cache_len = self._und_layers(), kvp, cache.cap, L
+            a.rows, a.causal = T, int(causal)
+            a.final_norm, a.inv_freq, a.position_ids = self.norm_und.data_ptr(), self.inv_freq.data_ptr(), pos.data_ptr()
+            a.work, a.n_items = work.data_ptr(), work.shape[0]
+            a.x, a.y, a.h, a.qkv, a.attn, a.act = (xs.data_ptr(), y.data_ptr(), hbuf.data_ptr(), qkv.data_ptr(), attn.data_ptr(),
+                                                   act.data_ptr())
+            a.cos, a.sin = cos.data_ptr(), sin.data_ptr()
+            ops.und_prefill(a)
+            if update:
+                cache.len = L + T
+            return y
         w = nkv * hd
         for i, Lw in enumerate(self.layers):
             kvbuf = cache.buf[i]
@@ -790,7 +812,6 @@ class G2VLMFast:
             # all rows belong to the und expert: group 0 (geo) is empty
             self._mot_layer(Lw, xs, T, 0, qkv, attn, act, hbuf, cos, sin, work, L + T, causal, True,
                             kv_exchange=kv_append, kv_len_dev=len_dev)
-        y = self.buf.get("und.y", (T, H), torch.float32)   # reused workspace (valid until the next und step)
         ops.rmsnorm_routed(xs, y, self.norm_geo, self.norm_und, 0, cfg.rms_norm_eps, rows=T)
         if update and len_dev is None:
             cache.len = L + T
@@ -815,14 +836,12 @@ class G2VLMFast:
         self._und_forward(x, packed_text_position_ids, cache, causal=True)
         return cache
 
-    def _decode_args(self, cache: "KVCache", bound: int, cur, pos, len_dev, fused: bool = True):
-        """Plain-C argument block of g2vlm_und_decode_step for this generation (und-expert weight pointers).
-        fused: run the step as one persistent kernel (csrc/decode_fused.cu) instead of ~280 launches."""
-        import ctypes
-        cfg = self.cfg
-        H, I, nq, nkv, hd = cfg.hidden_size, cfg.intermediate_size, cfg.num_heads, cfg.num_kv_heads, cfg.head_dim
-        qkv_w = (nq + 2 * nkv) * hd
+    def _und_layers(self):
+        """HOST array of the und expert's weight pointers per layer (g2vlm_und_layer_weights), built once."""
         if not hasattr(self, "_und_layer_array"):
+            cfg = self.cfg
+            H, I, nq, nkv, hd = cfg.hidden_size, cfg.intermediate_size, cfg.num_heads, cfg.num_kv_heads, cfg.head_dim
+            qkv_w = (nq + 2 * nkv) * hd
             arr = (ops.UndLayerWeights * cfg.num_layers)()
             for i, L in enumerate(self.layers):
                 w = arr[i]
@@ -837,6 +856,16 @@ class G2VLMFast:
                 w.q_norm = L["q_norm_und"].data_ptr()
                 w.k_norm = L["k_norm_und"].data_ptr()
             self._und_layer_array = arr
+        return self._und_layer_array
+
+    def _decode_args(self, cache: "KVCache", bound: int, cur, pos, len_dev, fused: bool = True):
+        """Plain-C argument block of g2vlm_und_decode_step for this generation (und-expert weight pointers).
+        fused: run the step as one persistent kernel (csrc/decode_fused.cu) instead of ~280 launches."""
+        import ctypes
+        cfg = self.cfg
+        H, I, nq, nkv, hd = cfg.hidden_size, cfg.intermediate_size, cfg.num_heads, cfg.num_kv_heads, cfg.head_dim
+        qkv_w = (nq + 2 * nkv) * hd
+        self._und_layers()
         V = self.lm_head.shape[0]
         kv = (ctypes.c_void_p * cfg.num_layers)(*[b.data_ptr() for b in cache.buf])
         g = self.buf.get

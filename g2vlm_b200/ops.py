@@ -441,6 +441,25 @@ def und_decode_step(args: DecodeStepArgs) -> None:
     _check(_lib.load().g2vlm_und_decode_step(ctypes.byref(args), _stream()))
 
 
+class UndPrefillArgs(ctypes.Structure):
+    _fields_ = [
+        ("num_layers", ctypes.c_int32), ("hidden", ctypes.c_int32), ("intermediate", ctypes.c_int32),
+        ("n_q_heads", ctypes.c_int32), ("n_kv_heads", ctypes.c_int32), ("head_dim", ctypes.c_int32),
+        ("rms_eps", ctypes.c_float), ("mrope_s0", ctypes.c_int32), ("mrope_s1", ctypes.c_int32),
+        ("layers", ctypes.POINTER(UndLayerWeights)), ("kv", ctypes.POINTER(ctypes.c_void_p)),
+        ("kv_capacity", ctypes.c_int64), ("cache_len", ctypes.c_int64), ("rows", ctypes.c_int32), ("causal", ctypes.c_int32),
+        ("final_norm", ctypes.c_void_p), ("inv_freq", ctypes.c_void_p), ("position_ids", ctypes.c_void_p),
+        ("work", ctypes.c_void_p), ("n_items", ctypes.c_int32),
+        ("x", ctypes.c_void_p), ("y", ctypes.c_void_p), ("h", ctypes.c_void_p), ("qkv", ctypes.c_void_p),
+        ("attn", ctypes.c_void_p), ("act", ctypes.c_void_p), ("cos", ctypes.c_void_p), ("sin", ctypes.c_void_p),
+    ]
+
+
+def und_prefill(args: UndPrefillArgs) -> None:
+    """Text prefill / ViT step of the und expert (T >= 2 rows) issued natively (see g2vlm_und_prefill)."""
+    _check(_lib.load().g2vlm_und_prefill(ctypes.byref(args), _stream()))
+
+
 def und_decode_workspace_bytes(n_q_heads: int, n_kv_heads: int) -> int:
     """Bytes of the zero-initialised workspace of the one-kernel decode step (current device)."""
     fn = _lib.load().g2vlm_und_decode_workspace_bytes

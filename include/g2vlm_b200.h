@@ -28,7 +28,7 @@ extern "C" {
 #define G2VLM_ABI_VERSION 4 /* 2: gemm out_col_group/out_col_stride, attention item_causal + out_head_cols;
                                3: gemm FORCE_PAIR/FORCE_SINGLE flags, attention lse_out + max_ctas, g2vlm_attention_merge;
                                4: g2vlm_ply_pack filter_nonfinite; decode_step fused_ws (one-kernel step),
-                                  g2vlm_und_decode_workspace_bytes */
+                                  g2vlm_und_decode_workspace_bytes, g2vlm_und_prefill */
 
 /* Version of this ABI (G2VLM_ABI_VERSION of the built library). */
 int g2vlm_abi_version(void);
@@ -392,6 +392,34 @@ typedef struct g2vlm_decode_step_args {
 int g2vlm_und_decode_step(const g2vlm_decode_step_args* args, void* stream);
 /* Size of `fused_ws` for this head geometry on the current device. */
 int64_t g2vlm_und_decode_workspace_bytes(int32_t n_q_heads, int32_t n_kv_heads);
+
+/* Qwen2VLModel.forward_inference(mode="und") for T >= 2 rows on top of an append-style cache, enqueued as ONE call: text
+ * prefill (causal; g2vlm.py:701-733), the ViT step (non-causal; g2vlm.py:735-790) — the und branches of
+ * g2vlm/qwen2vl.py:570-576, 859-860, 891-893, 1322-1323.  M-RoPE table of the rows' positions, then per layer RMSNorm -> qkv
+ * GEMM (+bias) -> q/k-norm on the bf16 tensor + M-RoPE -> append K|V at rows [cache_len, cache_len + rows) -> attention over
+ * cache_len + rows keys -> o_proj (+residual) -> RMSNorm -> gate/up + SwiGLU -> down (+residual); final RMSNorm -> y.
+ * The same per-op entry points in the same order as the host mirror issues them one by one (~9 x num_layers FFI calls).
+ * `layers` and `kv` are HOST arrays like in g2vlm_decode_step_args; everything else is device memory. */
+typedef struct g2vlm_und_prefill_args {
+  int32_t num_layers, hidden, intermediate, n_q_heads, n_kv_heads, head_dim;
+  float rms_eps;
+  int32_t mrope_s0, mrope_s1;
+  const g2vlm_und_layer_weights* layers;
+  void* const* kv;
+  int64_t kv_capacity;
+  int64_t cache_len;                 /* rows already in the cache */
+  int32_t rows, causal;
+  const float* final_norm;           /* fp32 [H] */
+  const float* inv_freq;             /* fp32 [head_dim/2] */
+  const int64_t* position_ids;       /* int64 [3, rows] */
+  const int32_t* work;  int32_t n_items;   /* attention work table (g2vlm_attention) over q rows [0, rows), keys [0, cache_len + rows) */
+  float* x;                          /* fp32 [rows, H]: in = the embedded rows, updated in place (residual stream) */
+  float* y;                          /* fp32 [rows, H]: out = `norm`-ed hidden states */
+  void* h;  void* qkv;  void* attn;  void* act;   /* bf16 workspaces [rows, H], [rows, (nq+2nkv)*hd], [rows, nq*hd], [rows, I] */
+  float* cos;  float* sin;           /* fp32 workspaces [rows, head_dim/2] */
+} g2vlm_und_prefill_args;
+
+int g2vlm_und_prefill(const g2vlm_und_prefill_args* args, void* stream);
 
 /* Greedy token selection of generate_text (g2vlm.py:1122-1126, `torch.argmax(pred_logits, dim=-1)`):
  * logits bf16 [rows, vocab] (leading dim ld) -> int64 [rows]; ties resolve to the lowest index. */

@@ -129,3 +129,33 @@ def test_stage_calls_are_cuda_graph_capturable(tiny):
     eager1 = step()
     assert all(torch.equal(replayed[k], eager1[k]) for k in KEYS)
     assert not torch.equal(replayed["points"], eager0["points"])
+
+
+def test_native_und_prefill_is_bit_identical_to_the_per_op_path():
+    """g2vlm_und_prefill (text prefill / ViT step of the und expert as ONE C call) issues the per-op entry points of
+    G2VLMFast._und_forward in the same order: caches and hidden states are bit-identical, causal and non-causal, on an
+    empty cache and on top of one, short (<= 8 rows: GEMV path) and long (tensor-core tiles) steps."""
+    from g2vlm_b200.model import G2VLMFast, KVCache, NaiveCache
+    cfg = schema.TINY
+    model = G2VLMFast(cfg, schema.init_synthetic(cfg, seed=4, device="cuda"))
+
+    def run(native):
+        model.native = native
+        outs, cache, kvlen = [], NaiveCache(cfg.num_layers), 0
+        for n, causal in ((5, True), (300, True), (9, False), (2, True)):
+            ids = (torch.arange(n) * 13 + 7) % cfg.vocab_size
+            x = model.embed[ids.cuda()].contiguous()
+            cache = KVCache.adopt(cache, cfg, model.device)
+            y = model._und_forward(x, (kvlen + torch.arange(n)).expand(3, -1), cache, causal=causal)
+            kvlen += n
+            outs.append(y.clone())
+        torch.cuda.synchronize()
+        return outs, [b[:kvlen].clone() for b in cache.buf], cache.seq_lens
+
+    a, ka, la = run(False)
+    b, kb, lb = run(True)
+    assert la == lb == 316
+    for x, y in zip(a, b):
+        assert torch.equal(x, y)
+    for x, y in zip(ka, kb):
+        assert torch.equal(x, y)
