@@ -241,14 +241,124 @@ __global__ void __launch_bounds__(NW * 32) gemv_skinny_mma_kernel(const GemvPara
   }
 }
 
+
+// 9..32 rows (system prompt, short questions of the chat path): the same mapping with RB blocks of 8 x-rows per weight
+// fragment — the weights still stream ONCE, every k block feeds 2 x RB MMAs (x RB more for SwiGLU).  The legacy MMA of
+// sm_100 retires one m16n8k16 per 2 cycles and SM (tools/micro/mma_sync_bench.cu), so the MMAs stay within
+// reach of the HBM rate, while a 128-row tcgen05 tile would put the whole [N, K] weight on N / 256 CTAs (6 CTAs for the
+// o / down projections: measured 5 ms for a 20-token prefill, 0.5 TB/s).  8 warps split K; partial tiles meet in shared memory.
+constexpr int ROWS_MMA_MAX = 32;   // (RB = 8, 33..64 rows, measured SLOWER than the tile kernel: 7.5 vs 5.7 ms for a 60-token prefill —
+                                   //  every CTA re-reads all x rows from L2)
+template <int EPI, int RB>
+__global__ void __launch_bounds__(256) gemv_rows_mma_kernel(const GemvParams p) {
+  constexpr bool SW = EPI == G2VLM_EPI_SWIGLU_BF16;
+  constexpr int NW = 8, NH = SW ? 2 : 1, XR = 8 * RB;
+  constexpr int U = RB <= 2 ? 4 : 2;  // k blocks in flight per warp
+  extern __shared__ float part_dyn[];  // [NW][NH][16][XR]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int n0 = blockIdx.x * 16;
+  long long r0 = n0;
+  if constexpr (SW) r0 = (long long)(n0 >> 7) * 256 + (n0 & 127);
+  const uint4* wg0 = reinterpret_cast<const uint4*>(p.w + (r0 + g) * p.ldw) + t;
+  const uint4* wg1 = reinterpret_cast<const uint4*>(p.w + (r0 + g + 8) * p.ldw) + t;
+  const uint4* wu0 = reinterpret_cast<const uint4*>(p.w + (r0 + 128 + g) * p.ldw) + t;
+  const uint4* wu1 = reinterpret_cast<const uint4*>(p.w + (r0 + 128 + g + 8) * p.ldw) + t;
+  const uint4* xp[RB];
+  bool xok[RB];
+#pragma unroll
+  for (int rb = 0; rb < RB; ++rb) {
+    xok[rb] = rb * 8 + g < p.rows;
+    xp[rb] = reinterpret_cast<const uint4*>(p.x + (xok[rb] ? rb * 8 + g : 0) * p.ldx) + t;
+  }
+  const int kb_total = p.K >> 5;
+  const int per = (kb_total + NW - 1) / NW;
+  const int kb0 = warp * per, kb1 = min(kb_total, kb0 + per);
+  float dg[RB][4], du[SW ? RB : 1][4];
+#pragma unroll
+  for (int rb = 0; rb < RB; ++rb)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { dg[rb][e] = 0.f; if constexpr (SW) du[rb][e] = 0.f; }
+  const uint4 zero = make_uint4(0, 0, 0, 0);
+  for (int kb = kb0; kb < kb1; kb += U) {
+    uint4 a0[U], a1[U], b0[U], b1[U], xv[RB][U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const bool ok = kb + u < kb1;
+      const int o = (kb + u) * 4;
+      a0[u] = ok ? __ldg(wg0 + o) : zero;
+      a1[u] = ok ? __ldg(wg1 + o) : zero;
+      if constexpr (SW) {
+        b0[u] = ok ? __ldg(wu0 + o) : zero;
+        b1[u] = ok ? __ldg(wu1 + o) : zero;
+      }
+#pragma unroll
+      for (int rb = 0; rb < RB; ++rb) xv[rb][u] = (ok && xok[rb]) ? __ldg(xp[rb] + o) : zero;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+#pragma unroll
+      for (int rb = 0; rb < RB; ++rb) {
+        mma_bf16_16816(dg[rb], a0[u].x, a1[u].x, a0[u].y, a1[u].y, xv[rb][u].x, xv[rb][u].y);
+        mma_bf16_16816(dg[rb], a0[u].z, a1[u].z, a0[u].w, a1[u].w, xv[rb][u].z, xv[rb][u].w);
+        if constexpr (SW) {
+          mma_bf16_16816(du[rb], b0[u].x, b1[u].x, b0[u].y, b1[u].y, xv[rb][u].x, xv[rb][u].y);
+          mma_bf16_16816(du[rb], b0[u].z, b1[u].z, b0[u].w, b1[u].w, xv[rb][u].z, xv[rb][u].w);
+        }
+      }
+    }
+  }
+  // C fragment: d0,d1 = (weight row g, x rows 8 rb + 2t, +1), d2,d3 = (weight row g + 8, same x rows)
+  float* pw = part_dyn + (long long)warp * NH * 16 * XR;
+#pragma unroll
+  for (int rb = 0; rb < RB; ++rb) {
+    pw[g * XR + rb * 8 + 2 * t] = dg[rb][0];
+    pw[g * XR + rb * 8 + 2 * t + 1] = dg[rb][1];
+    pw[(g + 8) * XR + rb * 8 + 2 * t] = dg[rb][2];
+    pw[(g + 8) * XR + rb * 8 + 2 * t + 1] = dg[rb][3];
+    if constexpr (SW) {
+      pw[(16 + g) * XR + rb * 8 + 2 * t] = du[rb][0];
+      pw[(16 + g) * XR + rb * 8 + 2 * t + 1] = du[rb][1];
+      pw[(16 + g + 8) * XR + rb * 8 + 2 * t] = du[rb][2];
+      pw[(16 + g + 8) * XR + rb * 8 + 2 * t + 1] = du[rb][3];
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 16 * XR; i += 256) {
+    const int m = i >> 4, c = i & 15;  // 16 consecutive columns per row: coalesced stores
+    if (m < p.rows) {
+      float f = 0.f, fu = 0.f;
+#pragma unroll
+      for (int w = 0; w < NW; ++w) {
+        f += part_dyn[((long long)w * NH * 16 + c) * XR + m];
+        if constexpr (SW) fu += part_dyn[((long long)w * NH * 16 + 16 + c) * XR + m];
+      }
+      gemv_store<EPI>(p, n0 + c, m, f, fu);
+    }
+  }
+}
+
+template <int EPI, int RB>
+static int launch_rows_mma(const GemvParams& p, int n_out, cudaStream_t stream) {
+  constexpr int NH = EPI == G2VLM_EPI_SWIGLU_BF16 ? 2 : 1;
+  const int smem = 8 * NH * 16 * 8 * RB * 4;
+  if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(gemv_rows_mma_kernel<EPI, RB>), smem)) return rc;
+  gemv_rows_mma_kernel<EPI, RB><<<n_out / 16, 256, smem, stream>>>(p);
+  return G2VLM_OK;
+}
+
 template <int EPI>
-static void launch_gemv_epi(const GemvParams& p, int n_out, cudaStream_t stream) {
+static int launch_gemv_epi(const GemvParams& p, int n_out, cudaStream_t stream) {
   const bool one = p.rows == 1;
   const bool split = p.K >= 4096;
+  if (p.rows > GEMV_MAX_ROWS) {   // 9..32 rows (the caller checked the shape)
+    if (p.rows <= 16) return launch_rows_mma<EPI, 2>(p, n_out, stream);
+    return launch_rows_mma<EPI, 4>(p, n_out, stream);
+  }
   if (!one && n_out % 16 == 0 && p.K % 32 == 0 && p.ldw % 8 == 0 && p.ldx % 8 == 0) {
     if (split) gemv_skinny_mma_kernel<EPI, 16><<<n_out / 16, 16 * 32, 0, stream>>>(p);
     else gemv_skinny_mma_kernel<EPI, 8><<<n_out / 16, 8 * 32, 0, stream>>>(p);
-    return;
+    return G2VLM_OK;
   }
   const int cols = split ? GEMV_WARPS / 4 : GEMV_WARPS;
   const unsigned grid = (n_out + cols - 1) / cols;
@@ -256,6 +366,7 @@ static void launch_gemv_epi(const GemvParams& p, int n_out, cudaStream_t stream)
   else if (one) gemv_bf16_kernel<EPI, 1, 1><<<grid, GEMV_WARPS * 32, 0, stream>>>(p);
   else if (split) gemv_bf16_kernel<EPI, GEMV_MAX_ROWS, 4><<<grid, GEMV_WARPS * 32, 0, stream>>>(p);
   else gemv_bf16_kernel<EPI, GEMV_MAX_ROWS, 1><<<grid, GEMV_WARPS * 32, 0, stream>>>(p);
+  return G2VLM_OK;
 }
 
 // Called by g2vlm_gemm_bf16 when the call has <= GEMV_MAX_ROWS rows, all in ONE group.
@@ -278,12 +389,14 @@ int launch_gemv(const g2vlm_gemm_args* a, int group, cudaStream_t stream) {
   p.ldr = a->ldr;
   p.row0 = a->group_row0[group];
   const int n_out = a->epilogue == G2VLM_EPI_SWIGLU_BF16 ? a->N / 2 : a->N;
+  int rc;
   switch (a->epilogue) {
-    case G2VLM_EPI_STORE_BF16: launch_gemv_epi<G2VLM_EPI_STORE_BF16>(p, n_out, stream); break;
-    case G2VLM_EPI_SWIGLU_BF16: launch_gemv_epi<G2VLM_EPI_SWIGLU_BF16>(p, n_out, stream); break;
-    case G2VLM_EPI_RESID_F32: launch_gemv_epi<G2VLM_EPI_RESID_F32>(p, n_out, stream); break;
-    default: launch_gemv_epi<G2VLM_EPI_STORE_F32>(p, n_out, stream); break;
+    case G2VLM_EPI_STORE_BF16: rc = launch_gemv_epi<G2VLM_EPI_STORE_BF16>(p, n_out, stream); break;
+    case G2VLM_EPI_SWIGLU_BF16: rc = launch_gemv_epi<G2VLM_EPI_SWIGLU_BF16>(p, n_out, stream); break;
+    case G2VLM_EPI_RESID_F32: rc = launch_gemv_epi<G2VLM_EPI_RESID_F32>(p, n_out, stream); break;
+    default: rc = launch_gemv_epi<G2VLM_EPI_STORE_F32>(p, n_out, stream); break;
   }
+  if (rc) return rc;
   G2_CUDA_OK(cudaGetLastError());
   return G2VLM_OK;
 }

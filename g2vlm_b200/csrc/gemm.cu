@@ -744,8 +744,15 @@ extern "C" int g2vlm_gemm_bf16(const g2vlm_gemm_args* a, void* stream_) {
     int total = 0, nonempty = 0, grp = 0;
     for (int g = 0; g < a->n_groups; ++g)
       if (a->group_rows[g] > 0) { total += a->group_rows[g]; ++nonempty; grp = g; }
-    if (nonempty == 1 && total <= 8 && a->out_col_group == 0 && (reinterpret_cast<uintptr_t>(a->A) & 15) == 0 &&
-        (reinterpret_cast<uintptr_t>(a->B) & 15) == 0)
+    const bool aligned = a->out_col_group == 0 && (reinterpret_cast<uintptr_t>(a->A) & 15) == 0 &&
+                         (reinterpret_cast<uintptr_t>(a->B) & 15) == 0;
+    if (nonempty == 1 && total <= 8 && aligned) return launch_gemv(a, grp, stream);
+    // 9..32 rows (system prompt / short question prefill): still HBM-bound, and a 128-row tile would put the whole weight matrix
+    // on N / 256 CTAs -> warp-level MMA kernel that streams the weights once over N / 16 CTAs (csrc/decode.cu)
+    const int n_out = a->epilogue == G2VLM_EPI_SWIGLU_BF16 ? a->N / 2 : a->N;
+    if (nonempty == 1 && total <= 32 && aligned && n_out % 16 == 0 && a->K % 32 == 0 && a->k_chunk_blocks == 0 &&
+        a->epilogue != G2VLM_EPI_STORE_F32 &&   // (the fp32 heads keep the tile kernel's accumulation order)
+        !(a->flags & (G2VLM_GEMM_FORCE_PAIR | G2VLM_GEMM_FORCE_SINGLE)))
       return launch_gemv(a, grp, stream);
   }
   kp.n_groups = a->n_groups;

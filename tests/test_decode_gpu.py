@@ -12,7 +12,7 @@ def _relerr(a, b):
     return ((a.float() - b.float()).abs().max() / b.float().abs().max().clamp_min(1e-30)).item()
 
 
-@pytest.mark.parametrize("rows", [1, 2, 3, 7, 8])
+@pytest.mark.parametrize("rows", [1, 2, 3, 7, 8, 9, 16, 20, 33, 60, 64])
 def test_gemv_epilogues_match_reference(rows):
     from g2vlm_b200 import ops
     g = torch.Generator().manual_seed(rows)
@@ -36,6 +36,11 @@ def test_gemv_epilogues_match_reference(rows):
     f = torch.empty(rows, N, device="cuda")
     ops.gemm(x, w, f, epilogue=ops.EPI_STORE_F32, groups=groups, bias=bias, flags=ops.GEMM_RELU, residual=r0)
     assert _relerr(f, torch.relu(ref + bias[N:]) + r0) < 1e-4
+    if rows > 8:   # 9..64 rows: the warp-MMA kernel against the tcgen05 tile kernel on the same inputs
+        out2 = torch.empty_like(out)
+        ops.gemm(x, w, out, epilogue=ops.EPI_STORE_BF16, groups=groups, bias=bias)
+        ops.gemm(x, w, out2, epilogue=ops.EPI_STORE_BF16, groups=groups, bias=bias, flags=ops.GEMM_FORCE_SINGLE)
+        assert _relerr(out, out2) < 1e-2 and (out != out2).float().mean() < 0.05
     # SwiGLU: interleaved gate/up blocks of 128 rows
     I = 512
     wg = (torch.randn(I, K, generator=g) * 0.08).to(torch.bfloat16).cuda()
@@ -47,7 +52,8 @@ def test_gemv_epilogues_match_reference(rows):
     assert _relerr(o, torch.nn.functional.silu(gt.float()).to(torch.bfloat16).float() * up.float()) < 1.5e-2
 
 
-@pytest.mark.parametrize("rows,K,N", [(5, 1536, 648), (7, 1552, 640), (4, 8960, 1536), (7, 4096, 48)])
+@pytest.mark.parametrize("rows,K,N", [(5, 1536, 648), (7, 1552, 640), (4, 8960, 1536), (7, 4096, 48), (20, 8960, 1536),
+                                      (60, 1536, 2048), (64, 8960, 1536), (33, 1568, 656)])
 def test_gemv_skinny_shapes(rows, K, N):
     """2..8 rows: the mma.sync kernel (N % 16 == 0, K % 32 == 0; 8 or 16 warps split K, ragged K split) and the
     scalar fallback for the other shapes."""
