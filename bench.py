@@ -57,6 +57,25 @@ class StubTokenizer:
 TOKENS = dict(bos_token_id=1, eos_token_id=2, start_of_image=3, end_of_image=4)
 
 
+_REAL_STDOUT = None
+
+
+def isolate_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL's version banner, the reference's progress
+    prints): from here on file descriptor 1 goes to stderr and only emit() reaches the real stdout."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -256,7 +275,7 @@ def run_reference_arm(args):
                             scenes_per_step=1, parallelism="host cores (reference classes, CPU)"),
                 cpu_baseline=dict(value=v, unit=UNIT, cores=threads, kind=kind, sample=sample),
                 e2e=dict(value=v, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
-    print(json.dumps(line))
+    emit(line)
 
 
 def gpu_reference_leg(cfg, layerscale, u8, ours_pred, steps=3):
@@ -490,7 +509,7 @@ def run_view_sharded(args, cfg, dist, rank, world, local_rank):
         fl = algorithmic_flops(cfg, n_views, P)
         pk = peaks()
         per = ms / args.steps
-        print(json.dumps(dict(
+        emit(dict(
             metric=METRIC, value=n_views / (per / 1e3), unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
             ms_per_step=per, higher_is_better=True, scaling="strong", vs_baseline=None, dtype="bf16",
             data=DATA.format(ls=args.layerscale),
@@ -503,7 +522,7 @@ def run_view_sharded(args, cfg, dist, rank, world, local_rank):
                      d2h_bytes_per_step=0, note="timed through recon_view_sharded from host views; outputs stay on the GPUs"),
             whole_step=dict(algorithmic_tflop=fl["total"] / 1e12,
                             achieved_tflops_per_gpu=fl["total"] / 1e12 / (per / 1e3) / world,
-                            frac_of_peak=fl["total"] / 1e12 / (per / 1e3) / world / pk["tflops"]))))
+                            frac_of_peak=fl["total"] / 1e12 / (per / 1e3) / world / pk["tflops"])))
     if dist is not None:
         dist.destroy_process_group()
 
@@ -573,7 +592,7 @@ def run_fp32(args, cfg, local_rank):
         max_rel = dict(error=f"{type(e).__name__}: {e}")
     fl = algorithmic_flops(cfg, n_views, P)
     d2h = sum(v.numel() * v.element_size() for v in out_host.values())
-    print(json.dumps(dict(
+    emit(dict(
         metric=METRIC, value=n_views / ms * 1e3, unit=UNIT, n_gpus=1, steps=args.steps, warmup=max(3, args.warmup),
         ms_per_step=ms, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="fp32",
         data=DATA.format(ls=args.layerscale),
@@ -586,7 +605,7 @@ def run_fp32(args, cfg, local_rank):
         e2e=dict(value=n_views / ms_e2e * 1e3, unit=UNIT, h2d_bytes_per_step=views_host.numel() * 4, d2h_bytes_per_step=d2h,
                  ms_per_step=ms_e2e, note="one blocking recon() from pinned host views + download of all outputs per step"),
         max_rel_vs_fp32_oracle=max_rel, tolerance=1e-4,
-        whole_step=dict(algorithmic_tflop=fl["total"] / 1e12, achieved_tflops=fl["total"] / 1e12 / (ms / 1e3)))))
+        whole_step=dict(algorithmic_tflop=fl["total"] / 1e12, achieved_tflops=fl["total"] / 1e12 / (ms / 1e3))))
 
 
 # --------------------------------------------------------------------------------------------------
@@ -629,6 +648,7 @@ def main():
                     help="scenes: one 16-view scene per GPU (default, BASELINE configs[1]/[2]); views: ONE scene of "
                          "--views views split by view over the GPUs (BASELINE configs[3], sequence parallel)")
     args = ap.parse_args()
+    isolate_stdout()
 
     if args.impl == "reference":
         run_reference_arm(args)
@@ -881,7 +901,7 @@ def main():
             except Exception as e:  # the baseline must never take the GPU number down with it
                 line["cpu_baseline"] = dict(value=None, unit=UNIT, cores=cores, kind="reference",
                                             sample=f"failed: {type(e).__name__}: {e}")
-    print(json.dumps(line))
+    emit(line)
     if dist is not None:
         dist.destroy_process_group()
 
