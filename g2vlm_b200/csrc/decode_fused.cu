@@ -20,7 +20,7 @@
 // Every vector a phase needs (normalised hidden state, attention output, SwiGLU activations) is rebuilt per CTA in
 // shared memory from the L2-resident fp32 / bf16 vectors; everything written during the kernel is read back with
 // ld.global.cg (L2 only — the other CTAs' updates).
-// Inside a GEMV phase the weight stream runs at the HBM rate (6.3 TB/s); the step as a whole reaches 0.40 of it because the
+// Inside a GEMV phase the weight stream runs at the HBM rate (6.3 TB/s); the step as a whole reaches 0.41 of it because the
 // six grid-wide dependencies of a layer are latency.  Measurements, the earlier versions of this kernel and what was
 // tried and rejected: profiles/r02_decode_fused.txt.
 //
