@@ -1,6 +1,9 @@
 #!/usr/bin/env python
 """Row f1 measurement: decode tokens/s of generate_text on the full model after a 16-view 518px scene is in
-the KV cache (L = 21 943 + prompt tokens), and the prefill times.  usage: python tools/decode_bench.py [steps]"""
+the KV cache (L = 21 943 + prompt tokens), and the prefill times, for the ~280-launch step of round 1 and the one-kernel step.
+usage: python tools/decode_bench.py [steps]
+       G2VLM_DECODE_OPT_SWEEP=1,0,1,0 python tools/decode_bench.py [steps]   same-process A/B of G2VLM_DECODE_OPT values
+       (bit 0 of G2VLM_DECODE_OPT: grid barrier without explicit fences, the default)"""
 import os
 import sys
 import time
