@@ -59,6 +59,7 @@ struct DecFusedParams {
   float eps, scale_log2;
   int s0, s1;
   int ks_h, ks_a, ks_i;            // columns per ring stage for K = H, nq*128, I
+  int keep_token;                  // the caller samples the next token: *cur_token is left alone
   int opt;                         // G2VLM_DECODE_OPT, default 1: bit 0 = no explicit __threadfence around the grid barrier's
                                    //   release-add / acquire-poll (0: with fences, +0.1 ms per token)
   g2vlm_und_layer_weights layers[DF_MAX_LAYERS];
@@ -870,7 +871,7 @@ __global__ void __launch_bounds__(DF_THREADS, 1) und_decode_fused_kernel(const _
       if (argmax_better_df(ov, oi, bv, bi)) { bv = ov; bi = oi; }
     }
     if (lane == 0) {
-      *p.cur_token = bi;
+      if (!p.keep_token) *p.cur_token = bi;
       p.position[0] = pos0 + 1; p.position[1] = pos1 + 1; p.position[2] = pos2 + 1;
       *p.cache_len = L + 1;
       p.sync[1] = target;                                  // every CTA of the next launch starts from here
@@ -908,6 +909,7 @@ int launch_decode_fused(const g2vlm_decode_step_args* a, cudaStream_t stream) {
   q.eps = a->rms_eps;
   q.scale_log2 = static_cast<float>(1.0 / sqrt(static_cast<double>(a->head_dim))) * 1.4426950408889634f;
   q.s0 = a->mrope_s0; q.s1 = a->mrope_s1;
+  q.keep_token = a->keep_token;
   // columns per ring stage: the largest divisor of K that is a multiple of 64 and <= 1536
   auto stage_cols = [](int K) {
     for (int ks = DF_KS_MAX; ks >= 64; ks -= 64)

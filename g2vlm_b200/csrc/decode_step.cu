@@ -72,7 +72,7 @@ extern "C" int g2vlm_und_decode_step(const g2vlm_decode_step_args* a, void* stre
   g.A = a->h; g.lda = H; g.a_rows = 1; g.B = a->lm_head; g.ldb = H; g.N = a->vocab; g.K = H; g.n_groups = 1;
   g.group_rows[0] = 1; g.epilogue = G2VLM_EPI_STORE_BF16; g.out = a->logits; g.ldo = vpad;
   G2_TRY(g2vlm_gemm_bf16(&g, stream));
-  G2_TRY(g2vlm_argmax_bf16(a->logits, vpad, 1, a->vocab, a->cur_token, stream));
+  if (!a->keep_token) G2_TRY(g2vlm_argmax_bf16(a->logits, vpad, 1, a->vocab, a->cur_token, stream));
   advance_step_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(reinterpret_cast<long long*>(a->position), a->cache_len);
   G2_CUDA_OK(cudaGetLastError());
   return G2VLM_OK;

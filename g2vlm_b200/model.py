@@ -897,10 +897,12 @@ class G2VLMFast:
                       end_token_id: Optional[int] = None, return_logits: bool = False, use_cuda_graph: bool = False,
                       fused_step: Optional[bool] = None):
         """Decode loop of the reference (g2vlm.py:1070-1141), batch 1: returns the generated ids [steps, 1]
-        INCLUDING the start token, like the reference.  The KV cache is appended in place.  Greedy decoding runs
-        the native one-call step; do_sample=True keeps the reference's sampling tail — softmax(logits /
-        temperature) in fp32 and torch.multinomial (g2vlm.py:1122-1124) — as torch ops after the lm_head GEMM
-        (it draws from torch's CUDA generator, so a seed reproduces a run; not bit-comparable to a CPU reference)."""
+        INCLUDING the start token, like the reference.  The KV cache is appended in place.  Every step is the native
+        one-call step (g2vlm_und_decode_step: one persistent kernel, or ~280 launches with fused_step=False);
+        do_sample=True keeps the reference's sampling tail — softmax(logits / temperature) in fp32 and
+        torch.multinomial (g2vlm.py:1122-1124) — as torch ops on the step's logits (the step then leaves the token to
+        the sampler; it draws from torch's CUDA generator, so a seed reproduces a run; not bit-comparable to a CPU
+        reference).  return_logits: the fp32 copy of every step's bf16 logits."""
         cfg, dev = self.cfg, self.device
         if do_sample and not temperature > 0:
             raise ValueError("temperature must be positive")
@@ -914,37 +916,24 @@ class G2VLMFast:
         pos = packed_query_position_ids.to(dev, torch.long).reshape(3, 1).clone()
         len_dev = torch.tensor([L0], dtype=torch.int32, device=dev)
         H, V = cfg.hidden_size, self.lm_head.shape[0]
-        x = self.buf.get("gen.x", (1, H), torch.float32)
-        yb = self.buf.get("gen.yb", (1, H), torch.bfloat16)
-        logits = self.buf.get("gen.logits", (1, (V + 7) // 8 * 8), torch.bfloat16)
         tokens = torch.empty(max_length, dtype=torch.long, device=dev)
 
+        # native driver: the whole step is enqueued by ONE C-ABI call — one persistent kernel (fused_step, default) or ~280
+        # launches; with do_sample the call leaves the token alone (keep_token) and the reference's sampling tail follows
+        if fused_step is None:
+            fused_step = os.environ.get("G2VLM_DECODE_FUSED", "1") != "0"
+        fused_active = bool(fused_step)
+        args, keep = self._decode_args(cache, bound, cur, pos, len_dev, fused=fused_active)
+        args.keep_token = int(do_sample)
+        logits = keep[1]["logits"].view(1, -1)
+
         def step():
-            # everything a step depends on (token, position, cache length) lives on the device, so the SAME
-            # launches serve every step: capture once, replay (row f1: no per-token host work)
-            ops.gather_rows(self.embed, x, cur, 1)
-            y = self._und_forward(x, pos, cache, causal=True, len_dev=len_dev, kv_bound=bound)
-            ops.cast_bf16(y, yb)
-            ops.gemm(yb, self.lm_head, logits, epilogue=ops.EPI_STORE_BF16)
+            # everything a step depends on (token, position, cache length) lives on the device, so the SAME call serves
+            # every step (row f1: no per-token host work)
+            ops.und_decode_step(args)
             if do_sample:
                 probs = torch.softmax((logits[:, :V] / temperature).float(), dim=-1)   # bf16 divide, fp32 softmax
                 cur.copy_(torch.multinomial(probs, num_samples=1).squeeze(1))
-            else:
-                ops.argmax_bf16(logits[:, :V], cur)
-            pos.add_(1)
-            len_dev.add_(1)
-
-        fused_active = False
-        if not return_logits and not do_sample:
-            # native driver: the whole step is enqueued by ONE C-ABI call — one persistent kernel (fused_step, default)
-            # or ~280 launches
-            if fused_step is None:
-                fused_step = os.environ.get("G2VLM_DECODE_FUSED", "1") != "0"
-            fused_active = bool(fused_step)
-            args, keep = self._decode_args(cache, bound, cur, pos, len_dev, fused=fused_active)
-
-            def step():  # noqa: F811
-                ops.und_decode_step(args)
         graph = None
         n_done, all_logits = 0, []
         check_every = 8

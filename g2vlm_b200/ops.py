@@ -431,7 +431,7 @@ class DecodeStepArgs(ctypes.Structure):
         ("x", ctypes.c_void_p), ("h", ctypes.c_void_p), ("qkv", ctypes.c_void_p), ("attn", ctypes.c_void_p),
         ("act", ctypes.c_void_p), ("y", ctypes.c_void_p), ("cos_sin", ctypes.c_void_p),
         ("attn_ws", ctypes.c_void_p), ("attn_ws_floats", ctypes.c_int64), ("logits", ctypes.c_void_p),
-        ("fused_ws", ctypes.c_void_p), ("fused_ws_bytes", ctypes.c_int64),
+        ("fused_ws", ctypes.c_void_p), ("fused_ws_bytes", ctypes.c_int64), ("keep_token", ctypes.c_int32),
     ]
 
 

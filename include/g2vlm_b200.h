@@ -387,6 +387,9 @@ typedef struct g2vlm_decode_step_args {
    * launches.  Device buffer of >= g2vlm_und_decode_workspace_bytes() bytes, 16-byte aligned, ZEROED ONCE by the caller
    * when it is allocated (it carries the barrier counter from step to step) and owned by ONE generation at a time. */
   void* fused_ws;  int64_t fused_ws_bytes;
+  /* ABI v4.  Non-zero: the step leaves *cur_token alone (the caller samples the next token from `logits`: the do_sample tail of
+   * generate_text, g2vlm.py:1122-1124); position and cache length advance as usual. */
+  int32_t keep_token;
 } g2vlm_decode_step_args;
 
 int g2vlm_und_decode_step(const g2vlm_decode_step_args* args, void* stream);
