@@ -31,3 +31,13 @@ def pytest_sessionstart(session):
         _lib.build()
     except Exception as e:  # reported by the tests that need the library
         print(f"[conftest] kernel library build failed: {e}")
+
+
+@pytest.fixture(autouse=True)
+def _seed_default_generators():
+    """Tests that draw device tensors without a generator (torch.randn(..., device="cuda")) must not change from run to
+    run: a check that sits at the edge of its tolerance would then fail once in a while on the driver's box."""
+    import torch
+
+    torch.manual_seed(20261019)
+    yield
