@@ -128,3 +128,5 @@ extern "C" int g2vlm_und_prefill(const g2vlm_und_prefill_args* a, void* stream) 
   G2_TRY(g2vlm_rmsnorm_routed(a->x, H, a->y, H, 0, a->final_norm, a->final_norm, T, 0, H, a->rms_eps, stream));
   return G2VLM_OK;
 }
+
+extern "C" int g2vlm_mot_prefill_und(const g2vlm_und_prefill_args* a, void* stream) { return g2vlm_und_prefill(a, stream); }

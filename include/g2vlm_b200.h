@@ -423,6 +423,8 @@ typedef struct g2vlm_und_prefill_args {
 } g2vlm_und_prefill_args;
 
 int g2vlm_und_prefill(const g2vlm_und_prefill_args* args, void* stream);
+/* The same entry point under the name SURVEY.md §8(b) gives it. */
+int g2vlm_mot_prefill_und(const g2vlm_und_prefill_args* args, void* stream);
 
 /* Greedy token selection of generate_text (g2vlm.py:1122-1126, `torch.argmax(pred_logits, dim=-1)`):
  * logits bf16 [rows, vocab] (leading dim ld) -> int64 [rows]; ties resolve to the lowest index. */
