@@ -28,7 +28,7 @@ extern "C" {
 #define G2VLM_ABI_VERSION 4 /* 2: gemm out_col_group/out_col_stride, attention item_causal + out_head_cols;
                                3: gemm FORCE_PAIR/FORCE_SINGLE flags, attention lse_out + max_ctas, g2vlm_attention_merge;
                                4: g2vlm_ply_pack filter_nonfinite; decode_step fused_ws (one-kernel step),
-                                  g2vlm_und_decode_workspace_bytes, g2vlm_und_prefill */
+                                  g2vlm_und_decode_workspace_bytes, g2vlm_und_prefill, g2vlm_sp_kv_exchange */
 
 /* Version of this ABI (G2VLM_ABI_VERSION of the built library). */
 int g2vlm_abi_version(void);
@@ -425,6 +425,20 @@ typedef struct g2vlm_und_prefill_args {
 int g2vlm_und_prefill(const g2vlm_und_prefill_args* args, void* stream);
 /* The same entry point under the name SURVEY.md §8(b) gives it. */
 int g2vlm_mot_prefill_und(const g2vlm_und_prefill_args* args, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * View-sharded scene (one long scene split by view over the GPUs of a node), for a host that owns a raw NCCL
+ * communicator (the Python mirror uses torch.distributed: symmetric memory + copy engines, or the same NCCL exchange).
+ * The K|V exchange of ONE MoT layer (the step the reference's dataflow g2vlm/qwen2vl.py:621-652 needs once its keys live on
+ * several GPUs): this rank's rows kv_send bf16 [rank_rows[rank], kvw] go to every peer, and peer j's rows land in kv_remote
+ * bf16 [sum of the other ranks' rows, kvw] at row offset sum(rank_rows[i] for i < j, i != rank) — ONE NCCL group of
+ * point-to-point sends / receives enqueued on `stream` (a side stream: the caller runs g2vlm_attention over its local keys
+ * with `lse_out` and a `max_ctas` bound meanwhile, then over kv_remote, and combines the two with g2vlm_attention_merge).
+ * nccl_comm: an ncclComm_t of `world` ranks created by the caller with the NCCL library of the process (resolved with
+ * dlopen("libnccl.so.2"): the library is not a link-time dependency).  rank_rows: HOST int64 [world].
+ * ---------------------------------------------------------------------------------------------- */
+int g2vlm_sp_kv_exchange(void* nccl_comm, int32_t rank, int32_t world, const int64_t* rank_rows, int64_t kvw,
+                         const void* kv_send, void* kv_remote, void* stream);
 
 /* Greedy token selection of generate_text (g2vlm.py:1122-1126, `torch.argmax(pred_logits, dim=-1)`):
  * logits bf16 [rows, vocab] (leading dim ld) -> int64 [rows]; ties resolve to the lowest index. */

@@ -72,3 +72,57 @@ def test_view_sharded_recon_matches_single_gpu(n_views, ranges):
             # same kernels; the key order inside attention differs (all-gather) / the two partials are rounded to
             # bf16 before the log-sum-exp merge (overlap)
             assert e < (5e-3 if k.startswith("allgather") else 1e-2), (r, k, e)
+
+
+def _sp_exchange_worker(rank, world, port, ret):
+    """g2vlm_sp_kv_exchange with a RAW ncclComm_t (created here through the NCCL C API, as a non-Python host would)."""
+    import ctypes
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("gloo", rank=rank, world_size=world)       # only to hand the unique id around
+    from g2vlm_b200 import _lib
+    lib = _lib.load()
+    nccl = ctypes.CDLL("libnccl.so.2")
+
+    class UniqueId(ctypes.Structure):
+        _fields_ = [("internal", ctypes.c_char * 128)]
+
+    uid = UniqueId()
+    if rank == 0:
+        assert nccl.ncclGetUniqueId(ctypes.byref(uid)) == 0
+    t = torch.tensor(list(bytes(uid)), dtype=torch.uint8)
+    dist.broadcast(t, 0)
+    uid = UniqueId.from_buffer_copy(bytes(t.tolist()))
+    comm = ctypes.c_void_p()
+    nccl.ncclCommInitRank.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int, UniqueId, ctypes.c_int]
+    assert nccl.ncclCommInitRank(ctypes.byref(comm), world, uid, rank) == 0
+    rows, kvw = [3, 5], 512                                              # uneven shards
+    send = torch.full((rows[rank], kvw), float(rank + 1), dtype=torch.bfloat16, device="cuda")
+    send += torch.arange(kvw, device="cuda").to(torch.bfloat16)[None, :] / 1024
+    remote = torch.zeros(sum(rows) - rows[rank], kvw, dtype=torch.bfloat16, device="cuda")
+    rr = (ctypes.c_int64 * world)(*rows)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    rc = lib.g2vlm_sp_kv_exchange(comm, ctypes.c_int32(rank), ctypes.c_int32(world), rr, ctypes.c_int64(kvw),
+                                  ctypes.c_void_p(send.data_ptr()), ctypes.c_void_p(remote.data_ptr()),
+                                  ctypes.c_void_p(side.cuda_stream))
+    side.synchronize()
+    peer = 1 - rank
+    want = torch.full((rows[peer], kvw), float(peer + 1), dtype=torch.bfloat16, device="cuda")
+    want += torch.arange(kvw, device="cuda").to(torch.bfloat16)[None, :] / 1024
+    ret[rank] = (rc, bool(torch.equal(remote, want)), lib.g2vlm_last_error().decode())
+    nccl.ncclCommDestroy.argtypes = [ctypes.c_void_p]
+    nccl.ncclCommDestroy(comm)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_sp_kv_exchange_with_a_raw_nccl_communicator():
+    world = 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_sp_exchange_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
+    for r in range(world):
+        rc, same, err = ret[r]
+        assert rc == 0 and same, (r, rc, err)
