@@ -29,7 +29,6 @@ constexpr int ATT_BN = 128;       // keys per block
 constexpr int ATT_THREADS = 384;  // 12 warps
 constexpr float ATT_RESCALE_TAU = 8.0f;
 constexpr int ATT_PCHUNKS = 4;    // P_t reaches the MMA warp in 4 chunks of 32 keys (PV overlaps the exp tail)
-constexpr int ATT_ROWSPLIT_DEFAULT = 0;  // see attention_rowsplit_kernel
 constexpr int ATT64_POLY = 0;     // head_dim 64: exp2 pairs (of every 8) on the FMA pipe instead of the MUFU — 0: measured slower (r02)
 
 struct AttnKParams {
@@ -168,7 +167,7 @@ __device__ __forceinline__ AttnUnit decode_unit(const AttnKParams& p, int u) {
   return a;
 }
 
-// The TMA producer thread of both kernels: Q tiles once per unit, K/V blocks of 128 keys through the mbarrier ring.
+// The TMA producer thread: Q tiles once per unit, K/V blocks of 128 keys through the mbarrier ring.
 template <int D, int KS>
 __device__ __forceinline__ void attn_tma_producer(const AttnKParams& p, uint8_t* sQ, uint8_t* sKV, uint64_t* q_full,
                                                   uint64_t* q_empty, uint64_t* k_full, uint64_t* v_full,
@@ -206,7 +205,7 @@ __device__ __forceinline__ void attn_tma_producer(const AttnKParams& p, uint8_t*
   }
 }
 
-template <int D, int POLY, bool OPAQ = false>
+template <int D, int POLY>
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 attention_tcgen05_kernel(const __grid_constant__ AttnKParams p) {
   using Cfg = AttnCfg<D>;
@@ -323,9 +322,9 @@ attention_tcgen05_kernel(const __grid_constant__ AttnKParams p) {
       auto issue_pv = [&](int t, int s, uint32_t par, bool first_block) {
         const uint32_t va = kv_addr + s * 2 * Cfg::kTileBytes + Cfg::kTileBytes;
         // opaque copy: otherwise ptxas precomputes the TMEM address of every chunk of both tiles outside the unit loop and
-        // spills them (two local-memory loads per chunk on the issuer's critical path)
+        // spills them (two local-memory loads per chunk on the issuer's critical path; profiles/r02_attention_rowsplit.txt)
         uint32_t tbase = tmem_base;
-        if constexpr (OPAQ) asm volatile("" : "+r"(tbase));
+        asm volatile("" : "+r"(tbase));
         const uint32_t tS_t = tbase + static_cast<uint32_t>(t) * 128u, tO_t = tbase + 256u + static_cast<uint32_t>(t) * 128u;
 #pragma unroll
         for (int c = 0; c < ATT_PCHUNKS; ++c) {
@@ -511,6 +510,8 @@ attention_tcgen05_kernel(const __grid_constant__ AttnKParams p) {
       for (int j = 0; j < a.nblk; ++j, ++g) {
         mbar_wait(&s_full[t], g & 1);
         tc_fence_after();
+        // all four 32-column loads in flight at once: taking the row maximum of one quarter while the next streams in
+        // (a wait::ld per quarter) measured 3-9 % slower on every shape (profiles/r02_attention_rowsplit.txt)
         uint32_t sv[128];
 #pragma unroll
         for (int c = 0; c < 4; ++c) tmem_ld32(tS_w + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&sv[c * 32]));
@@ -620,433 +621,6 @@ attention_tcgen05_kernel(const __grid_constant__ AttnKParams p) {
   }
 }
 
-// ------------------------------------------------------------------------------------------------------------------
-// Row-split variant (r02): TWO threads per query row.  In the kernel above each tile has its own four softmax warps, so the
-// two tiles' softmax phases overlap in time, share the MUFU of each scheduler, and every tile's chain
-// QK -> softmax -> PV -> QK sees a softmax of ~2000 clocks.  Here all eight softmax warps work on ONE tile at a time:
-// warp 4+s takes keys [0,64) of the block for the 32 rows of TMEM sub-partition s, warp 8+s keys [64,128) of the same
-// rows, and the warps alternate tile 0, tile 1, tile 0, ... in the order the MMA warp produces S.  A tile's softmax then
-// has the whole MUFU (1024 clocks per block + a 64-column load), the other tile's MMAs run underneath, and the chain
-// per tile is roughly halved.  The two threads of a row agree on the block maximum through shared memory (one named
-// barrier per warp pair and block), so the lazy-rescale decisions and every P value are those of the one-thread-per-row
-// kernel; row sums are combined once per unit.  P (bf16) is written over the S columns its own thread loaded:
-// keys [0,64) -> columns [0,32), keys [64,128) -> columns [64,96); it reaches the MMA warp in RS_CH chunks per half.
-// TMEM columns: S_t/P_t at t*128, O_t at 256 + t*128.
-#ifdef G2_ATTN_TRACE
-// debug build only (tools/attn_trace.py): clock64 stamps of CTA 0, [role 0..2][block 0..31][tile 0..1][event 0..7]
-__device__ long long g_attn_trace[3 * 32 * 2 * 8];
-#define G2_TR(role, blk, t, ev) \
-  do { if (blockIdx.x == 0 && (blk) < 32) g_attn_trace[(((role) * 32 + (blk)) * 2 + (t)) * 8 + (ev)] = clock64(); } while (0)
-#else
-#define G2_TR(role, blk, t, ev) do { } while (0)
-#endif
-
-template <int D>
-struct AttnSplitCfg {
-  static constexpr int kTileBytes = ATT_BM * D * 2;
-  static constexpr int kStages = (D == 128) ? 2 : 4;
-  static constexpr int kXchgBytes = 2 * 2 * ATT_BM * 4 + 2 * 2 * ATT_BM * 4;  // block maxima (double-buffered), row sums
-  static constexpr int kSmem = 2 * kTileBytes + kStages * 2 * kTileBytes + 1024 + 512 + kXchgBytes;
-};
-
-// P = 2^(s*scale - m) of this thread's 64 keys, handed to the MMA warp 64 / RS_CH keys at a time.
-template <int RS_CH, class Hook>
-__device__ __forceinline__ void softmax_half_block(const uint32_t (&sv)[64], float m_used, float scale_log2, uint64_t& sum2,
-                                                   uint32_t tP_w, uint64_t* p_full_h, int lane, Hook&& before_last_chunk) {
-  const uint64_t neg_m2 = pack2(-m_used, -m_used);
-  const uint64_t scale2 = pack2(scale_log2, scale_log2);
-  constexpr int CW = 64 / RS_CH;  // keys per chunk
-#pragma unroll
-  for (int c = 0; c < RS_CH; ++c) {
-    if (c == RS_CH - 1) before_last_chunk();
-    uint32_t pk[CW / 2];
-#pragma unroll
-    for (int i = 0; i < CW; i += 2) {
-      const uint64_t x2 = fma2(pack2(__uint_as_float(sv[c * CW + i]), __uint_as_float(sv[c * CW + i + 1])), scale2, neg_m2);
-      float x0, x1;
-      unpack2(x2, x0, x1);
-      const float p0 = ex2_approx(x0), p1 = ex2_approx(x1);
-      sum2 = add2(sum2, pack2(p0, p1));
-      pk[i >> 1] = pack_bf16x2(p0, p1);
-    }
-    if (c > 0) {  // the store of chunk c-1 has had a chunk of exp2 to land
-      tmem_wait_st();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&p_full_h[c - 1]);
-    }
-    if constexpr (CW == 16) tmem_st8(tP_w + c * 8, pk);
-    else tmem_st16(tP_w + c * 16, pk);
-  }
-  tmem_wait_st();
-  tc_fence_before();
-  __syncwarp();
-  if (lane == 0) mbar_arrive(&p_full_h[RS_CH - 1]);
-}
-
-template <int D, int RS_CH>   // RS_CH: P chunks per half block (64 / RS_CH keys each)
-__global__ void __launch_bounds__(ATT_THREADS, 1)
-attention_rowsplit_kernel(const __grid_constant__ AttnKParams p) {
-  using Cfg = AttnSplitCfg<D>;
-  constexpr int RS_NCH = 2 * RS_CH;        // P chunks per tile and block
-  constexpr int KSTEPS_QK = D / 16;
-  constexpr int BOX_BYTES = ATT_BM * 128;
-  constexpr int KS = Cfg::kStages;
-  constexpr int DH = D / 2;  // output columns per thread
-
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t raw_addr = smem_u32(smem_raw);
-  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
-  uint8_t* sQ = smem;
-  uint8_t* sKV = smem + 2 * Cfg::kTileBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sKV + KS * 2 * Cfg::kTileBytes);
-  uint64_t* q_full = bars;
-  uint64_t* q_empty = bars + 1;
-  uint64_t* k_full = bars + 2;
-  uint64_t* v_full = k_full + KS;
-  uint64_t* k_empty = v_full + KS;
-  uint64_t* v_empty = k_empty + KS;
-  uint64_t* s_full = v_empty + KS;                 // [2]
-  uint64_t* p_full = s_full + 2;                   // [2][RS_NCH]
-  uint64_t* o_done = p_full + 2 * RS_NCH;          // [2]
-  uint64_t* o_free = o_done + 2;                   // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_free + 2);
-  float* xmax = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 512);  // [2 buffers][2 halves][128 rows]
-  float* xsum = xmax + 2 * 2 * ATT_BM;                                              // [2 tiles][2 halves][128 rows]
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const int total_units = p.n_items * p.n_heads;
-
-  if (warp == 0 && elect_one()) {
-    tma_prefetch_desc(&p.tmQ);
-    tma_prefetch_desc(&p.tmK);
-    tma_prefetch_desc(&p.tmV);
-  }
-  if (warp == 1) {
-    if (elect_one()) {
-      mbar_init(q_full, 1);
-      mbar_init(q_empty, 1);
-      for (int s = 0; s < KS; ++s) {
-        mbar_init(&k_full[s], 1);
-        mbar_init(&v_full[s], 1);
-        mbar_init(&k_empty[s], 1);
-        mbar_init(&v_empty[s], 1);
-      }
-      for (int t = 0; t < 2; ++t) {
-        mbar_init(&s_full[t], 1);
-        for (int c = 0; c < RS_NCH; ++c) mbar_init(&p_full[t * RS_NCH + c], 4);  // the four warps of one half
-        mbar_init(&o_done[t], 1);
-        mbar_init(&o_free[t], 8);
-      }
-      fence_barrier_init();
-    }
-    __syncwarp();
-    tmem_alloc<512>(tmem_slot);
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  auto tS = [&](int t) { return tmem_base + static_cast<uint32_t>(t) * 128u; };
-  auto tO = [&](int t) { return tmem_base + 256u + static_cast<uint32_t>(t) * 128u; };
-
-  // register budget: every warp starts with 168 (launch bounds); the four control warps give back 4 x 32 x (168 - 96) =
-  // 9216 registers, the eight softmax warps take 8 x 32 x (200 - 168) = 8192 of them (a request the pool cannot cover
-  // blocks in setmaxnreg.inc forever)
-  if (warp == 0) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
-    if (elect_one()) attn_tma_producer<D, KS>(p, sQ, sKV, q_full, q_empty, k_full, v_full, k_empty, v_empty);
-  } else if (warp == 1) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
-    // ------------------------------------ MMA issuer: PV0_j, QK0_{j+1}, PV1_j, QK1_{j+1} --------------------------
-    if (elect_one()) {
-      constexpr uint32_t idesc_qk = umma_idesc_bf16(ATT_BM, ATT_BN, 0, 0);
-      constexpr uint32_t idesc_pv = umma_idesc_bf16(ATT_BM, D, 0, 1);  // B (= V) is MN-major
-      const uint32_t q_addr = smem_u32(sQ);
-      const uint32_t kv_addr = smem_u32(sKV);
-
-      auto issue_qk = [&](int t, int s) {
-        const uint32_t qa = q_addr + t * Cfg::kTileBytes;
-        const uint32_t ka = kv_addr + s * 2 * Cfg::kTileBytes;
-#pragma unroll
-        for (int k = 0; k < KSTEPS_QK; ++k) {
-          const uint32_t off = (k >> 2) * BOX_BYTES + (k & 3) * 32;
-          umma_ss(tS(t), umma_desc_kmajor(qa + off), umma_desc_kmajor(ka + off), idesc_qk, k != 0);
-        }
-        umma_commit(&s_full[t]);
-      };
-      // O_t += P_t V.  The two halves of the row publish their chunks at the same pace, so the chunks are consumed
-      // alternately: (half 0, chunk 0), (half 1, chunk 0), (half 0, chunk 1), ...
-      auto issue_pv = [&](int t, int s, uint32_t par, bool first_block, [[maybe_unused]] uint32_t gblk) {
-        const uint32_t va = kv_addr + s * 2 * Cfg::kTileBytes + Cfg::kTileBytes;
-        constexpr int KPC = (64 / RS_CH) / 16;  // 16-key MMA steps per chunk
-        // opaque copy: otherwise ptxas precomputes the TMEM address of every chunk of both tiles outside the unit loop and
-        // spills them (one local-memory load per chunk on the issuer's critical path)
-        uint32_t tbase = tmem_base;
-        asm volatile("" : "+r"(tbase));
-        const uint32_t tS_t = tbase + static_cast<uint32_t>(t) * 128u, tO_t = tbase + 256u + static_cast<uint32_t>(t) * 128u;
-        G2_TR(2, gblk, t, 0);
-#pragma unroll
-        for (int c = 0; c < RS_CH; ++c) {
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            mbar_wait(&p_full[t * RS_NCH + h * RS_CH + c], par);
-            tc_fence_after();
-            if (c == 0 && h == 0) G2_TR(2, gblk, t, 1);
-            if (c == RS_CH - 1 && h == 1) G2_TR(2, gblk, t, 2);
-#pragma unroll
-            for (int kk = 0; kk < KPC; ++kk) {
-              const int k = h * 4 + c * KPC + kk;  // 16-key step inside the block
-              // P of keys [64h, 64h+64) sits in bf16 pairs at columns 64h + [0,32)
-              umma_ts(tO_t, tS_t + h * 64 + (c * KPC + kk) * 8, umma_desc_mnmajor(va + k * 2048, BOX_BYTES), idesc_pv,
-                      !(first_block && c == 0 && h == 0 && kk == 0));
-            }
-          }
-        }
-        umma_commit(&o_done[t]);
-        G2_TR(2, gblk, t, 3);
-      };
-
-      uint32_t g = 0, n = 0;
-      for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
-        const AttnUnit a = decode_unit(p, u);
-        if (a.nblk == 0) continue;
-        mbar_wait(q_full, n & 1);
-        mbar_wait(&k_full[g % KS], (g / KS) & 1);
-        tc_fence_after();
-        issue_qk(0, g % KS);
-        issue_qk(1, g % KS);
-        umma_commit(&k_empty[g % KS]);
-        if (a.nblk == 1) umma_commit(q_empty);
-        for (int j = 0; j < a.nblk; ++j, ++g) {
-          const int s = g % KS;
-          const uint32_t par = (g / KS) & 1;
-          const int s1 = (g + 1) % KS;
-          const uint32_t par1 = ((g + 1) / KS) & 1;
-          const bool more = j + 1 < a.nblk;
-          mbar_wait(&v_full[s], par);
-          if (j == 0 && n > 0) {  // the first PV overwrites O_t: the previous unit's epilogue must have read it
-            mbar_wait(&o_free[0], (n - 1) & 1);
-            tc_fence_after();
-          }
-          issue_pv(0, s, g & 1, j == 0, g);
-          if (more) {
-            mbar_wait(&k_full[s1], par1);
-            tc_fence_after();
-            issue_qk(0, s1);
-            G2_TR(2, g, 0, 4);
-          }
-          if (j == 0 && n > 0) {
-            mbar_wait(&o_free[1], (n - 1) & 1);
-            tc_fence_after();
-          }
-          issue_pv(1, s, g & 1, j == 0, g);
-          umma_commit(&v_empty[s]);
-          if (more) {
-            issue_qk(1, s1);
-            G2_TR(2, g, 1, 4);
-            umma_commit(&k_empty[s1]);
-            if (j + 2 == a.nblk) umma_commit(q_empty);
-          }
-        }
-        ++n;
-      }
-    }
-  } else if (warp < 4) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
-  } else {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");
-    // ------------------------------------ softmax / correction / epilogue (two threads per row) -------------------
-    const int hf = (warp - 4) >> 2;             // which 64 keys of every block / which half of the output columns
-    const int sub = warp & 3;                   // TMEM sub-partition
-    const int r_in_tile = sub * 32 + lane;
-    const int pair_bar = 1 + sub;               // named barrier of the warp pair (4 + sub, 8 + sub)
-    const uint32_t lane_off = static_cast<uint32_t>(sub * 32) << 16;
-    float* xmax_mine = xmax + hf * ATT_BM + r_in_tile;
-    const float* xmax_peer = xmax + (hf ^ 1) * ATT_BM + r_in_tile;
-    uint32_t g = 0, xph = 0;
-    [[maybe_unused]] const bool tr_on = sub == 0 && lane == 0;
-
-    for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
-      const AttnUnit a = decode_unit(p, u);
-      const int row0 = a.q_tile_begin + r_in_tile;  // global query row in tile 0; tile 1: + ATT_BM
-      if (a.nblk == 0) {
-#pragma unroll
-        for (int t = 0; t < 2; ++t) {
-          const int row = row0 + t * ATT_BM;
-          if (row < a.q_seg_end) {  // no visible keys at all: flash-attn writes zeros
-            uint4* dst = reinterpret_cast<uint4*>(p.out + (long long)row * p.ldo + a.head * p.out_head_cols + hf * DH);
-#pragma unroll
-            for (int q = 0; q < DH / 8; ++q)
-              if (hf * DH + q * 8 < p.out_head_cols) dst[q] = make_uint4(0, 0, 0, 0);
-            if (p.lse != nullptr && hf == 0) p.lse[(long long)row * p.n_heads + a.head] = -INFINITY;
-          }
-        }
-        continue;
-      }
-      float m_used0 = 0.f, m_used1 = 0.f, l_run0 = 0.f, l_run1 = 0.f;
-      int limit0 = a.len_k, limit1 = a.len_k;  // number of keys the row of tile 0 / 1 may see
-      if (a.causal) {
-        limit0 = max(0, min(a.len_k, (row0 - a.q_seg_begin) + (a.len_k - a.len_q) + 1));
-        limit1 = max(0, min(a.len_k, (row0 + ATT_BM - a.q_seg_begin) + (a.len_k - a.len_q) + 1));
-      }
-
-      // S_t of one block -> registers (this thread's 64 keys); the wait is the caller's
-      auto load_s = [&](int t, uint32_t (&sv)[64]) {
-        const uint32_t tS_w = tS(t) + lane_off + hf * 64;
-        tmem_ld32(tS_w, *reinterpret_cast<uint32_t(*)[32]>(&sv[0]));
-        tmem_ld32(tS_w + 32, *reinterpret_cast<uint32_t(*)[32]>(&sv[32]));
-      };
-      // mask, maximum of this thread's 64 keys, then the two threads of the row agree on the block maximum through
-      // shared memory (double-buffered slot: a thread may be one exchange ahead of its partner)
-      auto block_max = [&](uint32_t (&sv)[64], int j, int limit) -> float {
-        const int col_base = j * ATT_BN + hf * 64;
-        if (col_base + 64 > limit) {
-#pragma unroll
-          for (int i = 0; i < 64; ++i)
-            if (col_base + i >= limit) sv[i] = 0xff800000u;  // -inf
-        }
-        float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
-#pragma unroll
-        for (int i = 0; i < 64; i += 4) {
-          mx0 = fmaxf(mx0, __uint_as_float(sv[i]));
-          mx1 = fmaxf(mx1, __uint_as_float(sv[i + 1]));
-          mx2 = fmaxf(mx2, __uint_as_float(sv[i + 2]));
-          mx3 = fmaxf(mx3, __uint_as_float(sv[i + 3]));
-        }
-        const float m_half = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
-        xmax_mine[(xph & 1) * 2 * ATT_BM] = m_half;
-        bar_sync_named(pair_bar, 64);
-        const float m = fmaxf(m_half, xmax_peer[(xph & 1) * 2 * ATT_BM]) * p.scale_log2;  // may be -inf
-        ++xph;
-        return m;
-      };
-      // One phase = the softmax of one (block, tile): `sv` and its maximum `m_blk` are in registers.  While the last
-      // chunk of exp2 runs, the NEXT phase's S (the other tile: its QK^T was issued a phase ago) is loaded into
-      // `sv_next`, so the TMEM read latency (~250 clocks per tile) is off the chain; its maximum follows at the end.
-      auto phase = [&](int t, int j, uint32_t (&sv)[64], float& m_blk, float& m_used, float& l_run, bool has_next,
-                       int t_next, uint32_t par_next, int j_next, int limit_next, uint32_t (&sv_next)[64]) {
-        if (j == 0) {
-          m_used = (m_blk == -INFINITY) ? 0.f : m_blk;
-        } else {
-          const bool need = m_blk > m_used + ATT_RESCALE_TAU;
-          if (__any_sync(0xffffffffu, need)) {
-            // rare path (identical decision in both warps of the pair: same rows, same maxima): this thread scales
-            // its half of the O columns; no P chunk of this block may be published before both halves are done
-            mbar_wait(&o_done[t], (g - 1) & 1);
-            tc_fence_after();
-            const float m_new = need ? m_blk : m_used;
-            const float alpha = ex2_approx(m_used - m_new);
-            const uint32_t tO_w = tO(t) + lane_off + hf * DH;
-#pragma unroll 1
-            for (int c = 0; c < DH / 32; ++c) {
-              uint32_t ov[32];
-              tmem_ld32(tO_w + c * 32, ov);
-              tmem_wait_ld();
-#pragma unroll
-              for (int i = 0; i < 32; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * alpha);
-              tmem_st32(tO_w + c * 32, ov);
-            }
-            tmem_wait_st();
-            tc_fence_before();
-            bar_sync_named(pair_bar, 64);
-            tc_fence_after();
-            l_run *= alpha;
-            m_used = m_new;
-          }
-        }
-        if (tr_on) G2_TR(hf, g, t, 1);
-        bool prefetched = false;
-        auto prefetch = [&]() {  // non-blocking: only if S of the next phase is already there (warp-uniform decision)
-          if (has_next && __all_sync(0xffffffffu, mbar_test_wait(&s_full[t_next], par_next))) {
-            tc_fence_after();
-            load_s(t_next, sv_next);
-            prefetched = true;
-          }
-        };
-        uint64_t sum2 = pack2(0.f, 0.f);
-        softmax_half_block<RS_CH>(sv, m_used, p.scale_log2, sum2, tS(t) + lane_off + hf * 64,
-                                  &p_full[t * RS_NCH + hf * RS_CH], lane, prefetch);
-        float sum0, sum1;
-        unpack2(sum2, sum0, sum1);
-        l_run += sum0 + sum1;
-        if (tr_on) G2_TR(hf, g, t, 2);
-        if (has_next) {
-          if (!prefetched) {
-            mbar_wait(&s_full[t_next], par_next);
-            tc_fence_after();
-            load_s(t_next, sv_next);
-          }
-          tmem_wait_ld();
-          if (tr_on) G2_TR(hf, g, t, 3);
-          m_blk = block_max(sv_next, j_next, limit_next);
-          if (tr_on) G2_TR(hf, g, t, 4);
-        }
-      };
-
-      uint32_t sva[64], svb[64];
-      mbar_wait(&s_full[0], g & 1);
-      tc_fence_after();
-      load_s(0, sva);
-      tmem_wait_ld();
-      float m_blk = block_max(sva, 0, limit0);
-      for (int j = 0; j < a.nblk; ++j, ++g) {
-        if (tr_on) G2_TR(hf, g, 0, 0);
-        phase(0, j, sva, m_blk, m_used0, l_run0, true, 1, g & 1, j, limit1, svb);
-        if (tr_on) G2_TR(hf, g, 1, 0);
-        // no prefetch across units: the next unit's QK^T is issued behind this unit's last PV, which needs this phase's P
-        phase(1, j, svb, m_blk, m_used1, l_run1, j + 1 < a.nblk, 0, (g + 1) & 1, j + 1, limit0, sva);
-      }
-
-      // epilogue: the two partial row sums meet in shared memory; each thread normalises and stores its half of the row
-      xsum[(0 * 2 + hf) * ATT_BM + r_in_tile] = l_run0;
-      xsum[(1 * 2 + hf) * ATT_BM + r_in_tile] = l_run1;
-      bar_sync_named(pair_bar, 64);
-#pragma unroll
-      for (int t = 0; t < 2; ++t) {
-        const int row = row0 + t * ATT_BM;
-        const float l_mine = t == 0 ? l_run0 : l_run1;
-        const float l_peer = xsum[(t * 2 + (hf ^ 1)) * ATT_BM + r_in_tile];
-        const float l_tot = hf == 0 ? l_mine + l_peer : l_peer + l_mine;  // same operand order in both threads
-        const float m_fin = t == 0 ? m_used0 : m_used1;
-        const uint32_t tO_w = tO(t) + lane_off + hf * DH;
-        mbar_wait(&o_done[t], (g - 1) & 1);
-        tc_fence_after();
-        uint32_t ov[DH];
-#pragma unroll
-        for (int c = 0; c < DH / 32; ++c) tmem_ld32(tO_w + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&ov[c * 32]));
-        tmem_wait_ld();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&o_free[t]);
-        if (row < a.q_seg_end) {
-          if (p.lse != nullptr && hf == 0)
-            p.lse[(long long)row * p.n_heads + a.head] =
-                l_tot > 0.f ? (m_fin + log2f(l_tot)) * 0.69314718055994531f : -INFINITY;
-          const float inv_l = l_tot > 0.f ? 1.0f / l_tot : 0.f;
-          uint4* dst = reinterpret_cast<uint4*>(p.out + (long long)row * p.ldo + a.head * p.out_head_cols + hf * DH);
-#pragma unroll
-          for (int q = 0; q < DH / 8; ++q) {
-            if (hf * DH + q * 8 < p.out_head_cols) dst[q] = make_uint4(
-                pack_bf16x2(__uint_as_float(ov[8 * q]) * inv_l, __uint_as_float(ov[8 * q + 1]) * inv_l),
-                pack_bf16x2(__uint_as_float(ov[8 * q + 2]) * inv_l, __uint_as_float(ov[8 * q + 3]) * inv_l),
-                pack_bf16x2(__uint_as_float(ov[8 * q + 4]) * inv_l, __uint_as_float(ov[8 * q + 5]) * inv_l),
-                pack_bf16x2(__uint_as_float(ov[8 * q + 6]) * inv_l, __uint_as_float(ov[8 * q + 7]) * inv_l));
-          }
-        }
-      }
-    }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    tc_fence_after();
-    tmem_dealloc<512>(tmem_base);
-  }
-}
-
 // out = softmax-weighted combination of two partial attention results over disjoint key sets.
 // One thread per 8 output columns (16-byte loads/stores); memory-bound: 3 x rows x heads x cols x 2 B.
 __global__ void attention_merge_kernel(const __nv_bfloat16* __restrict__ oa, long long lda, const float* __restrict__ lse_a,
@@ -1087,26 +661,14 @@ __global__ void attention_merge_kernel(const __nv_bfloat16* __restrict__ oa, lon
   }
 }
 
-template <int D, int POLY, bool OPAQ = false>
+template <int D, int POLY>
 static int launch_attention(const AttnKParams& kp, int max_ctas, cudaStream_t stream) {
-  if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(attention_tcgen05_kernel<D, POLY, OPAQ>), AttnCfg<D>::kSmem)) return rc;
+  if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(attention_tcgen05_kernel<D, POLY>), AttnCfg<D>::kSmem)) return rc;
   const long long units = (long long)kp.n_items * kp.n_heads;
   long long cap = num_sms();                                                   // one persistent CTA per SM
   if (max_ctas > 0 && max_ctas < cap) cap = max_ctas;
   const unsigned grid = (unsigned)(units < cap ? units : cap);
-  attention_tcgen05_kernel<D, POLY, OPAQ><<<grid, ATT_THREADS, AttnCfg<D>::kSmem, stream>>>(kp);
-  G2_CUDA_OK(cudaGetLastError());
-  return G2VLM_OK;
-}
-
-template <int D, int CH>
-static int launch_attention_rowsplit(const AttnKParams& kp, int max_ctas, cudaStream_t stream) {
-  if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(attention_rowsplit_kernel<D, CH>), AttnSplitCfg<D>::kSmem)) return rc;
-  const long long units = (long long)kp.n_items * kp.n_heads;
-  long long cap = num_sms();
-  if (max_ctas > 0 && max_ctas < cap) cap = max_ctas;
-  const unsigned grid = (unsigned)(units < cap ? units : cap);
-  attention_rowsplit_kernel<D, CH><<<grid, ATT_THREADS, AttnSplitCfg<D>::kSmem, stream>>>(kp);
+  attention_tcgen05_kernel<D, POLY><<<grid, ATT_THREADS, AttnCfg<D>::kSmem, stream>>>(kp);
   G2_CUDA_OK(cudaGetLastError());
   return G2VLM_OK;
 }
@@ -1154,18 +716,7 @@ extern "C" int g2vlm_attention(const g2vlm_attn_args* a, void* stream_) {
   kp.out_head_cols = a->out_head_cols ? a->out_head_cols : D;
   kp.lse = a->lse_out;
   G2_REQUIRE(a->max_ctas >= 0, "attention: negative max_ctas");
-  // G2VLM_ATTN_ROWSPLIT: bit 0 -> head_dim 128, bit 1 -> head_dim 64 on the two-threads-per-row kernel; bit 2: P in
-  // 2 chunks of 32 keys per half block instead of 4 of 16
-  int rowsplit = ATT_ROWSPLIT_DEFAULT;
-  if (const char* e = getenv("G2VLM_ATTN_ROWSPLIT")) rowsplit = atoi(e);
-  if (D == 128) {
-    if ((rowsplit & 5) == 5) return launch_attention_rowsplit<128, 2>(kp, a->max_ctas, stream);
-    if (rowsplit & 1) return launch_attention_rowsplit<128, 4>(kp, a->max_ctas, stream);
-    if (rowsplit & 8) return launch_attention<128, 0, true>(kp, a->max_ctas, stream);
-    return launch_attention<128, 0>(kp, a->max_ctas, stream);
-  }
-  if ((rowsplit & 6) == 6) return launch_attention_rowsplit<64, 2>(kp, a->max_ctas, stream);
-  if (rowsplit & 2) return launch_attention_rowsplit<64, 4>(kp, a->max_ctas, stream);
+  if (D == 128) return launch_attention<128, 0>(kp, a->max_ctas, stream);
   // head_dim 64 needs 1024 MUFU clocks per 128 x 128 tile against 512 tensor clocks, so part of the exp2 was moved to
   // the FMA pipe (softmax_block<POLY>).  Measured on the DINO shape (profiles/r02_attention64_poly.txt): 224.6 us with
   // 0/8, 247.7 / 239.3 / 247.6 / 312.6 us with 1..4 of 8 pairs offloaded — the softmax warps are bound by their own
@@ -1176,12 +727,6 @@ extern "C" int g2vlm_attention(const g2vlm_attn_args* a, void* stream_) {
   if (poly == 2) return launch_attention<64, 2>(kp, a->max_ctas, stream);
   return launch_attention<64, 0>(kp, a->max_ctas, stream);
 }
-
-#ifdef G2_ATTN_TRACE
-extern "C" int g2vlm_debug_attn_trace(long long* host_out) {
-  return cudaMemcpyFromSymbol(host_out, g2::g_attn_trace, sizeof(g2::g_attn_trace)) == cudaSuccess ? 0 : 1;
-}
-#endif
 
 extern "C" int g2vlm_attention_merge(const void* o_a, int64_t lda, const float* lse_a, const void* o_b, int64_t ldb,
                                      const float* lse_b, void* out, int64_t ldo, int64_t rows, int32_t heads,
