@@ -78,6 +78,15 @@ __device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
   return d;
 }
 
+#ifdef G2_ATTN_TRACE
+// debug build only (tools/attn_trace.py): clock64 stamps of CTA 0, [role 0..2][block 0..31][tile 0..1][event 0..15]
+__device__ long long g_attn_trace[3 * 32 * 2 * 16];
+#define G2_TR(role, blk, t, ev) \
+  do { if (blockIdx.x == 0 && (blk) < 32) g_attn_trace[(((role) * 32 + (blk)) * 2 + (t)) * 16 + (ev)] = clock64(); } while (0)
+#else
+#define G2_TR(role, blk, t, ev) do { } while (0)
+#endif
+
 // One (work item, head) unit of a persistent CTA, decoded identically by every role.
 struct AttnUnit {
   int q_tile_begin, q_seg_begin, q_seg_end, k_begin, len_q, len_k, head, kv_head, nblk;
@@ -92,7 +101,8 @@ struct AttnUnit {
 // measured: tools/micro/mufu_bench.cu) against 512 tensor clocks, so the kernel is MUFU-bound and the FMA pipe is idle.
 template <int POLY>
 __device__ __forceinline__ void softmax_block(const uint32_t (&sv)[128], float m_used, float scale_log2, uint64_t& sum2,
-                                              uint32_t tP_w, uint64_t* p_full_t, int lane) {
+                                              uint32_t tP_w, uint64_t* p_full_t, int lane, [[maybe_unused]] bool tr_on = false,
+                                              [[maybe_unused]] int tr_t = 0, [[maybe_unused]] uint32_t tr_g = 0) {
   const uint64_t neg_m2 = pack2(-m_used, -m_used);
   const uint64_t scale2 = pack2(scale_log2, scale_log2);
   [[maybe_unused]] const uint64_t magic2 = pack2(12582912.f, 12582912.f), nmagic2 = pack2(-12582912.f, -12582912.f);
@@ -127,6 +137,7 @@ __device__ __forceinline__ void softmax_block(const uint32_t (&sv)[128], float m
       sum2 = add2(sum2, pack2(p0, p1));
       pk[i >> 1] = pack_bf16x2(p0, p1);
     }
+    if (tr_on) G2_TR(tr_t, tr_g, tr_t, 5 + 2 * c);       // exp2 of chunk c issued
     // the store of chunk c-1 has had a whole chunk of exp2 to land: publishing it here keeps the
     // tcgen05.wait::st latency off the critical path
     if (c > 0) {
@@ -134,6 +145,7 @@ __device__ __forceinline__ void softmax_block(const uint32_t (&sv)[128], float m
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full_t[c - 1]);
+      if (tr_on) G2_TR(tr_t, tr_g, tr_t, 4 + 2 * c);     // chunk c-1 handed over
     }
     if constexpr (CW == 32) tmem_st16(tP_w + c * 16, pk);
     else tmem_st32(tP_w + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&pk[0]));
@@ -319,8 +331,9 @@ attention_tcgen05_kernel(const __grid_constant__ AttnKParams p) {
         umma_commit(&s_full[t]);
       };
       // O_t += P_t V, issued chunk by chunk as the softmax warps publish 32 keys of P at a time
-      auto issue_pv = [&](int t, int s, uint32_t par, bool first_block) {
+      auto issue_pv = [&](int t, int s, uint32_t par, bool first_block, [[maybe_unused]] uint32_t gblk) {
         const uint32_t va = kv_addr + s * 2 * Cfg::kTileBytes + Cfg::kTileBytes;
+        G2_TR(2, gblk, t, 0);
         // opaque copy: otherwise ptxas precomputes the TMEM address of every chunk of both tiles outside the unit loop and
         // spills them (two local-memory loads per chunk on the issuer's critical path; profiles/r02_attention_rowsplit.txt)
         uint32_t tbase = tmem_base;
@@ -330,6 +343,8 @@ attention_tcgen05_kernel(const __grid_constant__ AttnKParams p) {
         for (int c = 0; c < ATT_PCHUNKS; ++c) {
           mbar_wait(&p_full[t * ATT_PCHUNKS + c], par);
           tc_fence_after();
+          if (c == 0) G2_TR(2, gblk, t, 1);
+          if (c == ATT_PCHUNKS - 1) G2_TR(2, gblk, t, 2);
 #pragma unroll
           for (int kk = 0; kk < KSTEPS_PV / ATT_PCHUNKS; ++kk) {
             const int k = c * (KSTEPS_PV / ATT_PCHUNKS) + kk;
@@ -339,6 +354,7 @@ attention_tcgen05_kernel(const __grid_constant__ AttnKParams p) {
           }
         }
         umma_commit(&o_done[t]);
+        G2_TR(2, gblk, t, 3);
       };
 
       uint32_t g = 0, n = 0;
@@ -364,20 +380,22 @@ attention_tcgen05_kernel(const __grid_constant__ AttnKParams p) {
             mbar_wait(&o_free[0], (n - 1) & 1);
             tc_fence_after();
           }
-          issue_pv(0, s, g & 1, j == 0);
+          issue_pv(0, s, g & 1, j == 0, g);
           if (more) {
             mbar_wait(&k_full[s1], par1);
             tc_fence_after();
             issue_qk(0, s1);
+            G2_TR(2, g, 0, 4);
           }
           if (j == 0 && n > 0) {
             mbar_wait(&o_free[1], (n - 1) & 1);
             tc_fence_after();
           }
-          issue_pv(1, s, g & 1, j == 0);
+          issue_pv(1, s, g & 1, j == 0, g);
           umma_commit(&v_empty[s]);
           if (more) {
             issue_qk(1, s1);
+            G2_TR(2, g, 1, 4);
             umma_commit(&k_empty[s1]);
             if (j + 2 == a.nblk) umma_commit(q_empty);  // that was the unit's last QK^T
           }
@@ -485,6 +503,7 @@ attention_tcgen05_kernel(const __grid_constant__ AttnKParams p) {
     const uint32_t tP_w = tP(t) + lane_off;
     const uint32_t tO_w = tO(t) + lane_off;
     uint32_t g = 0, n = 0;
+    [[maybe_unused]] const bool tr_on = sub == 0 && lane == 0;
 
     for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
       const AttnUnit a = decode(u);
@@ -508,14 +527,17 @@ attention_tcgen05_kernel(const __grid_constant__ AttnKParams p) {
       float l_run = 0.f;
 
       for (int j = 0; j < a.nblk; ++j, ++g) {
+        if (tr_on) G2_TR(t, g, t, 0);
         mbar_wait(&s_full[t], g & 1);
         tc_fence_after();
+        if (tr_on) G2_TR(t, g, t, 1);
         // all four 32-column loads in flight at once: taking the row maximum of one quarter while the next streams in
         // (a wait::ld per quarter) measured 3-9 % slower on every shape (profiles/r02_attention_rowsplit.txt)
         uint32_t sv[128];
 #pragma unroll
         for (int c = 0; c < 4; ++c) tmem_ld32(tS_w + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&sv[c * 32]));
         tmem_wait_ld();
+        if (tr_on) G2_TR(t, g, t, 2);
         if constexpr (kSepP) {
           tc_fence_before();
           __syncwarp();
@@ -571,15 +593,17 @@ attention_tcgen05_kernel(const __grid_constant__ AttnKParams p) {
             tc_fence_after();
           }
         }
+        if (tr_on) G2_TR(t, g, t, 3);
         uint64_t sum2 = pack2(0.f, 0.f);
         // fully unmasked block of a non-causal item: part of the exp2 may run on the FMA pipe (never for a block
         // that holds a masked -inf score: the polynomial would turn it into 2^-125 instead of an exact 0)
         const bool poly_ok = POLY > 0 && !a.causal && col_base + ATT_BN <= a.len_k;
         if (poly_ok) softmax_block<POLY>(sv, m_used, p.scale_log2, sum2, tP_w, &p_full[t * ATT_PCHUNKS], lane);
-        else softmax_block<0>(sv, m_used, p.scale_log2, sum2, tP_w, &p_full[t * ATT_PCHUNKS], lane);
+        else softmax_block<0>(sv, m_used, p.scale_log2, sum2, tP_w, &p_full[t * ATT_PCHUNKS], lane, tr_on, t, g);
         float sum0, sum1;
         unpack2(sum2, sum0, sum1);
         l_run += sum0 + sum1;
+        if (tr_on) G2_TR(t, g, t, 4);
       }
 
       // epilogue: O_t leaves TMEM in one go (so the next unit's first PV may overwrite it), then
@@ -727,6 +751,12 @@ extern "C" int g2vlm_attention(const g2vlm_attn_args* a, void* stream_) {
   if (poly == 2) return launch_attention<64, 2>(kp, a->max_ctas, stream);
   return launch_attention<64, 0>(kp, a->max_ctas, stream);
 }
+
+#ifdef G2_ATTN_TRACE
+extern "C" int g2vlm_debug_attn_trace(long long* host_out) {
+  return cudaMemcpyFromSymbol(host_out, g2::g_attn_trace, sizeof(g2::g_attn_trace)) == cudaSuccess ? 0 : 1;
+}
+#endif
 
 extern "C" int g2vlm_attention_merge(const void* o_a, int64_t lda, const float* lse_a, const void* o_b, int64_t ldb,
                                      const float* lse_b, void* out, int64_t ldo, int64_t rows, int32_t heads,

@@ -1,0 +1,51 @@
+"""Clock-stamped timeline of attention_tcgen05_kernel<128> on CTA 0 (steady-state key blocks of the first unit, MoT shape of
+config 2).  Needs a debug build of the library with -DG2_ATTN_TRACE (the stamps cost ~10 %, product builds carry none):
+    python tools/attn_trace.py --build          # compiles g2vlm_b200/libg2vlm_b200_trace.so next to the product library
+    G2VLM_B200_LIB=g2vlm_b200/libg2vlm_b200_trace.so python tools/attn_trace.py
+Events per (block, tile) — softmax warp (sub-partition 0, lane 0): wait_s (phase begins), s_full (S_t complete), ld_done
+(S in registers), max_done (row maximum / rescale decision taken), published (last P chunk handed over), exp<c> (exp2 of
+chunk c done), pub<c> (chunk c handed to the MMA warp);
+MMA issuer thread: pv_begin, pv_chunk0 (first P chunk seen), pv_last (last P chunk seen), pv_issued, qk_issued (next block's QK^T)."""
+import ctypes, math, os, subprocess, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+if "--build" in sys.argv:
+    from g2vlm_b200 import _lib
+    _lib.build()
+    obj = "/tmp/attention_trace.o"
+    subprocess.check_call(["nvcc", *_lib.NVCC_FLAGS, "-DG2_ATTN_TRACE", "-c", "-o", obj, str(_lib.CSRC / "attention.cu")])
+    others = [str(o) for o in sorted(_lib.OBJ_DIR.glob("*.o")) if o.name != "attention.o"]
+    out = str(_lib.PKG_DIR / "libg2vlm_b200_trace.so")
+    subprocess.check_call(["nvcc", "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", out, obj, *others])
+    print("built", out)
+    sys.exit(0)
+
+import torch
+from g2vlm_b200 import ops, _lib
+
+T, K0 = 16 * 1371, 7
+g = torch.Generator().manual_seed(0)
+qkv = torch.randn(T + K0, 2048, generator=g).to(torch.bfloat16).cuda()
+out = torch.zeros(T, 1536, device="cuda", dtype=torch.bfloat16)
+work = ops.attention_work_table([0, T], [0, T + K0]).cuda()
+for _ in range(2):
+    ops.attention(qkv[:T, :1536], qkv[:, 1536:1792], qkv[:, 1792:], out, work, num_q_heads=12, num_kv_heads=2,
+                  head_dim=128, scale=1 / math.sqrt(128))
+torch.cuda.synchronize()
+buf = (ctypes.c_longlong * (3 * 32 * 2 * 16))()
+lib = _lib.load()
+if not hasattr(lib, "g2vlm_debug_attn_trace"):
+    sys.exit("this library has no trace points: build with --build and point G2VLM_B200_LIB at the trace library")
+assert lib.g2vlm_debug_attn_trace(buf) == 0
+tr = torch.tensor(list(buf)).view(3, 32, 2, 16)
+t0 = int(tr[0, 8, 0, 0])
+sm = ["wait_s", "s_full", "ld_done", "max_done", "published", "exp0", "pub0", "exp1", "pub1", "exp2", "pub2", "exp3"]
+iss = ["pv_begin", "pv_chunk0", "pv_last", "pv_issued", "qk_issued"]
+print("# clocks relative to block 8 / tile 0 / wait_s (CTA 0, first unit)")
+for blk in range(8, 14):
+    for t in range(2):
+        print(f"blk {blk:2d} tile {t} softmax: " + " ".join(f"{n}={int(tr[t, blk, t, i]) - t0:6d}" for i, n in enumerate(sm)))
+        print(f"blk {blk:2d} tile {t} issuer : " + " ".join(f"{n}={int(tr[2, blk, t, i]) - t0:6d}" for i, n in enumerate(iss)))
+per = (int(tr[0, 24, 0, 0]) - int(tr[0, 8, 0, 0])) / 16
+print(f"# period per key block (tile 0, blocks 8..24): {per:.0f} clocks for 2 x 1024 clocks of tensor work")
