@@ -15,8 +15,8 @@
 //                 tcgen05.ld S -> running max / exp2 / row sum -> bf16 P written back to TMEM over S
 //                 (tcgen05.st); lazy rescale of O in TMEM only when the running max grows by > 2^8
 //                 (exact: the stale max cancels in the final 1/l normalisation); final O/l -> global.
-//                 P reaches the MMA warp in 4 chunks of 32 keys (own mbarrier each) so PV starts while
-//                 the rest of the row is still in exp2.  Measured and rejected on B200 (r01): moving
+//                 P reaches the MMA warp in two pieces, keys [0,96) and [96,128) of the block (own mbarrier
+//                 each), so the PV MMAs of the first piece run while the last keys are still in exp2.  Measured and rejected on B200 (r01): moving
 //                 25/50 % of the exp2 to a degree-3 FMA-pipe polynomial (-1 % / -6 %: the extra issue
 //                 slots cost more than the MUFU relief gains).
 // TMEM columns: S0/P0 [0,128)  S1/P1 [128,256)  O0 [256,256+D)  O1 [384,384+D).
@@ -28,7 +28,8 @@ constexpr int ATT_BM = 128;       // query rows per tile
 constexpr int ATT_BN = 128;       // keys per block
 constexpr int ATT_THREADS = 384;  // 12 warps
 constexpr float ATT_RESCALE_TAU = 8.0f;
-constexpr int ATT_PCHUNKS = 4;    // P_t reaches the MMA warp in 4 chunks of 32 keys (PV overlaps the exp tail)
+constexpr int ATT_PCHUNKS = 2;    // P_t reaches the MMA warp in two pieces: keys [0,96) and [96,128) of a block
+constexpr int ATT_PSPLIT = 96;    // (the six PV MMAs of the first piece run under the exp2 of the last 32 keys)
 constexpr int ATT64_POLY = 0;     // head_dim 64: exp2 pairs (of every 8) on the FMA pipe instead of the MUFU — 0: measured slower (r02)
 
 struct AttnKParams {
@@ -93,8 +94,8 @@ struct AttnUnit {
   bool causal;
 };
 
-// P = 2^(s*scale - m) of one 128-key block: packed to bf16 pairs, written to the P columns of TMEM and handed to the MMA
-// warp 32 keys at a time so PV starts while the rest of the row is still in exp2.
+// P = 2^(s*scale - m) of one 128-key block: packed to bf16 pairs, written to the P columns of TMEM 32 keys per store and handed
+// to the MMA warp in two pieces (ATT_PSPLIT keys, then the rest) so PV starts while the last keys are still in exp2.
 // POLY (0..8): of every 8 score pairs, POLY take exp2 on the FMA pipe (round-to-nearest split x = n + f, degree-3 minimax
 // polynomial for 2^f on [-0.5, 0.5], max rel error 7.5e-5 — far below the bf16 rounding of P — and n added to the
 // exponent field) instead of MUFU.EX2.  At head_dim 64 a 128 x 128 tile needs 1024 MUFU clocks (16 exp2 / clk / SM,
@@ -103,15 +104,28 @@ template <int POLY>
 __device__ __forceinline__ void softmax_block(const uint32_t (&sv)[128], float m_used, float scale_log2, uint64_t& sum2,
                                               uint32_t tP_w, uint64_t* p_full_t, int lane, [[maybe_unused]] bool tr_on = false,
                                               [[maybe_unused]] int tr_t = 0, [[maybe_unused]] uint32_t tr_g = 0) {
-  const uint64_t neg_m2 = pack2(-m_used, -m_used);
+  uint64_t neg_m2 = pack2(-m_used, -m_used);
   const uint64_t scale2 = pack2(scale_log2, scale_log2);
   [[maybe_unused]] const uint64_t magic2 = pack2(12582912.f, 12582912.f), nmagic2 = pack2(-12582912.f, -12582912.f);
   [[maybe_unused]] const uint64_t none2 = pack2(-1.f, -1.f);
   [[maybe_unused]] const uint64_t c0 = pack2(0.99992806f, 0.99992806f), c1 = pack2(0.69326097f, 0.69326097f);
   [[maybe_unused]] const uint64_t c2 = pack2(0.24261113f, 0.24261113f), c3 = pack2(0.05517167f, 0.05517167f);
+  constexpr int CW = 32;  // keys per TMEM store
 #pragma unroll
-  for (int c = 0; c < ATT_PCHUNKS; ++c) {
-    constexpr int CW = ATT_BN / ATT_PCHUNKS;  // keys per chunk
+  for (int c = 0; c < ATT_BN / CW; ++c) {
+    if (c * CW == ATT_PSPLIT) {
+      // First hand-over: keys [0, ATT_PSPLIT).  ptxas issues every exp2 it can reach in one burst and sinks TMEM stores,
+      // waits and arrives behind it (profiles/r02_attention_timeline.txt: with a hand-over per 32 keys all four ended up
+      // behind the whole burst, ~120 clocks of exposed store latency each), so the exp2 of the remaining keys are made to
+      // depend on a value read AFTER the arrive: +0 or -0 added to -m, numerically the same number.
+      tmem_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full_t[0]);
+      if (tr_on) G2_TR(tr_t, tr_g, tr_t, 5);
+      const float z = mbar_test_wait(&p_full_t[0], 0) ? 0.f : -0.f;
+      neg_m2 = pack2(-m_used + z, -m_used + z);
+    }
     uint32_t pk[CW / 2];
 #pragma unroll
     for (int i = 0; i < CW; i += 2) {
@@ -137,23 +151,12 @@ __device__ __forceinline__ void softmax_block(const uint32_t (&sv)[128], float m
       sum2 = add2(sum2, pack2(p0, p1));
       pk[i >> 1] = pack_bf16x2(p0, p1);
     }
-    if (tr_on) G2_TR(tr_t, tr_g, tr_t, 5 + 2 * c);       // exp2 of chunk c issued
-    // the store of chunk c-1 has had a whole chunk of exp2 to land: publishing it here keeps the
-    // tcgen05.wait::st latency off the critical path
-    if (c > 0) {
-      tmem_wait_st();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&p_full_t[c - 1]);
-      if (tr_on) G2_TR(tr_t, tr_g, tr_t, 4 + 2 * c);     // chunk c-1 handed over
-    }
-    if constexpr (CW == 32) tmem_st16(tP_w + c * 16, pk);
-    else tmem_st32(tP_w + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&pk[0]));
+    tmem_st16(tP_w + c * (CW / 2), pk);
   }
   tmem_wait_st();
   tc_fence_before();
   __syncwarp();
-  if (lane == 0) mbar_arrive(&p_full_t[ATT_PCHUNKS - 1]);
+  if (lane == 0) mbar_arrive(&p_full_t[1]);
 }
 
 // Units blockIdx.x, blockIdx.x + gridDim.x, ... of a persistent CTA: unit u = (work item u / n_heads, head u % n_heads).
@@ -330,7 +333,7 @@ attention_tcgen05_kernel(const __grid_constant__ AttnKParams p) {
         }
         umma_commit(&s_full[t]);
       };
-      // O_t += P_t V, issued chunk by chunk as the softmax warps publish 32 keys of P at a time
+      // O_t += P_t V, issued piece by piece as the softmax warps hand P over
       auto issue_pv = [&](int t, int s, uint32_t par, bool first_block, [[maybe_unused]] uint32_t gblk) {
         const uint32_t va = kv_addr + s * 2 * Cfg::kTileBytes + Cfg::kTileBytes;
         G2_TR(2, gblk, t, 0);
@@ -346,8 +349,7 @@ attention_tcgen05_kernel(const __grid_constant__ AttnKParams p) {
           if (c == 0) G2_TR(2, gblk, t, 1);
           if (c == ATT_PCHUNKS - 1) G2_TR(2, gblk, t, 2);
 #pragma unroll
-          for (int kk = 0; kk < KSTEPS_PV / ATT_PCHUNKS; ++kk) {
-            const int k = c * (KSTEPS_PV / ATT_PCHUNKS) + kk;
+          for (int k = (c == 0 ? 0 : ATT_PSPLIT / 16); k < (c == 0 ? ATT_PSPLIT / 16 : KSTEPS_PV); ++k) {
             // 16 keys = 16 rows of 128 B inside each 64-column box; boxes are BOX_BYTES apart (LBO)
             umma_ts(tO_t, tS_t + k * 8, umma_desc_mnmajor(va + k * 2048, BOX_BYTES), idesc_pv,
                     !(first_block && k == 0));
@@ -428,7 +430,7 @@ attention_tcgen05_kernel(const __grid_constant__ AttnKParams p) {
         umma_commit(&s_full[t]);
         umma_commit(&k_empty[s]);
       };
-      // O_t += P_t V, issued chunk by chunk as the softmax warps publish 32 keys of P at a time
+      // O_t += P_t V, issued piece by piece as the softmax warps hand P over
       auto issue_pv = [&](int s, uint32_t par, bool first_block) {
         const uint32_t va = kv_addr + s * 2 * Cfg::kTileBytes + Cfg::kTileBytes;
 #pragma unroll
@@ -436,8 +438,7 @@ attention_tcgen05_kernel(const __grid_constant__ AttnKParams p) {
           mbar_wait(&p_full[t * ATT_PCHUNKS + c], par);
           tc_fence_after();
 #pragma unroll
-          for (int kk = 0; kk < KSTEPS_PV / ATT_PCHUNKS; ++kk) {
-            const int k = c * (KSTEPS_PV / ATT_PCHUNKS) + kk;
+          for (int k = (c == 0 ? 0 : ATT_PSPLIT / 16); k < (c == 0 ? ATT_PSPLIT / 16 : KSTEPS_PV); ++k) {
             // 16 keys = 16 rows of 128 B inside each 64-column box; boxes are BOX_BYTES apart (LBO)
             umma_ts(tO_t, tP_t + k * 8, umma_desc_mnmajor(va + k * 2048, BOX_BYTES), idesc_pv,
                     !(first_block && k == 0));

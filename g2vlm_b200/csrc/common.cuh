@@ -118,6 +118,18 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// one non-blocking look at the barrier (mbarrier.test_wait never suspends the thread)
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 // Spin with a watchdog: a protocol bug must trap (→ CUDA error at the C ABI) instead of
 // hanging the GPU. ~4e9 cycles ≈ 2-3 s at B200 clocks, far beyond any legitimate wait here.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {

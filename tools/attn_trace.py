@@ -3,8 +3,8 @@ config 2).  Needs a debug build of the library with -DG2_ATTN_TRACE (the stamps 
     python tools/attn_trace.py --build          # compiles g2vlm_b200/libg2vlm_b200_trace.so next to the product library
     G2VLM_B200_LIB=g2vlm_b200/libg2vlm_b200_trace.so python tools/attn_trace.py
 Events per (block, tile) — softmax warp (sub-partition 0, lane 0): wait_s (phase begins), s_full (S_t complete), ld_done
-(S in registers), max_done (row maximum / rescale decision taken), published (last P chunk handed over), exp<c> (exp2 of
-chunk c done), pub<c> (chunk c handed to the MMA warp);
+(S in registers), max_done (row maximum / rescale decision taken), published (all of P handed over), first_piece (keys
+[0,96) handed over);
 MMA issuer thread: pv_begin, pv_chunk0 (first P chunk seen), pv_last (last P chunk seen), pv_issued, qk_issued (next block's QK^T)."""
 import ctypes, math, os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -40,7 +40,7 @@ if not hasattr(lib, "g2vlm_debug_attn_trace"):
 assert lib.g2vlm_debug_attn_trace(buf) == 0
 tr = torch.tensor(list(buf)).view(3, 32, 2, 16)
 t0 = int(tr[0, 8, 0, 0])
-sm = ["wait_s", "s_full", "ld_done", "max_done", "published", "exp0", "pub0", "exp1", "pub1", "exp2", "pub2", "exp3"]
+sm = ["wait_s", "s_full", "ld_done", "max_done", "published", "first_piece"]
 iss = ["pv_begin", "pv_chunk0", "pv_last", "pv_issued", "qk_issued"]
 print("# clocks relative to block 8 / tile 0 / wait_s (CTA 0, first unit)")
 for blk in range(8, 14):
