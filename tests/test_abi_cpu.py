@@ -43,6 +43,18 @@ def test_invalid_arguments_are_rejected_without_launching(lib):
                                  None, ctypes.c_int64(1), ctypes.c_int64(16), ctypes.c_int32(0), None) == 1
 
 
+def test_attention_trace_build_compiles(lib):
+    """The -DG2_ATTN_TRACE debug build (tools/attn_trace.py: clock-stamped timeline of the attention kernel) must keep
+    compiling next to the product build, and only IT carries the trace export."""
+    import subprocess
+    import sys
+    tool = os.path.join(os.path.dirname(os.path.dirname(__file__)), "tools", "attn_trace.py")
+    subprocess.run([sys.executable, tool, "--build"], check=True, capture_output=True, timeout=600)
+    trace = ctypes.CDLL(str(_lib.PKG_DIR / "libg2vlm_b200_trace.so"))
+    assert hasattr(trace, "g2vlm_debug_attn_trace") and not hasattr(lib, "g2vlm_debug_attn_trace")
+    assert all(hasattr(trace, n) for n in _lib.declared_symbols())
+
+
 def test_ops_refuse_cpu_tensors():
     x = torch.zeros(4, 64, dtype=torch.bfloat16)
     with pytest.raises(ops.G2Error, match="CUDA tensor"):
