@@ -43,6 +43,23 @@ def _views_u8(n, h, w, seed):
     return (schema.synthetic_views(n, h, w, seed=seed) * 255).round().to(torch.uint8)
 
 
+def _check_scene_invariants(out):
+    """Size-independent properties of a reconstructed scene (checked at BASELINE's full sizes, where no CPU oracle runs in
+    seconds): every pose is a rigid transform (g2vlm.py:1215-1226, camera_head.py:81-93: SVD-orthogonalised rotation,
+    det +1, bottom row 0 0 0 1), depth is an exponential (> 0; g2vlm.py:1203-1205), and the world points are exactly the
+    local points moved by the view's pose (geometry.py:108-113)."""
+    poses = out["camera_poses"][0].double()                                   # (N, 4, 4)
+    R, t = poses[:, :3, :3], poses[:, :3, 3]
+    eye = torch.eye(3, dtype=torch.float64, device=R.device)
+    assert (R.transpose(1, 2) @ R - eye).abs().max() < 1e-4
+    assert (torch.linalg.det(R) - 1).abs().max() < 1e-4
+    assert torch.equal(poses[:, 3].float().cpu(), torch.tensor([0., 0., 0., 1.]).expand(poses.shape[0], 4))
+    local = out["local_points"][0].double()                                    # (N, H, W, 3)
+    assert torch.isfinite(local).all() and (local[..., 2] > 0).all()
+    world = torch.einsum("nij,nhwj->nhwi", R, local) + t[:, None, None, :]
+    assert (world - out["points"][0].double()).abs().max() <= 1e-5 * world.abs().max()
+
+
 def _quiet(fn, *a, **k):
     with contextlib.redirect_stdout(io.StringIO()):   # the reference prints progress lines
         return fn(*a, **k)
@@ -112,6 +129,9 @@ def test_full_model_matches_reference_on_gpu(full_pair, name, n, h, w):
         assert got[k].shape == want[k].shape
     assert torch.equal(got["images"].cpu(), want["images"].cpu())
     assert all(e < TOL for e in errs.values()), errs
+    _check_scene_invariants(got)
+    again = fast.recon(rh.StubTokenizer(), dict(rh.NEW_TOKEN_IDS), None, u8.float() / 255.0)
+    assert all(torch.equal(got[k], again[k]) for k in KEYS)                    # no atomics / run-to-run variation on the path
 
 
 def test_full_model_synthetic_layerscale_vs_reference_and_fp32(full_pair):
